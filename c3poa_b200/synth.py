@@ -1,0 +1,109 @@
+"""Seeded synthetic R2C2 read generator (SURVEY.md §8(d) read model).
+
+A read is a window of the concatemer (insert + splint)^k with partial inserts at
+both ends, i.i.d. errors (4 % substitution, 3 % insertion, 3 % deletion), on a
+random strand.  ACGT only.  Also writes the PSL that lets the reference's
+preprocess() skip BLAT (/root/reference/bin/preprocess.py:17,30-32).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SPLINT1 = (
+    "TGAGGCTGATGAGTTCCATATTTGAAAAGTTTTCATCACTACTTAGTTTTTTGATAGCTTCAAGCCAGAGTTGTCTTTTTCTATCTACTCTCATACAACCAAT"
+    "AAATGCTGAAATGAATTCTAAGCGGAGATCGCCTAGTGATTTTAAACTATTGCTGGCAGCATTCTTGAGTCCAATATAAAAGTATTGTGTACCTTTTGCTGGG"
+    "TCAGGTTGTTCTTTAGGAGGAGTAAAAGGATCAAATGCACTAAACGAAACTGAAACAAGCGATCGAAAATATCCCTTT"
+)  # Splint1, 284 nt: the sequence in the reference's splint.fasta
+BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.zeros(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGTNacgtn", b"TGCANtgcan"):
+    _COMP[_a] = _b
+
+
+def revcomp(seq: str) -> str:
+    a = np.frombuffer(seq.encode(), dtype=np.uint8)
+    return _COMP[a][::-1].tobytes().decode()
+
+
+def random_seq(rng: np.random.Generator, n: int) -> np.ndarray:
+    return BASES[rng.integers(0, 4, size=n)]
+
+
+def mutate(rng: np.random.Generator, seq: np.ndarray, sub=0.04, ins=0.03, dele=0.03) -> np.ndarray:
+    """i.i.d. per-base errors; vectorised."""
+    n = seq.size
+    u = rng.random(n)
+    keep = u >= dele
+    is_sub = (u >= dele) & (u < dele + sub)
+    out = seq.copy()
+    ns = int(is_sub.sum())
+    if ns:
+        # substitute with a different base
+        cur = np.searchsorted(BASES, out[is_sub])
+        out[is_sub] = BASES[(cur + rng.integers(1, 4, size=ns)) % 4]
+    is_ins = rng.random(n) < ins
+    reps = keep.astype(np.int64) + is_ins.astype(np.int64)
+    res = np.repeat(out, reps)
+    # positions of inserted bases: the first copy where both keep and ins, or the only copy when deleted+ins
+    starts = np.cumsum(reps) - reps
+    ins_pos = starts[is_ins]
+    res[ins_pos] = BASES[rng.integers(0, 4, size=ins_pos.size)]
+    return res
+
+
+def make_reads(n_reads: int, insert_len=1000, repeats=5, splints=None, seed=20251018,
+               insert_choices=None, repeat_range=None, err=(0.04, 0.03, 0.03), flank=(100, 400),
+               both_strands=True):
+    """Returns dict with names, seqs (str), quals (str), splint_name, strand, truth inserts.
+
+    repeats = number of complete insert copies (subreads); the read holds repeats+1 splints.
+    """
+    rng = np.random.default_rng(seed)
+    if splints is None:
+        splints = {"Splint1": SPLINT1}
+    sp_names = list(splints)
+    sp_arr = {k: np.frombuffer(v.encode(), dtype=np.uint8) for k, v in splints.items()}
+    names, seqs, quals, spn, strands, truths = [], [], [], [], [], []
+    for i in range(n_reads):
+        il = int(rng.choice(insert_choices)) if insert_choices is not None else (
+            int(rng.integers(insert_len[0], insert_len[1] + 1)) if isinstance(insert_len, tuple) else insert_len)
+        k = int(rng.integers(repeat_range[0], repeat_range[1] + 1)) if repeat_range else repeats
+        sname = sp_names[int(rng.integers(0, len(sp_names)))]
+        sp = sp_arr[sname]
+        ins = random_seq(rng, il)
+        head = int(rng.integers(flank[0], min(flank[1], il) + 1))
+        tail = int(rng.integers(flank[0], min(flank[1], il) + 1))
+        parts = [ins[il - head:], sp]
+        for _ in range(k):
+            parts += [ins, sp]
+        parts.append(ins[:tail])
+        clean = np.concatenate(parts)
+        noisy = mutate(rng, clean, *err)
+        strand = "+"
+        if both_strands and rng.random() < 0.5:
+            noisy = _COMP[noisy][::-1]
+            strand = "-"
+        q = rng.integers(7, 21, size=noisy.size).astype(np.uint8) + 33
+        names.append(f"r{i:07d}")
+        seqs.append(noisy.tobytes().decode())
+        quals.append(q.tobytes().decode())
+        spn.append(sname)
+        strands.append(strand)
+        truths.append(ins.tobytes().decode())
+    return dict(names=names, seqs=seqs, quals=quals, splint_name=spn, strand=strands, truth=truths,
+                splints=dict(splints))
+
+
+def write_fastq(path, names, seqs, quals):
+    with open(path, "w") as f:
+        for n, s, q in zip(names, seqs, quals):
+            f.write(f"@{n}\n{s}\n+\n{q}\n")
+
+
+def write_psl(path, names, splint_names, strands):
+    """One PSL line per read: cols 0=matches, 5=gaps, 8=strand, 9=read, 13=splint."""
+    with open(path, "w") as f:
+        for n, s, st in zip(names, splint_names, strands):
+            cols = ["0"] * 21
+            cols[0], cols[5], cols[8], cols[9], cols[13] = "250", "0", st, n, s
+            f.write("\t".join(cols) + "\n")
