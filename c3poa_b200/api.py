@@ -1,0 +1,212 @@
+"""Host-side API over the C ABI: batch containers and the GpuConsensus handle.
+
+Mirrors the reference's three call sites batch-wise (see include/c3poa_gpu.h):
+  conk.conk            -> GpuConsensus.conk_batch        (C3POa.py:123)
+  call_peaks           -> GpuConsensus.peaks_batch       (C3POa.py:124)
+  msa_aligner().msa    -> GpuConsensus.poa_batch         (bin/determine_consensus.py:30-47)
+  analyze_reads body   -> GpuConsensus.consensus_batch   (C3POa.py:112-165, pre-racon)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import PoaParams, RESULT_DTYPE, Timings
+
+
+def sg_coeffs(window: int = 41, order: int = 2) -> np.ndarray:
+    """Savitzky-Golay coefficients exactly as the reference computes them
+    (/root/reference/bin/savitzky_golay.py:27-31, deriv=0, rate=1)."""
+    half = (window - 1) // 2
+    b = np.asmatrix([[k ** i for i in range(order + 1)] for k in range(-half, half + 1)])
+    return np.ascontiguousarray(np.linalg.pinv(b).A[0], dtype=np.float64)
+
+
+def default_poa_params(**kw) -> PoaParams:
+    p = PoaParams()
+    _lib.load().c3_default_poa_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _pack(strs):
+    """list[str|bytes] -> (uint8 blob, int64 offsets)."""
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in strs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs])
+    blob = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, dtype=np.uint8)
+    return blob, off
+
+
+@dataclass
+class ReadBatch:
+    """Packed reads + strand-resolved splints, ready for the device."""
+    blob: np.ndarray          # uint8 ASCII
+    off: np.ndarray           # int64 [n+1]
+    sp_blob: np.ndarray       # uint8 ASCII
+    sp_off: np.ndarray        # int32 [n_splints+1]
+    sp_idx: np.ndarray        # int32 [n]
+
+    @property
+    def n(self) -> int:
+        return self.off.size - 1
+
+    @classmethod
+    def from_strings(cls, seqs, splints, splint_idx):
+        blob, off = _pack(seqs)
+        sp_blob, sp_off = _pack(splints)
+        return cls(blob, off, sp_blob, sp_off.astype(np.int32), np.ascontiguousarray(splint_idx, dtype=np.int32))
+
+    def seq(self, i: int) -> str:
+        return self.blob[self.off[i]:self.off[i + 1]].tobytes().decode()
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory owned by the library."""
+
+    def __init__(self, shape, dtype):
+        self._L = _lib.load()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        self._p = self._L.c3_host_alloc(max(n, 1))
+        if not self._p:
+            raise MemoryError("c3_host_alloc failed")
+        buf = (C.c_uint8 * max(n, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._p:
+                self.array = None
+                self._L.c3_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+class GpuError(RuntimeError):
+    pass
+
+
+class GpuConsensus:
+    """One handle per device (not thread-safe; use one per host thread/GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = self._L.c3_init(device, C.byref(h))
+        if rc != 0:
+            raise GpuError(f"c3_init(device={device}) failed with {rc}: no usable CUDA device "
+                           "(the GPU stages have no CPU fallback)")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.c3_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise GpuError(f"{what} failed ({rc}): {self._L.c3_last_error(self._h).decode()}")
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._L.c3_get_timings(self._h, C.byref(t))
+        return {k: getattr(t, k) for k, _ in Timings._fields_}
+
+    def int_peak_ops(self) -> float:
+        v = C.c_double()
+        self._ck(self._L.c3_measure_int_peak(self._h, C.byref(v)), "c3_measure_int_peak")
+        return v.value
+
+    # ---- B1 ----
+    def conk_batch(self, batch: ReadBatch, penalty: int = 20):
+        """Returns the int32 profile blob (CSR with batch.off)."""
+        prof = np.empty(int(batch.off[-1]), dtype=np.int32)
+        self._ck(self._L.c3_conk_batch(self._h, batch.n, batch.blob.ctypes.data, batch.off.ctypes.data,
+                                       batch.sp_off.size - 1, batch.sp_blob.ctypes.data, batch.sp_off.ctypes.data,
+                                       batch.sp_idx.ctypes.data, penalty, prof.ctypes.data), "c3_conk_batch")
+        return prof
+
+    # ---- B2 ----
+    def peaks_batch(self, prof: np.ndarray, off: np.ndarray, min_dist=500, iters=3, window=41, order=2,
+                    coef=None, want_smoothed=False, max_peaks=64, height_mult=3.0, gate_mult=6.0):
+        prof = np.ascontiguousarray(prof, dtype=np.int32)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        n = off.size - 1
+        coef = sg_coeffs(window, order) if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
+        peaks = np.zeros((n, max_peaks), dtype=np.int32)
+        npk = np.zeros(n, dtype=np.int32)
+        med = np.zeros(n, dtype=np.float64)
+        sm = np.empty(prof.size, dtype=np.float64) if want_smoothed else None
+        self._ck(self._L.c3_peaks_batch(self._h, n, prof.ctypes.data, off.ctypes.data, coef.ctypes.data, coef.size,
+                                        iters, min_dist, height_mult, gate_mult,
+                                        sm.ctypes.data if want_smoothed else None, med.ctypes.data,
+                                        peaks.ctypes.data, max_peaks, npk.ctypes.data), "c3_peaks_batch")
+        return dict(peaks=peaks, n_peaks=npk, median=med, smoothed=sm)
+
+    # ---- B3 ----
+    def poa_batch(self, groups, params: PoaParams | None = None, cons_cap: int | None = None):
+        """groups: list of list[str].  Returns dict(cons=list[str], status, cells, nodes)."""
+        params = params or default_poa_params()
+        flat = [s for g in groups for s in g]
+        blob, off = _pack(flat)
+        goff = np.zeros(len(groups) + 1, dtype=np.int32)
+        goff[1:] = np.cumsum([len(g) for g in groups])
+        n = len(groups)
+        if cons_cap is None:
+            cons_cap = int(max((len(s) for s in flat), default=1)) * 2 + 64
+        cons = np.zeros((n, cons_cap), dtype=np.uint8)
+        clen = np.zeros(n, dtype=np.int32)
+        cells = np.zeros(n, dtype=np.int64)
+        nodes = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        self._ck(self._L.c3_poa_batch(self._h, n, blob.ctypes.data, off.ctypes.data, goff.ctypes.data,
+                                      C.byref(params), cons.ctypes.data, cons_cap, clen.ctypes.data,
+                                      cells.ctypes.data, nodes.ctypes.data, status.ctypes.data, None, 0, None),
+                 "c3_poa_batch")
+        return dict(cons=[cons[i, :clen[i]].tobytes().decode() for i in range(n)], status=status, cells=cells,
+                    nodes=nodes)
+
+    # ---- B4 ----
+    def stage(self, batch: ReadBatch):
+        self._ck(self._L.c3_stage(self._h, batch.n, batch.blob.ctypes.data, batch.off.ctypes.data,
+                                  batch.sp_off.size - 1, batch.sp_blob.ctypes.data, batch.sp_off.ctypes.data,
+                                  batch.sp_idx.ctypes.data), "c3_stage")
+        self._n = batch.n
+
+    def run(self, penalty=20, min_dist=500, iters=3, window=41, order=2, coef=None, params=None,
+            max_peaks=64, cons_cap=4096):
+        coef = sg_coeffs(window, order) if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
+        params = params or default_poa_params()
+        self._ck(self._L.c3_run(self._h, penalty, coef.ctypes.data, coef.size, iters, min_dist, C.byref(params),
+                                max_peaks, cons_cap), "c3_run")
+        self._max_peaks, self._cons_cap = max_peaks, cons_cap
+
+    def fetch(self, out=None):
+        n, mp, cc = self._n, self._max_peaks, self._cons_cap
+        if out is None:
+            out = dict(peaks=np.zeros((n, mp), dtype=np.int32), sub_bounds=np.zeros((n, mp, 2), dtype=np.int32),
+                       dang_bounds=np.zeros((n, 2, 2), dtype=np.int32), cons=np.zeros((n, cc), dtype=np.uint8),
+                       results=np.zeros(n, dtype=RESULT_DTYPE))
+        self._ck(self._L.c3_fetch(self._h, out["peaks"].ctypes.data, out["sub_bounds"].ctypes.data,
+                                  out["dang_bounds"].ctypes.data, out["cons"].ctypes.data,
+                                  out["results"].ctypes.data), "c3_fetch")
+        return out
+
+    def consensus_batch(self, batch: ReadBatch, out=None, **kw):
+        self.stage(batch)
+        self.run(**kw)
+        return self.fetch(out)

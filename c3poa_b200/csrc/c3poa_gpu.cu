@@ -1,0 +1,608 @@
+// c3poa_gpu.cu -- C ABI (include/c3poa_gpu.h) over the sm_100a kernels.
+// No torch types, no CPU fallback: every entry point needs a working device.
+#include "../../include/c3poa_gpu.h"
+#include "common.cuh"
+#include "conk.cuh"
+#include "peaks.cuh"
+#include "poa.cuh"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define C3_VERSION "c3poa_b200 0.1.0 (sm_100a)"
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct c3_handle {
+    int device = 0, sm_count = 0;
+    size_t total_mem = 0;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    cudaEvent_t ev[8] = {nullptr};
+    c3_timings tim{};
+    // staged batch
+    int n_reads = 0, n_splints = 0, max_lr = 0, max_ls = 0, max_peaks = 0, cons_cap = 0;
+    int64_t total_bases = 0, total_sp = 0;
+    bool staged = false, ran = false;
+    DevBuf d_ascii, d_codes, d_off, d_sp_ascii, d_sp_codes, d_sp_off, d_sp_idx;
+    DevBuf d_prof, d_brow, d_counter, d_coef, d_pk_scratch, d_smoothed, d_median;
+    DevBuf d_peaks, d_npk, d_sub, d_dang, d_res, d_stats, d_cons, d_ws;
+    // B3 staging
+    DevBuf d_item_base, d_bounds, d_nseq, d_status, d_clen, d_nodes, d_cells;
+};
+
+static int fail(c3_handle *h, int code, const char *fmt, ...)
+{
+    if (h) {
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(h, -1, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+extern "C" const char *c3_version(void) { return C3_VERSION; }
+
+extern "C" int c3_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" void c3_default_poa_params(c3_poa_params *p)
+{
+    p->match = 5; p->mismatch = 4; p->gap_open1 = 4; p->gap_ext1 = 2; p->gap_open2 = 24; p->gap_ext2 = 1;
+    p->wb = 10; p->simd_bits = 256; p->wf = 0.01;
+}
+
+extern "C" int c3_init(int device, c3_handle **out)
+{
+    if (!out) return -1;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return -2;   // no CPU fallback
+    c3_handle *h = new c3_handle();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return -3; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return -3; }
+    h->sm_count = prop.multiProcessorCount;
+    h->total_mem = prop.totalGlobalMem;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -4; }
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
+    *out = h;
+    return 0;
+}
+
+extern "C" void c3_destroy(c3_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->d_ascii, &h->d_codes, &h->d_off, &h->d_sp_ascii, &h->d_sp_codes, &h->d_sp_off, &h->d_sp_idx,
+                      &h->d_prof, &h->d_brow, &h->d_counter, &h->d_coef, &h->d_pk_scratch, &h->d_smoothed, &h->d_median,
+                      &h->d_peaks, &h->d_npk, &h->d_sub, &h->d_dang, &h->d_res, &h->d_stats, &h->d_cons, &h->d_ws,
+                      &h->d_item_base, &h->d_bounds, &h->d_nseq, &h->d_status, &h->d_clen, &h->d_nodes, &h->d_cells};
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" void *c3_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+extern "C" void c3_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" const char *c3_last_error(const c3_handle *h) { return h ? h->err : "null handle"; }
+
+extern "C" int c3_get_timings(const c3_handle *h, c3_timings *out)
+{
+    if (!h || !out) return -1;
+    *out = h->tim;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------
+static int launch_encode(c3_handle *h, const void *in, void *out, int64_t n)
+{
+    if (n <= 0) return 0;
+    int blocks = (int)std::min<int64_t>((n / 16 + 255) / 256 + 1, (int64_t)h->sm_count * 8);
+    c3_encode_kernel<<<blocks, 256, 0, h->stream>>>((const uint8_t *)in, (uint8_t *)out, n);
+    CK(cudaGetLastError());
+    h->tim.kernel_launches++;
+    return 0;
+}
+
+template <int R>
+static cudaError_t launch_conk_R(c3_handle *h, int grid, int penalty, int32_t *brow, int64_t brow_stride)
+{
+    c3_conk_kernel<R><<<grid, C3_CONK_THREADS, 0, h->stream>>>(
+        h->d_codes.as<uint8_t>(), h->d_off.as<int64_t>(), h->n_reads, h->d_sp_codes.as<uint8_t>(),
+        h->d_sp_off.as<int32_t>(), h->d_sp_idx.as<int32_t>(), penalty, h->d_prof.as<int32_t>(), brow, brow_stride,
+        h->d_counter.as<unsigned>());
+    return cudaGetLastError();
+}
+
+static int launch_conk(c3_handle *h, int penalty)
+{
+    CK(h->d_prof.ensure((size_t)h->total_bases * 4 + 16));
+    CK(h->d_counter.ensure(64));
+    CK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
+    int R = (h->max_ls + 31) / 32;
+    if (R < 1) R = 1;
+    if (R > C3_CONK_MAXR) R = C3_CONK_MAXR;
+    const int warps_per_block = C3_CONK_THREADS / 32;
+    int grid = h->sm_count * 4;
+    grid = std::max(1, std::min(grid, (h->n_reads + warps_per_block - 1) / warps_per_block));
+    int32_t *brow = nullptr; int64_t bstride = 0;
+    if (h->max_ls > 32 * R) {
+        bstride = ((int64_t)h->max_lr + 31) & ~31ll;
+        CK(h->d_brow.ensure((size_t)grid * warps_per_block * 2 * bstride * 4));
+        brow = h->d_brow.as<int32_t>();
+    }
+    cudaError_t e;
+    switch (R) {
+#define C3_CASE(r) case r: e = launch_conk_R<r>(h, grid, penalty, brow, bstride); break;
+        C3_CASE(1) C3_CASE(2) C3_CASE(3) C3_CASE(4) C3_CASE(5) C3_CASE(6) C3_CASE(7) C3_CASE(8)
+        C3_CASE(9) C3_CASE(10) C3_CASE(11) C3_CASE(12) C3_CASE(13) C3_CASE(14) C3_CASE(15) C3_CASE(16)
+#undef C3_CASE
+        default: e = cudaErrorInvalidValue;
+    }
+    CK(e);
+    h->tim.kernel_launches++;
+    return 0;
+}
+
+static int launch_peaks(c3_handle *h, const int32_t *d_prof, const int64_t *d_off, int n, int max_len,
+                        const double *coef, int window, int iters, int min_dist, double hm, double gm,
+                        bool want_smoothed, bool want_median, int max_peaks, int64_t total)
+{
+    if (window < 1 || window > C3_PK_MAXWIN || !(window & 1)) return fail(h, -5, "window must be odd and <= %d", C3_PK_MAXWIN);
+    CK(h->d_coef.ensure((size_t)window * 8));
+    CK(cudaMemcpyAsync(h->d_coef.p, coef, (size_t)window * 8, cudaMemcpyHostToDevice, h->stream));
+    int grid = std::max(1, std::min(h->sm_count * 4, n));
+    int64_t stride = ((int64_t)max_len + 63) & ~63ll;
+    CK(h->d_pk_scratch.ensure((size_t)grid * 2 * stride * 8));
+    CK(h->d_peaks.ensure((size_t)n * max_peaks * 4 + 16));
+    CK(h->d_npk.ensure((size_t)n * 4 + 16));
+    if (want_smoothed) CK(h->d_smoothed.ensure((size_t)total * 8 + 16));
+    if (want_median) CK(h->d_median.ensure((size_t)n * 8 + 16));
+    CK(h->d_counter.ensure(64));
+    CK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
+    c3_peaks_args A;
+    A.prof = d_prof; A.off = d_off; A.n = n; A.coef = h->d_coef.as<double>(); A.window = window; A.iters = iters;
+    A.min_dist = min_dist; A.height_mult = hm; A.gate_mult = gm; A.scratch = h->d_pk_scratch.as<double>();
+    A.scratch_stride = stride; A.out_smoothed = want_smoothed ? h->d_smoothed.as<double>() : nullptr;
+    A.out_median = want_median ? h->d_median.as<double>() : nullptr; A.out_peaks = h->d_peaks.as<int32_t>();
+    A.out_n_peaks = h->d_npk.as<int32_t>(); A.max_peaks = max_peaks; A.counter = h->d_counter.as<unsigned>();
+    c3_peaks_kernel<<<grid, C3_PK_THREADS, 0, h->stream>>>(A);
+    CK(cudaGetLastError());
+    h->tim.kernel_launches++;
+    return 0;
+}
+
+static void to_dev_para(const c3_poa_params *p, c3_poa_para_dev *d)
+{
+    d->match = p->match; d->mismatch = p->mismatch; d->o1 = p->gap_open1; d->e1 = p->gap_ext1;
+    d->o2 = p->gap_open2; d->e2 = p->gap_ext2; d->wb = p->wb; d->simd_bits = p->simd_bits; d->wf = p->wf;
+}
+
+// workspace sizing from the batch maxima (longest sequence, most sequences, largest total)
+static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int64_t max_total, const c3_poa_params *pp)
+{
+    to_dev_para(pp, &A.P);
+    if (A.P.simd_bits != 128 && A.P.simd_bits != 256 && A.P.simd_bits != 512) return fail(h, -5, "simd_bits must be 128/256/512");
+    int64_t est = 2 + (int64_t)max_q + (int64_t)(max_nseq - 1) * ((int64_t)max_q * 35 / 100 + 16);
+    int64_t node_cap = std::min<int64_t>(std::min<int64_t>(est, max_total + 2), 65534);
+    node_cap = std::max<int64_t>((node_cap + 31) & ~31ll, 64);
+    if (node_cap > 65534) node_cap = 65534;
+    int pool_cap = (int)std::min<int64_t>(node_cap, 65534);
+    int w = pp->wb < 0 ? max_q : pp->wb + (int)(pp->wf * max_q);
+    int64_t width = std::min<int64_t>(2ll * w + 64 + 16, (int64_t)max_q + 1);
+    int64_t cell_cap = std::min<int64_t>(5 * node_cap * width, 0x7ffffff0ll / 4);
+    int cigar_cap = (int)(max_q + node_cap + 64);
+    int64_t ws_bytes = c3_poa_ws_bytes((int)node_cap, pool_cap, (int)cell_cap, cigar_cap);
+    const int wpb = C3_POA_THREADS / 32;
+    int grid = h->sm_count * 4;
+    grid = std::max(1, std::min(grid, (A.n_items + wpb - 1) / wpb));
+    size_t free_b = 0, tot_b = 0;
+    CK(cudaMemGetInfo(&free_b, &tot_b));
+    int64_t budget = (int64_t)((double)(free_b + h->d_ws.cap) * 0.8);
+    int64_t max_warps = budget / ws_bytes;
+    if (max_warps < 1) return fail(h, -6, "POA workspace of %lld bytes per warp does not fit", (long long)ws_bytes);
+    if ((int64_t)grid * wpb > max_warps) grid = (int)std::max<int64_t>(1, max_warps / wpb);
+    CK(h->d_ws.ensure((size_t)grid * wpb * ws_bytes));
+    CK(h->d_counter.ensure(64));
+    CK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
+    A.ws = h->d_ws.as<uint8_t>(); A.ws_stride = ws_bytes;
+    A.node_cap = (int)node_cap; A.pool_cap = pool_cap; A.cell_cap = (int)cell_cap; A.cigar_cap = cigar_cap;
+    A.counter = h->d_counter.as<unsigned>();
+    c3_poa_kernel<<<grid, C3_POA_THREADS, 0, h->stream>>>(A);
+    CK(cudaGetLastError());
+    h->tim.kernel_launches++;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// staging of reads + splints (shared by B1 and B4)
+// ---------------------------------------------------------------------------
+static int stage_reads(c3_handle *h, int32_t n_reads, const char *reads, const int64_t *read_off,
+                       int32_t n_splints, const char *splints, const int32_t *splint_off, const int32_t *splint_idx)
+{
+    if (!h) return -1;
+    if (n_reads <= 0 || !reads || !read_off || n_splints <= 0 || !splints || !splint_off || !splint_idx)
+        return fail(h, -5, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    int64_t total = read_off[n_reads] - read_off[0];
+    if (read_off[0] != 0) return fail(h, -5, "read_off[0] must be 0");
+    int max_lr = 0;
+    for (int i = 0; i < n_reads; ++i) {
+        int64_t L = read_off[i + 1] - read_off[i];
+        if (L <= 0 || L > 0x3fffffff) return fail(h, -5, "read %d has invalid length %lld", i, (long long)L);
+        max_lr = std::max(max_lr, (int)L);
+        if (splint_idx[i] < 0 || splint_idx[i] >= n_splints) return fail(h, -5, "splint_idx[%d] out of range", i);
+    }
+    int max_ls = 0;
+    for (int i = 0; i < n_splints; ++i) {
+        int L = splint_off[i + 1] - splint_off[i];
+        if (L <= 0) return fail(h, -5, "splint %d is empty", i);
+        max_ls = std::max(max_ls, L);
+    }
+    int64_t total_sp = splint_off[n_splints];
+    h->n_reads = n_reads; h->n_splints = n_splints; h->max_lr = max_lr; h->max_ls = max_ls;
+    h->total_bases = total; h->total_sp = total_sp;
+    CK(h->d_ascii.ensure((size_t)total + 64));
+    CK(h->d_codes.ensure((size_t)total + 64));
+    CK(h->d_off.ensure((size_t)(n_reads + 1) * 8));
+    CK(h->d_sp_ascii.ensure((size_t)total_sp + 64));
+    CK(h->d_sp_codes.ensure((size_t)total_sp + 64));
+    CK(h->d_sp_off.ensure((size_t)(n_splints + 1) * 4));
+    CK(h->d_sp_idx.ensure((size_t)n_reads * 4));
+    CK(cudaMemcpyAsync(h->d_ascii.p, reads, (size_t)total, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_off.p, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_sp_ascii.p, splints, (size_t)total_sp, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_sp_off.p, splint_off, (size_t)(n_splints + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_sp_idx.p, splint_idx, (size_t)n_reads * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->staged = true; h->ran = false;
+    return 0;
+}
+
+static int encode_staged(c3_handle *h)
+{
+    int rc = launch_encode(h, h->d_ascii.p, h->d_codes.p, h->total_bases);
+    if (rc) return rc;
+    return launch_encode(h, h->d_sp_ascii.p, h->d_sp_codes.p, h->total_sp);
+}
+
+// ---------------------------------------------------------------------------
+// B1
+// ---------------------------------------------------------------------------
+extern "C" int c3_conk_batch(c3_handle *h, int32_t n_reads, const char *reads, const int64_t *read_off,
+                             int32_t n_splints, const char *splints, const int32_t *splint_off,
+                             const int32_t *splint_idx, int32_t penalty, int32_t *out_profile)
+{
+    int rc = stage_reads(h, n_reads, reads, read_off, n_splints, splints, splint_off, splint_idx);
+    if (rc) return rc;
+    if (!out_profile) return fail(h, -5, "out_profile is null");
+    h->tim = c3_timings{};
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = encode_staged(h))) return rc;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    if ((rc = launch_conk(h, penalty))) return rc;
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(cudaMemcpyAsync(out_profile, h->d_prof.p, (size_t)h->total_bases * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->tim.encode_ms, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->tim.conk_ms, h->ev[1], h->ev[2]);
+    h->tim.total_ms = h->tim.encode_ms + h->tim.conk_ms;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// B2
+// ---------------------------------------------------------------------------
+extern "C" int c3_peaks_batch(c3_handle *h, int32_t n, const int32_t *profile, const int64_t *off,
+                              const double *coef, int32_t window, int32_t iters, int32_t min_dist,
+                              double height_mult, double gate_mult, double *out_smoothed,
+                              double *out_median, int32_t *out_peaks, int32_t max_peaks, int32_t *out_n_peaks)
+{
+    if (!h) return -1;
+    if (n <= 0 || !profile || !off || !coef || !out_peaks || !out_n_peaks || max_peaks <= 0)
+        return fail(h, -5, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    int64_t total = off[n];
+    int max_len = 0;
+    for (int i = 0; i < n; ++i) max_len = std::max<int64_t>(max_len, off[i + 1] - off[i]);
+    CK(h->d_prof.ensure((size_t)total * 4 + 16));
+    CK(h->d_off.ensure((size_t)(n + 1) * 8));
+    CK(cudaMemcpyAsync(h->d_prof.p, profile, (size_t)total * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_off.p, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    h->tim = c3_timings{};
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    int rc = launch_peaks(h, h->d_prof.as<int32_t>(), h->d_off.as<int64_t>(), n, max_len, coef, window, iters, min_dist,
+                          height_mult, gate_mult, out_smoothed != nullptr, out_median != nullptr, max_peaks, total);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaMemcpyAsync(out_peaks, h->d_peaks.p, (size_t)n * max_peaks * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out_n_peaks, h->d_npk.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (out_smoothed) CK(cudaMemcpyAsync(out_smoothed, h->d_smoothed.p, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (out_median) CK(cudaMemcpyAsync(out_median, h->d_median.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->tim.peaks_ms, h->ev[0], h->ev[1]);
+    h->tim.total_ms = h->tim.peaks_ms;
+    h->staged = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// B3
+// ---------------------------------------------------------------------------
+extern "C" int c3_poa_batch(c3_handle *h, int32_t n_groups, const char *seqs, const int64_t *seq_off,
+                            const int32_t *group_off, const c3_poa_params *params, char *out_cons,
+                            int32_t cons_cap, int32_t *out_cons_len, int64_t *out_cells,
+                            int32_t *out_nodes, int32_t *out_status, char *out_msa, int32_t msa_cap,
+                            int32_t *out_msa_len)
+{
+    if (!h) return -1;
+    if (n_groups <= 0 || !seqs || !seq_off || !group_off || !params || !out_cons || cons_cap <= 0 || !out_cons_len || !out_status)
+        return fail(h, -5, "bad arguments");
+    if (out_msa || msa_cap || out_msa_len) return fail(h, -7, "MSA rows are not produced by this build");
+    CK(cudaSetDevice(h->device));
+    const int n_seqs = group_off[n_groups];
+    const int64_t total = seq_off[n_seqs];
+    int max_nseq = 0, max_q = 0; int64_t max_total = 0;
+    std::vector<int64_t> item_base(n_groups);
+    std::vector<int32_t> nseq(n_groups);
+    for (int g = 0; g < n_groups; ++g) {
+        nseq[g] = group_off[g + 1] - group_off[g];
+        max_nseq = std::max(max_nseq, nseq[g]);
+    }
+    if (max_nseq <= 0) return fail(h, -5, "empty groups");
+    std::vector<int32_t> bounds((size_t)n_groups * max_nseq * 2, 0);
+    for (int g = 0; g < n_groups; ++g) {
+        const int s0 = group_off[g];
+        item_base[g] = seq_off[s0];
+        int64_t tot = 0;
+        for (int k = 0; k < nseq[g]; ++k) {
+            const int64_t a = seq_off[s0 + k] - item_base[g], b = seq_off[s0 + k + 1] - item_base[g];
+            if (b - a > 65000 || b > 0x7fffffff) return fail(h, -5, "sequence too long in group %d", g);
+            bounds[((size_t)g * max_nseq + k) * 2] = (int32_t)a;
+            bounds[((size_t)g * max_nseq + k) * 2 + 1] = (int32_t)b;
+            max_q = std::max<int>(max_q, (int)(b - a));
+            tot += b - a;
+        }
+        max_total = std::max(max_total, tot);
+    }
+    CK(h->d_ascii.ensure((size_t)total + 64));
+    CK(h->d_codes.ensure((size_t)total + 64));
+    CK(h->d_item_base.ensure((size_t)n_groups * 8));
+    CK(h->d_bounds.ensure(bounds.size() * 4));
+    CK(h->d_nseq.ensure((size_t)n_groups * 4));
+    CK(h->d_status.ensure((size_t)n_groups * 4));
+    CK(h->d_clen.ensure((size_t)n_groups * 4));
+    CK(h->d_nodes.ensure((size_t)n_groups * 4));
+    CK(h->d_cells.ensure((size_t)n_groups * 8));
+    CK(h->d_cons.ensure((size_t)n_groups * cons_cap));
+    CK(cudaMemcpyAsync(h->d_ascii.p, seqs, (size_t)total, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_item_base.p, item_base.data(), (size_t)n_groups * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_bounds.p, bounds.data(), bounds.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_nseq.p, nseq.data(), (size_t)n_groups * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_status.p, 0, (size_t)n_groups * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_clen.p, 0, (size_t)n_groups * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_nodes.p, 0, (size_t)n_groups * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_cells.p, 0, (size_t)n_groups * 8, h->stream));
+    h->tim = c3_timings{};
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    int rc = launch_encode(h, h->d_ascii.p, h->d_codes.p, total);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    c3_poa_args A;
+    memset(&A, 0, sizeof(A));
+    A.codes = h->d_codes.as<uint8_t>(); A.item_base = h->d_item_base.as<int64_t>(); A.bounds = h->d_bounds.as<int32_t>();
+    A.n_seqs = h->d_nseq.as<int32_t>(); A.n_seqs_stride = 1; A.n_items = n_groups; A.max_seqs = max_nseq; A.min_seqs = 1;
+    A.cons = h->d_cons.as<char>(); A.cons_cap = cons_cap; A.status = h->d_status.as<int32_t>();
+    A.cons_len = h->d_clen.as<int32_t>(); A.nodes_out = h->d_nodes.as<int32_t>(); A.cells_out = h->d_cells.as<long long>();
+    A.out_stride = 1; A.cells_stride = 2;
+    if ((rc = launch_poa(h, A, max_q, max_nseq, max_total, params))) return rc;
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(cudaMemcpyAsync(out_cons, h->d_cons.p, (size_t)n_groups * cons_cap, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out_cons_len, h->d_clen.p, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out_status, h->d_status.p, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (out_cells) CK(cudaMemcpyAsync(out_cells, h->d_cells.p, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (out_nodes) CK(cudaMemcpyAsync(out_nodes, h->d_nodes.p, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->tim.encode_ms, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->tim.poa_ms, h->ev[1], h->ev[2]);
+    h->tim.total_ms = h->tim.encode_ms + h->tim.poa_ms;
+    h->tim.poa_items = n_groups;
+    h->staged = false;
+    return 0;
+}
+
+// repeats == 1: the consensus is the subread itself (bin/determine_consensus.py:31-32)
+__global__ void c3_copy_single_kernel(int n, const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off,
+                                      const int32_t *__restrict__ sub, int max_peaks, char *cons, int cons_cap,
+                                      c3_read_result_dev *res)
+{
+    const int r = blockIdx.x;
+    if (r >= n) return;
+    if (res[r].status != 0 || res[r].n_sub != 1) return;
+    const int32_t *sb = sub + (int64_t)r * max_peaks * 2;
+    const int L = sb[1] - sb[0];
+    if (L > cons_cap) { if (threadIdx.x == 0) res[r].status = C3_E_CONS; return; }
+    const uint8_t *src = ascii + off[r] + sb[0];
+    char *dst = cons + (int64_t)r * cons_cap;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) dst[i] = (char)src[i];
+    if (threadIdx.x == 0) res[r].cons_len = L;
+}
+
+// ---------------------------------------------------------------------------
+// B4
+// ---------------------------------------------------------------------------
+extern "C" int c3_stage(c3_handle *h, int32_t n_reads, const char *reads, const int64_t *read_off,
+                        int32_t n_splints, const char *splints, const int32_t *splint_off, const int32_t *splint_idx)
+{
+    return stage_reads(h, n_reads, reads, read_off, n_splints, splints, splint_off, splint_idx);
+}
+
+extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t window, int32_t iters,
+                      int32_t min_dist, const c3_poa_params *params, int32_t max_peaks, int32_t cons_cap)
+{
+    if (!h) return -1;
+    if (!h->staged) return fail(h, -8, "c3_run without c3_stage");
+    if (!coef || !params || max_peaks <= 0 || max_peaks > C3_SPLIT_MAXP || cons_cap <= 0) return fail(h, -5, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    const int n = h->n_reads;
+    h->max_peaks = max_peaks; h->cons_cap = cons_cap;
+    h->tim = c3_timings{};
+    CK(h->d_sub.ensure((size_t)n * max_peaks * 2 * 4 + 16));
+    CK(h->d_dang.ensure((size_t)n * 4 * 4 + 16));
+    CK(h->d_res.ensure((size_t)n * sizeof(c3_read_result)));
+    CK(h->d_stats.ensure(64));
+    CK(h->d_cons.ensure((size_t)n * cons_cap + 16));
+    CK(cudaMemsetAsync(h->d_stats.p, 0, 64, h->stream));
+    int rc;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = encode_staged(h))) return rc;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    if ((rc = launch_conk(h, penalty))) return rc;
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    if ((rc = launch_peaks(h, h->d_prof.as<int32_t>(), h->d_off.as<int64_t>(), n, h->max_lr, coef, window, iters,
+                           min_dist, 3.0, 6.0, false, false, max_peaks, h->total_bases))) return rc;
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    c3_split_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+        n, h->d_off.as<int64_t>(), h->d_sp_off.as<int32_t>(), h->d_sp_idx.as<int32_t>(), h->d_peaks.as<int32_t>(),
+        h->d_npk.as<int32_t>(), max_peaks, h->d_sub.as<int32_t>(), h->d_dang.as<int32_t>(),
+        h->d_res.as<c3_read_result_dev>(), h->d_stats.as<int32_t>());
+    CK(cudaGetLastError());
+    h->tim.kernel_launches++;
+    c3_copy_single_kernel<<<n, 128, 0, h->stream>>>(n, h->d_ascii.as<uint8_t>(), h->d_off.as<int64_t>(),
+                                                     h->d_sub.as<int32_t>(), max_peaks, h->d_cons.as<char>(), cons_cap,
+                                                     h->d_res.as<c3_read_result_dev>());
+    CK(cudaGetLastError());
+    h->tim.kernel_launches++;
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    int32_t stats[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(stats, h->d_stats.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));        // 16-byte readback: sizes the POA workspace
+    h->tim.poa_items = stats[3];
+    if (stats[3] > 0) {
+        c3_poa_args A;
+        memset(&A, 0, sizeof(A));
+        c3_read_result *res = h->d_res.as<c3_read_result>();
+        A.codes = h->d_codes.as<uint8_t>(); A.item_base = h->d_off.as<int64_t>(); A.bounds = h->d_sub.as<int32_t>();
+        A.n_seqs = &res->n_sub; A.n_seqs_stride = sizeof(c3_read_result) / 4; A.n_items = n; A.max_seqs = max_peaks; A.min_seqs = 3;
+        A.cons = h->d_cons.as<char>(); A.cons_cap = cons_cap; A.status = &res->status; A.cons_len = &res->cons_len;
+        A.nodes_out = &res->poa_nodes; A.cells_out = (long long *)&res->poa_cells;
+        A.out_stride = sizeof(c3_read_result) / 4; A.cells_stride = sizeof(c3_read_result) / 4;
+        if ((rc = launch_poa(h, A, stats[0], stats[1], stats[2], params))) return rc;
+    }
+    CK(cudaEventRecord(h->ev[5], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->tim.encode_ms, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->tim.conk_ms, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&h->tim.peaks_ms, h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&h->tim.split_ms, h->ev[3], h->ev[4]);
+    cudaEventElapsedTime(&h->tim.poa_ms, h->ev[4], h->ev[5]);
+    cudaEventElapsedTime(&h->tim.total_ms, h->ev[0], h->ev[5]);
+    h->ran = true;
+    return 0;
+}
+
+extern "C" int c3_fetch(c3_handle *h, int32_t *out_peaks, int32_t *out_sub_bounds, int32_t *out_dang_bounds,
+                        char *out_cons, c3_read_result *out_results)
+{
+    if (!h) return -1;
+    if (!h->ran) return fail(h, -8, "c3_fetch without c3_run");
+    if (!out_results) return fail(h, -5, "out_results is null");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n_reads;
+    if (out_peaks) CK(cudaMemcpyAsync(out_peaks, h->d_peaks.p, n * h->max_peaks * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (out_sub_bounds) CK(cudaMemcpyAsync(out_sub_bounds, h->d_sub.p, n * h->max_peaks * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (out_dang_bounds) CK(cudaMemcpyAsync(out_dang_bounds, h->d_dang.p, n * 16, cudaMemcpyDeviceToHost, h->stream));
+    if (out_cons) CK(cudaMemcpyAsync(out_cons, h->d_cons.p, n * h->cons_cap, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out_results, h->d_res.p, n * sizeof(c3_read_result), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int c3_consensus_batch(c3_handle *h, int32_t n_reads, const char *reads, const int64_t *read_off,
+                                  int32_t n_splints, const char *splints, const int32_t *splint_off,
+                                  const int32_t *splint_idx, int32_t penalty, const double *coef,
+                                  int32_t window, int32_t iters, int32_t min_dist,
+                                  const c3_poa_params *params, int32_t max_peaks, int32_t cons_cap,
+                                  int32_t *out_peaks, int32_t *out_sub_bounds, int32_t *out_dang_bounds,
+                                  char *out_cons, c3_read_result *out_results)
+{
+    int rc = c3_stage(h, n_reads, reads, read_off, n_splints, splints, splint_off, splint_idx);
+    if (rc) return rc;
+    if ((rc = c3_run(h, penalty, coef, window, iters, min_dist, params, max_peaks, cons_cap))) return rc;
+    if ((rc = c3_fetch(h, out_peaks, out_sub_bounds, out_dang_bounds, out_cons, out_results))) return rc;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// integer-pipe peak micro-benchmark (roofline denominator for the DP kernels)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) c3_intpeak_kernel(int iters, int *sink)
+{
+    int a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const int b = blockIdx.x | 1, c = -7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = __viaddmax_s32(a0, c, b); a1 = __viaddmax_s32(a1, c, b); a2 = __viaddmax_s32(a2, c, b); a3 = __viaddmax_s32(a3, c, b);
+            a4 = __viaddmax_s32(a4, c, b); a5 = __viaddmax_s32(a5, c, b); a6 = __viaddmax_s32(a6, c, b); a7 = __viaddmax_s32(a7, c, b);
+        }
+    }
+    if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x7fffffff) *sink = a0;
+}
+
+extern "C" int c3_measure_int_peak(c3_handle *h, double *out_ops_per_s)
+{
+    if (!h || !out_ops_per_s) return -1;
+    CK(cudaSetDevice(h->device));
+    CK(h->d_stats.ensure(64));
+    const int iters = 4096, grid = h->sm_count * 8;
+    double best = 0;
+    for (int rep = 0; rep < 12; ++rep) {
+        CK(cudaEventRecord(h->ev[6], h->stream));
+        c3_intpeak_kernel<<<grid, 256, 0, h->stream>>>(iters, h->d_stats.as<int>());
+        CK(cudaEventRecord(h->ev[7], h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
+        // one VIADDMNMX = 2 integer ops (add + max)
+        double ops = 2.0 * 64.0 * iters * 256.0 * grid;
+        if (rep >= 2 && ms > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    *out_ops_per_s = best;
+    return 0;
+}

@@ -1,0 +1,205 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+vectors produced by the reference's own Python.  Bit-exact for integer / index / byte outputs;
+smoothed profiles: bit-exact against the oracle, <= 1e-5 relative against the reference (north_star)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from c3poa_b200 import synth
+from c3poa_b200.api import ReadBatch, default_poa_params, sg_coeffs
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _resolve_splints(d):
+    names = sorted(d["splints"])
+    sp = []
+    for nme in names:
+        sp += [d["splints"][nme], synth.revcomp(d["splints"][nme])]
+    idx = [2 * names.index(s) + (1 if st == "-" else 0) for s, st in zip(d["splint_name"], d["strand"])]
+    return sp, np.array(idx, dtype=np.int32)
+
+
+def _mixed_reads(seed=5):
+    rng = np.random.default_rng(seed)
+    sp2 = synth.random_seq(rng, 150).tobytes().decode()
+    sp3 = synth.random_seq(rng, 700).tobytes().decode()       # > 512 rows: multi-pass conk
+    d1 = synth.make_reads(12, insert_len=1000, repeats=5, seed=seed)
+    d2 = synth.make_reads(8, insert_len=400, repeat_range=(1, 6), seed=seed + 1, splints={"S2": sp2})
+    d3 = synth.make_reads(6, insert_len=800, repeats=3, seed=seed + 2, splints={"S3": sp3})
+    seqs, sps, idx = [], [], []
+    for d in (d1, d2, d3):
+        sp, ix = _resolve_splints(d)
+        idx += list(ix + len(sps))
+        sps += sp
+        seqs += d["seqs"]
+    # Ns and lower case
+    s = list(seqs[0]); s[100] = "N"; s[2000] = "n"; s[2001] = "a"; seqs[0] = "".join(s)
+    seqs.append(synth.random_seq(rng, 1000).tobytes().decode()); idx.append(0)      # no splint
+    seqs.append(synth.random_seq(rng, 33).tobytes().decode()); idx.append(1)        # tiny read
+    return seqs, sps, np.array(idx, dtype=np.int32)
+
+
+def test_conk_parity(gpu, oracle):
+    seqs, sps, idx = _mixed_reads()
+    b = ReadBatch.from_strings(seqs, sps, idx)
+    prof = gpu.conk_batch(b, penalty=20)
+    bad = []
+    for i, s in enumerate(seqs):
+        ref = oracle.conk(sps[idx[i]], s, 20)
+        got = prof[b.off[i]:b.off[i + 1]]
+        if not np.array_equal(ref, got):
+            w = np.flatnonzero(ref != got)
+            bad.append((i, len(s), len(sps[idx[i]]), int(w[0]), int(w.size), int(ref[w[0]]), int(got[w[0]])))
+    assert not bad, f"conk mismatches (read, Lr, Ls, first d, count, ref, got): {bad[:8]}"
+
+
+def test_conk_penalties(gpu, oracle):
+    d = synth.make_reads(4, insert_len=300, repeats=2, seed=9)
+    sp, idx = _resolve_splints(d)
+    b = ReadBatch.from_strings(d["seqs"], sp, idx)
+    for pen in (1, 7, 20, 50):
+        prof = gpu.conk_batch(b, penalty=pen)
+        for i, s in enumerate(d["seqs"]):
+            assert np.array_equal(oracle.conk(sp[idx[i]], s, pen), prof[b.off[i]:b.off[i + 1]]), (pen, i)
+
+
+def test_peaks_golden(gpu, oracle):
+    z = np.load(os.path.join(GOLD, "stage2.npz"))
+    n = int(z["n_cases"])
+    coef = z["coef"]
+    assert np.array_equal(coef, sg_coeffs(41, 2))
+    profs = [z[f"profile_{i}"] for i in range(n)]
+    off = np.zeros(n + 1, dtype=np.int64); off[1:] = np.cumsum([p.size for p in profs])
+    blob = np.concatenate(profs).astype(np.int32)
+    for md, key in ((500, "peaks_"), (120, "peaks_d120_")):
+        r = gpu.peaks_batch(blob, off, min_dist=md, coef=coef, want_smoothed=True)
+        for i in range(n):
+            got = r["peaks"][i, :r["n_peaks"][i]]
+            assert r["n_peaks"][i] >= 0, (i, r["n_peaks"][i])
+            assert np.array_equal(got, z[f"{key}{i}"]), (md, i, got.tolist(), z[f"{key}{i}"].tolist())
+            sm = r["smoothed"][off[i]:off[i + 1]]
+            ref = z[f"smoothed_{i}"]
+            # reference numpy (BLAS summation order): 1e-5 relative (north_star tolerance)
+            assert np.all(np.abs(sm - ref) <= 1e-5 * np.maximum(np.abs(ref), 1.0)), i
+            # oracle (same fixed summation order): bit-exact
+            _, osm, omed = oracle.call_peaks(profs[i], md, coef=coef)
+            assert np.array_equal(sm.view(np.int64), osm.view(np.int64)), f"smoothed not bit-exact, case {i}"
+            assert r["median"][i] == omed, (i, r["median"][i], omed)
+
+
+def _poa_groups(seed=3):
+    rng = np.random.default_rng(seed)
+    groups = []
+    for L, k in ((300, 3), (500, 5), (1284, 5), (784, 12), (200, 8), (1500, 4), (64, 3), (40, 20)):
+        a = synth.random_seq(rng, L)
+        groups.append([synth.mutate(rng, a).tobytes().decode() for _ in range(k)])
+    a = synth.random_seq(rng, 400).tobytes().decode()
+    groups.append([a, a, a])                                   # identical copies
+    groups.append([a])                                         # single sequence
+    groups.append([a, a[:350], a[50:], a[:200] + a[230:]])     # length outliers, big deletion
+    s = list(a); s[10] = "N"; s[200] = "N"
+    groups.append(["".join(s), a, a[:100] + "N" + a[100:]])    # N bases
+    b = synth.random_seq(rng, 400).tobytes().decode()
+    groups.append([a, b, a, b, a])                             # unrelated sequences mixed
+    return groups
+
+
+def test_poa_parity(gpu, oracle):
+    groups = _poa_groups()
+    r = gpu.poa_batch(groups)
+    bad = []
+    for i, g in enumerate(groups):
+        o = oracle.poa_msa(g)
+        if r["status"][i] != 0 or r["cons"][i] != o["cons"] or r["cells"][i] != o["cells"] or r["nodes"][i] != o["node_n"]:
+            bad.append((i, int(r["status"][i]), len(r["cons"][i]), len(o["cons"]), int(r["cells"][i]), int(o["cells"]),
+                        int(r["nodes"][i]), int(o["node_n"])))
+    assert not bad, f"poa mismatches (group, status, |cons| gpu/oracle, cells gpu/oracle, nodes gpu/oracle): {bad}"
+
+
+def test_poa_error_free_copies(gpu):
+    rng = np.random.default_rng(1)
+    seqs = [synth.random_seq(rng, L).tobytes().decode() for L in (100, 333, 1000, 2048)]
+    r = gpu.poa_batch([[s] * k for s, k in zip(seqs, (3, 4, 5, 6))])
+    assert list(r["status"]) == [0, 0, 0, 0]
+    assert r["cons"] == seqs
+
+
+def _check_fused(gpu, oracle, d, cons_cap=4096, **kw):
+    sp, idx = _resolve_splints(d)
+    b = ReadBatch.from_strings(d["seqs"], sp, idx)
+    out = gpu.consensus_batch(b, max_peaks=64, cons_cap=cons_cap, **kw)
+    ref = oracle.consensus_batch(d["seqs"], sp, idx, max_peaks=64, cons_cap=cons_cap, n_threads=8)
+    R, G = ref["results"], out["results"]
+    bad = []
+    for i in range(b.n):
+        ok = (R["status"][i] == G["status"][i] and R["n_peaks"][i] == G["n_peaks"][i] and R["n_sub"][i] == G["n_sub"][i]
+              and R["n_dang"][i] == G["n_dang"][i])
+        if ok and R["status"][i] in (0, 2):
+            npk, ns, nd = R["n_peaks"][i], R["n_sub"][i], R["n_dang"][i]
+            ok = (np.array_equal(ref["peaks"][i, :npk], out["peaks"][i, :npk])
+                  and np.array_equal(ref["sub_bounds"][i, :ns], out["sub_bounds"][i, :ns])
+                  and np.array_equal(ref["dang_bounds"][i, :nd], out["dang_bounds"][i, :nd]))
+        if ok and R["status"][i] == 0:
+            ok = (R["cons_len"][i] == G["cons_len"][i]
+                  and np.array_equal(ref["cons"][i, :R["cons_len"][i]], out["cons"][i, :G["cons_len"][i]])
+                  and R["poa_cells"][i] == G["poa_cells"][i])
+        if not ok:
+            bad.append((i, [int(x) for x in (R["status"][i], G["status"][i], R["n_peaks"][i], G["n_peaks"][i],
+                                             R["n_sub"][i], G["n_sub"][i], R["cons_len"][i], G["cons_len"][i],
+                                             R["poa_cells"][i], G["poa_cells"][i])]))
+    assert not bad, f"{len(bad)} of {b.n} reads differ; first: {bad[:5]}"
+    return out
+
+
+def test_fused_cfg2_like(gpu, oracle):
+    d = synth.make_reads(192, insert_len=1000, repeats=5, seed=21)
+    out = _check_fused(gpu, oracle, d)
+    assert (out["results"]["status"] == 0).mean() > 0.9
+
+
+def test_fused_cfg1_mixed_repeats(gpu, oracle):
+    d = synth.make_reads(128, insert_len=1000, repeat_range=(1, 5), seed=22)
+    _check_fused(gpu, oracle, d)
+
+
+def test_fused_short_insert_deep(gpu, oracle):
+    d = synth.make_reads(24, insert_len=500, repeat_range=(15, 30), seed=23)
+    _check_fused(gpu, oracle, d)
+
+
+def test_fused_long_insert(gpu, oracle):
+    d = synth.make_reads(12, insert_len=(3000, 5000), repeat_range=(2, 4), seed=24, flank=(300, 2500))
+    _check_fused(gpu, oracle, d, cons_cap=8192)
+
+
+def test_fused_multi_splint(gpu, oracle):
+    rng = np.random.default_rng(4)
+    splints = {"Splint1": synth.SPLINT1}
+    for k in range(2, 5):
+        splints[f"Splint{k}"] = synth.random_seq(rng, 284).tobytes().decode()
+    d = synth.make_reads(96, insert_choices=[500, 1000, 2000], repeat_range=(2, 8), seed=25, splints=splints)
+    _check_fused(gpu, oracle, d)
+
+
+def test_properties_at_scale(gpu):
+    """Size-independent properties on a batch too large for the oracle to be the checker."""
+    d = synth.make_reads(4000, insert_len=1000, repeats=5, seed=26, err=(0.0, 0.0, 0.0))
+    sp, idx = _resolve_splints(d)
+    b = ReadBatch.from_strings(d["seqs"], sp, idx)
+    out = gpu.consensus_batch(b, max_peaks=64, cons_cap=2048)
+    R = out["results"]
+    assert np.all(R["status"] == 0), np.unique(R["status"], return_counts=True)
+    assert np.all(R["n_sub"] == 5) and np.all(R["n_peaks"] == 6)
+    unit = len(synth.SPLINT1) + 1000
+    assert np.all(R["cons_len"] == unit)
+    # error-free copies: the consensus is the repeat unit itself, wherever the peak offsets landed
+    for i in range(0, b.n, 97):
+        a, e = out["sub_bounds"][i, 0]
+        assert out["cons"][i, :unit].tobytes().decode() == d["seqs"][i][a:e]
+    # idempotence: running the same batch again gives identical bytes
+    out2 = gpu.consensus_batch(b, max_peaks=64, cons_cap=2048)
+    assert np.array_equal(out["cons"], out2["cons"]) and np.array_equal(out["results"], out2["results"])
