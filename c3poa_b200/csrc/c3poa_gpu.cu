@@ -224,12 +224,16 @@ static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int
     if (node_cap > 65534) node_cap = 65534;
     int pool_cap = (int)std::min<int64_t>(node_cap, 65534);
     int w = pp->wb < 0 ? max_q : pp->wb + (int)(pp->wf * max_q);
-    int64_t width = std::min<int64_t>(2ll * w + 64 + 16, (int64_t)max_q + 1);
-    int64_t cell_cap = std::min<int64_t>(5 * node_cap * width, 0x7ffffff0ll / 4);
-    int cigar_cap = (int)(max_q + node_cap + 64);
-    int64_t ws_bytes = c3_poa_ws_bytes((int)node_cap, pool_cap, (int)cell_cap, cigar_cap);
+    int64_t width = std::min<int64_t>(2ll * w + 64 + 16, (int64_t)max_q + 4);
+    width = (width + 3) & ~3ll;
+    int64_t cell_cap = std::min<int64_t>(5 * node_cap * width, 0x7ffffff0ll / 4) & ~3ll;
+    int cigar_cap = (int)((max_q + node_cap + 64 + 1) & ~1ll);
+    int qp_stride = (max_q + 8) & ~3;
+    int64_t ws_bytes = c3_poa_ws_bytes((int)node_cap, pool_cap, (int)cell_cap, cigar_cap, qp_stride);
     const int wpb = C3_POA_THREADS / 32;
-    int grid = h->sm_count * 4;
+    int bps = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_kernel, C3_POA_THREADS, 0) != cudaSuccess || bps < 1) bps = 4;
+    int grid = h->sm_count * bps;
     grid = std::max(1, std::min(grid, (A.n_items + wpb - 1) / wpb));
     size_t free_b = 0, tot_b = 0;
     CK(cudaMemGetInfo(&free_b, &tot_b));
@@ -241,7 +245,7 @@ static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int
     CK(h->d_counter.ensure(64));
     CK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
     A.ws = h->d_ws.as<uint8_t>(); A.ws_stride = ws_bytes;
-    A.node_cap = (int)node_cap; A.pool_cap = pool_cap; A.cell_cap = (int)cell_cap; A.cigar_cap = cigar_cap;
+    A.node_cap = (int)node_cap; A.pool_cap = pool_cap; A.cell_cap = (int)cell_cap; A.cigar_cap = cigar_cap; A.qp_stride = qp_stride;
     A.counter = h->d_counter.as<unsigned>();
     c3_poa_kernel<<<grid, C3_POA_THREADS, 0, h->stream>>>(A);
     CK(cudaGetLastError());

@@ -68,7 +68,10 @@ struct __align__(16) c3_pnode {
 static_assert(sizeof(c3_pnode) == 32, "node record must be 32 bytes");
 
 struct c3_pedge { uint16_t id, w, next, pad; };              // overflow edge (in or out list)
-struct c3_prow { int32_t off; uint16_t beg, end; };          // banded row: cells at off, columns beg..end
+// banded row: columns beg..end stored as ng = ceil(width/4) groups of 4 int32 per array, arrays
+// H,E1,E2,F1,F2 back to back at cells[off + a*4*ng]; pad cells (> end) hold NEG_INF.
+struct c3_prow { int32_t off; uint16_t beg, end; };
+__device__ __forceinline__ int c3_row_ng(const c3_prow &r) { return ((int)r.end - (int)r.beg + 4) >> 2; }
 
 struct c3_poa_para_dev {
     int match, mismatch, o1, e1, o2, e2, wb, simd_bits;
@@ -85,7 +88,7 @@ struct c3_poa_args {
     c3_poa_para_dev P;
     // per-warp workspace
     uint8_t *ws; int64_t ws_stride;
-    int node_cap, pool_cap, cell_cap, cigar_cap;
+    int node_cap, pool_cap, cell_cap, cigar_cap, qp_stride;   // cell_cap in int32, multiple of 4
     // outputs
     char *cons; int cons_cap;
     int32_t *status; int32_t *cons_len; int32_t *nodes_out; long long *cells_out;
@@ -95,17 +98,19 @@ struct c3_poa_args {
 
 struct c3_poa_ws {
     c3_pnode *nodes; c3_pedge *pool; c3_prow *rows; uint32_t *hr; int32_t *cells; unsigned long long *cigar;
+    int8_t *qp;       // query profile: 4 rows (A,C,G,T node base) x qp_stride scores, index j = column
 };
 
-__host__ __device__ inline int64_t c3_poa_ws_bytes(int node_cap, int pool_cap, int cell_cap, int cigar_cap)
+__host__ __device__ inline int64_t c3_poa_ws_bytes(int node_cap, int pool_cap, int cell_cap, int cigar_cap, int qp_stride)
 {
     int64_t b = 0;
     b += (int64_t)node_cap * 32; b += (int64_t)pool_cap * 8; b += (int64_t)node_cap * 8;
     b += (int64_t)node_cap * 4; b += (int64_t)cell_cap * 4; b += (int64_t)cigar_cap * 8;
+    b += (int64_t)qp_stride * 4;
     return (b + 255) & ~(int64_t)255;
 }
 
-__device__ __forceinline__ c3_poa_ws c3_poa_ws_carve(uint8_t *base, int node_cap, int pool_cap, int cell_cap)
+__device__ __forceinline__ c3_poa_ws c3_poa_ws_carve(uint8_t *base, int node_cap, int pool_cap, int cell_cap, int cigar_cap)
 {
     c3_poa_ws w;
     w.nodes = (c3_pnode *)base; base += (int64_t)node_cap * 32;
@@ -113,7 +118,8 @@ __device__ __forceinline__ c3_poa_ws c3_poa_ws_carve(uint8_t *base, int node_cap
     w.rows = (c3_prow *)base; base += (int64_t)node_cap * 8;
     w.hr = (uint32_t *)base; base += (int64_t)node_cap * 4;
     w.cells = (int32_t *)base; base += (int64_t)cell_cap * 4;
-    w.cigar = (unsigned long long *)base;
+    w.cigar = (unsigned long long *)base; base += (int64_t)cigar_cap * 8;
+    w.qp = (int8_t *)base;
     return w;
 }
 
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + wib;
-    const c3_poa_ws W = c3_poa_ws_carve(A.ws + (int64_t)gwarp * A.ws_stride, A.node_cap, A.pool_cap, A.cell_cap);
+    const c3_poa_ws W = c3_poa_ws_carve(A.ws + (int64_t)gwarp * A.ws_stride, A.node_cap, A.pool_cap, A.cell_cap, A.cigar_cap);
     const c3_poa_para_dev P = A.P;
     const int o1 = P.o1, e1 = P.e1, o2 = P.o2, e2 = P.e2, oe1 = o1 + e1, oe2 = o2 + e2;
     int *poff = s_poff[wib], *pbe = s_pbe[wib];
@@ -314,6 +320,17 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
             }
             // remain(v) = hops(v -> sink) - 1  (sink: -1)
 
+            // ---- query profile (int8 scores per node base, indexed by column j; j = 0 scores 0) ----
+            {
+                const int qs = A.qp_stride;
+                for (int j = lane; j < qs; j += 32) {
+                    const int qc = (j >= 1 && j <= qlen) ? (int)q[j - 1] : 4;
+#pragma unroll
+                    for (int b4 = 0; b4 < 4; ++b4)
+                        W.qp[b4 * qs + j] = (int8_t)((j >= 1 && j <= qlen) ? c3_score(P, b4, qc) : 0);
+                }
+            }
+            const int pn_shift = 31 - __clz(pn);
             // ---- DP ----
             int cell_used = 0;
             // source row
@@ -329,21 +346,20 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                 const int rr = qlen - rem;
                 const int beg = max(0, min(0, rr) - w);
                 const int end = min(qlen, max(0, rr) + w);
-                const int beg_sn = beg / pn, end_sn = end / pn;
-                const int b0 = beg_sn * pn, e0 = min(qlen, (end_sn + 1) * pn - 1);
-                const int wd = e0 - b0 + 1;
-                if (5 * wd > A.cell_cap) { err = C3_E_CELLS; break; }
+                const int b0 = (beg >> pn_shift) << pn_shift, e0 = min(qlen, (((end >> pn_shift) + 1) << pn_shift) - 1);
+                const int wd = e0 - b0 + 1, ng = (wd + 3) >> 2;
+                if (20 * ng > A.cell_cap) { err = C3_E_CELLS; break; }
                 if (lane == 0) { c3_prow ri; ri.off = 0; ri.beg = (uint16_t)b0; ri.end = (uint16_t)e0; W.rows[C3_SRC] = ri; }
-                int32_t *H = W.cells, *E1 = H + wd, *E2 = E1 + wd, *F1 = E2 + wd, *F2 = F1 + wd;
-                for (int c = lane; c < wd; c += 32) {
+                int32_t *H = W.cells, *E1 = H + 4 * ng, *E2 = E1 + 4 * ng, *F1 = E2 + 4 * ng, *F2 = F1 + 4 * ng;
+                for (int c = lane; c < 4 * ng; c += 32) {
                     int h = C3_NEG_INF, x1 = C3_NEG_INF, x2 = C3_NEG_INF, f1 = C3_NEG_INF, f2 = C3_NEG_INF;
-                    if (b0 == 0) {
+                    if (b0 == 0 && c < wd) {
                         if (c == 0) { h = 0; x1 = -oe1; x2 = -oe2; }
                         else { f1 = -(o1 + e1 * c); f2 = -(o2 + e2 * c); h = max(f1, f2); }
                     }
                     H[c] = h; E1[c] = x1; E2[c] = x2; F1[c] = f1; F2[c] = f2;
                 }
-                cell_used = 5 * wd;
+                cell_used = 20 * ng;
                 __syncwarp();
             }
             int v = W.nodes[C3_SRC].next;
@@ -353,7 +369,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                 const int rr = qlen - rem;
                 int beg = max(0, min((int)nd.mpl, rr) - w);
                 int end = min(qlen, max((int)nd.mpr, rr) + w);
-                int beg_sn = beg / pn, end_sn = end / pn;
+                int beg_sn = beg >> pn_shift, end_sn = end >> pn_shift;
                 // predecessors (in-edge order), cached in shared memory
                 const int npre = nd.in_n;
                 if (npre > C3_MAXPRE) { err = C3_E_PRE; break; }
@@ -368,73 +384,124 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                         min_pre_beg = min(min_pre_beg, (int)ri.beg);
                     }
                 }
-                if (beg_sn < min_pre_beg / pn) beg_sn = min_pre_beg / pn;
-                if (end_sn < beg_sn) end_sn = beg_sn;
-                beg = beg_sn * pn; end = min(qlen, (end_sn + 1) * pn - 1);
+                beg_sn = max(beg_sn, min_pre_beg >> pn_shift);
+                end_sn = max(end_sn, beg_sn);
+                beg = beg_sn << pn_shift; end = min(qlen, ((end_sn + 1) << pn_shift) - 1);
                 const int wd = end - beg + 1;
                 if (wd <= 0) { err = C3_E_BAND; break; }
-                if (cell_used + 5 * wd > A.cell_cap) { err = C3_E_CELLS; break; }
-                const int off = cell_used; cell_used += 5 * wd; cells_total += wd;
+                const int ng = (wd + 3) >> 2;
+                if (cell_used + 20 * ng > A.cell_cap) { err = C3_E_CELLS; break; }
+                const int off = cell_used; cell_used += 20 * ng; cells_total += wd;
                 if (lane == 0) { c3_prow ri; ri.off = off; ri.beg = (uint16_t)beg; ri.end = (uint16_t)end; W.rows[v] = ri; }
                 __syncwarp();
-                int32_t *H = W.cells + off, *E1 = H + wd, *E2 = E1 + wd, *F1 = E2 + wd, *F2 = F1 + wd;
-                const int base = nd.base;
-                int carry1 = C3_NEG_INF, carry2 = C3_NEG_INF;
-                long long bestkey = c3_mkkey(C3_NEG_INF, 0u);           // value | priority
-                for (int c0 = 0; c0 < wd; c0 += 32) {
-                    const int c = c0 + lane, j = beg + c;
-                    const bool act = c < wd;
-                    int M = C3_NEG_INF, x1 = C3_NEG_INF, x2 = C3_NEG_INF;
+                int4 *rowv = reinterpret_cast<int4 *>(W.cells + off);
+                const int8_t *qprow = W.qp + (nd.base < 4 ? nd.base : 0) * A.qp_stride;
+                const bool base_n = nd.base >= 4;
+                int carry1 = C3_NEG_INF, carry2 = C3_NEG_INF;      // F entering lane 0 of the pass
+                int bestv = C3_NEG_INF; unsigned bestp = 0;
+                for (int g00 = 0; g00 < ng; g00 += 32) {
+                    const int gl = g00 + lane;                     // group index within the row
+                    const int g0 = beg + 4 * gl;                   // first column of this lane's group
+                    const bool gact = gl < ng;
+                    int m[4], x1[4], x2[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { m[k] = C3_NEG_INF; x1[k] = C3_NEG_INF; x2[k] = C3_NEG_INF; }
                     for (int k = 0; k < npre; ++k) {
-                        const int po = poff[k], pb = pbe[k] & 0xffff, pe = (pbe[k] >> 16) & 0xffff, pw = pe - pb + 1;
-                        const int32_t *pH = W.cells + po;
-                        if (act && j - 1 >= max(pb, beg) && j - 1 <= pe) M = max(M, pH[j - 1 - pb]);
-                        if (act && j >= pb && j <= pe) { x1 = max(x1, pH[pw + j - pb]); x2 = max(x2, pH[2 * pw + j - pb]); }
+                        const int po = poff[k], pb = pbe[k] & 0xffff, pe = (pbe[k] >> 16) & 0xffff;
+                        const int png = (pe - pb + 4) >> 2;
+                        const int gi = (g0 - pb) >> 2;
+                        const bool val = gact && g0 >= pb && gi < png;
+                        int4 hv = make_int4(C3_NEG_INF, C3_NEG_INF, C3_NEG_INF, C3_NEG_INF), ev1 = hv, ev2 = hv;
+                        if (val) {
+                            const int4 *pr = reinterpret_cast<const int4 *>(W.cells + po);
+                            hv = pr[gi]; ev1 = pr[png + gi]; ev2 = pr[2 * png + gi];
+                        }
+                        int prev = __shfl_up_sync(C3_FULL, hv.w, 1);
+                        if (lane == 0) {
+                            // column g0-1: never from outside this row's band on the first pass (j-1 >= beg)
+                            const int jc = g0 - 1;
+                            prev = (g00 > 0 && jc >= pb && jc <= pe) ? W.cells[po + jc - pb] : C3_NEG_INF;
+                        }
+                        m[0] = max(m[0], prev); m[1] = max(m[1], hv.x); m[2] = max(m[2], hv.y); m[3] = max(m[3], hv.z);
+                        x1[0] = max(x1[0], ev1.x); x1[1] = max(x1[1], ev1.y); x1[2] = max(x1[2], ev1.z); x1[3] = max(x1[3], ev1.w);
+                        x2[0] = max(x2[0], ev2.x); x2[1] = max(x2[1], ev2.y); x2[2] = max(x2[2], ev2.z); x2[3] = max(x2[3], ev2.w);
                     }
-                    const int s = (act && j > 0) ? c3_score(P, base, q[j - 1]) : 0;
-                    const int m = M + s;
-                    int hme = max(m, max(x1, x2));
-                    if (!act) hme = C3_NEG_INF;
-                    int a1 = hme + e1 * j, a2 = hme + e2 * j;
+                    // scores of the 4 columns (int8 profile; g0 is a multiple of 4)
+                    int sw = 0;
+                    if (gact && !base_n) sw = *reinterpret_cast<const int *>(qprow + g0);
+                    int hme[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int sc = (int)(int8_t)(sw >> (8 * k));
+                        const int hv_ = __vimax3_s32(m[k] + sc, x1[k], x2[k]);
+                        hme[k] = (gact && g0 + k <= end) ? hv_ : C3_NEG_INF;
+                    }
+                    // F: in-lane recurrence, warp prefix-max of the lane aggregates, combine
+                    int ga[4], gb[4];
+                    ga[0] = C3_NEG_INF; gb[0] = C3_NEG_INF;
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) {
+                        ga[k] = __viaddmax_s32(ga[k - 1], -e1, hme[k - 1] - oe1);
+                        gb[k] = __viaddmax_s32(gb[k - 1], -e2, hme[k - 1] - oe2);
+                    }
+                    const int A1 = __viaddmax_s32(ga[3], -e1, hme[3] - oe1);
+                    const int A2 = __viaddmax_s32(gb[3], -e2, hme[3] - oe2);
+                    int t1 = A1 + 4 * e1 * lane, t2 = A2 + 4 * e2 * lane;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
-                        const int t1 = __shfl_up_sync(C3_FULL, a1, d), t2 = __shfl_up_sync(C3_FULL, a2, d);
-                        if (lane >= d) { a1 = max(a1, t1); a2 = max(a2, t2); }
+                        const int u1 = __shfl_up_sync(C3_FULL, t1, d), u2 = __shfl_up_sync(C3_FULL, t2, d);
+                        if (lane >= d) { t1 = max(t1, u1); t2 = max(t2, u2); }
                     }
-                    int p1 = __shfl_up_sync(C3_FULL, a1, 1), p2 = __shfl_up_sync(C3_FULL, a2, 1);
-                    if (lane == 0) { p1 = C3_NEG_INF; p2 = C3_NEG_INF; }
-                    p1 = max(p1, carry1); p2 = max(p2, carry2);
-                    carry1 = max(carry1, __shfl_sync(C3_FULL, a1, 31));
-                    carry2 = max(carry2, __shfl_sync(C3_FULL, a2, 31));
-                    const int f1 = p1 - o1 - e1 * j, f2 = p2 - o2 - e2 * j;
-                    const int h = max(hme, max(f1, f2));
-                    if (act) {
-                        H[c] = h; F1[c] = f1; F2[c] = f2;
-                        E1[c] = max(h - oe1, x1 - e1);
-                        E2[c] = max(h - oe2, x2 - e2);
-                        // simd_abpoa_ada_max_i tie-break: lowest SIMD lane, then last vector, then earliest vector
-                        const int sl = c % pn, sn = j / pn;
-                        const unsigned vp = (sn == end_sn) ? 0xfffffu : (0xffffeu - (unsigned)(sn - beg_sn));
-                        const unsigned prio = ((unsigned)(pn - 1 - sl) << 20) | vp;
-                        const long long key = c3_mkkey(h, prio);
-                        if (key > bestkey) bestkey = key;
-                    }
-                }
+                    int c1 = __shfl_up_sync(C3_FULL, t1, 1), c2 = __shfl_up_sync(C3_FULL, t2, 1);
+                    c1 = (lane == 0) ? C3_NEG_INF : c1 - 4 * e1 * (lane - 1);
+                    c2 = (lane == 0) ? C3_NEG_INF : c2 - 4 * e2 * (lane - 1);
+                    c1 = max(c1, carry1 - 4 * e1 * lane);
+                    c2 = max(c2, carry2 - 4 * e2 * lane);
+                    carry1 = max(__shfl_sync(C3_FULL, t1, 31) - 4 * e1 * 31, carry1 - 4 * e1 * 32);
+                    carry2 = max(__shfl_sync(C3_FULL, t2, 31) - 4 * e2 * 31, carry2 - 4 * e2 * 32);
+                    int hh[4], n1v[4], n2v[4], f1v[4], f2v[4];
+                    int lmax = C3_NEG_INF;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    const long long o = __shfl_xor_sync(C3_FULL, bestkey, d);
-                    if (o > bestkey) bestkey = o;
+                    for (int k = 0; k < 4; ++k) {
+                        const int f1 = max(ga[k], c1 - k * e1), f2 = max(gb[k], c2 - k * e2);
+                        const bool cact = gact && g0 + k <= end;
+                        const int h = __vimax3_s32(hme[k], f1, f2);
+                        const int n1 = __viaddmax_s32(h, -oe1, x1[k] - e1), n2 = __viaddmax_s32(h, -oe2, x2[k] - e2);
+                        hh[k] = cact ? h : C3_NEG_INF;
+                        n1v[k] = cact ? n1 : C3_NEG_INF;
+                        n2v[k] = cact ? n2 : C3_NEG_INF;
+                        f1v[k] = f1; f2v[k] = f2;
+                        lmax = max(lmax, hh[k]);
+                    }
+                    if (gact) {
+                        rowv[gl] = make_int4(hh[0], hh[1], hh[2], hh[3]);
+                        rowv[ng + gl] = make_int4(n1v[0], n1v[1], n1v[2], n1v[3]);
+                        rowv[2 * ng + gl] = make_int4(n2v[0], n2v[1], n2v[2], n2v[3]);
+                        rowv[3 * ng + gl] = make_int4(f1v[0], f1v[1], f1v[2], f1v[3]);
+                        rowv[4 * ng + gl] = make_int4(f2v[0], f2v[1], f2v[2], f2v[3]);
+                    }
+                    // simd_abpoa_ada_max_i: row max, ties -> lowest SIMD lane, then last vector, then earliest vector
+                    const int pm = __reduce_max_sync(C3_FULL, lmax);
+                    if (pm >= bestv) {
+                        unsigned pr_ = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int j = g0 + k;
+                            const int sl = j & (pn - 1), sn = j >> pn_shift;
+                            const unsigned vp = (sn == end_sn) ? 0xfffu : (0xffeu - (unsigned)(sn - beg_sn));
+                            const unsigned pk = ((unsigned)(pn - 1 - sl) << 12) | vp;
+                            if (hh[k] == pm && gact && j <= end) pr_ = max(pr_, pk);
+                        }
+                        pr_ = __reduce_max_sync(C3_FULL, pr_);
+                        if (pm > bestv) { bestv = pm; bestp = pr_; } else bestp = max(bestp, pr_);
+                    }
                 }
                 int best_i = -1;
-                {
-                    const int bv = (int)(bestkey >> 32);
-                    if (bv >= C3_NEG_HALF) {
-                        const unsigned prio = (unsigned)(bestkey & 0xffffffffll);
-                        const int sl = pn - 1 - (int)(prio >> 20);
-                        const unsigned vp = prio & 0xfffffu;
-                        const int sn = (vp == 0xfffffu) ? end_sn : beg_sn + (int)(0xffffeu - vp);
-                        best_i = sn * pn + sl;
-                    }
+                if (bestv >= C3_NEG_HALF) {
+                    const int sl = pn - 1 - (int)(bestp >> 12);
+                    const unsigned vp = bestp & 0xfffu;
+                    const int sn = (vp == 0xfffu) ? end_sn : beg_sn + (int)(0xffeu - vp);
+                    best_i = (sn << pn_shift) + sl;
                 }
                 if (lane == 0) {
                     const int mp = best_i + 1;
@@ -480,8 +547,8 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                 while (!err && i != C3_SRC && j > 0) {
                     const c3_pnode nd = W.nodes[i];
                     const c3_prow ri = W.rows[i];
-                    const int b = ri.beg, wd = (int)ri.end - b + 1;
-                    const int32_t *H = W.cells + ri.off, *E1 = H + wd, *E2 = E1 + wd, *F1 = E2 + wd, *F2 = F1 + wd;
+                    const int b = ri.beg, st = 4 * c3_row_ng(ri);
+                    const int32_t *H = W.cells + ri.off, *E1 = H + st, *E2 = E1 + st, *F1 = E2 + st, *F2 = F1 + st;
                     if (j < b || j > (int)ri.end) { err = C3_E_BT; break; }
                     const int s = c3_score(P, nd.base, q[j - 1]);
                     const int hij = H[j - b];
@@ -507,7 +574,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                             if (k == 0) p = nd.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
                             const c3_prow pr = W.rows[p];
                             if (j < (int)pr.beg || j > (int)pr.end) continue;
-                            const int pw = (int)pr.end - pr.beg + 1, pc = j - pr.beg;
+                            const int pw = 4 * c3_row_ng(pr), pc = j - pr.beg;
                             const int32_t *pH = W.cells + pr.off;
                             const int ph = pH[pc], pe1 = pH[pw + pc], pe2 = pH[2 * pw + pc];
                             if (cur_op & C3_OP_E1) {

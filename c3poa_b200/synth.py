@@ -107,3 +107,67 @@ def write_psl(path, names, splint_names, strands):
             cols = ["0"] * 21
             cols[0], cols[5], cols[8], cols[9], cols[13] = "250", "0", st, n, s
             f.write("\t".join(cols) + "\n")
+
+
+def _make_chunk(m, il, k, sp, seed, c0, err, flank, both_strands):
+    rng = np.random.default_rng([seed, c0])
+    ls = sp.size
+    U = il + ls
+    ins = BASES[rng.integers(0, 4, size=(m, il), dtype=np.uint8)]
+    unit = np.concatenate([ins, np.broadcast_to(sp, (m, ls))], axis=1)
+    full = np.tile(unit, (1, k + 2))
+    head = rng.integers(flank[0], min(flank[1], il) + 1, size=m)
+    tail = rng.integers(flank[0], min(flank[1], il) + 1, size=m)
+    start = il - head
+    stop = (k + 1) * U + tail
+    cols = np.arange(full.shape[1], dtype=np.int32)[None, :]
+    mask = (cols >= start[:, None]) & (cols < stop[:, None])
+    clean = full[mask]                                   # row-major: reads stay contiguous
+    clen = (stop - start).astype(np.int64)
+    # errors over the whole chunk at once (16-bit uniform draws: resolution 1.5e-5)
+    nb = clean.size
+    sub, ins_p, dele = err
+    u = rng.integers(0, 65536, size=nb, dtype=np.uint16)
+    t_del, t_sub = int(round(dele * 65536)), int(round((dele + sub) * 65536))
+    keep = u >= t_del
+    is_sub = keep & (u < t_sub)
+    out = clean
+    idx_sub = np.flatnonzero(is_sub)
+    if idx_sub.size:
+        cur = (out[idx_sub] >> 1) & 3                      # A,C,G,T -> 0,1,3,2 (distinct)
+        lut = np.array([0, 1, 3, 2], dtype=np.uint8)        # back to the index in BASES
+        out[idx_sub] = BASES[(lut[cur] + rng.integers(1, 4, size=idx_sub.size, dtype=np.uint8)) % 4]
+    is_ins = rng.integers(0, 65536, size=nb, dtype=np.uint16) < int(round(ins_p * 65536))
+    reps = keep.astype(np.int32) + is_ins.astype(np.int32)
+    noisy = np.repeat(out, reps)
+    cs = np.cumsum(reps, dtype=np.int64)
+    pos = cs[is_ins] - reps[is_ins]
+    noisy[pos] = BASES[rng.integers(0, 4, size=pos.size, dtype=np.uint8)]
+    bounds = np.concatenate(([0], np.cumsum(clen)))
+    new_bounds = np.concatenate(([0], cs[bounds[1:] - 1]))
+    st = (rng.random(m) < 0.5) if both_strands else np.zeros(m, dtype=bool)
+    for i in np.flatnonzero(st):
+        a, b = new_bounds[i], new_bounds[i + 1]
+        noisy[a:b] = _COMP[noisy[a:b]][::-1]
+    return noisy, np.diff(new_bounds), st
+
+
+def make_batch(n_reads: int, insert_len=1000, repeats=5, seed=20251018, splint: str = SPLINT1,
+               err=(0.04, 0.03, 0.03), flank=(100, 400), both_strands=True, workers=None):
+    """Vectorised generator for uniform configs (same insert length and repeat count for every
+    read): returns (blob uint8 ASCII, off int64[n+1], strand bool[n] (True = '-')).
+    Same read model as make_reads; used where 1e5+ reads are needed quickly.  Deterministic in
+    (seed, n_reads): every 4096-read chunk has its own generator."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    sp = np.frombuffer(splint.encode(), dtype=np.uint8)
+    chunk = 4096
+    jobs = [(min(chunk, n_reads - c0), int(insert_len), int(repeats), sp, seed, c0, err, flank, both_strands)
+            for c0 in range(0, n_reads, chunk)]
+    workers = workers or min(16, os.cpu_count() or 1)
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        parts = list(ex.map(lambda a: _make_chunk(*a), jobs))
+    blob = np.concatenate([p[0] for p in parts])
+    off = np.zeros(n_reads + 1, dtype=np.int64)
+    off[1:] = np.cumsum(np.concatenate([p[1] for p in parts]))
+    return blob, off, np.concatenate([p[2] for p in parts])
