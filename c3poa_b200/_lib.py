@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libc3poa_gpu.so")
+SO_PATH = os.environ.get("C3POA_GPU_LIB") or os.path.join(_HERE, "libc3poa_gpu.so")   # env: tuning variants only
 
 EXPORTS = [
     "c3_version", "c3_device_count", "c3_init", "c3_destroy", "c3_last_error", "c3_default_poa_params",

@@ -17,15 +17,16 @@ def nvcc_path() -> str:
     return "nvcc"
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
-        return OUT
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
+        return out
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-o", OUT, SRC]
+           "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-o", out, SRC]
+    cmd += [f"-D{d}" for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -226,7 +226,7 @@ static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int
     int w = pp->wb < 0 ? max_q : pp->wb + (int)(pp->wf * max_q);
     int64_t width = std::min<int64_t>(2ll * w + 64 + 16, (int64_t)max_q + 4);
     width = (width + 3) & ~3ll;
-    int64_t cell_cap = std::min<int64_t>(5 * node_cap * width, 0x7ffffff0ll / 4) & ~3ll;
+    int64_t cell_cap = std::min<int64_t>(3 * node_cap * width, 0x7ffffff0ll / 4) & ~3ll;
     int cigar_cap = (int)((max_q + node_cap + 64 + 1) & ~1ll);
     int qp_stride = (max_q + 8) & ~3;
     int64_t ws_bytes = c3_poa_ws_bytes((int)node_cap, pool_cap, (int)cell_cap, cigar_cap, qp_stride);

@@ -23,12 +23,16 @@
 #include "common.cuh"
 
 #define C3_POA_THREADS 128
+#ifndef C3_POA_MINB
+#define C3_POA_MINB 4       // resident CTAs per SM the register allocation is bounded for
+#endif
 #define C3_NONE 0xffffu
 #define C3_SRC 0
 #define C3_SINK 1
 #define C3_NEG_INF (-(1 << 29))
 #define C3_NEG_HALF (-(1 << 28))
-#define C3_MAXPRE 64
+#define C3_MAXPRE 48
+#define C3_RING 4            // recent DP rows kept in shared memory per warp (rows of <= 128 columns)
 
 #define C3_OP_M 0x1
 #define C3_OP_E1 0x2
@@ -68,10 +72,31 @@ struct __align__(16) c3_pnode {
 static_assert(sizeof(c3_pnode) == 32, "node record must be 32 bytes");
 
 struct c3_pedge { uint16_t id, w, next, pad; };              // overflow edge (in or out list)
-// banded row: columns beg..end stored as ng = ceil(width/4) groups of 4 int32 per array, arrays
-// H,E1,E2,F1,F2 back to back at cells[off + a*4*ng]; pad cells (> end) hold NEG_INF.
-struct c3_prow { int32_t off; uint16_t beg, end; };
+// banded row: columns beg..end stored as ng = ceil(width/4) groups of 4 int32 per array; arrays
+// H,E1,E2 back to back at cells[off + a*4*ng]; pad cells (> end) hold NEG_INF.  F is not stored:
+// the backtrack recomputes it along one row when it needs it.  mp = (arg-max column of the row)+1,
+// pulled by the successors for their adaptive band; in0/base/npre spare the node-record load.
+struct __align__(16) c3_prow { int32_t off; uint16_t beg, end; int32_t mp; uint16_t in0; uint8_t base, npre; };
+static_assert(sizeof(c3_prow) == 16, "row record must be 16 bytes");
 __device__ __forceinline__ int c3_row_ng(const c3_prow &r) { return ((int)r.end - (int)r.beg + 4) >> 2; }
+
+// node record as two 128-bit loads + field decode (avoids a local-memory struct copy)
+struct c3_nrec { uint4 a, b; };
+__device__ __forceinline__ c3_nrec c3_ld_node(const c3_pnode *p)
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    c3_nrec r; r.a = q[0]; r.b = q[1]; return r;
+}
+#define C3_N_NEXT(r) ((int)((r).a.x & 0xffffu))
+#define C3_N_PREV(r) ((int)((r).a.x >> 16))
+#define C3_N_IN0(r) ((int)((r).a.y & 0xffffu))
+#define C3_N_OUT0(r) ((int)((r).a.y >> 16))
+#define C3_N_W0(r) ((int)((r).a.z & 0xffffu))
+#define C3_N_INMORE(r) ((int)((r).a.z >> 16))
+#define C3_N_OUTMORE(r) ((int)((r).a.w & 0xffffu))
+#define C3_N_BASE(r) ((int)((r).b.w & 0xffu))
+#define C3_N_INN(r) ((int)(((r).b.w >> 8) & 0xffu))
+#define C3_N_OUTN(r) ((int)(((r).b.w >> 16) & 0xffu))
 
 struct c3_poa_para_dev {
     int match, mismatch, o1, e1, o2, e2, wb, simd_bits;
@@ -104,7 +129,7 @@ struct c3_poa_ws {
 __host__ __device__ inline int64_t c3_poa_ws_bytes(int node_cap, int pool_cap, int cell_cap, int cigar_cap, int qp_stride)
 {
     int64_t b = 0;
-    b += (int64_t)node_cap * 32; b += (int64_t)pool_cap * 8; b += (int64_t)node_cap * 8;
+    b += (int64_t)node_cap * 32; b += (int64_t)pool_cap * 8; b += (int64_t)node_cap * 16;
     b += (int64_t)node_cap * 4; b += (int64_t)cell_cap * 4; b += (int64_t)cigar_cap * 8;
     b += (int64_t)qp_stride * 4;
     return (b + 255) & ~(int64_t)255;
@@ -115,7 +140,7 @@ __device__ __forceinline__ c3_poa_ws c3_poa_ws_carve(uint8_t *base, int node_cap
     c3_poa_ws w;
     w.nodes = (c3_pnode *)base; base += (int64_t)node_cap * 32;
     w.pool = (c3_pedge *)base; base += (int64_t)pool_cap * 8;
-    w.rows = (c3_prow *)base; base += (int64_t)node_cap * 8;
+    w.rows = (c3_prow *)base; base += (int64_t)node_cap * 16;
     w.hr = (uint32_t *)base; base += (int64_t)node_cap * 4;
     w.cells = (int32_t *)base; base += (int64_t)cell_cap * 4;
     w.cigar = (unsigned long long *)base; base += (int64_t)cigar_cap * 8;
@@ -219,17 +244,24 @@ __device__ int c3_group_tail(const c3_graph &g, int a)
 }
 
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
+__global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_poa_args A)
 {
-    __shared__ int s_poff[C3_POA_THREADS / 32][C3_MAXPRE];
-    __shared__ int s_pbe[C3_POA_THREADS / 32][C3_MAXPRE];     // beg | end << 16
+    __shared__ int4 s_ring[C3_POA_THREADS / 32][C3_RING][3 * 32];   // H,E1,E2 of recent rows: 32 groups each
+    __shared__ c3_prow s_rrec[C3_POA_THREADS / 32][C3_RING];
+    __shared__ int s_rid[C3_POA_THREADS / 32][C3_RING];              // node id held by each ring slot (-1: none)
+    __shared__ const int4 *s_pptr[C3_POA_THREADS / 32][C3_MAXPRE];   // predecessors 1..: row base (ring or HBM)
+    __shared__ int s_pstr[C3_POA_THREADS / 32][C3_MAXPRE];           // array stride in groups
+    __shared__ int s_pbe[C3_POA_THREADS / 32][C3_MAXPRE];            // beg | end << 16
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + wib;
     const c3_poa_ws W = c3_poa_ws_carve(A.ws + (int64_t)gwarp * A.ws_stride, A.node_cap, A.pool_cap, A.cell_cap, A.cigar_cap);
     const c3_poa_para_dev P = A.P;
     const int o1 = P.o1, e1 = P.e1, o2 = P.o2, e2 = P.e2, oe1 = o1 + e1, oe2 = o2 + e2;
-    int *poff = s_poff[wib], *pbe = s_pbe[wib];
+    const int4 **pptr = s_pptr[wib];
+    int *pstr = s_pstr[wib], *pbe = s_pbe[wib], *rid = s_rid[wib];
+    c3_prow *rrec = s_rrec[wib];
+    int4 (*ring)[3 * 32] = s_ring[wib];
 
     for (;;) {
         int item = 0;
@@ -287,8 +319,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
 
             // ---- prepare: band bookkeeping reset, heaviest successor, remain by pointer jumping ----
             for (int v = lane; v < n; v += 32) {
-                c3_pnode *nd = &W.nodes[v];
-                nd->mpl = (uint16_t)n; nd->mpr = 0;
+                const c3_pnode *nd = &W.nodes[v];
                 uint32_t hv;
                 if (v == C3_SINK) hv = C3_SINK;
                 else {
@@ -335,68 +366,88 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
             int cell_used = 0;
             // source row
             {
-                if (lane == 0) {
-                    c3_pnode *s = &W.nodes[C3_SRC];
-                    s->mpl = 0; s->mpr = 0;
-                    W.nodes[s->out0].mpl = 1; W.nodes[s->out0].mpr = 1;
-                    uint16_t e = s->out_more;
-                    while (e != C3_NONE) { const c3_pedge pe = W.pool[e]; W.nodes[pe.id].mpl = 1; W.nodes[pe.id].mpr = 1; e = pe.next; }
-                }
                 const int rem = (int)(W.hr[C3_SRC] >> 16) - 1;
                 const int rr = qlen - rem;
                 const int beg = max(0, min(0, rr) - w);
                 const int end = min(qlen, max(0, rr) + w);
                 const int b0 = (beg >> pn_shift) << pn_shift, e0 = min(qlen, (((end >> pn_shift) + 1) << pn_shift) - 1);
                 const int wd = e0 - b0 + 1, ng = (wd + 3) >> 2;
-                if (20 * ng > A.cell_cap) { err = C3_E_CELLS; break; }
-                if (lane == 0) { c3_prow ri; ri.off = 0; ri.beg = (uint16_t)b0; ri.end = (uint16_t)e0; W.rows[C3_SRC] = ri; }
-                int32_t *H = W.cells, *E1 = H + 4 * ng, *E2 = E1 + 4 * ng, *F1 = E2 + 4 * ng, *F2 = F1 + 4 * ng;
+                if (12 * ng > A.cell_cap) { err = C3_E_CELLS; break; }
+                const bool in_ring = ng <= 32;
+                if (lane == 0) {
+                    c3_prow ri; ri.off = 0; ri.beg = (uint16_t)b0; ri.end = (uint16_t)e0; ri.mp = 1;   // successors of the source start at column 1
+                    ri.in0 = C3_NONE; ri.base = 4; ri.npre = 0;
+                    W.rows[C3_SRC] = ri;
+                    rrec[0] = ri; rid[0] = in_ring ? C3_SRC : -1;
+                    for (int t = 1; t < C3_RING; ++t) rid[t] = -1;
+                }
+                int32_t *H = W.cells, *E1 = H + 4 * ng, *E2 = E1 + 4 * ng;
+                int32_t *rg = reinterpret_cast<int32_t *>(&ring[0][0]);
                 for (int c = lane; c < 4 * ng; c += 32) {
-                    int h = C3_NEG_INF, x1 = C3_NEG_INF, x2 = C3_NEG_INF, f1 = C3_NEG_INF, f2 = C3_NEG_INF;
+                    int h = C3_NEG_INF, x1 = C3_NEG_INF, x2 = C3_NEG_INF;
                     if (b0 == 0 && c < wd) {
                         if (c == 0) { h = 0; x1 = -oe1; x2 = -oe2; }
-                        else { f1 = -(o1 + e1 * c); f2 = -(o2 + e2 * c); h = max(f1, f2); }
+                        else h = max(-(o1 + e1 * c), -(o2 + e2 * c));
                     }
-                    H[c] = h; E1[c] = x1; E2[c] = x2; F1[c] = f1; F2[c] = f2;
+                    H[c] = h; E1[c] = x1; E2[c] = x2;
+                    if (in_ring) { rg[c] = h; rg[128 + c] = x1; rg[256 + c] = x2; }
                 }
-                cell_used = 20 * ng;
+                cell_used = 12 * ng;
                 __syncwarp();
             }
             int v = W.nodes[C3_SRC].next;
+            int rcount = 1;                                        // rows written so far (ring slot = rcount % C3_RING)
+            c3_nrec nd = c3_ld_node(&W.nodes[v]);
+            uint32_t hrv = W.hr[v];
             while (v != C3_SINK) {
-                const c3_pnode nd = W.nodes[v];
-                const int rem = (int)(W.hr[v] >> 16) - 1;
+                // prefetch the next row's node record while this row computes
+                const int vnext = C3_N_NEXT(nd);
+                const c3_nrec nd_next = c3_ld_node(&W.nodes[vnext]);
+                const uint32_t hr_next = W.hr[vnext];
+                const int rem = (int)(hrv >> 16) - 1;
                 const int rr = qlen - rem;
-                int beg = max(0, min((int)nd.mpl, rr) - w);
-                int end = min(qlen, max((int)nd.mpr, rr) + w);
-                int beg_sn = beg >> pn_shift, end_sn = end >> pn_shift;
-                // predecessors (in-edge order), cached in shared memory
-                const int npre = nd.in_n;
+                const int npre = C3_N_INN(nd), nbase = C3_N_BASE(nd);
                 if (npre > C3_MAXPRE) { err = C3_E_PRE; break; }
-                int min_pre_beg = 0x7fffffff;
+                // predecessors (in-edge order): recent rows come from the shared-memory ring, others from HBM
+                const int rid0 = rid[0], rid1 = rid[1], rid2 = rid[2], rid3 = rid[3];
+                c3_prow r0; const int4 *p0ptr; int p0str;
                 {
-                    uint16_t e = nd.in_more;
-                    for (int k = 0; k < npre; ++k) {
-                        int p;
-                        if (k == 0) p = nd.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
-                        const c3_prow ri = W.rows[p];
-                        if (lane == 0) { poff[k] = ri.off; pbe[k] = (int)ri.beg | ((int)ri.end << 16); }
-                        min_pre_beg = min(min_pre_beg, (int)ri.beg);
+                    const int p = C3_N_IN0(nd);
+                    const int sl = p == rid0 ? 0 : p == rid1 ? 1 : p == rid2 ? 2 : p == rid3 ? 3 : -1;
+                    if (sl >= 0) { r0 = rrec[sl]; p0ptr = &ring[sl][0]; p0str = 32; }
+                    else { r0 = W.rows[p]; p0ptr = reinterpret_cast<const int4 *>(W.cells + r0.off); p0str = c3_row_ng(r0); }
+                }
+                int mpl = min(n, r0.mp), mpr = max(0, r0.mp), min_pre_beg = r0.beg;
+                if (npre > 1) {
+                    int e = C3_N_INMORE(nd);
+                    for (int k = 1; k < npre; ++k) {
+                        const c3_pedge pe = W.pool[e]; e = pe.next;
+                        const int p = pe.id;
+                        const int sl = p == rid0 ? 0 : p == rid1 ? 1 : p == rid2 ? 2 : p == rid3 ? 3 : -1;
+                        c3_prow ri; const int4 *pp; int ps;
+                        if (sl >= 0) { ri = rrec[sl]; pp = &ring[sl][0]; ps = 32; }
+                        else { ri = W.rows[p]; pp = reinterpret_cast<const int4 *>(W.cells + ri.off); ps = c3_row_ng(ri); }
+                        if (lane == 0) { pptr[k] = pp; pstr[k] = ps; pbe[k] = (int)ri.beg | ((int)ri.end << 16); }
+                        mpl = min(mpl, ri.mp); mpr = max(mpr, ri.mp); min_pre_beg = min(min_pre_beg, (int)ri.beg);
                     }
                 }
-                beg_sn = max(beg_sn, min_pre_beg >> pn_shift);
-                end_sn = max(end_sn, beg_sn);
+                int beg = max(0, min(mpl, rr) - w);
+                int end = min(qlen, max(mpr, rr) + w);
+                const int beg_sn = max(beg >> pn_shift, min_pre_beg >> pn_shift);
+                const int end_sn = max(end >> pn_shift, beg_sn);
                 beg = beg_sn << pn_shift; end = min(qlen, ((end_sn + 1) << pn_shift) - 1);
                 const int wd = end - beg + 1;
                 if (wd <= 0) { err = C3_E_BAND; break; }
                 const int ng = (wd + 3) >> 2;
-                if (cell_used + 20 * ng > A.cell_cap) { err = C3_E_CELLS; break; }
-                const int off = cell_used; cell_used += 20 * ng; cells_total += wd;
-                if (lane == 0) { c3_prow ri; ri.off = off; ri.beg = (uint16_t)beg; ri.end = (uint16_t)end; W.rows[v] = ri; }
-                __syncwarp();
+                if (cell_used + 12 * ng > A.cell_cap) { err = C3_E_CELLS; break; }
+                const int off = cell_used; cell_used += 12 * ng; cells_total += wd;
+                if (npre > 1) __syncwarp();
                 int4 *rowv = reinterpret_cast<int4 *>(W.cells + off);
-                const int8_t *qprow = W.qp + (nd.base < 4 ? nd.base : 0) * A.qp_stride;
-                const bool base_n = nd.base >= 4;
+                const int slot = rcount & (C3_RING - 1);
+                const bool to_ring = ng <= 32;
+                int4 *ringv = &ring[slot][0];
+                const int8_t *qprow = W.qp + (nbase < 4 ? nbase : 0) * A.qp_stride;
+                const int p0b = r0.beg, p0e = r0.end, p0ng = (p0e - p0b + 4) >> 2;
                 int carry1 = C3_NEG_INF, carry2 = C3_NEG_INF;      // F entering lane 0 of the pass
                 int bestv = C3_NEG_INF; unsigned bestp = 0;
                 for (int g00 = 0; g00 < ng; g00 += 32) {
@@ -404,23 +455,32 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                     const int g0 = beg + 4 * gl;                   // first column of this lane's group
                     const bool gact = gl < ng;
                     int m[4], x1[4], x2[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { m[k] = C3_NEG_INF; x1[k] = C3_NEG_INF; x2[k] = C3_NEG_INF; }
-                    for (int k = 0; k < npre; ++k) {
-                        const int po = poff[k], pb = pbe[k] & 0xffff, pe = (pbe[k] >> 16) & 0xffff;
-                        const int png = (pe - pb + 4) >> 2;
-                        const int gi = (g0 - pb) >> 2;
-                        const bool val = gact && g0 >= pb && gi < png;
+                    {   // predecessor 0 (registers)
+                        const int gi = (g0 - p0b) >> 2;
                         int4 hv = make_int4(C3_NEG_INF, C3_NEG_INF, C3_NEG_INF, C3_NEG_INF), ev1 = hv, ev2 = hv;
-                        if (val) {
-                            const int4 *pr = reinterpret_cast<const int4 *>(W.cells + po);
-                            hv = pr[gi]; ev1 = pr[png + gi]; ev2 = pr[2 * png + gi];
+                        if (gact && g0 >= p0b && gi < p0ng) {
+                            hv = p0ptr[gi]; ev1 = p0ptr[p0str + gi]; ev2 = p0ptr[2 * p0str + gi];
                         }
                         int prev = __shfl_up_sync(C3_FULL, hv.w, 1);
-                        if (lane == 0) {
-                            // column g0-1: never from outside this row's band on the first pass (j-1 >= beg)
+                        if (lane == 0) {   // column g0-1: never from outside this row's band on the first pass
                             const int jc = g0 - 1;
-                            prev = (g00 > 0 && jc >= pb && jc <= pe) ? W.cells[po + jc - pb] : C3_NEG_INF;
+                            prev = (g00 > 0 && jc >= p0b && jc <= p0e) ? reinterpret_cast<const int *>(p0ptr)[jc - p0b] : C3_NEG_INF;
+                        }
+                        m[0] = prev; m[1] = hv.x; m[2] = hv.y; m[3] = hv.z;
+                        x1[0] = ev1.x; x1[1] = ev1.y; x1[2] = ev1.z; x1[3] = ev1.w;
+                        x2[0] = ev2.x; x2[1] = ev2.y; x2[2] = ev2.z; x2[3] = ev2.w;
+                    }
+                    for (int k = 1; k < npre; ++k) {
+                        const int4 *pr = pptr[k];
+                        const int ps = pstr[k], pb = pbe[k] & 0xffff, pe = (pbe[k] >> 16) & 0xffff;
+                        const int png = (pe - pb + 4) >> 2;
+                        const int gi = (g0 - pb) >> 2;
+                        int4 hv = make_int4(C3_NEG_INF, C3_NEG_INF, C3_NEG_INF, C3_NEG_INF), ev1 = hv, ev2 = hv;
+                        if (gact && g0 >= pb && gi < png) { hv = pr[gi]; ev1 = pr[ps + gi]; ev2 = pr[2 * ps + gi]; }
+                        int prev = __shfl_up_sync(C3_FULL, hv.w, 1);
+                        if (lane == 0) {
+                            const int jc = g0 - 1;
+                            prev = (g00 > 0 && jc >= pb && jc <= pe) ? reinterpret_cast<const int *>(pr)[jc - pb] : C3_NEG_INF;
                         }
                         m[0] = max(m[0], prev); m[1] = max(m[1], hv.x); m[2] = max(m[2], hv.y); m[3] = max(m[3], hv.z);
                         x1[0] = max(x1[0], ev1.x); x1[1] = max(x1[1], ev1.y); x1[2] = max(x1[2], ev1.z); x1[3] = max(x1[3], ev1.w);
@@ -428,13 +488,14 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                     }
                     // scores of the 4 columns (int8 profile; g0 is a multiple of 4)
                     int sw = 0;
-                    if (gact && !base_n) sw = *reinterpret_cast<const int *>(qprow + g0);
+                    if (gact && nbase < 4) sw = *reinterpret_cast<const int *>(qprow + g0);
+                    const int nact = gact ? min(4, end - g0 + 1) : 0;      // active cells in this group
                     int hme[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int sc = (int)(int8_t)(sw >> (8 * k));
                         const int hv_ = __vimax3_s32(m[k] + sc, x1[k], x2[k]);
-                        hme[k] = (gact && g0 + k <= end) ? hv_ : C3_NEG_INF;
+                        hme[k] = (k < nact) ? hv_ : C3_NEG_INF;
                     }
                     // F: in-lane recurrence, warp prefix-max of the lane aggregates, combine
                     int ga[4], gb[4];
@@ -444,53 +505,62 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                         ga[k] = __viaddmax_s32(ga[k - 1], -e1, hme[k - 1] - oe1);
                         gb[k] = __viaddmax_s32(gb[k - 1], -e2, hme[k - 1] - oe2);
                     }
-                    const int A1 = __viaddmax_s32(ga[3], -e1, hme[3] - oe1);
-                    const int A2 = __viaddmax_s32(gb[3], -e2, hme[3] - oe2);
-                    int t1 = A1 + 4 * e1 * lane, t2 = A2 + 4 * e2 * lane;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int u1 = __shfl_up_sync(C3_FULL, t1, d), u2 = __shfl_up_sync(C3_FULL, t2, d);
-                        if (lane >= d) { t1 = max(t1, u1); t2 = max(t2, u2); }
-                    }
+                    int t1 = __viaddmax_s32(ga[3], -e1, hme[3] - oe1) + 4 * e1 * lane;
+                    int t2 = __viaddmax_s32(gb[3], -e2, hme[3] - oe2) + 4 * e2 * lane;
                     int c1 = __shfl_up_sync(C3_FULL, t1, 1), c2 = __shfl_up_sync(C3_FULL, t2, 1);
+                    // fast path: if the lane aggregates are non-decreasing over the active lanes, the
+                    // exclusive prefix max is just the left neighbour
+                    const int s1 = __shfl_up_sync(C3_FULL, c1, 1), s2 = __shfl_up_sync(C3_FULL, c2, 1);
+                    const bool mono = lane < 2 || !gact || (s1 <= c1 && s2 <= c2);
+                    int tot1, tot2;
+                    if (__all_sync(C3_FULL, mono)) {
+                        tot1 = max(__shfl_sync(C3_FULL, t1, 31), __shfl_sync(C3_FULL, c1, 31));
+                        tot2 = max(__shfl_sync(C3_FULL, t2, 31), __shfl_sync(C3_FULL, c2, 31));
+                    } else {
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int u1 = __shfl_up_sync(C3_FULL, t1, d), u2 = __shfl_up_sync(C3_FULL, t2, d);
+                            if (lane >= d) { t1 = max(t1, u1); t2 = max(t2, u2); }
+                        }
+                        c1 = __shfl_up_sync(C3_FULL, t1, 1); c2 = __shfl_up_sync(C3_FULL, t2, 1);
+                        tot1 = __shfl_sync(C3_FULL, t1, 31); tot2 = __shfl_sync(C3_FULL, t2, 31);
+                    }
                     c1 = (lane == 0) ? C3_NEG_INF : c1 - 4 * e1 * (lane - 1);
                     c2 = (lane == 0) ? C3_NEG_INF : c2 - 4 * e2 * (lane - 1);
                     c1 = max(c1, carry1 - 4 * e1 * lane);
                     c2 = max(c2, carry2 - 4 * e2 * lane);
-                    carry1 = max(__shfl_sync(C3_FULL, t1, 31) - 4 * e1 * 31, carry1 - 4 * e1 * 32);
-                    carry2 = max(__shfl_sync(C3_FULL, t2, 31) - 4 * e2 * 31, carry2 - 4 * e2 * 32);
-                    int hh[4], n1v[4], n2v[4], f1v[4], f2v[4];
+                    carry1 = max(tot1 - 4 * e1 * 31, carry1 - 4 * e1 * 32);
+                    carry2 = max(tot2 - 4 * e2 * 31, carry2 - 4 * e2 * 32);
+                    int hh[4], n1v[4], n2v[4];
                     int lmax = C3_NEG_INF;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int f1 = max(ga[k], c1 - k * e1), f2 = max(gb[k], c2 - k * e2);
-                        const bool cact = gact && g0 + k <= end;
                         const int h = __vimax3_s32(hme[k], f1, f2);
                         const int n1 = __viaddmax_s32(h, -oe1, x1[k] - e1), n2 = __viaddmax_s32(h, -oe2, x2[k] - e2);
+                        const bool cact = k < nact;
                         hh[k] = cact ? h : C3_NEG_INF;
                         n1v[k] = cact ? n1 : C3_NEG_INF;
                         n2v[k] = cact ? n2 : C3_NEG_INF;
-                        f1v[k] = f1; f2v[k] = f2;
                         lmax = max(lmax, hh[k]);
                     }
                     if (gact) {
-                        rowv[gl] = make_int4(hh[0], hh[1], hh[2], hh[3]);
-                        rowv[ng + gl] = make_int4(n1v[0], n1v[1], n1v[2], n1v[3]);
-                        rowv[2 * ng + gl] = make_int4(n2v[0], n2v[1], n2v[2], n2v[3]);
-                        rowv[3 * ng + gl] = make_int4(f1v[0], f1v[1], f1v[2], f1v[3]);
-                        rowv[4 * ng + gl] = make_int4(f2v[0], f2v[1], f2v[2], f2v[3]);
+                        const int4 vh = make_int4(hh[0], hh[1], hh[2], hh[3]);
+                        const int4 v1 = make_int4(n1v[0], n1v[1], n1v[2], n1v[3]);
+                        const int4 v2 = make_int4(n2v[0], n2v[1], n2v[2], n2v[3]);
+                        rowv[gl] = vh; rowv[ng + gl] = v1; rowv[2 * ng + gl] = v2;
+                        if (to_ring) { ringv[gl] = vh; ringv[32 + gl] = v1; ringv[64 + gl] = v2; }
                     }
-                    // simd_abpoa_ada_max_i: row max, ties -> lowest SIMD lane, then last vector, then earliest vector
+                    // simd_abpoa_ada_max_i: row max; ties -> lowest SIMD lane, then last vector, then earliest.
+                    // The 4 columns of a group share one SIMD vector; the SIMD lane grows with k.
                     const int pm = __reduce_max_sync(C3_FULL, lmax);
                     if (pm >= bestv) {
                         unsigned pr_ = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int j = g0 + k;
-                            const int sl = j & (pn - 1), sn = j >> pn_shift;
+                        if (lmax == pm && gact) {
+                            const int kf = hh[0] == pm ? 0 : hh[1] == pm ? 1 : hh[2] == pm ? 2 : 3;
+                            const int sl = (g0 & (pn - 1)) + kf, sn = g0 >> pn_shift;
                             const unsigned vp = (sn == end_sn) ? 0xfffu : (0xffeu - (unsigned)(sn - beg_sn));
-                            const unsigned pk = ((unsigned)(pn - 1 - sl) << 12) | vp;
-                            if (hh[k] == pm && gact && j <= end) pr_ = max(pr_, pk);
+                            pr_ = ((unsigned)(pn - 1 - sl) << 12) | vp;
                         }
                         pr_ = __reduce_max_sync(C3_FULL, pr_);
                         if (pm > bestv) { bestv = pm; bestp = pr_; } else bestp = max(bestp, pr_);
@@ -504,35 +574,33 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                     best_i = (sn << pn_shift) + sl;
                 }
                 if (lane == 0) {
-                    const int mp = best_i + 1;
-                    uint16_t e = nd.out_more;
-                    for (int k = 0; k < nd.out_n; ++k) {
-                        int o;
-                        if (k == 0) o = nd.out0; else { const c3_pedge pe = W.pool[e]; o = pe.id; e = pe.next; }
-                        c3_pnode *on = &W.nodes[o];
-                        if (mp > (int)on->mpr) on->mpr = (uint16_t)mp;
-                        if (mp < (int)on->mpl) on->mpl = (uint16_t)mp;
-                    }
+                    c3_prow ri; ri.off = off; ri.beg = (uint16_t)beg; ri.end = (uint16_t)end; ri.mp = best_i + 1;
+                    ri.in0 = (uint16_t)C3_N_IN0(nd); ri.base = (uint8_t)nbase; ri.npre = (uint8_t)npre;
+                    W.rows[v] = ri;
+                    rrec[slot] = ri; rid[slot] = to_ring ? v : -1;
                 }
+                ++rcount;
                 __syncwarp();
-                v = nd.next;
+                v = vnext; nd = nd_next; hrv = hr_next;
             }
             if (err) break;
 
             // ---- best end cell over the sink's predecessors + backtrack + merge (lane 0) ----
             int n_new_nodes = node_n, n_new_pool = pool_n;
             if (lane == 0) {
-                const c3_pnode sk = W.nodes[C3_SINK];
+                const c3_nrec sk = c3_ld_node(&W.nodes[C3_SINK]);
                 int best_score = -0x7fffffff - 1, bi = -1, bj = -1;
+                c3_prow ri;
                 {
-                    uint16_t e = sk.in_more;
-                    for (int k = 0; k < sk.in_n; ++k) {
+                    int e = C3_N_INMORE(sk);
+                    const int skn = C3_N_INN(sk);
+                    for (int k = 0; k < skn; ++k) {
                         int p;
-                        if (k == 0) p = sk.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
-                        const c3_prow ri = W.rows[p];
-                        const int en = min(qlen, (int)ri.end);
-                        const int val = W.cells[ri.off + en - ri.beg];
-                        if (val > best_score) { best_score = val; bi = p; bj = en; }
+                        if (k == 0) p = C3_N_IN0(sk); else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
+                        const c3_prow rp = W.rows[p];
+                        const int en = min(qlen, (int)rp.end);
+                        const int val = W.cells[rp.off + en - rp.beg];
+                        if (val > best_score) { best_score = val; bi = p; bj = en; ri = rp; }
                     }
                 }
                 int nc = 0;
@@ -545,33 +613,33 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                 }
                 int cur_op = C3_OP_ALL;
                 while (!err && i != C3_SRC && j > 0) {
-                    const c3_pnode nd = W.nodes[i];
-                    const c3_prow ri = W.rows[i];
                     const int b = ri.beg, st = 4 * c3_row_ng(ri);
-                    const int32_t *H = W.cells + ri.off, *E1 = H + st, *E2 = E1 + st, *F1 = E2 + st, *F2 = F1 + st;
+                    const int32_t *H = W.cells + ri.off, *E1 = H + st, *E2 = E1 + st;
                     if (j < b || j > (int)ri.end) { err = C3_E_BT; break; }
-                    const int s = c3_score(P, nd.base, q[j - 1]);
+                    const int s = c3_score(P, ri.base, q[j - 1]);
                     const int hij = H[j - b];
+                    const int npre = ri.npre;
+                    const int in_more = npre > 1 ? (int)W.nodes[i].in_more : (int)C3_NONE;
                     int hit = 0;
                     if (cur_op & C3_OP_M) {
-                        uint16_t e = nd.in_more;
-                        for (int k = 0; k < nd.in_n; ++k) {
+                        int e = in_more;
+                        for (int k = 0; k < npre; ++k) {
                             int p;
-                            if (k == 0) p = nd.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
+                            if (k == 0) p = ri.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
                             const c3_prow pr = W.rows[p];
                             if (j - 1 < max((int)pr.beg, b) || j - 1 > (int)pr.end) continue;
                             if (W.cells[pr.off + j - 1 - pr.beg] + s == hij) {
                                 cg[nc++] = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                                i = p; --j; hit = 1; cur_op = C3_OP_ALL;
+                                i = p; ri = pr; --j; hit = 1; cur_op = C3_OP_ALL;
                                 break;
                             }
                         }
                     }
                     if (!hit && (cur_op & C3_OP_E)) {
-                        uint16_t e = nd.in_more;
-                        for (int k = 0; k < nd.in_n; ++k) {
+                        int e = in_more;
+                        for (int k = 0; k < npre; ++k) {
                             int p;
-                            if (k == 0) p = nd.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
+                            if (k == 0) p = ri.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
                             const c3_prow pr = W.rows[p];
                             if (j < (int)pr.beg || j > (int)pr.end) continue;
                             const int pw = 4 * c3_row_ng(pr), pc = j - pr.beg;
@@ -593,26 +661,31 @@ __global__ void __launch_bounds__(C3_POA_THREADS) c3_poa_kernel(c3_poa_args A)
                             }
                             if (hit) {
                                 cg[nc++] = C3_CG_DEL | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                                i = p;
+                                i = p; ri = pr;
                                 break;
                             }
                         }
                     }
                     if (!hit && (cur_op & C3_OP_F)) {
                         if (j - 1 >= b) {
-                            const int hl = H[j - 1 - b];
+                            // F is not stored: rebuild F[j] and F[j-1] of this row from its H
+                            // (F[c+1] = max(F[c]-e, H[c]-o-e); equal to the DP's F wherever F decides)
+                            int f1 = C3_NEG_INF, f2 = C3_NEG_INF, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
+                            for (int c = 0; c < j - b; ++c) {
+                                hl = H[c];
+                                f1l = f1; f2l = f2;
+                                f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
+                            }
                             if (cur_op & C3_OP_F1) {
-                                const int f = F1[j - b], fl = F1[j - 1 - b];
-                                if (!(cur_op & C3_OP_M) || hij == f) {
-                                    if (hl - oe1 == f) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
-                                    else if (fl - e1 == f) { cur_op = C3_OP_F1; hit = 1; }
+                                if (!(cur_op & C3_OP_M) || hij == f1) {
+                                    if (hl - oe1 == f1) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                                    else if (f1l - e1 == f1) { cur_op = C3_OP_F1; hit = 1; }
                                 }
                             }
                             if (!hit && (cur_op & C3_OP_F2)) {
-                                const int f = F2[j - b], fl = F2[j - 1 - b];
-                                if (!(cur_op & C3_OP_M) || hij == f) {
-                                    if (hl - oe2 == f) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
-                                    else if (fl - e2 == f) { cur_op = C3_OP_F2; hit = 1; }
+                                if (!(cur_op & C3_OP_M) || hij == f2) {
+                                    if (hl - oe2 == f2) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                                    else if (f2l - e2 == f2) { cur_op = C3_OP_F2; hit = 1; }
                                 }
                             }
                         }
