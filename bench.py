@@ -155,14 +155,9 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ native arm
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_
-        torch.cuda.set_device(local_rank)
-        dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist = dist_
     from c3poa_b200.api import GpuConsensus, PinnedArray, ReadBatch, RESULT_DTYPE
+    from c3poa_b200.dist import Group
+    grp = Group("nccl")
 
     gpu = GpuConsensus(local_rank)
     blob, off, sp_idx, splints = make_workload(a.config, a.reads, SEED + 1000 * rank)
@@ -180,25 +175,7 @@ def main():
     out = {k: v.array for k, v in out_pin.items()}
     kw = dict(max_peaks=max_peaks, cons_cap=cons_cap)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def allmax(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    barrier, allmax, allsum = grp.barrier, grp.allmax, grp.allsum
 
     # ---- device-resident measurement ----
     gpu.stage(batch)
@@ -301,8 +278,7 @@ def main():
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    grp.close()
     return 0
 
 

@@ -1,0 +1,210 @@
+"""C3POa-compatible driver over the GPU hot path.
+
+Keeps the reference's CLI flags, config file, c3poa.log, header naming
+(>readName_avgQ_len_repeats_consLen) and Splint_N/ directory layout
+(/root/reference/C3POa.py:26-84,167-173,175-272), but replaces the per-read loop of
+analyze_reads (C3POa.py:110-165) by batch calls into the C ABI.  BLAT (splint assignment) and
+racon (polishing) remain the reference's external steps: the PSL is read if it exists
+(bin/preprocess.py:17), else `blat` is run; consensi written here are the PRE-polish abPOA
+consensi unless --polish is given and racon + mappy are available.
+"""
+from __future__ import annotations
+
+import argparse
+import gzip
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from .api import GpuConsensus, ReadBatch
+from .fastx import fastx_read, revcomp
+from .pairwise import pairwise_consensus  # noqa: F401  (2-repeat path, host side)
+
+VERSION = "v2.2.3-b200"
+
+
+def parse_args(argv=None):
+    p = argparse.ArgumentParser(description="Makes consensus sequences from R2C2 reads (GPU hot path).")
+    p.add_argument("--reads", "-r", type=str)
+    p.add_argument("--splint_file", "-s", type=str)
+    p.add_argument("--out_path", "-o", type=str, default=os.getcwd())
+    p.add_argument("--config", "-c", type=str, default="")
+    p.add_argument("--lencutoff", "-l", type=int, default=1000)
+    p.add_argument("--mdistcutoff", "-d", type=int, default=500)
+    p.add_argument("--zero", "-z", action="store_false", default=True)
+    p.add_argument("--numThreads", "-n", type=int, default=1)
+    p.add_argument("--groupSize", "-g", type=int, default=1000)
+    p.add_argument("--blatThreads", "-b", action="store_true", default=False)
+    p.add_argument("--compress_output", "-co", action="store_true", default=False)
+    p.add_argument("--version", "-v", action="version", version=VERSION)
+    p.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
+    p.add_argument("--batch", type=int, default=50000, help="reads per GPU batch")
+    return p.parse_args(argv)
+
+
+def config_reader(config_in):
+    progs = {}
+    with open(config_in) as f:
+        for line in f:
+            if line.startswith("#") or not line.rstrip().split():
+                continue
+            k, v = line.rstrip().split("\t")[:2]
+            progs[k] = v
+    for missing in {"racon", "blat"} - set(progs):
+        progs[missing] = missing
+        sys.stderr.write(f"Using {missing} from your path, not the config file.\n")
+    return progs
+
+
+def read_psl(align_psl, names):
+    """bin/preprocess.py:22-45: best splint + strand per read (gaps < 50 and score > 50)."""
+    cand = {n: [(None, 1.0, None)] for n in names}
+    adapter_set = set()
+    with open(align_psl) as f:
+        for line in f:
+            c = line.rstrip().split("\t")
+            if len(c) < 14:
+                continue
+            read_name, adapter, strand = c[9], c[13], c[8]
+            gaps, score = float(c[5]), float(c[0])
+            if gaps < 50 and score > 50 and read_name in cand:
+                cand[read_name].append((adapter, score, strand))
+                adapter_set.add(adapter)
+    adapter_dict, no_splint = {}, 0
+    for name, al in cand.items():
+        best = sorted(al, key=lambda x: x[1], reverse=True)[0]
+        if not best[0]:
+            no_splint += 1
+            continue
+        adapter_dict[name] = (best[0], best[2])
+    return adapter_dict, adapter_set, no_splint
+
+
+def run_blat(blat, reads_fastq, splint_file, tmp_dir, lencutoff):
+    fa = os.path.join(tmp_dir, "R2C2_temp_for_BLAT.fasta")
+    with open(fa, "w") as f:
+        for name, seq, _ in fastx_read(reads_fastq):
+            if len(seq) >= lencutoff:
+                f.write(f">{name}\n{seq}\n")
+    psl = os.path.join(tmp_dir, "splint_to_read_alignments.psl")
+    with open(os.path.join(tmp_dir, "blat_messages.log"), "w") as log:
+        subprocess.run([blat, "-noHead", "-stepSize=1", "-tileSize=6", "-t=DNA", "-q=DNA", "-minScore=15",
+                        "-minIdentity=10", splint_file, fa, psl], stdout=log, stderr=log, check=True)
+    os.remove(fa)
+    return psl
+
+
+def header(name, qual, seq_len, repeats, cons_len):
+    """C3POa.py:168-171."""
+    avg_qual = round(sum(ord(x) - 33 for x in qual) / seq_len, 2)
+    return ">" + name + "_" + "_".join(str(x) for x in (avg_qual, seq_len, repeats, cons_len))
+
+
+def process_batch(gpu, reads, splint_dict, adapter_dict, mdist, handles):
+    """reads: list of (name, seq, qual) that have a splint.  Writes consensus FASTA + subread FASTQ."""
+    sp_names = sorted(splint_dict)
+    splints = []
+    for n in sp_names:
+        splints += splint_dict[n]
+    idx = np.array([2 * sp_names.index(adapter_dict[r[0]][0]) + (1 if adapter_dict[r[0]][1] == "-" else 0)
+                    for r in reads], dtype=np.int32)
+    batch = ReadBatch.from_strings([r[1] for r in reads], splints, idx)
+    max_len = int(np.diff(batch.off).max())
+    out = gpu.consensus_batch(batch, min_dist=mdist, max_peaks=128, cons_cap=min(max_len, 65536))
+    R = out["results"]
+    stats = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)
+    for i, (name, seq, qual) in enumerate(reads):
+        st = int(R["status"][i])
+        adapter = adapter_dict[name][0]
+        cons_fh, sub_fh = handles[adapter]
+        if st == 1:
+            stats["no_peaks"] += 1
+            continue
+        if st < 0:
+            stats["errors"] += 1
+            continue
+        ns, nd = int(R["n_sub"][i]), int(R["n_dang"][i])
+        sb, db = out["sub_bounds"][i, :ns], out["dang_bounds"][i, :nd]
+        qual = qual if qual is not None else "I" * len(seq)
+        if st == 2:                         # 2-repeat / 0-repeat paths need MSA rows / mappy: not produced here
+            stats["pairwise"] += 1
+            continue
+        cons = out["cons"][i, :R["cons_len"][i]].tobytes().decode()
+        print(header(name, qual, len(seq), ns, len(cons)), file=cons_fh)
+        print(cons, file=cons_fh)
+        # subreads: @name_1..n, dangling @name_0 / @name_{n+1}  (bin/determine_consensus.py:57-77)
+        for k, (a, b) in enumerate(sb):
+            print(f"@{name}_{k + 1}\n{seq[a:b]}\n+\n{qual[a:b]}", file=sub_fh)
+        for k, (a, b) in enumerate(db):
+            tag = 0 if k == 0 else ns + 1
+            print(f"@{name}_{tag}\n{seq[a:b]}\n+\n{qual[a:b]}", file=sub_fh)
+        stats["consensus"] += 1
+    return stats
+
+
+def main(args):
+    if not args.out_path.endswith("/"):
+        args.out_path += "/"
+    os.makedirs(args.out_path, exist_ok=True)
+    progs = config_reader(args.config) if args.config else {"racon": "racon", "blat": "blat"}
+    tmp_dir = args.out_path + "tmp/"
+    os.makedirs(tmp_dir, exist_ok=True)
+    names, short_reads = [], 0
+    for name, seq, _ in fastx_read(args.reads):
+        if len(seq) < args.lencutoff:
+            short_reads += 1
+        else:
+            names.append(name)
+    align_psl = tmp_dir + "splint_to_read_alignments.psl"
+    if not os.path.exists(align_psl) or os.stat(align_psl).st_size == 0:
+        print("Aligning splints to reads with blat", file=sys.stderr)
+        run_blat(progs["blat"], args.reads, args.splint_file, tmp_dir, args.lencutoff)
+    else:
+        print("Reading existing psl file", file=sys.stderr)
+    adapter_dict, adapter_set, no_splint = read_psl(align_psl, names)
+    all_reads = len(names) + short_reads
+    with open(args.out_path + "c3poa.log", "w") as log:     # C3POa.py:214-229
+        print("C3POa version:", VERSION, file=log)
+        print("Total reads:", all_reads, file=log)
+        print("No splint reads:", no_splint, "({:.2f}%)".format(no_splint / max(all_reads, 1) * 100), file=log)
+        print("Under len cutoff:", short_reads, "({:.2f}%)".format(short_reads / max(all_reads, 1) * 100), file=log)
+        print("Total thrown away reads:", short_reads + no_splint,
+              "({:.2f}%)".format((short_reads + no_splint) / max(all_reads, 1) * 100), file=log)
+        print("Reads after preprocessing:", all_reads - (short_reads + no_splint), file=log)
+    splint_dict = {n: [s, revcomp(s)] for n, s, _ in fastx_read(args.splint_file)}
+    handles = {}
+    op = (lambda p: gzip.open(p + ".gz", "wt")) if args.compress_output else (lambda p: open(p, "w"))
+    for adapter in adapter_set:
+        os.makedirs(args.out_path + adapter, exist_ok=True)
+        handles[adapter] = (op(args.out_path + adapter + "/R2C2_Consensus.fasta"),
+                            op(args.out_path + adapter + "/R2C2_Subreads.fastq"))
+    gpu = GpuConsensus(args.device)
+    totals = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)
+    buf = []
+    for read in fastx_read(args.reads):
+        if len(read[1]) < args.lencutoff or read[0] not in adapter_dict:
+            continue
+        buf.append(read)
+        if len(buf) == args.batch:
+            for k, v in process_batch(gpu, buf, splint_dict, adapter_dict, args.mdistcutoff, handles).items():
+                totals[k] += v
+            buf = []
+    if buf:
+        for k, v in process_batch(gpu, buf, splint_dict, adapter_dict, args.mdistcutoff, handles).items():
+            totals[k] += v
+    for a, b in handles.values():
+        a.close(); b.close()
+    gpu.close()
+    print("GPU consensus:", totals, file=sys.stderr)
+    return totals
+
+
+def cli(argv=None):
+    args = parse_args(argv)
+    if not args.reads or not args.splint_file:
+        print("Reads (--reads/-r) and splint (--splint_file/-s) are required", file=sys.stderr)
+        return 1
+    main(args)
+    return 0
