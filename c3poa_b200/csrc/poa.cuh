@@ -76,7 +76,8 @@ struct c3_pedge { uint16_t id, w, next, pad; };              // overflow edge (i
 // H,E1,E2 back to back at cells[off + a*4*ng]; pad cells (> end) hold NEG_INF.  F is not stored:
 // the backtrack recomputes it along one row when it needs it.  mp = (arg-max column of the row)+1,
 // pulled by the successors for their adaptive band; in0/base/npre spare the node-record load.
-struct __align__(16) c3_prow { int32_t off; uint16_t beg, end; int32_t mp; uint16_t in0; uint8_t base, npre; };
+// link: position in processing order (rows[], indexed by node id) or node id (ord[], indexed by position).
+struct __align__(16) c3_prow { int32_t off; uint16_t beg, end; uint16_t mp, in0; uint16_t link; uint8_t base, npre; };
 static_assert(sizeof(c3_prow) == 16, "row record must be 16 bytes");
 __device__ __forceinline__ int c3_row_ng(const c3_prow &r) { return ((int)r.end - (int)r.beg + 4) >> 2; }
 
@@ -122,14 +123,14 @@ struct c3_poa_args {
 };
 
 struct c3_poa_ws {
-    c3_pnode *nodes; c3_pedge *pool; c3_prow *rows; uint32_t *hr; int32_t *cells; unsigned long long *cigar;
+    c3_pnode *nodes; c3_pedge *pool; c3_prow *rows; c3_prow *ord; uint32_t *hr; int32_t *cells; unsigned long long *cigar;
     int8_t *qp;       // query profile: 4 rows (A,C,G,T node base) x qp_stride scores, index j = column
 };
 
 __host__ __device__ inline int64_t c3_poa_ws_bytes(int node_cap, int pool_cap, int cell_cap, int cigar_cap, int qp_stride)
 {
     int64_t b = 0;
-    b += (int64_t)node_cap * 32; b += (int64_t)pool_cap * 8; b += (int64_t)node_cap * 16;
+    b += (int64_t)node_cap * 32; b += (int64_t)pool_cap * 8; b += (int64_t)node_cap * 32;
     b += (int64_t)node_cap * 4; b += (int64_t)cell_cap * 4; b += (int64_t)cigar_cap * 8;
     b += (int64_t)qp_stride * 4;
     return (b + 255) & ~(int64_t)255;
@@ -141,6 +142,7 @@ __device__ __forceinline__ c3_poa_ws c3_poa_ws_carve(uint8_t *base, int node_cap
     w.nodes = (c3_pnode *)base; base += (int64_t)node_cap * 32;
     w.pool = (c3_pedge *)base; base += (int64_t)pool_cap * 8;
     w.rows = (c3_prow *)base; base += (int64_t)node_cap * 16;
+    w.ord = (c3_prow *)base; base += (int64_t)node_cap * 16;
     w.hr = (uint32_t *)base; base += (int64_t)node_cap * 4;
     w.cells = (int32_t *)base; base += (int64_t)cell_cap * 4;
     w.cigar = (unsigned long long *)base; base += (int64_t)cigar_cap * 8;
@@ -376,8 +378,9 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                 const bool in_ring = ng <= 32;
                 if (lane == 0) {
                     c3_prow ri; ri.off = 0; ri.beg = (uint16_t)b0; ri.end = (uint16_t)e0; ri.mp = 1;   // successors of the source start at column 1
-                    ri.in0 = C3_NONE; ri.base = 4; ri.npre = 0;
+                    ri.in0 = C3_NONE; ri.base = 4; ri.npre = 0; ri.link = 0;
                     W.rows[C3_SRC] = ri;
+                    W.ord[0] = ri;                                   // link = node id of the source = 0
                     rrec[0] = ri; rid[0] = in_ring ? C3_SRC : -1;
                     for (int t = 1; t < C3_RING; ++t) rid[t] = -1;
                 }
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     if (sl >= 0) { r0 = rrec[sl]; p0ptr = &ring[sl][0]; p0str = 32; }
                     else { r0 = W.rows[p]; p0ptr = reinterpret_cast<const int4 *>(W.cells + r0.off); p0str = c3_row_ng(r0); }
                 }
-                int mpl = min(n, r0.mp), mpr = max(0, r0.mp), min_pre_beg = r0.beg;
+                int mpl = min(n, (int)r0.mp), mpr = r0.mp, min_pre_beg = r0.beg;
                 if (npre > 1) {
                     int e = C3_N_INMORE(nd);
                     for (int k = 1; k < npre; ++k) {
@@ -428,7 +431,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                         if (sl >= 0) { ri = rrec[sl]; pp = &ring[sl][0]; ps = 32; }
                         else { ri = W.rows[p]; pp = reinterpret_cast<const int4 *>(W.cells + ri.off); ps = c3_row_ng(ri); }
                         if (lane == 0) { pptr[k] = pp; pstr[k] = ps; pbe[k] = (int)ri.beg | ((int)ri.end << 16); }
-                        mpl = min(mpl, ri.mp); mpr = max(mpr, ri.mp); min_pre_beg = min(min_pre_beg, (int)ri.beg);
+                        mpl = min(mpl, (int)ri.mp); mpr = max(mpr, (int)ri.mp); min_pre_beg = min(min_pre_beg, (int)ri.beg);
                     }
                 }
                 int beg = max(0, min(mpl, rr) - w);
@@ -574,10 +577,13 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     best_i = (sn << pn_shift) + sl;
                 }
                 if (lane == 0) {
-                    c3_prow ri; ri.off = off; ri.beg = (uint16_t)beg; ri.end = (uint16_t)end; ri.mp = best_i + 1;
+                    c3_prow ri; ri.off = off; ri.beg = (uint16_t)beg; ri.end = (uint16_t)end; ri.mp = (uint16_t)(best_i + 1);
                     ri.in0 = (uint16_t)C3_N_IN0(nd); ri.base = (uint8_t)nbase; ri.npre = (uint8_t)npre;
+                    ri.link = (uint16_t)rcount;
                     W.rows[v] = ri;
                     rrec[slot] = ri; rid[slot] = to_ring ? v : -1;
+                    ri.link = (uint16_t)v;
+                    W.ord[rcount] = ri;
                 }
                 ++rcount;
                 __syncwarp();
@@ -585,172 +591,266 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
             }
             if (err) break;
 
-            // ---- best end cell over the sink's predecessors + backtrack + merge (lane 0) ----
-            int n_new_nodes = node_n, n_new_pool = pool_n;
-            if (lane == 0) {
+            // ---- best end cell over the sink's predecessors (uniform across the warp) ----
+            unsigned long long *cg = W.cigar;
+            int nc = 0;
+            int i, j;
+            c3_prow ri;
+            {
                 const c3_nrec sk = c3_ld_node(&W.nodes[C3_SINK]);
                 int best_score = -0x7fffffff - 1, bi = -1, bj = -1;
-                c3_prow ri;
-                {
-                    int e = C3_N_INMORE(sk);
-                    const int skn = C3_N_INN(sk);
-                    for (int k = 0; k < skn; ++k) {
+                int e = C3_N_INMORE(sk);
+                const int skn = C3_N_INN(sk);
+                for (int k = 0; k < skn; ++k) {
+                    int p;
+                    if (k == 0) p = C3_N_IN0(sk); else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
+                    const c3_prow rp = W.rows[p];
+                    const int en = min(qlen, (int)rp.end);
+                    const int val = W.cells[rp.off + en - rp.beg];
+                    if (val > best_score) { best_score = val; bi = p; bj = en; ri = rp; }
+                }
+                if (bi < 0) { err = C3_E_BEST; break; }
+                i = bi; j = bj;
+                if (qlen - bj + 8 > A.cigar_cap) { err = C3_E_CIGAR; break; }
+                for (int t = qlen - lane; t > bj; t -= 32)          // trailing query bases: insertions
+                    cg[qlen - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
+                nc = qlen - bj;
+            }
+            // ---- backtrack: warp-cooperative.  Runs of match/mismatch moves along consecutively
+            // processed rows are verified 31 at a time (one gather of row records, one of cells);
+            // everything else takes the generic one-step path (abPOA's M -> E1 -> E2 -> F1 -> F2 order). ----
+            int cur_op = C3_OP_ALL;
+            while (!err && i != C3_SRC && j > 0) {
+                if (cur_op == C3_OP_ALL) {
+                    const int kt = (int)ri.link - lane, jt = j - lane;
+                    const bool have = kt >= 0;
+                    c3_prow rt = ri;
+                    if (have && lane > 0) rt = W.ord[kt];
+                    if (lane == 0) rt.link = (uint16_t)i;                       // ord-style record: link = node id
+                    const bool inb = have && jt >= 1 && jt >= (int)rt.beg && jt <= (int)rt.end;
+                    int ht = C3_NEG_INF;
+                    if (inb) ht = W.cells[rt.off + jt - rt.beg];
+                    const int id_next = __shfl_down_sync(C3_FULL, (int)rt.link, 1);
+                    const int beg_next = __shfl_down_sync(C3_FULL, (int)rt.beg, 1);
+                    const int end_next = __shfl_down_sync(C3_FULL, (int)rt.end, 1);
+                    const int h_next = __shfl_down_sync(C3_FULL, ht, 1);
+                    const int st = inb ? c3_score(P, rt.base, q[jt - 1]) : 0;
+                    const bool ok = lane < 31 && inb && kt >= 1 && rt.link != C3_SRC && (int)rt.in0 == id_next &&
+                                    jt - 1 >= max(beg_next, (int)rt.beg) && jt - 1 <= end_next && ht == h_next + st;
+                    const unsigned okm = __ballot_sync(C3_FULL, ok);
+                    int L = __ffs(~okm) - 1;                                    // leading run of verified moves
+                    L = min(L, A.cigar_cap - 8 - j - nc);
+                    if (L > 0) {
+                        if (lane < L) cg[nc + lane] = C3_CG_MATCH | ((unsigned long long)rt.link << 8) | ((unsigned long long)(jt - 1) << 32);
+                        nc += L; j -= L;
+                        i = __shfl_sync(C3_FULL, (int)rt.link, L);
+                        const int4 rv = *reinterpret_cast<const int4 *>(&rt);
+                        int4 nv;
+                        nv.x = __shfl_sync(C3_FULL, rv.x, L); nv.y = __shfl_sync(C3_FULL, rv.y, L);
+                        nv.z = __shfl_sync(C3_FULL, rv.z, L); nv.w = __shfl_sync(C3_FULL, rv.w, L);
+                        ri = *reinterpret_cast<const c3_prow *>(&nv);
+                        ri.link = (uint16_t)((int)ri.link == i ? (kt + lane - L) : 0);  // back to rows[]-style: position
+                        continue;
+                    }
+                }
+                // generic single step
+                const int b = ri.beg, st4 = 4 * c3_row_ng(ri);
+                const int32_t *H = W.cells + ri.off, *E1 = H + st4, *E2 = E1 + st4;
+                if (j < b || j > (int)ri.end) { err = C3_E_BT; break; }
+                const int s = c3_score(P, ri.base, q[j - 1]);
+                const int hij = H[j - b];
+                const int npre = ri.npre;
+                const int in_more = npre > 1 ? (int)W.nodes[i].in_more : (int)C3_NONE;
+                int hit = 0;
+                unsigned long long opw = 0;
+                if (cur_op & C3_OP_M) {
+                    int e = in_more;
+                    for (int k = 0; k < npre; ++k) {
                         int p;
-                        if (k == 0) p = C3_N_IN0(sk); else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
-                        const c3_prow rp = W.rows[p];
-                        const int en = min(qlen, (int)rp.end);
-                        const int val = W.cells[rp.off + en - rp.beg];
-                        if (val > best_score) { best_score = val; bi = p; bj = en; ri = rp; }
+                        if (k == 0) p = ri.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
+                        const c3_prow pr = W.rows[p];
+                        if (j - 1 < max((int)pr.beg, b) || j - 1 > (int)pr.end) continue;
+                        if (W.cells[pr.off + j - 1 - pr.beg] + s == hij) {
+                            opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                            i = p; ri = pr; --j; hit = 1; cur_op = C3_OP_ALL;
+                            break;
+                        }
                     }
                 }
-                int nc = 0;
-                unsigned long long *cg = W.cigar;
-                if (bi < 0) err = C3_E_BEST;
-                int i = bi, j = bj;
-                if (!err) {
-                    if (qlen - bj + 8 > A.cigar_cap) err = C3_E_CIGAR;
-                    else for (int t = qlen; t > bj; --t) cg[nc++] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
+                if (!hit && (cur_op & C3_OP_E)) {
+                    int e = in_more;
+                    for (int k = 0; k < npre; ++k) {
+                        int p;
+                        if (k == 0) p = ri.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
+                        const c3_prow pr = W.rows[p];
+                        if (j < (int)pr.beg || j > (int)pr.end) continue;
+                        const int pw = 4 * c3_row_ng(pr), pc = j - pr.beg;
+                        const int32_t *pH = W.cells + pr.off;
+                        const int ph = pH[pc], pe1 = pH[pw + pc], pe2 = pH[2 * pw + pc];
+                        if (cur_op & C3_OP_E1) {
+                            if (cur_op & C3_OP_M) {
+                                if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
+                            } else if (E1[j - b] == pe1 - e1) {
+                                cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1;
+                            }
+                        }
+                        if (!hit && (cur_op & C3_OP_E2)) {
+                            if (cur_op & C3_OP_M) {
+                                if (hij == pe2) { cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1; }
+                            } else if (E2[j - b] == pe2 - e2) {
+                                cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1;
+                            }
+                        }
+                        if (hit) {
+                            opw = C3_CG_DEL | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                            i = p; ri = pr;
+                            break;
+                        }
+                    }
                 }
-                int cur_op = C3_OP_ALL;
-                while (!err && i != C3_SRC && j > 0) {
-                    const int b = ri.beg, st = 4 * c3_row_ng(ri);
-                    const int32_t *H = W.cells + ri.off, *E1 = H + st, *E2 = E1 + st;
-                    if (j < b || j > (int)ri.end) { err = C3_E_BT; break; }
-                    const int s = c3_score(P, ri.base, q[j - 1]);
-                    const int hij = H[j - b];
-                    const int npre = ri.npre;
-                    const int in_more = npre > 1 ? (int)W.nodes[i].in_more : (int)C3_NONE;
-                    int hit = 0;
-                    if (cur_op & C3_OP_M) {
-                        int e = in_more;
-                        for (int k = 0; k < npre; ++k) {
-                            int p;
-                            if (k == 0) p = ri.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
-                            const c3_prow pr = W.rows[p];
-                            if (j - 1 < max((int)pr.beg, b) || j - 1 > (int)pr.end) continue;
-                            if (W.cells[pr.off + j - 1 - pr.beg] + s == hij) {
-                                cg[nc++] = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                                i = p; ri = pr; --j; hit = 1; cur_op = C3_OP_ALL;
-                                break;
+                if (!hit && (cur_op & C3_OP_F)) {
+                    if (j - 1 >= b) {
+                        // F is not stored: rebuild F[j] and F[j-1] of this row from its H
+                        // (F[c+1] = max(F[c]-e, H[c]-o-e); equal to the DP's F wherever F decides)
+                        int f1 = C3_NEG_INF, f2 = C3_NEG_INF, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
+                        for (int c = 0; c < j - b; ++c) {
+                            hl = H[c];
+                            f1l = f1; f2l = f2;
+                            f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
+                        }
+                        if (cur_op & C3_OP_F1) {
+                            if (!(cur_op & C3_OP_M) || hij == f1) {
+                                if (hl - oe1 == f1) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                                else if (f1l - e1 == f1) { cur_op = C3_OP_F1; hit = 1; }
+                            }
+                        }
+                        if (!hit && (cur_op & C3_OP_F2)) {
+                            if (!(cur_op & C3_OP_M) || hij == f2) {
+                                if (hl - oe2 == f2) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                                else if (f2l - e2 == f2) { cur_op = C3_OP_F2; hit = 1; }
                             }
                         }
                     }
-                    if (!hit && (cur_op & C3_OP_E)) {
-                        int e = in_more;
-                        for (int k = 0; k < npre; ++k) {
-                            int p;
-                            if (k == 0) p = ri.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
-                            const c3_prow pr = W.rows[p];
-                            if (j < (int)pr.beg || j > (int)pr.end) continue;
-                            const int pw = 4 * c3_row_ng(pr), pc = j - pr.beg;
-                            const int32_t *pH = W.cells + pr.off;
-                            const int ph = pH[pc], pe1 = pH[pw + pc], pe2 = pH[2 * pw + pc];
-                            if (cur_op & C3_OP_E1) {
-                                if (cur_op & C3_OP_M) {
-                                    if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
-                                } else if (E1[j - b] == pe1 - e1) {
-                                    cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1;
-                                }
-                            }
-                            if (!hit && (cur_op & C3_OP_E2)) {
-                                if (cur_op & C3_OP_M) {
-                                    if (hij == pe2) { cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1; }
-                                } else if (E2[j - b] == pe2 - e2) {
-                                    cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1;
-                                }
-                            }
-                            if (hit) {
-                                cg[nc++] = C3_CG_DEL | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                                i = p; ri = pr;
-                                break;
-                            }
-                        }
-                    }
-                    if (!hit && (cur_op & C3_OP_F)) {
-                        if (j - 1 >= b) {
-                            // F is not stored: rebuild F[j] and F[j-1] of this row from its H
-                            // (F[c+1] = max(F[c]-e, H[c]-o-e); equal to the DP's F wherever F decides)
-                            int f1 = C3_NEG_INF, f2 = C3_NEG_INF, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
-                            for (int c = 0; c < j - b; ++c) {
-                                hl = H[c];
-                                f1l = f1; f2l = f2;
-                                f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
-                            }
-                            if (cur_op & C3_OP_F1) {
-                                if (!(cur_op & C3_OP_M) || hij == f1) {
-                                    if (hl - oe1 == f1) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
-                                    else if (f1l - e1 == f1) { cur_op = C3_OP_F1; hit = 1; }
-                                }
-                            }
-                            if (!hit && (cur_op & C3_OP_F2)) {
-                                if (!(cur_op & C3_OP_M) || hij == f2) {
-                                    if (hl - oe2 == f2) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
-                                    else if (f2l - e2 == f2) { cur_op = C3_OP_F2; hit = 1; }
-                                }
-                            }
-                        }
-                        if (hit) { cg[nc++] = C3_CG_INS | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32); --j; }
-                    }
-                    if (!hit) { err = C3_E_BT; break; }
-                    if (nc + j + 8 > A.cigar_cap) { err = C3_E_CIGAR; break; }
+                    if (hit) { opw = C3_CG_INS | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32); --j; }
                 }
-                if (!err) for (; j > 0; --j) cg[nc++] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(j - 1) << 32);
+                if (!hit) { err = C3_E_BT; break; }
+                if (lane == 0) cg[nc] = opw;
+                ++nc;
+                if (nc + j + 8 > A.cigar_cap) { err = C3_E_CIGAR; break; }
+            }
+            if (err) break;
+            for (int t = j - lane; t > 0; t -= 32)                      // leading query bases: insertions
+                cg[nc + j - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
+            nc += j;
+            __syncwarp();
 
-                // ---- merge (abpoa_add_graph_alignment), cigar walked from its tail = forward order ----
-                if (!err) {
-                    c3_graph g; g.nodes = W.nodes; g.pool = W.pool; g.node_n = node_n; g.pool_n = pool_n;
-                    g.node_cap = A.node_cap; g.pool_cap = A.pool_cap; g.err = 0;
-                    int last_id = C3_SRC, last_new = 0;
-                    for (int t = nc - 1; t >= 0 && !g.err; --t) {
-                        const unsigned long long op = cg[t];
-                        const int kind = (int)(op & 0xff), node_id = (int)((op >> 8) & 0xffff), qpos = (int)(op >> 32);
-                        if (kind == (int)C3_CG_MATCH) {
-                            const uint8_t bq = q[qpos];
-                            const c3_pnode nm = g.nodes[node_id];
-                            if (nm.base != bq) {
-                                int al = -1;
-                                for (int k = 0; k < nm.aln_n; ++k) {
-                                    const int a = c3_aln_get(nm, k);
-                                    if (g.nodes[a].base == bq) { al = a; break; }
+            // ---- merge (abpoa_add_graph_alignment); the cigar is walked from its tail = forward order.
+            // 32 ops at a time: ops that only bump the weight of an existing edge between two matched
+            // nodes are applied by all lanes at once; the rest (new nodes / edges) goes through lane 0
+            // in order. ----
+            {
+                c3_graph g; g.nodes = W.nodes; g.pool = W.pool; g.node_n = node_n; g.pool_n = pool_n;
+                g.node_cap = A.node_cap; g.pool_cap = A.pool_cap; g.err = 0;
+                int last_id = C3_SRC, last_new = 0;                     // uniform
+                for (int tb = nc - 1; tb >= 0; tb -= 32) {
+                    const int t = tb - lane;
+                    const bool have = t >= 0;
+                    const unsigned long long op = have ? cg[t] : C3_CG_DEL;
+                    const int kind = (int)(op & 0xff), node_id = (int)((op >> 8) & 0xffff), qpos = (int)(op >> 32);
+                    const bool is_match = have && kind == (int)C3_CG_MATCH;
+                    bool eq = false;
+                    if (is_match) eq = W.nodes[node_id].base == q[qpos];
+                    const unsigned m_nondel = __ballot_sync(C3_FULL, have && kind != (int)C3_CG_DEL);
+                    const unsigned m_eq = __ballot_sync(C3_FULL, eq);
+                    const unsigned lower = m_nondel & ((1u << lane) - 1u);
+                    const int pl = lower ? 31 - __clz(lower) : -1;      // lane of the previous non-deletion op
+                    const int pred_node = __shfl_sync(C3_FULL, node_id, pl < 0 ? 0 : pl);
+                    const int from = pl >= 0 ? pred_node : last_id;
+                    const bool from_ok = pl >= 0 ? ((m_eq >> pl) & 1u) != 0 : last_new == 0;
+                    bool done = false;
+                    if (eq && from_ok) {                                 // bump the existing edge from -> node_id
+                        c3_pnode *f = &W.nodes[from];
+                        if (f->out_n > 0) {
+                            if ((int)f->out0 == node_id) { f->w0 = (uint16_t)(f->w0 + 1); done = true; }
+                            else {
+                                uint16_t e = f->out_more;
+                                while (e != C3_NONE) {
+                                    if ((int)W.pool[e].id == node_id) { W.pool[e].w = (uint16_t)(W.pool[e].w + 1); done = true; break; }
+                                    e = W.pool[e].next;
                                 }
-                                if (al != -1) {
-                                    c3_g_add_edge(g, last_id, al, 1 - last_new);
-                                    last_id = al; last_new = 0;
-                                } else {
-                                    const int id = c3_g_add_node(g, bq);
+                            }
+                        }
+                    }
+                    const unsigned m_cx = m_nondel & ~__ballot_sync(C3_FULL, done);
+                    __syncwarp();
+                    if (m_cx) {
+                        if (lane == 0) {
+                            unsigned mc = m_cx;
+                            while (mc && !g.err) {
+                                const int c = __ffs(mc) - 1; mc &= mc - 1;
+                                const unsigned lowc = m_nondel & ((1u << c) - 1u);
+                                const int pc = lowc ? 31 - __clz(lowc) : -1;
+                                if (pc >= 0 && ((m_eq >> pc) & 1u)) { last_id = (int)((cg[tb - pc] >> 8) & 0xffff); last_new = 0; }
+                                const unsigned long long opc = cg[tb - c];
+                                const int kc = (int)(opc & 0xff), nid = (int)((opc >> 8) & 0xffff), qp = (int)(opc >> 32);
+                                if (kc == (int)C3_CG_MATCH) {
+                                    const uint8_t bq = q[qp];
+                                    const c3_pnode nm = g.nodes[nid];
+                                    if (nm.base != bq) {
+                                        int al = -1;
+                                        for (int k = 0; k < nm.aln_n; ++k) {
+                                            const int a = c3_aln_get(nm, k);
+                                            if (g.nodes[a].base == bq) { al = a; break; }
+                                        }
+                                        if (al != -1) {
+                                            c3_g_add_edge(g, last_id, al, 1 - last_new);
+                                            last_id = al; last_new = 0;
+                                        } else {
+                                            const int id = c3_g_add_node(g, bq);
+                                            if (g.err) break;
+                                            c3_list_insert_before(g, id, nid);
+                                            c3_g_add_edge(g, last_id, id, 0);
+                                            last_id = id; last_new = 1;
+                                            for (int k = 0; k < nm.aln_n; ++k) {     // abpoa_add_graph_aligned_node
+                                                const int a = c3_aln_get(nm, k);
+                                                c3_aln_push(&g.nodes[a], (uint16_t)id);
+                                                c3_aln_push(&g.nodes[id], (uint16_t)a);
+                                            }
+                                            c3_aln_push(&g.nodes[nid], (uint16_t)id);
+                                            c3_aln_push(&g.nodes[id], (uint16_t)nid);
+                                        }
+                                    } else {
+                                        c3_g_add_edge(g, last_id, nid, 1 - last_new);
+                                        last_id = nid; last_new = 0;
+                                    }
+                                } else {                                     // insertion
+                                    const int id = c3_g_add_node(g, q[qp]);
                                     if (g.err) break;
-                                    c3_list_insert_before(g, id, node_id);
+                                    c3_list_insert_after(g, id, c3_group_tail(g, last_id));
                                     c3_g_add_edge(g, last_id, id, 0);
                                     last_id = id; last_new = 1;
-                                    // abpoa_add_graph_aligned_node
-                                    for (int k = 0; k < nm.aln_n; ++k) {
-                                        const int a = c3_aln_get(nm, k);
-                                        c3_aln_push(&g.nodes[a], (uint16_t)id);
-                                        c3_aln_push(&g.nodes[id], (uint16_t)a);
-                                    }
-                                    c3_aln_push(&g.nodes[node_id], (uint16_t)id);
-                                    c3_aln_push(&g.nodes[id], (uint16_t)node_id);
                                 }
-                            } else {
-                                c3_g_add_edge(g, last_id, node_id, 1 - last_new);
-                                last_id = node_id; last_new = 0;
                             }
-                        } else if (kind == (int)C3_CG_INS) {
-                            const int id = c3_g_add_node(g, q[qpos]);
-                            if (g.err) break;
-                            c3_list_insert_after(g, id, c3_group_tail(g, last_id));
-                            c3_g_add_edge(g, last_id, id, 0);
-                            last_id = id; last_new = 1;
                         }
+                        g.err = __shfl_sync(C3_FULL, g.err, 0);
+                        g.node_n = __shfl_sync(C3_FULL, g.node_n, 0);
+                        g.pool_n = __shfl_sync(C3_FULL, g.pool_n, 0);
+                        last_id = __shfl_sync(C3_FULL, last_id, 0);
+                        last_new = __shfl_sync(C3_FULL, last_new, 0);
                     }
-                    if (!g.err) c3_g_add_edge(g, last_id, C3_SINK, 1 - last_new);
-                    err = g.err;
-                    n_new_nodes = g.node_n; n_new_pool = g.pool_n;
+                    if (m_nondel) {                                          // state after the chunk
+                        const int ln = 31 - __clz(m_nondel);
+                        if ((m_eq >> ln) & 1u) { last_id = __shfl_sync(C3_FULL, node_id, ln); last_new = 0; }
+                    }
+                    __syncwarp();
+                    if (g.err) break;
                 }
+                if (!g.err && lane == 0) c3_g_add_edge(g, last_id, C3_SINK, 1 - last_new);
+                g.err = __shfl_sync(C3_FULL, g.err, 0);
+                g.pool_n = __shfl_sync(C3_FULL, g.pool_n, 0);
+                err = g.err;
+                node_n = g.node_n; pool_n = g.pool_n;
             }
-            err = __shfl_sync(C3_FULL, err, 0);
-            node_n = __shfl_sync(C3_FULL, n_new_nodes, 0);
-            pool_n = __shfl_sync(C3_FULL, n_new_pool, 0);
             __syncwarp();
         }
 
