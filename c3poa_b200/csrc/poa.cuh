@@ -22,9 +22,11 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef C3_POA_THREADS
 #define C3_POA_THREADS 128
+#endif
 #ifndef C3_POA_MINB
-#define C3_POA_MINB 4       // resident CTAs per SM the register allocation is bounded for
+#define C3_POA_MINB 5       // resident CTAs per SM the register allocation is bounded for (<= 102 regs; measured best)
 #endif
 #define C3_NONE 0xffffu
 #define C3_SRC 0
