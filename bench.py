@@ -242,8 +242,16 @@ def main():
         alg_bytes = int(blob.nbytes) / 4 + 4 * int(blob.nbytes)
         k_s, int_ops = conk_s, OPS_PER_CONK_CELL * conk_cells
     achieved = alg_bytes / k_s / 1e9 if k_s > 0 else 0.0
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "r01_poa_traffic.json")
+    if dominant == "c3_poa_kernel" and os.path.exists(tf):      # from one `ncu --set full` capture, per launch
+        try:
+            t = json.load(open(tf))
+            traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * (n / t["reads_per_launch"])
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": hbm_src,
                 "note": "integer-ALU bound kernel: see roofline_int for the binding resource"}
     roofline_int = {"kernel": dominant, "achieved_ops_per_s": int_ops / k_s if k_s > 0 else 0.0,
                     "peak_ops_per_s": int_peak, "frac": (int_ops / k_s / int_peak) if (k_s > 0 and int_peak > 0) else None,
