@@ -158,8 +158,10 @@ class GpuConsensus:
         return dict(peaks=peaks, n_peaks=npk, median=med, smoothed=sm)
 
     # ---- B3 ----
-    def poa_batch(self, groups, params: PoaParams | None = None, cons_cap: int | None = None):
-        """groups: list of list[str].  Returns dict(cons=list[str], status, cells, nodes)."""
+    def poa_batch(self, groups, params: PoaParams | None = None, cons_cap: int | None = None, want_msa: bool = False):
+        """groups: list of list[str].  Returns dict(cons=list[str], status, cells, nodes[, msa]).
+        want_msa: groups of exactly two sequences return their two MSA rows (msa[g] = [row0, row1])
+        instead of a consensus, as the reference's 2-repeat path asks abPOA for."""
         params = params or default_poa_params()
         flat = [s for g in groups for s in g]
         blob, off = _pack(flat)
@@ -167,7 +169,10 @@ class GpuConsensus:
         goff[1:] = np.cumsum([len(g) for g in groups])
         n = len(groups)
         if cons_cap is None:
-            cons_cap = int(max((len(s) for s in flat), default=1)) * 2 + 64
+            cons_cap = int(max((len(s) for s in flat), default=1)) * (4 if want_msa else 2) + 64
+        msa_cap = cons_cap // 2
+        msa = np.zeros((len(flat), msa_cap), dtype=np.uint8) if want_msa else None
+        msa_len = np.zeros(n, dtype=np.int32)
         cons = np.zeros((n, cons_cap), dtype=np.uint8)
         clen = np.zeros(n, dtype=np.int32)
         cells = np.zeros(n, dtype=np.int64)
@@ -175,10 +180,15 @@ class GpuConsensus:
         status = np.zeros(n, dtype=np.int32)
         self._ck(self._L.c3_poa_batch(self._h, n, blob.ctypes.data, off.ctypes.data, goff.ctypes.data,
                                       C.byref(params), cons.ctypes.data, cons_cap, clen.ctypes.data,
-                                      cells.ctypes.data, nodes.ctypes.data, status.ctypes.data, None, 0, None),
-                 "c3_poa_batch")
-        return dict(cons=[cons[i, :clen[i]].tobytes().decode() for i in range(n)], status=status, cells=cells,
-                    nodes=nodes)
+                                      cells.ctypes.data, nodes.ctypes.data, status.ctypes.data,
+                                      msa.ctypes.data if want_msa else None, msa_cap if want_msa else 0,
+                                      msa_len.ctypes.data if want_msa else None), "c3_poa_batch")
+        out = dict(cons=[cons[i, :clen[i]].tobytes().decode() for i in range(n)], status=status, cells=cells,
+                   nodes=nodes)
+        if want_msa:
+            out["msa"] = [[msa[goff[g] + k, :msa_len[g]].tobytes().decode() for k in range(2)] if msa_len[g] > 0 else []
+                          for g in range(n)]
+        return out
 
     # ---- B4 ----
     def stage(self, batch: ReadBatch):
@@ -210,3 +220,10 @@ class GpuConsensus:
         self.stage(batch)
         self.run(**kw)
         return self.fetch(out)
+
+
+def pairwise_rows(out, i):
+    """The two MSA rows of a 2-repeat read (status 2, n_sub 2) from a fused-batch result."""
+    L = int(out["results"]["cons_len"][i])
+    row = out["cons"][i]
+    return [row[:L].tobytes().decode(), row[L:2 * L].tobytes().decode()]

@@ -377,7 +377,8 @@ extern "C" int c3_poa_batch(c3_handle *h, int32_t n_groups, const char *seqs, co
     if (!h) return -1;
     if (n_groups <= 0 || !seqs || !seq_off || !group_off || !params || !out_cons || cons_cap <= 0 || !out_cons_len || !out_status)
         return fail(h, -5, "bad arguments");
-    if (out_msa || msa_cap || out_msa_len) return fail(h, -7, "MSA rows are not produced by this build");
+    const bool want_msa = out_msa != nullptr;
+    if (want_msa && (msa_cap <= 0 || !out_msa_len || cons_cap < 2 * msa_cap)) return fail(h, -5, "out_msa needs msa_cap > 0, out_msa_len and cons_cap >= 2*msa_cap");
     CK(cudaSetDevice(h->device));
     const int n_seqs = group_off[n_groups];
     const int64_t total = seq_off[n_seqs];
@@ -433,7 +434,7 @@ extern "C" int c3_poa_batch(c3_handle *h, int32_t n_groups, const char *seqs, co
     A.n_seqs = h->d_nseq.as<int32_t>(); A.n_seqs_stride = 1; A.n_items = n_groups; A.max_seqs = max_nseq; A.min_seqs = 1;
     A.cons = h->d_cons.as<char>(); A.cons_cap = cons_cap; A.status = h->d_status.as<int32_t>();
     A.cons_len = h->d_clen.as<int32_t>(); A.nodes_out = h->d_nodes.as<int32_t>(); A.cells_out = h->d_cells.as<long long>();
-    A.out_stride = 1; A.cells_stride = 2;
+    A.out_stride = 1; A.cells_stride = 2; A.msa2 = want_msa ? 1 : 0; A.ok_status = 0;
     if ((rc = launch_poa(h, A, max_q, max_nseq, max_total, params))) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));
     CK(cudaMemcpyAsync(out_cons, h->d_cons.p, (size_t)n_groups * cons_cap, cudaMemcpyDeviceToHost, h->stream));
@@ -442,6 +443,19 @@ extern "C" int c3_poa_batch(c3_handle *h, int32_t n_groups, const char *seqs, co
     if (out_cells) CK(cudaMemcpyAsync(out_cells, h->d_cells.p, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, h->stream));
     if (out_nodes) CK(cudaMemcpyAsync(out_nodes, h->d_nodes.p, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (want_msa) {      // 2-sequence groups: the consensus slot holds [row0 | row1], cons_len = columns
+        memset(out_msa, '-', (size_t)n_seqs * msa_cap);
+        for (int g = 0; g < n_groups; ++g) {
+            out_msa_len[g] = 0;
+            if (nseq[g] != 2 || out_status[g] != 0) continue;
+            const int L = out_cons_len[g];
+            if (L > msa_cap) { out_status[g] = C3_E_CONS; continue; }
+            const char *src = out_cons + (size_t)g * cons_cap;
+            memcpy(out_msa + (size_t)group_off[g] * msa_cap, src, (size_t)L);
+            memcpy(out_msa + (size_t)(group_off[g] + 1) * msa_cap, src + L, (size_t)L);
+            out_msa_len[g] = L; out_cons_len[g] = 0;
+        }
+    }
     cudaEventElapsedTime(&h->tim.encode_ms, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->tim.poa_ms, h->ev[1], h->ev[2]);
     h->tim.total_ms = h->tim.encode_ms + h->tim.poa_ms;
@@ -522,7 +536,8 @@ extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t
         memset(&A, 0, sizeof(A));
         c3_read_result *res = h->d_res.as<c3_read_result>();
         A.codes = h->d_codes.as<uint8_t>(); A.item_base = h->d_off.as<int64_t>(); A.bounds = h->d_sub.as<int32_t>();
-        A.n_seqs = &res->n_sub; A.n_seqs_stride = sizeof(c3_read_result) / 4; A.n_items = n; A.max_seqs = max_peaks; A.min_seqs = 3;
+        A.n_seqs = &res->n_sub; A.n_seqs_stride = sizeof(c3_read_result) / 4; A.n_items = n; A.max_seqs = max_peaks; A.min_seqs = 2;
+        A.msa2 = 1; A.ok_status = 2;    // 2-repeat reads: [row0 | row1] of the pairwise MSA in the consensus slot
         A.cons = h->d_cons.as<char>(); A.cons_cap = cons_cap; A.status = &res->status; A.cons_len = &res->cons_len;
         A.nodes_out = &res->poa_nodes; A.cells_out = (long long *)&res->poa_cells;
         A.out_stride = sizeof(c3_read_result) / 4; A.cells_stride = sizeof(c3_read_result) / 4;

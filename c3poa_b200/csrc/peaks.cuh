@@ -305,9 +305,10 @@ __global__ void c3_split_kernel(int n_reads, const int64_t *__restrict__ read_of
         if (pk[0] > 100) { db[0] = 0; db[1] = pk[0]; nd = 1; }
         if (lr - pk[np - 1] > 100) { db[2 * nd] = pk[np - 1]; db[2 * nd + 1] = lr; ++nd; }
         out.n_dang = nd;
-        if (ns >= 3) {
+        if (ns >= 2) {                                     // POA work: consensus (>=3) or the two MSA rows (==2)
             atomicMax(&stats[0], mq); atomicMax(&stats[1], ns); atomicMax(&stats[2], tot); atomicAdd(&stats[3], 1);
-        } else if (ns != 1) out.status = 2;                // pairwise / zero-repeat paths: bounds only
+        }
+        if (ns == 2 || ns == 0) out.status = 2;            // pairwise / zero-repeat paths
     } else {
         db[0] = 0; db[1] = pk[0]; db[2] = pk[0]; db[3] = lr;
         out.n_dang = 2; out.status = 2;

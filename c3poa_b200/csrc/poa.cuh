@@ -113,6 +113,8 @@ struct c3_poa_args {
     const int32_t *n_seqs;         // [n_items] (via stride, see n_seqs_stride)
     int n_seqs_stride;             // in int32 units (lets n_seqs alias c3_read_result.n_sub)
     int n_items, max_seqs, min_seqs;
+    int msa2;                      // 1: groups of exactly 2 sequences return their two MSA rows instead of a consensus
+    int ok_status;                 // status written for a successful msa2 item (fused path keeps 2, c3_poa_batch uses 0)
     c3_poa_para_dev P;
     // per-warp workspace
     uint8_t *ws; int64_t ws_stride;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
             else {
                 for (int i = lane; i < L + 2; i += 32) {
                     c3_pnode n;
-                    n.in_more = n.out_more = C3_NONE; n.mpl = 0; n.mpr = 0;
+                    n.in_more = n.out_more = C3_NONE; n.mpl = 1; n.mpr = 0;    // mpl: bit r set = read r passes here (r < 16)
                     n.aln0 = n.aln1 = n.aln2 = n.aln3 = C3_NONE; n.max_out = C3_NONE; n.aln_n = 0;
                     if (i == C3_SRC) {
                         n.base = 4; n.in_n = 0; n.out_n = 1; n.in0 = C3_NONE; n.out0 = 2; n.w0 = 1;
@@ -762,6 +764,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     const bool is_match = have && kind == (int)C3_CG_MATCH;
                     bool eq = false;
                     if (is_match) eq = W.nodes[node_id].base == q[qpos];
+                    if (eq && sq < 16) W.nodes[node_id].mpl |= (uint16_t)(1u << sq);
                     const unsigned m_nondel = __ballot_sync(C3_FULL, have && kind != (int)C3_CG_DEL);
                     const unsigned m_eq = __ballot_sync(C3_FULL, eq);
                     const unsigned lower = m_nondel & ((1u << lane) - 1u);
@@ -807,12 +810,14 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                                         if (al != -1) {
                                             c3_g_add_edge(g, last_id, al, 1 - last_new);
                                             last_id = al; last_new = 0;
+                                            if (sq < 16) g.nodes[al].mpl |= (uint16_t)(1u << sq);
                                         } else {
                                             const int id = c3_g_add_node(g, bq);
                                             if (g.err) break;
                                             c3_list_insert_before(g, id, nid);
                                             c3_g_add_edge(g, last_id, id, 0);
                                             last_id = id; last_new = 1;
+                                            if (sq < 16) g.nodes[id].mpl = (uint16_t)(1u << sq);
                                             for (int k = 0; k < nm.aln_n; ++k) {     // abpoa_add_graph_aligned_node
                                                 const int a = c3_aln_get(nm, k);
                                                 c3_aln_push(&g.nodes[a], (uint16_t)id);
@@ -831,6 +836,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                                     c3_list_insert_after(g, id, c3_group_tail(g, last_id));
                                     c3_g_add_edge(g, last_id, id, 0);
                                     last_id = id; last_new = 1;
+                                    if (sq < 16) g.nodes[id].mpl = (uint16_t)(1u << sq);
                                 }
                             }
                         }
@@ -856,9 +862,63 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
             __syncwarp();
         }
 
-        // ---------------- heaviest bundling + consensus walk (lane 0) ----------------
+        // ---------------- two MSA rows (2-sequence groups: the reference's pairwise path,
+        // bin/determine_consensus.py:33-41 -> abpoa_generate_rc_msa with LIFO rank order) ----------------
         int cons_len = 0;
-        if (!err && lane == 0) {
+        const bool do_msa = A.msa2 && nseq == 2;
+        if (!err && do_msa) {
+            int32_t *rank = (int32_t *)W.hr, *indeg = (int32_t *)W.rows, *stk = (int32_t *)W.ord;
+            for (int v = lane; v < node_n; v += 32) { rank[v] = 0; indeg[v] = W.nodes[v].in_n; }
+            __syncwarp();
+            int msa_len = 0;
+            if (lane == 0) {
+                int top = 0, msa_rank = 0, ok = 0;
+                stk[top++] = C3_SRC; rank[C3_SRC] = -1;
+                while (top > 0) {
+                    const int cur = stk[--top];
+                    const c3_pnode nd = W.nodes[cur];
+                    if (rank[cur] < 0) {
+                        rank[cur] = msa_rank;
+                        for (int k = 0; k < nd.aln_n; ++k) rank[c3_aln_get(nd, k)] = msa_rank;
+                        ++msa_rank;
+                    }
+                    if (cur == C3_SINK) { ok = 1; break; }
+                    uint16_t e = nd.out_more;
+                    for (int k = 0; k < nd.out_n; ++k) {
+                        int o;
+                        if (k == 0) o = nd.out0; else { const c3_pedge pe = W.pool[e]; o = pe.id; e = pe.next; }
+                        if (--indeg[o] == 0) {
+                            const c3_pnode on = W.nodes[o];
+                            bool ready = true;
+                            for (int a = 0; a < on.aln_n; ++a) if (indeg[c3_aln_get(on, a)] != 0) { ready = false; break; }
+                            if (!ready) continue;
+                            stk[top++] = o; rank[o] = -1;
+                            for (int a = 0; a < on.aln_n; ++a) { const int al = c3_aln_get(on, a); stk[top++] = al; rank[al] = -1; }
+                        }
+                    }
+                }
+                msa_len = ok ? rank[C3_SINK] - 1 : -1;
+            }
+            msa_len = __shfl_sync(C3_FULL, msa_len, 0);
+            __syncwarp();
+            if (msa_len < 0 || 2 * msa_len > A.cons_cap) err = C3_E_CONS;
+            else {
+                char *co = A.cons + (int64_t)item * A.cons_cap;
+                for (int c = lane; c < 2 * msa_len; c += 32) co[c] = '-';
+                __syncwarp();
+                for (int v = 2 + lane; v < node_n; v += 32) {
+                    const c3_pnode nd = W.nodes[v];
+                    int rk = rank[v];
+                    for (int k = 0; k < nd.aln_n; ++k) rk = max(rk, rank[c3_aln_get(nd, k)]);
+                    const char ch = "ACGTN"[nd.base];
+                    if (nd.mpl & 1) co[rk - 1] = ch;
+                    if (nd.mpl & 2) co[msa_len + rk - 1] = ch;
+                }
+                cons_len = msa_len;
+            }
+        }
+        // ---------------- heaviest bundling + consensus walk (lane 0) ----------------
+        if (!err && !do_msa && lane == 0) {
             int32_t *score = (int32_t *)W.hr;
             int v = C3_SINK;
             while (v != C3_NONE) {
@@ -899,7 +959,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
         err = __shfl_sync(C3_FULL, err, 0);
         if (lane == 0) {
             const int64_t o = (int64_t)item * A.out_stride;
-            A.status[o] = err;
+            A.status[o] = err ? err : (do_msa ? A.ok_status : 0);
             A.cons_len[o] = err ? 0 : cons_len;
             A.nodes_out[o] = node_n;
             *(long long *)((int32_t *)A.cells_out + (int64_t)item * A.cells_stride) = cells_total;

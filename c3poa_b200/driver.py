@@ -18,7 +18,7 @@ import sys
 
 import numpy as np
 
-from .api import GpuConsensus, ReadBatch
+from .api import GpuConsensus, ReadBatch, pairwise_rows
 from .fastx import fastx_read, revcomp
 from .pairwise import pairwise_consensus  # noqa: F401  (2-repeat path, host side)
 
@@ -114,7 +114,7 @@ def process_batch(gpu, reads, splint_dict, adapter_dict, mdist, handles):
     max_len = int(np.diff(batch.off).max())
     out = gpu.consensus_batch(batch, min_dist=mdist, max_peaks=128, cons_cap=min(max_len, 65536))
     R = out["results"]
-    stats = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)
+    stats = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)     # pairwise: subset of consensus (2 repeats)
     for i, (name, seq, qual) in enumerate(reads):
         st = int(R["status"][i])
         adapter = adapter_dict[name][0]
@@ -128,10 +128,18 @@ def process_batch(gpu, reads, splint_dict, adapter_dict, mdist, handles):
         ns, nd = int(R["n_sub"][i]), int(R["n_dang"][i])
         sb, db = out["sub_bounds"][i, :ns], out["dang_bounds"][i, :nd]
         qual = qual if qual is not None else "I" * len(seq)
-        if st == 2:                         # 2-repeat / 0-repeat paths need MSA rows / mappy: not produced here
+        if st == 2 and ns == 2 and R["cons_len"][i] > 0:
+            # 2-repeat path: abPOA pairwise MSA rows from the GPU + quality-aware consensus
+            # (bin/determine_consensus.py:33-41, bin/consensus.py)
+            rows = pairwise_rows(out, i)
+            subs = [seq[a:b] for a, b in sb]
+            cons = pairwise_consensus(rows, subs, [qual[a:b] for a, b in sb])
             stats["pairwise"] += 1
+        elif st == 2:                       # 0-repeat path (mappy overlap of the dangling halves): not produced
+            stats["zero"] = stats.get("zero", 0) + 1
             continue
-        cons = out["cons"][i, :R["cons_len"][i]].tobytes().decode()
+        else:
+            cons = out["cons"][i, :R["cons_len"][i]].tobytes().decode()
         print(header(name, qual, len(seq), ns, len(cons)), file=cons_fh)
         print(cons, file=cons_fh)
         # subreads: @name_1..n, dangling @name_0 / @name_{n+1}  (bin/determine_consensus.py:57-77)

@@ -1,20 +1,20 @@
 """Drop-in for the part of pyabpoa 1.0.5 the reference uses (bin/determine_consensus.py:30-47):
     res = msa_aligner(match=5).msa(seqs, out_cons=True, out_msa=True); res.cons_seq[0]
-The alignment and consensus run on the GPU (c3_poa_batch).  MSA rows are not produced by the GPU path
-yet, so out_msa=True returns an empty msa_seq (the reference only reads msa_seq on its 2-repeat path)."""
+The alignment and consensus run on the GPU (c3_poa_batch).  MSA rows are produced for exactly two
+sequences with out_cons=False (the only case in which the reference reads msa_seq: its 2-repeat path)."""
 from ..api import GpuConsensus, default_poa_params
 
 _GPU = None
 
 
 class msa_result:
-    def __init__(self, n_seq, cons):
+    def __init__(self, n_seq, cons, msa=()):
         self.n_seq = n_seq
         self.n_cons = 1 if cons else 0
         self.cons_len = [len(cons)] if cons else []
         self.cons_seq = [cons] if cons else []
-        self.msa_len = 0
-        self.msa_seq = []
+        self.msa_seq = list(msa)
+        self.msa_len = len(self.msa_seq[0]) if self.msa_seq else 0
 
 
 class msa_aligner:
@@ -31,7 +31,8 @@ class msa_aligner:
             _GPU = GpuConsensus(0)
         if not seqs:
             return msa_result(0, "")
-        r = _GPU.poa_batch([list(seqs)], params=self.params)
+        pair = out_msa and not out_cons and len(seqs) == 2
+        r = _GPU.poa_batch([list(seqs)], params=self.params, want_msa=pair)
         if r["status"][0] != 0:
             raise RuntimeError(f"GPU POA failed with status {int(r['status'][0])}")
-        return msa_result(len(seqs), r["cons"][0] if out_cons else "")
+        return msa_result(len(seqs), r["cons"][0] if out_cons else "", r["msa"][0] if pair else ())

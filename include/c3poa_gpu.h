@@ -45,7 +45,9 @@ typedef struct {
 typedef struct {
     int32_t status;     /* 0 consensus produced (n_sub>=3 POA, or n_sub==1 copy);
                            1 read skipped: no peaks                (C3POa.py:125-126,131-132);
-                           2 n_sub==2 (pairwise path) or 0 (zero-repeat path): bounds only;
+                           2 n_sub==2: pairwise path, out_cons holds the two abPOA MSA rows [row0|row1],
+                             cons_len columns each (bin/determine_consensus.py:33-41);
+                             n_sub==0: zero-repeat path, bounds only;
                            <0 device-side error (workspace overflow ...), never silent */
     int32_t n_peaks;    /* after shift/filter (C3POa.py:127-130) */
     int32_t n_sub;      /* repeats */

@@ -967,8 +967,18 @@ static void batch_one(batch_job_t *J, int r, poa_ctx_t *ctx, int32_t **prof, int
         int L = sb[1] - sb[0];
         if (L > J->cons_cap) { res->status = -3; J->err = 1; return; }
         memcpy(co, seq + sb[0], (size_t)L); res->cons_len = L;
+    } else if (nsub == 2) {
+        /* 2-repeat path (determine_consensus.py:33-41): msa(out_cons=False, out_msa=True); the two MSA
+         * rows go to the consensus slot as [row0 | row1], cons_len = number of columns; the quality-aware
+         * pairwise_consensus runs on the host (it needs the quality strings) */
+        for (int k = 0; k < 2; ++k) { sp[k] = seq + sb[2 * k]; sl[k] = sb[2 * k + 1] - sb[2 * k]; }
+        c3o_poa_stats_t st; int ml = 0, half = J->cons_cap / 2;
+        int rc = poa_run(ctx, J->para, 2, sp, sl, NULL, 0, NULL, co, half, &ml, &st, NULL);
+        if (rc) { res->status = rc == -21 ? -209 : rc; if (rc != -21) J->err = 1; return; }
+        memmove(co + ml, co + half, (size_t)ml);
+        res->status = 2; res->cons_len = ml; res->poa_cells = st.cells;
     } else {
-        res->status = 2;                                  /* 2-repeat / 0-repeat paths: not in this leg */
+        res->status = 2;                                  /* 0-repeat path (needs mappy): bounds only */
     }
 }
 

@@ -120,6 +120,27 @@ def test_poa_parity(gpu, oracle):
     assert not bad, f"poa mismatches (group, status, |cons| gpu/oracle, cells gpu/oracle, nodes gpu/oracle): {bad}"
 
 
+def test_poa_pairwise_msa(gpu, oracle):
+    """2-repeat path: the two MSA rows (abpoa_generate_rc_msa order) and the reference's pairwise consensus."""
+    import json
+    from c3poa_b200.pairwise import pairwise_consensus
+    cases = json.load(open(os.path.join(GOLD, "pairwise.json")))
+    groups = [[c["s1"], c["s2"]] for c in cases]
+    rng = np.random.default_rng(17)
+    for L in (50, 700, 1300, 2500):
+        a = synth.random_seq(rng, L)
+        groups.append([synth.mutate(rng, a).tobytes().decode(), synth.mutate(rng, a).tobytes().decode()])
+    groups.append([groups[0][0], groups[0][0]])
+    r = gpu.poa_batch(groups, want_msa=True)
+    for i, g in enumerate(groups):
+        o = oracle.poa_msa(g, out_cons=False, out_msa=True)
+        assert r["status"][i] == 0 and r["msa"][i] == o["msa"], i
+        assert r["msa"][i][0].replace("-", "") == g[0] and r["msa"][i][1].replace("-", "") == g[1]
+    for i, c in enumerate(cases):      # golden: reference bin/consensus.py on these rows
+        assert r["msa"][i] == c["msa"]
+        assert pairwise_consensus(r["msa"][i], [c["s1"], c["s2"]], [c["q1"], c["q2"]]) == c["cons"]
+
+
 def test_poa_error_free_copies(gpu):
     rng = np.random.default_rng(1)
     seqs = [synth.random_seq(rng, L).tobytes().decode() for L in (100, 333, 1000, 2048)]
@@ -143,6 +164,10 @@ def _check_fused(gpu, oracle, d, cons_cap=4096, **kw):
             ok = (np.array_equal(ref["peaks"][i, :npk], out["peaks"][i, :npk])
                   and np.array_equal(ref["sub_bounds"][i, :ns], out["sub_bounds"][i, :ns])
                   and np.array_equal(ref["dang_bounds"][i, :nd], out["dang_bounds"][i, :nd]))
+        if ok and R["status"][i] == 2 and R["n_sub"][i] == 2:      # pairwise path: [row0 | row1] of the MSA
+            L = R["cons_len"][i]
+            ok = (L == G["cons_len"][i] and L > 0 and np.array_equal(ref["cons"][i, :2 * L], out["cons"][i, :2 * L])
+                  and R["poa_cells"][i] == G["poa_cells"][i])
         if ok and R["status"][i] == 0:
             ok = (R["cons_len"][i] == G["cons_len"][i]
                   and np.array_equal(ref["cons"][i, :R["cons_len"][i]], out["cons"][i, :G["cons_len"][i]])
@@ -203,3 +228,48 @@ def test_properties_at_scale(gpu):
     # idempotence: running the same batch again gives identical bytes
     out2 = gpu.consensus_batch(b, max_peaks=64, cons_cap=2048)
     assert np.array_equal(out["cons"], out2["cons"]) and np.array_equal(out["results"], out2["results"])
+
+
+def test_driver_end_to_end(gpu, oracle, tmp_path):
+    """The C3POa-compatible driver: CLI flags, PSL hook (BLAT skipped), c3poa.log, Splint_N/ layout,
+    header naming and the pre-polish consensus of every repeat count (>=3 POA, 2 pairwise, 1 copy)."""
+    from c3poa_b200 import driver
+    from c3poa_b200.fastx import fastx_read
+    from c3poa_b200.pairwise import pairwise_consensus
+    d = synth.make_reads(60, insert_len=700, repeat_range=(1, 5), seed=31)
+    short = synth.make_reads(3, insert_len=100, repeats=1, seed=32)          # below --lencutoff
+    out = tmp_path / "out"
+    (out / "tmp").mkdir(parents=True)
+    names = d["names"] + [f"s{i}" for i in range(3)]
+    synth.write_fastq(tmp_path / "reads.fastq", names, d["seqs"] + short["seqs"], d["quals"] + short["quals"])
+    (tmp_path / "splint.fasta").write_text(f">Splint1\n{synth.SPLINT1}\n")
+    synth.write_psl(out / "tmp" / "splint_to_read_alignments.psl", d["names"], d["splint_name"], d["strand"])
+    args = driver.parse_args(["-r", str(tmp_path / "reads.fastq"), "-s", str(tmp_path / "splint.fasta"),
+                              "-o", str(out), "-l", "1000", "-d", "500"])
+    totals = driver.main(args)
+    log = (out / "c3poa.log").read_text()
+    assert "Total reads: 63" in log and "Under len cutoff: 3" in log and "No splint reads: 0" in log
+    cons = {n: s for n, s, _ in fastx_read(str(out / "Splint1" / "R2C2_Consensus.fasta"))}
+    subs = list(fastx_read(str(out / "Splint1" / "R2C2_Subreads.fastq")))
+    assert totals["errors"] == 0 and totals["consensus"] == len(cons) > 40 and 0 < totals["pairwise"] < len(cons)
+    sp, idx = _resolve_splints(d)
+    ref = oracle.consensus_batch(d["seqs"], sp, idx, max_peaks=128, cons_cap=8192)
+    R = ref["results"]
+    seen = 0
+    for i, name in enumerate(d["names"]):
+        ns = int(R["n_sub"][i])
+        sb = ref["sub_bounds"][i, :ns]
+        if R["status"][i] == 0:
+            exp = ref["cons"][i, :R["cons_len"][i]].tobytes().decode()
+        elif R["status"][i] == 2 and ns == 2:
+            L = R["cons_len"][i]
+            rows = [ref["cons"][i, :L].tobytes().decode(), ref["cons"][i, L:2 * L].tobytes().decode()]
+            exp = pairwise_consensus(rows, [d["seqs"][i][a:b] for a, b in sb], [d["quals"][i][a:b] for a, b in sb])
+        else:
+            continue
+        hdr = driver.header(name, d["quals"][i], len(d["seqs"][i]), ns, len(exp))[1:]
+        assert cons.get(hdr) == exp, (i, hdr)
+        seen += 1
+    assert seen == len(cons)
+    assert {s[0].rsplit("_", 1)[0] for s in subs} <= set(d["names"])
+    assert sum(1 for s in subs if s[0].endswith("_1")) == len(cons)
