@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
             const int len = qlen > n ? qlen : n;
             const int max_score = max(qlen * 5, len * e1 + o1);
             const int pn = (max_score <= 32767 - P.mismatch - o1 - e1) ? P.simd_bits / 16 : P.simd_bits / 32;
-            const int w = P.wb < 0 ? qlen : P.wb + (int)(P.wf * (double)qlen);
+            int w = P.wb < 0 ? qlen : P.wb + (int)(P.wf * (double)qlen);
+            asm volatile("" : "+r"(w));      // keep the band half-width in a register (ptxas re-derived the fp64 product per row)
 
             // ---- prepare: band bookkeeping reset, heaviest successor, remain by pointer jumping ----
             for (int v = lane; v < n; v += 32) {

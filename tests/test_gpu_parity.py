@@ -273,3 +273,103 @@ def test_driver_end_to_end(gpu, oracle, tmp_path):
     assert seen == len(cons)
     assert {s[0].rsplit("_", 1)[0] for s in subs} <= set(d["names"])
     assert sum(1 for s in subs if s[0].endswith("_1")) == len(cons)
+
+
+def test_poa_parameter_sweep(gpu, oracle):
+    """abPOA keyword arguments other than the reference's (match=5): scoring, band and SIMD-granule variants."""
+    rng = np.random.default_rng(41)
+    groups = []
+    for L, k in ((250, 4), (900, 3), (1284, 5), (600, 7)):
+        a = synth.random_seq(rng, L)
+        groups.append([synth.mutate(rng, a, 0.05, 0.04, 0.04).tobytes().decode() for _ in range(k)])
+    variants = [dict(match=2), dict(match=5, mismatch=2), dict(gap_open1=6, gap_ext1=1, gap_open2=30, gap_ext2=1),
+                dict(wb=4, wf=0.0), dict(wb=40, wf=0.05), dict(wb=-1), dict(simd_bits=128), dict(simd_bits=512),
+                dict(match=1, mismatch=1, gap_open1=1, gap_ext1=1, gap_open2=2, gap_ext2=1)]
+    for kw in variants:
+        r = gpu.poa_batch(groups, params=default_poa_params(**kw))
+        for i, g in enumerate(groups):
+            o = oracle.poa_msa(g, para=oracle.default_para(**kw))
+            assert r["status"][i] == 0 and r["cons"][i] == o["cons"] and r["cells"][i] == o["cells"] \
+                and r["nodes"][i] == o["node_n"], (kw, i, int(r["status"][i]), int(r["cells"][i]), int(o["cells"]))
+
+
+def test_poa_band_too_narrow_fails_loudly(gpu, oracle):
+    """extra_b = extra_f = 0: the alignment leaves the band; oracle and GPU both report a backtrack failure."""
+    rng = np.random.default_rng(41)
+    a = synth.random_seq(rng, 900)
+    g = [synth.mutate(rng, a, 0.05, 0.04, 0.04).tobytes().decode() for _ in range(3)]
+    with pytest.raises(RuntimeError):
+        oracle.poa_msa(g, para=oracle.default_para(wb=0, wf=0.0))
+    r = gpu.poa_batch([g], params=default_poa_params(wb=0, wf=0.0))
+    assert r["status"][0] < 0 and r["cons"][0] == "", (int(r["status"][0]), len(r["cons"][0]))   # -206 backtrack / -203 cell pool
+
+
+def test_wide_int32_mode_and_long_sequences(gpu, oracle):
+    """qlen*5 > 32767-10 switches the reference build to int32 lanes (band granule 8): sequences > 6.5 kb."""
+    rng = np.random.default_rng(43)
+    a = synth.random_seq(rng, 7000)
+    g = [synth.mutate(rng, a, 0.03, 0.02, 0.02).tobytes().decode() for _ in range(3)]
+    r = gpu.poa_batch([g])
+    o = oracle.poa_msa(g)
+    assert r["status"][0] == 0 and r["cons"][0] == o["cons"] and r["cells"][0] == o["cells"]
+
+
+def test_peaks_edge_cases(gpu, oracle):
+    """Ragged batch: short, flat, monotone and spiky profiles in one call; every count must match the oracle."""
+    rng = np.random.default_rng(47)
+    profs = [np.zeros(30, np.int32), np.full(1000, 3, np.int32), np.arange(2000, dtype=np.int32),
+             np.arange(2000, dtype=np.int32)[::-1].copy(), rng.integers(0, 50, 5000).astype(np.int32),
+             (rng.integers(0, 20, 9000) + 5000 * (np.arange(9000) % 1500 == 700)).astype(np.int32),
+             np.zeros(20, np.int32)]
+    off = np.zeros(len(profs) + 1, dtype=np.int64); off[1:] = np.cumsum([p.size for p in profs])
+    r = gpu.peaks_batch(np.concatenate(profs), off, min_dist=500, want_smoothed=True)
+    for i, p in enumerate(profs):
+        if p.size < 22:
+            assert r["n_peaks"][i] == -1          # the reference's padding needs 21 samples; flagged, never silent
+            continue
+        pk, sm, med = oracle.call_peaks(p, 500)
+        assert r["n_peaks"][i] == len(pk) and np.array_equal(r["peaks"][i, :len(pk)], pk), i
+        assert np.array_equal(r["smoothed"][off[i]:off[i + 1]].view(np.int64), sm.view(np.int64)), i
+
+
+def test_capacity_errors_are_reported(gpu):
+    """Overflows surface as negative per-read status codes (never silently wrong)."""
+    d = synth.make_reads(6, insert_len=400, repeats=4, seed=51)
+    sp, idx = _resolve_splints(d)
+    b = ReadBatch.from_strings(d["seqs"], sp, idx)
+    out = gpu.consensus_batch(b, max_peaks=16, cons_cap=64)         # consensus does not fit 64 bytes
+    assert np.all(out["results"]["status"] == -209)
+    out = gpu.consensus_batch(b, max_peaks=2, cons_cap=2048)        # more peaks than max_peaks
+    assert np.all(out["results"]["status"] < 0)
+    out = gpu.consensus_batch(b, max_peaks=16, cons_cap=2048)
+    assert np.all(out["results"]["status"] == 0)
+
+
+def test_cfg5_like_mixed_batch_properties(gpu, oracle):
+    """cfg 5 shape (mixed inserts, 4 splints, 2-10 repeats): oracle parity on a sample + batch invariants."""
+    rng = np.random.default_rng(4)
+    splints = {"Splint1": synth.SPLINT1}
+    for k in range(2, 5):
+        splints[f"Splint{k}"] = synth.random_seq(rng, 284).tobytes().decode()
+    d = synth.make_reads(1500, insert_choices=[500, 1000, 2000, 4000], repeat_range=(2, 10), seed=55, splints=splints)
+    sp, idx = _resolve_splints(d)
+    b = ReadBatch.from_strings(d["seqs"], sp, idx)
+    out = gpu.consensus_batch(b, max_peaks=32, cons_cap=16384)
+    R = out["results"]
+    assert np.all(R["status"] >= 0), np.unique(R["status"], return_counts=True)
+    ok = R["status"] == 0
+    assert ok.mean() > 0.8
+    # consensus length tracks the repeat unit (insert + splint) within 3 %
+    unit = np.array([len(t) + 284 for t in d["truth"]])
+    assert np.all(np.abs(R["cons_len"][ok] - unit[ok]) <= 0.06 * unit[ok] + 10)
+    # subread bounds are ordered, inside the read, and contiguous peak to peak
+    for i in range(0, b.n, 37):
+        ns = R["n_sub"][i]
+        sb = out["sub_bounds"][i, :ns]
+        assert np.all(sb[:, 0] < sb[:, 1]) and sb.min(initial=0) >= 0 and sb.max(initial=0) <= len(d["seqs"][i])
+    sample = list(range(0, b.n, 25))
+    ref = oracle.consensus_batch([d["seqs"][i] for i in sample], sp, idx[sample], max_peaks=32, cons_cap=16384, n_threads=8)
+    for k, i in enumerate(sample):
+        assert ref["results"]["status"][k] == R["status"][i] and ref["results"]["cons_len"][k] == R["cons_len"][i], i
+        L = R["cons_len"][i] * (2 if (R["status"][i] == 2 and R["n_sub"][i] == 2) else 1)
+        assert np.array_equal(ref["cons"][k, :L], out["cons"][i, :L]), i
