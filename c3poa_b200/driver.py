@@ -13,6 +13,7 @@ from __future__ import annotations
 import argparse
 import gzip
 import os
+import shutil
 import subprocess
 import sys
 
@@ -41,6 +42,7 @@ def parse_args(argv=None):
     p.add_argument("--version", "-v", action="version", version=VERSION)
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     p.add_argument("--batch", type=int, default=50000, help="reads per GPU batch")
+    p.add_argument("--gpus", type=int, default=1, help="GPUs of this node to shard the reads over (one process each)")
     return p.parse_args(argv)
 
 
@@ -182,30 +184,71 @@ def main(args):
               "({:.2f}%)".format((short_reads + no_splint) / max(all_reads, 1) * 100), file=log)
         print("Reads after preprocessing:", all_reads - (short_reads + no_splint), file=log)
     splint_dict = {n: [s, revcomp(s)] for n, s, _ in fastx_read(args.splint_file)}
-    handles = {}
-    op = (lambda p: gzip.open(p + ".gz", "wt")) if args.compress_output else (lambda p: open(p, "w"))
     for adapter in adapter_set:
         os.makedirs(args.out_path + adapter, exist_ok=True)
-        handles[adapter] = (op(args.out_path + adapter + "/R2C2_Consensus.fasta"),
-                            op(args.out_path + adapter + "/R2C2_Subreads.fastq"))
-    gpu = GpuConsensus(args.device)
+    if args.gpus <= 1:
+        totals = _consume(args, args.device, 0, 1, adapter_dict, splint_dict, adapter_set, final=True)
+    else:
+        # one process per GPU (spawn, like the reference's pool: C3POa.py:236,279); reads are sharded by
+        # index, every rank writes <splint>/tmp<rank>/ and the parent concatenates (cat_files, C3POa.py:259-271)
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(args.gpus) as pool:
+            parts = pool.starmap(_consume, [(args, r, r, args.gpus, adapter_dict, splint_dict, adapter_set, False)
+                                            for r in range(args.gpus)])
+        totals = {k: sum(p.get(k, 0) for p in parts) for k in set().union(*parts)}
+        for adapter in adapter_set:
+            base = args.out_path + adapter
+            for fn in ("R2C2_Consensus.fasta", "R2C2_Subreads.fastq"):
+                with _opener(args)(base + "/" + fn) as fh:
+                    for r in range(args.gpus):
+                        part = f"{base}/tmp{r}/{fn}"
+                        if os.path.exists(part):
+                            with open(part) as src:
+                                shutil.copyfileobj(src, fh)
+            for r in range(args.gpus):
+                shutil.rmtree(f"{base}/tmp{r}", ignore_errors=True)
+    print("GPU consensus:", totals, file=sys.stderr)
+    return totals
+
+
+def _opener(args):
+    return (lambda p: gzip.open(p + ".gz", "wt")) if args.compress_output else (lambda p: open(p, "w"))
+
+
+def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, final):
+    """Process the reads with index % world == rank on `device`; final=True writes the final files directly."""
+    handles = {}
+    for adapter in adapter_set:
+        base = args.out_path + adapter
+        if final:
+            op = _opener(args)
+        else:
+            base += f"/tmp{rank}"
+            os.makedirs(base, exist_ok=True)
+            op = lambda p: open(p, "w")      # noqa: E731
+        handles[adapter] = (op(base + "/R2C2_Consensus.fasta"), op(base + "/R2C2_Subreads.fastq"))
+    mod = int(os.environ.get("C3POA_DEVICE_MODULO", "0"))      # tests: fold ranks onto fewer GPUs
+    gpu = GpuConsensus(device % mod if mod > 0 else device)
     totals = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)
-    buf = []
+    buf, k = [], 0
     for read in fastx_read(args.reads):
         if len(read[1]) < args.lencutoff or read[0] not in adapter_dict:
             continue
+        k += 1
+        if (k - 1) % world != rank:
+            continue
         buf.append(read)
         if len(buf) == args.batch:
-            for k, v in process_batch(gpu, buf, splint_dict, adapter_dict, args.mdistcutoff, handles).items():
-                totals[k] += v
+            for key, v in process_batch(gpu, buf, splint_dict, adapter_dict, args.mdistcutoff, handles).items():
+                totals[key] = totals.get(key, 0) + v
             buf = []
     if buf:
-        for k, v in process_batch(gpu, buf, splint_dict, adapter_dict, args.mdistcutoff, handles).items():
-            totals[k] += v
+        for key, v in process_batch(gpu, buf, splint_dict, adapter_dict, args.mdistcutoff, handles).items():
+            totals[key] = totals.get(key, 0) + v
     for a, b in handles.values():
         a.close(); b.close()
     gpu.close()
-    print("GPU consensus:", totals, file=sys.stderr)
     return totals
 
 
