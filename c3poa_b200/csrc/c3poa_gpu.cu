@@ -604,6 +604,15 @@ __global__ void __launch_bounds__(256) c3_intpeak_kernel(int iters, int *sink)
     if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x7fffffff) *sink = a0;
 }
 
+#ifdef C3_POA_STATS
+extern "C" int c3_debug_stats(unsigned long long *out16, int reset)
+{
+    if (out16) cudaMemcpyFromSymbol(out16, c3_poa_stats, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(c3_poa_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 extern "C" int c3_measure_int_peak(c3_handle *h, double *out_ops_per_s)
 {
     if (!h || !out_ops_per_s) return -1;

@@ -78,7 +78,8 @@ struct c3_pedge { uint16_t id, w, next, pad; };              // overflow edge (i
 // H,E1,E2 back to back at cells[off + a*4*ng]; pad cells (> end) hold NEG_INF.  F is not stored:
 // the backtrack recomputes it along one row when it needs it.  mp = (arg-max column of the row)+1,
 // pulled by the successors for their adaptive band; in0/base/npre spare the node-record load.
-// link: position in processing order (rows[], indexed by node id) or node id (ord[], indexed by position).
+// rows[v] (by node id): link = position in processing order, mp = arg-max column + 1.
+// ord[k]  (by position): link = node id, mp = position of in0 (the first predecessor's row).
 struct __align__(16) c3_prow { int32_t off; uint16_t beg, end; uint16_t mp, in0; uint16_t link; uint8_t base, npre; };
 static_assert(sizeof(c3_prow) == 16, "row record must be 16 bytes");
 __device__ __forceinline__ int c3_row_ng(const c3_prow &r) { return ((int)r.end - (int)r.beg + 4) >> 2; }
@@ -105,6 +106,13 @@ struct c3_poa_para_dev {
     int match, mismatch, o1, e1, o2, e2, wb, simd_bits;
     double wf;
 };
+
+#ifdef C3_POA_STATS
+__device__ unsigned long long c3_poa_stats[16];
+#define C3_STAT(i, v) do { if (lane == 0) atomicAdd(&c3_poa_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define C3_STAT(i, v) do { } while (0)
+#endif
 
 struct c3_poa_args {
     const uint8_t *codes;          // base codes of all sequences
@@ -385,8 +393,9 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     c3_prow ri; ri.off = 0; ri.beg = (uint16_t)b0; ri.end = (uint16_t)e0; ri.mp = 1;   // successors of the source start at column 1
                     ri.in0 = C3_NONE; ri.base = 4; ri.npre = 0; ri.link = 0;
                     W.rows[C3_SRC] = ri;
-                    W.ord[0] = ri;                                   // link = node id of the source = 0
                     rrec[0] = ri; rid[0] = in_ring ? C3_SRC : -1;
+                    ri.mp = C3_NONE;
+                    W.ord[0] = ri;                                   // link = node id of the source = 0; no predecessor
                     for (int t = 1; t < C3_RING; ++t) rid[t] = -1;
                 }
                 int32_t *H = W.cells, *E1 = H + 4 * ng, *E2 = E1 + 4 * ng;
@@ -422,6 +431,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                 {
                     const int p = C3_N_IN0(nd);
                     const int sl = p == rid0 ? 0 : p == rid1 ? 1 : p == rid2 ? 2 : p == rid3 ? 3 : -1;
+                    C3_STAT(0, 1); C3_STAT(1, sl < 0); C3_STAT(2, npre > 1); C3_STAT(3, npre);
                     if (sl >= 0) { r0 = rrec[sl]; p0ptr = &ring[sl][0]; p0str = 32; }
                     else { r0 = W.rows[p]; p0ptr = reinterpret_cast<const int4 *>(W.cells + r0.off); p0str = c3_row_ng(r0); }
                 }
@@ -452,6 +462,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                 if (npre > 1) __syncwarp();
                 int4 *rowv = reinterpret_cast<int4 *>(W.cells + off);
                 const int slot = rcount & (C3_RING - 1);
+                C3_STAT(4, ng); C3_STAT(5, ng > 32); C3_STAT(6, wd);
                 const bool to_ring = ng <= 32;
                 int4 *ringv = &ring[slot][0];
                 const int8_t *qprow = W.qp + (nbase < 4 ? nbase : 0) * A.qp_stride;
@@ -515,24 +526,13 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     }
                     int t1 = __viaddmax_s32(ga[3], -e1, hme[3] - oe1) + 4 * e1 * lane;
                     int t2 = __viaddmax_s32(gb[3], -e2, hme[3] - oe2) + 4 * e2 * lane;
-                    int c1 = __shfl_up_sync(C3_FULL, t1, 1), c2 = __shfl_up_sync(C3_FULL, t2, 1);
-                    // fast path: if the lane aggregates are non-decreasing over the active lanes, the
-                    // exclusive prefix max is just the left neighbour
-                    const int s1 = __shfl_up_sync(C3_FULL, c1, 1), s2 = __shfl_up_sync(C3_FULL, c2, 1);
-                    const bool mono = lane < 2 || !gact || (s1 <= c1 && s2 <= c2);
-                    int tot1, tot2;
-                    if (__all_sync(C3_FULL, mono)) {
-                        tot1 = max(__shfl_sync(C3_FULL, t1, 31), __shfl_sync(C3_FULL, c1, 31));
-                        tot2 = max(__shfl_sync(C3_FULL, t2, 31), __shfl_sync(C3_FULL, c2, 31));
-                    } else {
 #pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const int u1 = __shfl_up_sync(C3_FULL, t1, d), u2 = __shfl_up_sync(C3_FULL, t2, d);
-                            if (lane >= d) { t1 = max(t1, u1); t2 = max(t2, u2); }
-                        }
-                        c1 = __shfl_up_sync(C3_FULL, t1, 1); c2 = __shfl_up_sync(C3_FULL, t2, 1);
-                        tot1 = __shfl_sync(C3_FULL, t1, 31); tot2 = __shfl_sync(C3_FULL, t2, 31);
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int u1 = __shfl_up_sync(C3_FULL, t1, d), u2 = __shfl_up_sync(C3_FULL, t2, d);
+                        if (lane >= d) { t1 = max(t1, u1); t2 = max(t2, u2); }
                     }
+                    int c1 = __shfl_up_sync(C3_FULL, t1, 1), c2 = __shfl_up_sync(C3_FULL, t2, 1);
+                    const int tot1 = __shfl_sync(C3_FULL, t1, 31), tot2 = __shfl_sync(C3_FULL, t2, 31);
                     c1 = (lane == 0) ? C3_NEG_INF : c1 - 4 * e1 * (lane - 1);
                     c2 = (lane == 0) ? C3_NEG_INF : c2 - 4 * e2 * (lane - 1);
                     c1 = max(c1, carry1 - 4 * e1 * lane);
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     ri.link = (uint16_t)rcount;
                     W.rows[v] = ri;
                     rrec[slot] = ri; rid[slot] = to_ring ? v : -1;
-                    ri.link = (uint16_t)v;
+                    ri.link = (uint16_t)v; ri.mp = r0.link;          // r0 is rows[]-style: link = position of in0
                     W.ord[rcount] = ri;
                 }
                 ++rcount;
@@ -599,11 +599,11 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
             // ---- best end cell over the sink's predecessors (uniform across the warp) ----
             unsigned long long *cg = W.cigar;
             int nc = 0;
-            int i, j;
-            c3_prow ri;
+            int j, kpos;                                  // current column, position (processing order) of the current row
+            c3_prow rt;                                   // ord[]-style record of the current row
             {
                 const c3_nrec sk = c3_ld_node(&W.nodes[C3_SINK]);
-                int best_score = -0x7fffffff - 1, bi = -1, bj = -1;
+                int best_score = -0x7fffffff - 1, bj = -1, bk = -1;
                 int e = C3_N_INMORE(sk);
                 const int skn = C3_N_INN(sk);
                 for (int k = 0; k < skn; ++k) {
@@ -612,72 +612,98 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     const c3_prow rp = W.rows[p];
                     const int en = min(qlen, (int)rp.end);
                     const int val = W.cells[rp.off + en - rp.beg];
-                    if (val > best_score) { best_score = val; bi = p; bj = en; ri = rp; }
+                    if (val > best_score) { best_score = val; bj = en; bk = rp.link; }
                 }
-                if (bi < 0) { err = C3_E_BEST; break; }
-                i = bi; j = bj;
+                if (bk < 0) { err = C3_E_BEST; break; }
+                kpos = bk; j = bj; rt = W.ord[kpos];
                 if (qlen - bj + 8 > A.cigar_cap) { err = C3_E_CIGAR; break; }
                 for (int t = qlen - lane; t > bj; t -= 32)          // trailing query bases: insertions
                     cg[qlen - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
                 nc = qlen - bj;
             }
-            // ---- backtrack: warp-cooperative.  Runs of match/mismatch moves along consecutively
-            // processed rows are verified 31 at a time (one gather of row records, one of cells);
-            // everything else takes the generic one-step path (abPOA's M -> E1 -> E2 -> F1 -> F2 order). ----
+            // ---- backtrack: warp-cooperative.  The chain of first predecessors (in0) inside a window of
+            // 32 processed rows is resolved by pointer doubling over warp shuffles; up to 31 consecutive
+            // match/mismatch moves along it are then verified at once (one gather of row records, one of
+            // cells).  Everything else takes the generic one-step path (abPOA's M -> E1 -> E2 -> F1 -> F2). ----
             int cur_op = C3_OP_ALL;
-            while (!err && i != C3_SRC && j > 0) {
+            while (!err && rt.link != C3_SRC && j > 0) {
                 if (cur_op == C3_OP_ALL) {
-                    const int kt = (int)ri.link - lane, jt = j - lane;
-                    const bool have = kt >= 0;
-                    c3_prow rt = ri;
-                    if (have && lane > 0) rt = W.ord[kt];
-                    if (lane == 0) rt.link = (uint16_t)i;                       // ord-style record: link = node id
-                    const bool inb = have && jt >= 1 && jt >= (int)rt.beg && jt <= (int)rt.end;
+                    // window slot w = lane  <->  position kpos - w
+                    const int kw = kpos - lane;
+                    c3_prow rw = rt;
+                    if (kw >= 0 && lane > 0) rw = W.ord[kw];
+                    // F0[w] = window slot of in0(w); 32 = outside the window / none
+                    int f = 32;
+                    if (kw >= 0 && rw.mp != C3_NONE) { const int d = kpos - (int)rw.mp; if (d < 32) f = d; }
+                    int tbl[5];
+                    tbl[0] = f;
+#pragma unroll
+                    for (int b2 = 1; b2 < 5; ++b2) {
+                        const int prev = tbl[b2 - 1];
+                        const int nx = __shfl_sync(C3_FULL, prev, prev & 31);
+                        tbl[b2] = prev < 32 ? nx : 32;
+                    }
+                    // slot of the t-th row of the chain (t = lane): compose the set bits of t
+                    int sl = 0;
+#pragma unroll
+                    for (int b2 = 0; b2 < 5; ++b2) {
+                        const int nx = __shfl_sync(C3_FULL, tbl[b2], sl & 31);
+                        if ((lane >> b2) & 1) sl = sl < 32 ? nx : 32;
+                    }
+                    const bool have = sl < 32;
+                    const int4 rv = *reinterpret_cast<const int4 *>(&rw);
+                    int4 cv;
+                    cv.x = __shfl_sync(C3_FULL, rv.x, sl & 31); cv.y = __shfl_sync(C3_FULL, rv.y, sl & 31);
+                    cv.z = __shfl_sync(C3_FULL, rv.z, sl & 31); cv.w = __shfl_sync(C3_FULL, rv.w, sl & 31);
+                    const c3_prow rc = *reinterpret_cast<const c3_prow *>(&cv);      // record of chain row t
+                    const int jt = j - lane;
+                    const bool inb = have && jt >= 1 && jt >= (int)rc.beg && jt <= (int)rc.end;
                     int ht = C3_NEG_INF;
-                    if (inb) ht = W.cells[rt.off + jt - rt.beg];
-                    const int id_next = __shfl_down_sync(C3_FULL, (int)rt.link, 1);
-                    const int beg_next = __shfl_down_sync(C3_FULL, (int)rt.beg, 1);
-                    const int end_next = __shfl_down_sync(C3_FULL, (int)rt.end, 1);
+                    if (inb) ht = W.cells[rc.off + jt - rc.beg];
+                    const int beg_next = __shfl_down_sync(C3_FULL, (int)rc.beg, 1);
+                    const int end_next = __shfl_down_sync(C3_FULL, (int)rc.end, 1);
                     const int h_next = __shfl_down_sync(C3_FULL, ht, 1);
-                    const int st = inb ? c3_score(P, rt.base, q[jt - 1]) : 0;
-                    const bool ok = lane < 31 && inb && kt >= 1 && rt.link != C3_SRC && (int)rt.in0 == id_next &&
-                                    jt - 1 >= max(beg_next, (int)rt.beg) && jt - 1 <= end_next && ht == h_next + st;
+                    const int have_next = __shfl_down_sync(C3_FULL, (int)have, 1);
+                    const int st = inb ? c3_score(P, rc.base, q[jt - 1]) : 0;
+                    const bool ok = lane < 31 && inb && have_next && rc.link != C3_SRC &&
+                                    jt - 1 >= max(beg_next, (int)rc.beg) && jt - 1 <= end_next && ht == h_next + st;
                     const unsigned okm = __ballot_sync(C3_FULL, ok);
                     int L = __ffs(~okm) - 1;                                    // leading run of verified moves
                     L = min(L, A.cigar_cap - 8 - j - nc);
+                    C3_STAT(9, 1); C3_STAT(10, L > 0 ? L : 0);
                     if (L > 0) {
-                        if (lane < L) cg[nc + lane] = C3_CG_MATCH | ((unsigned long long)rt.link << 8) | ((unsigned long long)(jt - 1) << 32);
+                        if (lane < L) cg[nc + lane] = C3_CG_MATCH | ((unsigned long long)rc.link << 8) | ((unsigned long long)(jt - 1) << 32);
                         nc += L; j -= L;
-                        i = __shfl_sync(C3_FULL, (int)rt.link, L);
-                        const int4 rv = *reinterpret_cast<const int4 *>(&rt);
+                        kpos -= __shfl_sync(C3_FULL, sl, L);
                         int4 nv;
-                        nv.x = __shfl_sync(C3_FULL, rv.x, L); nv.y = __shfl_sync(C3_FULL, rv.y, L);
-                        nv.z = __shfl_sync(C3_FULL, rv.z, L); nv.w = __shfl_sync(C3_FULL, rv.w, L);
-                        ri = *reinterpret_cast<const c3_prow *>(&nv);
-                        ri.link = (uint16_t)((int)ri.link == i ? (kt + lane - L) : 0);  // back to rows[]-style: position
+                        nv.x = __shfl_sync(C3_FULL, cv.x, L); nv.y = __shfl_sync(C3_FULL, cv.y, L);
+                        nv.z = __shfl_sync(C3_FULL, cv.z, L); nv.w = __shfl_sync(C3_FULL, cv.w, L);
+                        rt = *reinterpret_cast<const c3_prow *>(&nv);
                         continue;
                     }
                 }
                 // generic single step
-                const int b = ri.beg, st4 = 4 * c3_row_ng(ri);
-                const int32_t *H = W.cells + ri.off, *E1 = H + st4, *E2 = E1 + st4;
-                if (j < b || j > (int)ri.end) { err = C3_E_BT; break; }
-                const int s = c3_score(P, ri.base, q[j - 1]);
+                C3_STAT(11, 1);
+                const int i = rt.link;
+                const int b = rt.beg, st4 = 4 * c3_row_ng(rt);
+                const int32_t *H = W.cells + rt.off, *E1 = H + st4, *E2 = E1 + st4;
+                if (j < b || j > (int)rt.end) { err = C3_E_BT; break; }
+                const int s = c3_score(P, rt.base, q[j - 1]);
                 const int hij = H[j - b];
-                const int npre = ri.npre;
+                const int npre = rt.npre;
                 const int in_more = npre > 1 ? (int)W.nodes[i].in_more : (int)C3_NONE;
                 int hit = 0;
                 unsigned long long opw = 0;
                 if (cur_op & C3_OP_M) {
                     int e = in_more;
                     for (int k = 0; k < npre; ++k) {
-                        int p;
-                        if (k == 0) p = ri.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
-                        const c3_prow pr = W.rows[p];
+                        int pk;                                              // position of predecessor k
+                        if (k == 0) pk = rt.mp; else { const c3_pedge pe = W.pool[e]; pk = W.rows[pe.id].link; e = pe.next; }
+                        const c3_prow pr = W.ord[pk];
                         if (j - 1 < max((int)pr.beg, b) || j - 1 > (int)pr.end) continue;
                         if (W.cells[pr.off + j - 1 - pr.beg] + s == hij) {
                             opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                            i = p; ri = pr; --j; hit = 1; cur_op = C3_OP_ALL;
+                            kpos = pk; rt = pr; --j; hit = 1; cur_op = C3_OP_ALL;
                             break;
                         }
                     }
@@ -685,9 +711,9 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                 if (!hit && (cur_op & C3_OP_E)) {
                     int e = in_more;
                     for (int k = 0; k < npre; ++k) {
-                        int p;
-                        if (k == 0) p = ri.in0; else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
-                        const c3_prow pr = W.rows[p];
+                        int pk;
+                        if (k == 0) pk = rt.mp; else { const c3_pedge pe = W.pool[e]; pk = W.rows[pe.id].link; e = pe.next; }
+                        const c3_prow pr = W.ord[pk];
                         if (j < (int)pr.beg || j > (int)pr.end) continue;
                         const int pw = 4 * c3_row_ng(pr), pc = j - pr.beg;
                         const int32_t *pH = W.cells + pr.off;
@@ -708,7 +734,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                         }
                         if (hit) {
                             opw = C3_CG_DEL | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                            i = p; ri = pr;
+                            kpos = pk; rt = pr;
                             break;
                         }
                     }
@@ -788,6 +814,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                         }
                     }
                     const unsigned m_cx = m_nondel & ~__ballot_sync(C3_FULL, done);
+                    C3_STAT(12, __popc(m_nondel)); C3_STAT(13, __popc(m_cx));
                     __syncwarp();
                     if (m_cx) {
                         if (lane == 0) {
