@@ -258,6 +258,409 @@ __device__ int c3_group_tail(const c3_graph &g, int a)
 }
 
 // ---------------------------------------------------------------------------
+// Backtrack + graph merge of one aligned sequence.  All 32 lanes call it with identical
+// (warp-uniform) arguments; returns 0 or a C3_E_* code, updates node_n / pool_n.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int c3_bt_merge(const c3_poa_args &A, const c3_poa_para_dev &P, const c3_poa_ws &W,
+                                        const uint8_t *q, const int qlen, const int sq, const int lane,
+                                        int &node_n, int &pool_n)
+{
+    const int o1 = P.o1, e1 = P.e1, o2 = P.o2, e2 = P.e2, oe1 = o1 + e1, oe2 = o2 + e2;
+    (void)o1; (void)o2;
+    int err = 0;
+    // ---- best end cell over the sink's predecessors (uniform across the warp) ----
+    unsigned long long *cg = W.cigar;
+    int nc = 0;
+    int j, kpos;                                  // current column, position (processing order) of the current row
+    c3_prow rt;                                   // ord[]-style record of the current row
+    {
+        const c3_nrec sk = c3_ld_node(&W.nodes[C3_SINK]);
+        int best_score = -0x7fffffff - 1, bj = -1, bk = -1;
+        int e = C3_N_INMORE(sk);
+        const int skn = C3_N_INN(sk);
+        for (int k = 0; k < skn; ++k) {
+            int p;
+            if (k == 0) p = C3_N_IN0(sk); else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
+            const c3_prow rp = W.rows[p];
+            const int en = min(qlen, (int)rp.end);
+            const int val = W.cells[rp.off + en - rp.beg];
+            if (val > best_score) { best_score = val; bj = en; bk = rp.link; }
+        }
+        if (bk < 0) return C3_E_BEST;
+        kpos = bk; j = bj; rt = W.ord[kpos];
+        if (qlen - bj + 8 > A.cigar_cap) return C3_E_CIGAR;
+        for (int t = qlen - lane; t > bj; t -= 32)          // trailing query bases: insertions
+            cg[qlen - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
+        nc = qlen - bj;
+    }
+    // ---- backtrack: warp-cooperative.  The chain of first predecessors (in0) inside a window of
+    // 32 processed rows is resolved by pointer doubling over warp shuffles; up to 31 consecutive
+    // match/mismatch moves along it are then verified at once (one gather of row records, one of
+    // cells).  Everything else takes the generic one-step path (abPOA's M -> E1 -> E2 -> F1 -> F2). ----
+    int cur_op = C3_OP_ALL;
+    while (!err && rt.link != C3_SRC && j > 0) {
+        if (cur_op == C3_OP_ALL) {
+            // window slot w = lane  <->  position kpos - w
+            const int kw = kpos - lane;
+            c3_prow rw = rt;
+            if (kw >= 0 && lane > 0) rw = W.ord[kw];
+            // F0[w] = window slot of in0(w); 32 = outside the window / none
+            int f = 32;
+            if (kw >= 0 && rw.mp != C3_NONE) { const int d = kpos - (int)rw.mp; if (d < 32) f = d; }
+            int tbl[5];
+            tbl[0] = f;
+#pragma unroll
+            for (int b2 = 1; b2 < 5; ++b2) {
+                const int prev = tbl[b2 - 1];
+                const int nx = __shfl_sync(C3_FULL, prev, prev & 31);
+                tbl[b2] = prev < 32 ? nx : 32;
+            }
+            // slot of the t-th row of the chain (t = lane): compose the set bits of t
+            int sl = 0;
+#pragma unroll
+            for (int b2 = 0; b2 < 5; ++b2) {
+                const int nx = __shfl_sync(C3_FULL, tbl[b2], sl & 31);
+                if ((lane >> b2) & 1) sl = sl < 32 ? nx : 32;
+            }
+            const bool have = sl < 32;
+            const int4 rv = *reinterpret_cast<const int4 *>(&rw);
+            int4 cv;
+            cv.x = __shfl_sync(C3_FULL, rv.x, sl & 31); cv.y = __shfl_sync(C3_FULL, rv.y, sl & 31);
+            cv.z = __shfl_sync(C3_FULL, rv.z, sl & 31); cv.w = __shfl_sync(C3_FULL, rv.w, sl & 31);
+            const c3_prow rc = *reinterpret_cast<const c3_prow *>(&cv);      // record of chain row t
+            const int jt = j - lane;
+            const bool inb = have && jt >= 1 && jt >= (int)rc.beg && jt <= (int)rc.end;
+            int ht = C3_NEG_INF;
+            if (inb) ht = W.cells[rc.off + jt - rc.beg];
+            const int beg_next = __shfl_down_sync(C3_FULL, (int)rc.beg, 1);
+            const int end_next = __shfl_down_sync(C3_FULL, (int)rc.end, 1);
+            const int h_next = __shfl_down_sync(C3_FULL, ht, 1);
+            const int have_next = __shfl_down_sync(C3_FULL, (int)have, 1);
+            const int st = inb ? c3_score(P, rc.base, q[jt - 1]) : 0;
+            const bool ok = lane < 31 && inb && have_next && rc.link != C3_SRC &&
+                            jt - 1 >= max(beg_next, (int)rc.beg) && jt - 1 <= end_next && ht == h_next + st;
+            const unsigned okm = __ballot_sync(C3_FULL, ok);
+            int L = __ffs(~okm) - 1;                                    // leading run of verified moves
+            L = min(L, A.cigar_cap - 8 - j - nc);
+            C3_STAT(9, 1); C3_STAT(10, L > 0 ? L : 0);
+            if (L > 0) {
+                if (lane < L) cg[nc + lane] = C3_CG_MATCH | ((unsigned long long)rc.link << 8) | ((unsigned long long)(jt - 1) << 32);
+                nc += L; j -= L;
+                kpos -= __shfl_sync(C3_FULL, sl, L);
+                int4 nv;
+                nv.x = __shfl_sync(C3_FULL, cv.x, L); nv.y = __shfl_sync(C3_FULL, cv.y, L);
+                nv.z = __shfl_sync(C3_FULL, cv.z, L); nv.w = __shfl_sync(C3_FULL, cv.w, L);
+                rt = *reinterpret_cast<const c3_prow *>(&nv);
+                continue;
+            }
+        }
+        // generic single step
+        C3_STAT(11, 1);
+        const int i = rt.link;
+        const int b = rt.beg, st4 = 4 * c3_row_ng(rt);
+        const int32_t *H = W.cells + rt.off, *E1 = H + st4, *E2 = E1 + st4;
+        if (j < b || j > (int)rt.end) { err = C3_E_BT; break; }
+        const int s = c3_score(P, rt.base, q[j - 1]);
+        const int hij = H[j - b];
+        const int npre = rt.npre;
+        const int in_more = npre > 1 ? (int)W.nodes[i].in_more : (int)C3_NONE;
+        int hit = 0;
+        unsigned long long opw = 0;
+        if (cur_op & C3_OP_M) {
+            int e = in_more;
+            for (int k = 0; k < npre; ++k) {
+                int pk;                                              // position of predecessor k
+                if (k == 0) pk = rt.mp; else { const c3_pedge pe = W.pool[e]; pk = W.rows[pe.id].link; e = pe.next; }
+                const c3_prow pr = W.ord[pk];
+                if (j - 1 < max((int)pr.beg, b) || j - 1 > (int)pr.end) continue;
+                if (W.cells[pr.off + j - 1 - pr.beg] + s == hij) {
+                    opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                    kpos = pk; rt = pr; --j; hit = 1; cur_op = C3_OP_ALL;
+                    break;
+                }
+            }
+        }
+        if (!hit && (cur_op & C3_OP_E)) {
+            int e = in_more;
+            for (int k = 0; k < npre; ++k) {
+                int pk;
+                if (k == 0) pk = rt.mp; else { const c3_pedge pe = W.pool[e]; pk = W.rows[pe.id].link; e = pe.next; }
+                const c3_prow pr = W.ord[pk];
+                if (j < (int)pr.beg || j > (int)pr.end) continue;
+                const int pw = 4 * c3_row_ng(pr), pc = j - pr.beg;
+                const int32_t *pH = W.cells + pr.off;
+                const int ph = pH[pc], pe1 = pH[pw + pc], pe2 = pH[2 * pw + pc];
+                if (cur_op & C3_OP_E1) {
+                    if (cur_op & C3_OP_M) {
+                        if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
+                    } else if (E1[j - b] == pe1 - e1) {
+                        cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1;
+                    }
+                }
+                if (!hit && (cur_op & C3_OP_E2)) {
+                    if (cur_op & C3_OP_M) {
+                        if (hij == pe2) { cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1; }
+                    } else if (E2[j - b] == pe2 - e2) {
+                        cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1;
+                    }
+                }
+                if (hit) {
+                    opw = C3_CG_DEL | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                    kpos = pk; rt = pr;
+                    break;
+                }
+            }
+        }
+        if (!hit && (cur_op & C3_OP_F)) {
+            if (j - 1 >= b) {
+                // F is not stored: rebuild F[j] and F[j-1] of this row from its H
+                // (F[c+1] = max(F[c]-e, H[c]-o-e); equal to the DP's F wherever F decides)
+                int f1 = C3_NEG_INF, f2 = C3_NEG_INF, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
+                for (int c = 0; c < j - b; ++c) {
+                    hl = H[c];
+                    f1l = f1; f2l = f2;
+                    f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
+                }
+                if (cur_op & C3_OP_F1) {
+                    if (!(cur_op & C3_OP_M) || hij == f1) {
+                        if (hl - oe1 == f1) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                        else if (f1l - e1 == f1) { cur_op = C3_OP_F1; hit = 1; }
+                    }
+                }
+                if (!hit && (cur_op & C3_OP_F2)) {
+                    if (!(cur_op & C3_OP_M) || hij == f2) {
+                        if (hl - oe2 == f2) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                        else if (f2l - e2 == f2) { cur_op = C3_OP_F2; hit = 1; }
+                    }
+                }
+            }
+            if (hit) { opw = C3_CG_INS | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32); --j; }
+        }
+        if (!hit) { err = C3_E_BT; break; }
+        if (lane == 0) cg[nc] = opw;
+        ++nc;
+        if (nc + j + 8 > A.cigar_cap) { err = C3_E_CIGAR; break; }
+    }
+    if (err) return err;
+    for (int t = j - lane; t > 0; t -= 32)                      // leading query bases: insertions
+        cg[nc + j - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
+    nc += j;
+    __syncwarp();
+
+    // ---- merge (abpoa_add_graph_alignment); the cigar is walked from its tail = forward order.
+    // 32 ops at a time: ops that only bump the weight of an existing edge between two matched
+    // nodes are applied by all lanes at once; the rest (new nodes / edges) goes through lane 0
+    // in order. ----
+    {
+        c3_graph g; g.nodes = W.nodes; g.pool = W.pool; g.node_n = node_n; g.pool_n = pool_n;
+        g.node_cap = A.node_cap; g.pool_cap = A.pool_cap; g.err = 0;
+        int last_id = C3_SRC, last_new = 0;                     // uniform
+        for (int tb = nc - 1; tb >= 0; tb -= 32) {
+            const int t = tb - lane;
+            const bool have = t >= 0;
+            const unsigned long long op = have ? cg[t] : C3_CG_DEL;
+            const int kind = (int)(op & 0xff), node_id = (int)((op >> 8) & 0xffff), qpos = (int)(op >> 32);
+            const bool is_match = have && kind == (int)C3_CG_MATCH;
+            bool eq = false;
+            if (is_match) eq = W.nodes[node_id].base == q[qpos];
+            if (eq && sq < 16) W.nodes[node_id].mpl |= (uint16_t)(1u << sq);
+            const unsigned m_nondel = __ballot_sync(C3_FULL, have && kind != (int)C3_CG_DEL);
+            const unsigned m_eq = __ballot_sync(C3_FULL, eq);
+            const unsigned lower = m_nondel & ((1u << lane) - 1u);
+            const int pl = lower ? 31 - __clz(lower) : -1;      // lane of the previous non-deletion op
+            const int pred_node = __shfl_sync(C3_FULL, node_id, pl < 0 ? 0 : pl);
+            const int from = pl >= 0 ? pred_node : last_id;
+            const bool from_ok = pl >= 0 ? ((m_eq >> pl) & 1u) != 0 : last_new == 0;
+            bool done = false;
+            if (eq && from_ok) {                                 // bump the existing edge from -> node_id
+                c3_pnode *f = &W.nodes[from];
+                if (f->out_n > 0) {
+                    if ((int)f->out0 == node_id) { f->w0 = (uint16_t)(f->w0 + 1); done = true; }
+                    else {
+                        uint16_t e = f->out_more;
+                        while (e != C3_NONE) {
+                            if ((int)W.pool[e].id == node_id) { W.pool[e].w = (uint16_t)(W.pool[e].w + 1); done = true; break; }
+                            e = W.pool[e].next;
+                        }
+                    }
+                }
+            }
+            const unsigned m_cx = m_nondel & ~__ballot_sync(C3_FULL, done);
+            C3_STAT(12, __popc(m_nondel)); C3_STAT(13, __popc(m_cx));
+            __syncwarp();
+            if (m_cx) {
+                if (lane == 0) {
+                    unsigned mc = m_cx;
+                    while (mc && !g.err) {
+                        const int c = __ffs(mc) - 1; mc &= mc - 1;
+                        const unsigned lowc = m_nondel & ((1u << c) - 1u);
+                        const int pc = lowc ? 31 - __clz(lowc) : -1;
+                        if (pc >= 0 && ((m_eq >> pc) & 1u)) { last_id = (int)((cg[tb - pc] >> 8) & 0xffff); last_new = 0; }
+                        const unsigned long long opc = cg[tb - c];
+                        const int kc = (int)(opc & 0xff), nid = (int)((opc >> 8) & 0xffff), qp = (int)(opc >> 32);
+                        if (kc == (int)C3_CG_MATCH) {
+                            const uint8_t bq = q[qp];
+                            const c3_pnode nm = g.nodes[nid];
+                            if (nm.base != bq) {
+                                int al = -1;
+                                for (int k = 0; k < nm.aln_n; ++k) {
+                                    const int a = c3_aln_get(nm, k);
+                                    if (g.nodes[a].base == bq) { al = a; break; }
+                                }
+                                if (al != -1) {
+                                    c3_g_add_edge(g, last_id, al, 1 - last_new);
+                                    last_id = al; last_new = 0;
+                                    if (sq < 16) g.nodes[al].mpl |= (uint16_t)(1u << sq);
+                                } else {
+                                    const int id = c3_g_add_node(g, bq);
+                                    if (g.err) break;
+                                    c3_list_insert_before(g, id, nid);
+                                    c3_g_add_edge(g, last_id, id, 0);
+                                    last_id = id; last_new = 1;
+                                    if (sq < 16) g.nodes[id].mpl = (uint16_t)(1u << sq);
+                                    for (int k = 0; k < nm.aln_n; ++k) {     // abpoa_add_graph_aligned_node
+                                        const int a = c3_aln_get(nm, k);
+                                        c3_aln_push(&g.nodes[a], (uint16_t)id);
+                                        c3_aln_push(&g.nodes[id], (uint16_t)a);
+                                    }
+                                    c3_aln_push(&g.nodes[nid], (uint16_t)id);
+                                    c3_aln_push(&g.nodes[id], (uint16_t)nid);
+                                }
+                            } else {
+                                c3_g_add_edge(g, last_id, nid, 1 - last_new);
+                                last_id = nid; last_new = 0;
+                            }
+                        } else {                                     // insertion
+                            const int id = c3_g_add_node(g, q[qp]);
+                            if (g.err) break;
+                            c3_list_insert_after(g, id, c3_group_tail(g, last_id));
+                            c3_g_add_edge(g, last_id, id, 0);
+                            last_id = id; last_new = 1;
+                            if (sq < 16) g.nodes[id].mpl = (uint16_t)(1u << sq);
+                        }
+                    }
+                }
+                g.err = __shfl_sync(C3_FULL, g.err, 0);
+                g.node_n = __shfl_sync(C3_FULL, g.node_n, 0);
+                g.pool_n = __shfl_sync(C3_FULL, g.pool_n, 0);
+                last_id = __shfl_sync(C3_FULL, last_id, 0);
+                last_new = __shfl_sync(C3_FULL, last_new, 0);
+            }
+            if (m_nondel) {                                          // state after the chunk
+                const int ln = 31 - __clz(m_nondel);
+                if ((m_eq >> ln) & 1u) { last_id = __shfl_sync(C3_FULL, node_id, ln); last_new = 0; }
+            }
+            __syncwarp();
+            if (g.err) break;
+        }
+        if (!g.err && lane == 0) c3_g_add_edge(g, last_id, C3_SINK, 1 - last_new);
+        g.err = __shfl_sync(C3_FULL, g.err, 0);
+        g.pool_n = __shfl_sync(C3_FULL, g.pool_n, 0);
+        err = g.err;
+        node_n = g.node_n; pool_n = g.pool_n;
+    }
+    return err;
+}
+
+// Two MSA rows of a 2-sequence graph (the reference's pairwise path, bin/determine_consensus.py:33-41
+// -> abpoa_generate_rc_msa with LIFO rank order), written as [row0 | row1].  Warp-uniform call;
+// returns the number of columns or a C3_E_* code.
+__device__ __forceinline__ int c3_emit_msa(const c3_poa_args &A, const c3_poa_ws &W, const int node_n, const int lane, char *co)
+{
+    int32_t *rank = (int32_t *)W.hr, *indeg = (int32_t *)W.rows, *stk = (int32_t *)W.ord;
+    for (int v = lane; v < node_n; v += 32) { rank[v] = 0; indeg[v] = W.nodes[v].in_n; }
+    __syncwarp();
+    int msa_len = 0;
+    if (lane == 0) {
+        int top = 0, msa_rank = 0, ok = 0;
+        stk[top++] = C3_SRC; rank[C3_SRC] = -1;
+        while (top > 0) {
+            const int cur = stk[--top];
+            const c3_pnode nd = W.nodes[cur];
+            if (rank[cur] < 0) {
+                rank[cur] = msa_rank;
+                for (int k = 0; k < nd.aln_n; ++k) rank[c3_aln_get(nd, k)] = msa_rank;
+                ++msa_rank;
+            }
+            if (cur == C3_SINK) { ok = 1; break; }
+            uint16_t e = nd.out_more;
+            for (int k = 0; k < nd.out_n; ++k) {
+                int o;
+                if (k == 0) o = nd.out0; else { const c3_pedge pe = W.pool[e]; o = pe.id; e = pe.next; }
+                if (--indeg[o] == 0) {
+                    const c3_pnode on = W.nodes[o];
+                    bool ready = true;
+                    for (int a = 0; a < on.aln_n; ++a) if (indeg[c3_aln_get(on, a)] != 0) { ready = false; break; }
+                    if (!ready) continue;
+                    stk[top++] = o; rank[o] = -1;
+                    for (int a = 0; a < on.aln_n; ++a) { const int al = c3_aln_get(on, a); stk[top++] = al; rank[al] = -1; }
+                }
+            }
+        }
+        msa_len = ok ? rank[C3_SINK] - 1 : -1;
+    }
+    msa_len = __shfl_sync(C3_FULL, msa_len, 0);
+    __syncwarp();
+    if (msa_len < 0 || 2 * msa_len > A.cons_cap) return C3_E_CONS;
+    {
+        for (int c = lane; c < 2 * msa_len; c += 32) co[c] = '-';
+        __syncwarp();
+        for (int v = 2 + lane; v < node_n; v += 32) {
+            const c3_pnode nd = W.nodes[v];
+            int rk = rank[v];
+            for (int k = 0; k < nd.aln_n; ++k) rk = max(rk, rank[c3_aln_get(nd, k)]);
+            const char ch = "ACGTN"[nd.base];
+            if (nd.mpl & 1) co[rk - 1] = ch;
+            if (nd.mpl & 2) co[msa_len + rk - 1] = ch;
+        }
+    }
+    return msa_len;
+}
+
+// Heaviest bundling (abpoa_heaviest_bundling) + consensus walk.  Single-thread routine: called by
+// one lane per graph; returns the consensus length or a C3_E_* code.
+__device__ __forceinline__ int c3_consensus(const c3_poa_args &A, const c3_poa_ws &W, char *co)
+{
+    int cons_len = 0;
+    int32_t *score = (int32_t *)W.hr;
+    int v = C3_SINK;
+    while (v != C3_NONE) {
+        c3_pnode *nd = &W.nodes[v];
+        if (v == C3_SINK) { nd->max_out = C3_NONE; score[v] = 0; }
+        else if (v == C3_SRC) {
+            int max_id = -1, path_score = -1, path_w = -1;
+            uint16_t e = nd->out_more;
+            for (int k = 0; k < nd->out_n; ++k) {
+                int o, wv;
+                if (k == 0) { o = nd->out0; wv = nd->w0; } else { const c3_pedge pe = W.pool[e]; o = pe.id; wv = pe.w; e = pe.next; }
+                if (wv > path_w || (wv == path_w && score[o] > path_score)) { max_id = o; path_score = score[o]; path_w = wv; }
+            }
+            nd->max_out = (uint16_t)max_id;
+        } else {
+            int max_w = -0x7fffffff - 1, max_id = -1;
+            uint16_t e = nd->out_more;
+            for (int k = 0; k < nd->out_n; ++k) {
+                int o, wv;
+                if (k == 0) { o = nd->out0; wv = nd->w0; } else { const c3_pedge pe = W.pool[e]; o = pe.id; wv = pe.w; e = pe.next; }
+                if (max_w < wv) { max_w = wv; max_id = o; }
+                else if (max_w == wv && score[max_id] <= score[o]) max_id = o;
+            }
+            score[v] = max_w + score[max_id];
+            nd->max_out = (uint16_t)max_id;
+        }
+        v = nd->prev;
+    }
+    int id = W.nodes[C3_SRC].max_out;
+    while (id != C3_SINK) {
+        if (id == C3_NONE || cons_len >= A.cons_cap) return C3_E_CONS;
+        const c3_pnode nd = W.nodes[id];
+        co[cons_len++] = "ACGTN"[nd.base];
+        id = nd.max_out;
+    }
+    return cons_len;
+}
+
+// ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_poa_args A)
 {
     __shared__ int4 s_ring[C3_POA_THREADS / 32][C3_RING][3 * 32];   // H,E1,E2 of recent rows: 32 groups each
@@ -596,392 +999,22 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
             }
             if (err) break;
 
-            // ---- best end cell over the sink's predecessors (uniform across the warp) ----
-            unsigned long long *cg = W.cigar;
-            int nc = 0;
-            int j, kpos;                                  // current column, position (processing order) of the current row
-            c3_prow rt;                                   // ord[]-style record of the current row
-            {
-                const c3_nrec sk = c3_ld_node(&W.nodes[C3_SINK]);
-                int best_score = -0x7fffffff - 1, bj = -1, bk = -1;
-                int e = C3_N_INMORE(sk);
-                const int skn = C3_N_INN(sk);
-                for (int k = 0; k < skn; ++k) {
-                    int p;
-                    if (k == 0) p = C3_N_IN0(sk); else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
-                    const c3_prow rp = W.rows[p];
-                    const int en = min(qlen, (int)rp.end);
-                    const int val = W.cells[rp.off + en - rp.beg];
-                    if (val > best_score) { best_score = val; bj = en; bk = rp.link; }
-                }
-                if (bk < 0) { err = C3_E_BEST; break; }
-                kpos = bk; j = bj; rt = W.ord[kpos];
-                if (qlen - bj + 8 > A.cigar_cap) { err = C3_E_CIGAR; break; }
-                for (int t = qlen - lane; t > bj; t -= 32)          // trailing query bases: insertions
-                    cg[qlen - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
-                nc = qlen - bj;
-            }
-            // ---- backtrack: warp-cooperative.  The chain of first predecessors (in0) inside a window of
-            // 32 processed rows is resolved by pointer doubling over warp shuffles; up to 31 consecutive
-            // match/mismatch moves along it are then verified at once (one gather of row records, one of
-            // cells).  Everything else takes the generic one-step path (abPOA's M -> E1 -> E2 -> F1 -> F2). ----
-            int cur_op = C3_OP_ALL;
-            while (!err && rt.link != C3_SRC && j > 0) {
-                if (cur_op == C3_OP_ALL) {
-                    // window slot w = lane  <->  position kpos - w
-                    const int kw = kpos - lane;
-                    c3_prow rw = rt;
-                    if (kw >= 0 && lane > 0) rw = W.ord[kw];
-                    // F0[w] = window slot of in0(w); 32 = outside the window / none
-                    int f = 32;
-                    if (kw >= 0 && rw.mp != C3_NONE) { const int d = kpos - (int)rw.mp; if (d < 32) f = d; }
-                    int tbl[5];
-                    tbl[0] = f;
-#pragma unroll
-                    for (int b2 = 1; b2 < 5; ++b2) {
-                        const int prev = tbl[b2 - 1];
-                        const int nx = __shfl_sync(C3_FULL, prev, prev & 31);
-                        tbl[b2] = prev < 32 ? nx : 32;
-                    }
-                    // slot of the t-th row of the chain (t = lane): compose the set bits of t
-                    int sl = 0;
-#pragma unroll
-                    for (int b2 = 0; b2 < 5; ++b2) {
-                        const int nx = __shfl_sync(C3_FULL, tbl[b2], sl & 31);
-                        if ((lane >> b2) & 1) sl = sl < 32 ? nx : 32;
-                    }
-                    const bool have = sl < 32;
-                    const int4 rv = *reinterpret_cast<const int4 *>(&rw);
-                    int4 cv;
-                    cv.x = __shfl_sync(C3_FULL, rv.x, sl & 31); cv.y = __shfl_sync(C3_FULL, rv.y, sl & 31);
-                    cv.z = __shfl_sync(C3_FULL, rv.z, sl & 31); cv.w = __shfl_sync(C3_FULL, rv.w, sl & 31);
-                    const c3_prow rc = *reinterpret_cast<const c3_prow *>(&cv);      // record of chain row t
-                    const int jt = j - lane;
-                    const bool inb = have && jt >= 1 && jt >= (int)rc.beg && jt <= (int)rc.end;
-                    int ht = C3_NEG_INF;
-                    if (inb) ht = W.cells[rc.off + jt - rc.beg];
-                    const int beg_next = __shfl_down_sync(C3_FULL, (int)rc.beg, 1);
-                    const int end_next = __shfl_down_sync(C3_FULL, (int)rc.end, 1);
-                    const int h_next = __shfl_down_sync(C3_FULL, ht, 1);
-                    const int have_next = __shfl_down_sync(C3_FULL, (int)have, 1);
-                    const int st = inb ? c3_score(P, rc.base, q[jt - 1]) : 0;
-                    const bool ok = lane < 31 && inb && have_next && rc.link != C3_SRC &&
-                                    jt - 1 >= max(beg_next, (int)rc.beg) && jt - 1 <= end_next && ht == h_next + st;
-                    const unsigned okm = __ballot_sync(C3_FULL, ok);
-                    int L = __ffs(~okm) - 1;                                    // leading run of verified moves
-                    L = min(L, A.cigar_cap - 8 - j - nc);
-                    C3_STAT(9, 1); C3_STAT(10, L > 0 ? L : 0);
-                    if (L > 0) {
-                        if (lane < L) cg[nc + lane] = C3_CG_MATCH | ((unsigned long long)rc.link << 8) | ((unsigned long long)(jt - 1) << 32);
-                        nc += L; j -= L;
-                        kpos -= __shfl_sync(C3_FULL, sl, L);
-                        int4 nv;
-                        nv.x = __shfl_sync(C3_FULL, cv.x, L); nv.y = __shfl_sync(C3_FULL, cv.y, L);
-                        nv.z = __shfl_sync(C3_FULL, cv.z, L); nv.w = __shfl_sync(C3_FULL, cv.w, L);
-                        rt = *reinterpret_cast<const c3_prow *>(&nv);
-                        continue;
-                    }
-                }
-                // generic single step
-                C3_STAT(11, 1);
-                const int i = rt.link;
-                const int b = rt.beg, st4 = 4 * c3_row_ng(rt);
-                const int32_t *H = W.cells + rt.off, *E1 = H + st4, *E2 = E1 + st4;
-                if (j < b || j > (int)rt.end) { err = C3_E_BT; break; }
-                const int s = c3_score(P, rt.base, q[j - 1]);
-                const int hij = H[j - b];
-                const int npre = rt.npre;
-                const int in_more = npre > 1 ? (int)W.nodes[i].in_more : (int)C3_NONE;
-                int hit = 0;
-                unsigned long long opw = 0;
-                if (cur_op & C3_OP_M) {
-                    int e = in_more;
-                    for (int k = 0; k < npre; ++k) {
-                        int pk;                                              // position of predecessor k
-                        if (k == 0) pk = rt.mp; else { const c3_pedge pe = W.pool[e]; pk = W.rows[pe.id].link; e = pe.next; }
-                        const c3_prow pr = W.ord[pk];
-                        if (j - 1 < max((int)pr.beg, b) || j - 1 > (int)pr.end) continue;
-                        if (W.cells[pr.off + j - 1 - pr.beg] + s == hij) {
-                            opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                            kpos = pk; rt = pr; --j; hit = 1; cur_op = C3_OP_ALL;
-                            break;
-                        }
-                    }
-                }
-                if (!hit && (cur_op & C3_OP_E)) {
-                    int e = in_more;
-                    for (int k = 0; k < npre; ++k) {
-                        int pk;
-                        if (k == 0) pk = rt.mp; else { const c3_pedge pe = W.pool[e]; pk = W.rows[pe.id].link; e = pe.next; }
-                        const c3_prow pr = W.ord[pk];
-                        if (j < (int)pr.beg || j > (int)pr.end) continue;
-                        const int pw = 4 * c3_row_ng(pr), pc = j - pr.beg;
-                        const int32_t *pH = W.cells + pr.off;
-                        const int ph = pH[pc], pe1 = pH[pw + pc], pe2 = pH[2 * pw + pc];
-                        if (cur_op & C3_OP_E1) {
-                            if (cur_op & C3_OP_M) {
-                                if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
-                            } else if (E1[j - b] == pe1 - e1) {
-                                cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1;
-                            }
-                        }
-                        if (!hit && (cur_op & C3_OP_E2)) {
-                            if (cur_op & C3_OP_M) {
-                                if (hij == pe2) { cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1; }
-                            } else if (E2[j - b] == pe2 - e2) {
-                                cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1;
-                            }
-                        }
-                        if (hit) {
-                            opw = C3_CG_DEL | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                            kpos = pk; rt = pr;
-                            break;
-                        }
-                    }
-                }
-                if (!hit && (cur_op & C3_OP_F)) {
-                    if (j - 1 >= b) {
-                        // F is not stored: rebuild F[j] and F[j-1] of this row from its H
-                        // (F[c+1] = max(F[c]-e, H[c]-o-e); equal to the DP's F wherever F decides)
-                        int f1 = C3_NEG_INF, f2 = C3_NEG_INF, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
-                        for (int c = 0; c < j - b; ++c) {
-                            hl = H[c];
-                            f1l = f1; f2l = f2;
-                            f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
-                        }
-                        if (cur_op & C3_OP_F1) {
-                            if (!(cur_op & C3_OP_M) || hij == f1) {
-                                if (hl - oe1 == f1) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
-                                else if (f1l - e1 == f1) { cur_op = C3_OP_F1; hit = 1; }
-                            }
-                        }
-                        if (!hit && (cur_op & C3_OP_F2)) {
-                            if (!(cur_op & C3_OP_M) || hij == f2) {
-                                if (hl - oe2 == f2) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
-                                else if (f2l - e2 == f2) { cur_op = C3_OP_F2; hit = 1; }
-                            }
-                        }
-                    }
-                    if (hit) { opw = C3_CG_INS | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32); --j; }
-                }
-                if (!hit) { err = C3_E_BT; break; }
-                if (lane == 0) cg[nc] = opw;
-                ++nc;
-                if (nc + j + 8 > A.cigar_cap) { err = C3_E_CIGAR; break; }
-            }
-            if (err) break;
-            for (int t = j - lane; t > 0; t -= 32)                      // leading query bases: insertions
-                cg[nc + j - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
-            nc += j;
-            __syncwarp();
-
-            // ---- merge (abpoa_add_graph_alignment); the cigar is walked from its tail = forward order.
-            // 32 ops at a time: ops that only bump the weight of an existing edge between two matched
-            // nodes are applied by all lanes at once; the rest (new nodes / edges) goes through lane 0
-            // in order. ----
-            {
-                c3_graph g; g.nodes = W.nodes; g.pool = W.pool; g.node_n = node_n; g.pool_n = pool_n;
-                g.node_cap = A.node_cap; g.pool_cap = A.pool_cap; g.err = 0;
-                int last_id = C3_SRC, last_new = 0;                     // uniform
-                for (int tb = nc - 1; tb >= 0; tb -= 32) {
-                    const int t = tb - lane;
-                    const bool have = t >= 0;
-                    const unsigned long long op = have ? cg[t] : C3_CG_DEL;
-                    const int kind = (int)(op & 0xff), node_id = (int)((op >> 8) & 0xffff), qpos = (int)(op >> 32);
-                    const bool is_match = have && kind == (int)C3_CG_MATCH;
-                    bool eq = false;
-                    if (is_match) eq = W.nodes[node_id].base == q[qpos];
-                    if (eq && sq < 16) W.nodes[node_id].mpl |= (uint16_t)(1u << sq);
-                    const unsigned m_nondel = __ballot_sync(C3_FULL, have && kind != (int)C3_CG_DEL);
-                    const unsigned m_eq = __ballot_sync(C3_FULL, eq);
-                    const unsigned lower = m_nondel & ((1u << lane) - 1u);
-                    const int pl = lower ? 31 - __clz(lower) : -1;      // lane of the previous non-deletion op
-                    const int pred_node = __shfl_sync(C3_FULL, node_id, pl < 0 ? 0 : pl);
-                    const int from = pl >= 0 ? pred_node : last_id;
-                    const bool from_ok = pl >= 0 ? ((m_eq >> pl) & 1u) != 0 : last_new == 0;
-                    bool done = false;
-                    if (eq && from_ok) {                                 // bump the existing edge from -> node_id
-                        c3_pnode *f = &W.nodes[from];
-                        if (f->out_n > 0) {
-                            if ((int)f->out0 == node_id) { f->w0 = (uint16_t)(f->w0 + 1); done = true; }
-                            else {
-                                uint16_t e = f->out_more;
-                                while (e != C3_NONE) {
-                                    if ((int)W.pool[e].id == node_id) { W.pool[e].w = (uint16_t)(W.pool[e].w + 1); done = true; break; }
-                                    e = W.pool[e].next;
-                                }
-                            }
-                        }
-                    }
-                    const unsigned m_cx = m_nondel & ~__ballot_sync(C3_FULL, done);
-                    C3_STAT(12, __popc(m_nondel)); C3_STAT(13, __popc(m_cx));
-                    __syncwarp();
-                    if (m_cx) {
-                        if (lane == 0) {
-                            unsigned mc = m_cx;
-                            while (mc && !g.err) {
-                                const int c = __ffs(mc) - 1; mc &= mc - 1;
-                                const unsigned lowc = m_nondel & ((1u << c) - 1u);
-                                const int pc = lowc ? 31 - __clz(lowc) : -1;
-                                if (pc >= 0 && ((m_eq >> pc) & 1u)) { last_id = (int)((cg[tb - pc] >> 8) & 0xffff); last_new = 0; }
-                                const unsigned long long opc = cg[tb - c];
-                                const int kc = (int)(opc & 0xff), nid = (int)((opc >> 8) & 0xffff), qp = (int)(opc >> 32);
-                                if (kc == (int)C3_CG_MATCH) {
-                                    const uint8_t bq = q[qp];
-                                    const c3_pnode nm = g.nodes[nid];
-                                    if (nm.base != bq) {
-                                        int al = -1;
-                                        for (int k = 0; k < nm.aln_n; ++k) {
-                                            const int a = c3_aln_get(nm, k);
-                                            if (g.nodes[a].base == bq) { al = a; break; }
-                                        }
-                                        if (al != -1) {
-                                            c3_g_add_edge(g, last_id, al, 1 - last_new);
-                                            last_id = al; last_new = 0;
-                                            if (sq < 16) g.nodes[al].mpl |= (uint16_t)(1u << sq);
-                                        } else {
-                                            const int id = c3_g_add_node(g, bq);
-                                            if (g.err) break;
-                                            c3_list_insert_before(g, id, nid);
-                                            c3_g_add_edge(g, last_id, id, 0);
-                                            last_id = id; last_new = 1;
-                                            if (sq < 16) g.nodes[id].mpl = (uint16_t)(1u << sq);
-                                            for (int k = 0; k < nm.aln_n; ++k) {     // abpoa_add_graph_aligned_node
-                                                const int a = c3_aln_get(nm, k);
-                                                c3_aln_push(&g.nodes[a], (uint16_t)id);
-                                                c3_aln_push(&g.nodes[id], (uint16_t)a);
-                                            }
-                                            c3_aln_push(&g.nodes[nid], (uint16_t)id);
-                                            c3_aln_push(&g.nodes[id], (uint16_t)nid);
-                                        }
-                                    } else {
-                                        c3_g_add_edge(g, last_id, nid, 1 - last_new);
-                                        last_id = nid; last_new = 0;
-                                    }
-                                } else {                                     // insertion
-                                    const int id = c3_g_add_node(g, q[qp]);
-                                    if (g.err) break;
-                                    c3_list_insert_after(g, id, c3_group_tail(g, last_id));
-                                    c3_g_add_edge(g, last_id, id, 0);
-                                    last_id = id; last_new = 1;
-                                    if (sq < 16) g.nodes[id].mpl = (uint16_t)(1u << sq);
-                                }
-                            }
-                        }
-                        g.err = __shfl_sync(C3_FULL, g.err, 0);
-                        g.node_n = __shfl_sync(C3_FULL, g.node_n, 0);
-                        g.pool_n = __shfl_sync(C3_FULL, g.pool_n, 0);
-                        last_id = __shfl_sync(C3_FULL, last_id, 0);
-                        last_new = __shfl_sync(C3_FULL, last_new, 0);
-                    }
-                    if (m_nondel) {                                          // state after the chunk
-                        const int ln = 31 - __clz(m_nondel);
-                        if ((m_eq >> ln) & 1u) { last_id = __shfl_sync(C3_FULL, node_id, ln); last_new = 0; }
-                    }
-                    __syncwarp();
-                    if (g.err) break;
-                }
-                if (!g.err && lane == 0) c3_g_add_edge(g, last_id, C3_SINK, 1 - last_new);
-                g.err = __shfl_sync(C3_FULL, g.err, 0);
-                g.pool_n = __shfl_sync(C3_FULL, g.pool_n, 0);
-                err = g.err;
-                node_n = g.node_n; pool_n = g.pool_n;
-            }
+            // ---- backtrack + merge (warp-cooperative, see c3_bt_merge) ----
+            err = c3_bt_merge(A, P, W, q, qlen, sq, lane, node_n, pool_n);
             __syncwarp();
         }
 
-        // ---------------- two MSA rows (2-sequence groups: the reference's pairwise path,
-        // bin/determine_consensus.py:33-41 -> abpoa_generate_rc_msa with LIFO rank order) ----------------
+        // ---------------- two MSA rows (pairwise path) or heaviest-bundling consensus ----------------
         int cons_len = 0;
         const bool do_msa = A.msa2 && nseq == 2;
-        if (!err && do_msa) {
-            int32_t *rank = (int32_t *)W.hr, *indeg = (int32_t *)W.rows, *stk = (int32_t *)W.ord;
-            for (int v = lane; v < node_n; v += 32) { rank[v] = 0; indeg[v] = W.nodes[v].in_n; }
-            __syncwarp();
-            int msa_len = 0;
-            if (lane == 0) {
-                int top = 0, msa_rank = 0, ok = 0;
-                stk[top++] = C3_SRC; rank[C3_SRC] = -1;
-                while (top > 0) {
-                    const int cur = stk[--top];
-                    const c3_pnode nd = W.nodes[cur];
-                    if (rank[cur] < 0) {
-                        rank[cur] = msa_rank;
-                        for (int k = 0; k < nd.aln_n; ++k) rank[c3_aln_get(nd, k)] = msa_rank;
-                        ++msa_rank;
-                    }
-                    if (cur == C3_SINK) { ok = 1; break; }
-                    uint16_t e = nd.out_more;
-                    for (int k = 0; k < nd.out_n; ++k) {
-                        int o;
-                        if (k == 0) o = nd.out0; else { const c3_pedge pe = W.pool[e]; o = pe.id; e = pe.next; }
-                        if (--indeg[o] == 0) {
-                            const c3_pnode on = W.nodes[o];
-                            bool ready = true;
-                            for (int a = 0; a < on.aln_n; ++a) if (indeg[c3_aln_get(on, a)] != 0) { ready = false; break; }
-                            if (!ready) continue;
-                            stk[top++] = o; rank[o] = -1;
-                            for (int a = 0; a < on.aln_n; ++a) { const int al = c3_aln_get(on, a); stk[top++] = al; rank[al] = -1; }
-                        }
-                    }
-                }
-                msa_len = ok ? rank[C3_SINK] - 1 : -1;
-            }
-            msa_len = __shfl_sync(C3_FULL, msa_len, 0);
-            __syncwarp();
-            if (msa_len < 0 || 2 * msa_len > A.cons_cap) err = C3_E_CONS;
-            else {
-                char *co = A.cons + (int64_t)item * A.cons_cap;
-                for (int c = lane; c < 2 * msa_len; c += 32) co[c] = '-';
-                __syncwarp();
-                for (int v = 2 + lane; v < node_n; v += 32) {
-                    const c3_pnode nd = W.nodes[v];
-                    int rk = rank[v];
-                    for (int k = 0; k < nd.aln_n; ++k) rk = max(rk, rank[c3_aln_get(nd, k)]);
-                    const char ch = "ACGTN"[nd.base];
-                    if (nd.mpl & 1) co[rk - 1] = ch;
-                    if (nd.mpl & 2) co[msa_len + rk - 1] = ch;
-                }
-                cons_len = msa_len;
-            }
-        }
-        // ---------------- heaviest bundling + consensus walk (lane 0) ----------------
-        if (!err && !do_msa && lane == 0) {
-            int32_t *score = (int32_t *)W.hr;
-            int v = C3_SINK;
-            while (v != C3_NONE) {
-                c3_pnode *nd = &W.nodes[v];
-                if (v == C3_SINK) { nd->max_out = C3_NONE; score[v] = 0; }
-                else if (v == C3_SRC) {
-                    int max_id = -1, path_score = -1, path_w = -1;
-                    uint16_t e = nd->out_more;
-                    for (int k = 0; k < nd->out_n; ++k) {
-                        int o, wv;
-                        if (k == 0) { o = nd->out0; wv = nd->w0; } else { const c3_pedge pe = W.pool[e]; o = pe.id; wv = pe.w; e = pe.next; }
-                        if (wv > path_w || (wv == path_w && score[o] > path_score)) { max_id = o; path_score = score[o]; path_w = wv; }
-                    }
-                    nd->max_out = (uint16_t)max_id;
-                } else {
-                    int max_w = -0x7fffffff - 1, max_id = -1;
-                    uint16_t e = nd->out_more;
-                    for (int k = 0; k < nd->out_n; ++k) {
-                        int o, wv;
-                        if (k == 0) { o = nd->out0; wv = nd->w0; } else { const c3_pedge pe = W.pool[e]; o = pe.id; wv = pe.w; e = pe.next; }
-                        if (max_w < wv) { max_w = wv; max_id = o; }
-                        else if (max_w == wv && score[max_id] <= score[o]) max_id = o;
-                    }
-                    score[v] = max_w + score[max_id];
-                    nd->max_out = (uint16_t)max_id;
-                }
-                v = nd->prev;
-            }
+        if (!err) {
             char *co = A.cons + (int64_t)item * A.cons_cap;
-            int id = W.nodes[C3_SRC].max_out;
-            while (id != C3_SINK) {
-                if (id == C3_NONE || cons_len >= A.cons_cap) { err = C3_E_CONS; break; }
-                const c3_pnode nd = W.nodes[id];
-                co[cons_len++] = "ACGTN"[nd.base];
-                id = nd.max_out;
+            if (do_msa) { const int r = c3_emit_msa(A, W, node_n, lane, co); if (r < 0) err = r; else cons_len = r; }
+            else {
+                int r = 0;
+                if (lane == 0) r = c3_consensus(A, W, co);
+                r = __shfl_sync(C3_FULL, r, 0);
+                if (r < 0) err = r; else cons_len = r;
             }
         }
         err = __shfl_sync(C3_FULL, err, 0);
