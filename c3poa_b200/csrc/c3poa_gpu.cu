@@ -230,24 +230,27 @@ static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int
     int cigar_cap = (int)((max_q + node_cap + 64 + 1) & ~1ll);
     int qp_stride = (max_q + 8) & ~3;
     int64_t ws_bytes = c3_poa_ws_bytes((int)node_cap, pool_cap, (int)cell_cap, cigar_cap, qp_stride);
-    const int wpb = C3_POA_THREADS / 32;
+    // one warp per read.  (A two-reads-per-warp variant, 16 lanes each, was measured in round 1: no faster --
+    // the kernel is bound by per-row dependency latency, not by the lanes left idle -- and was dropped.)
+    const int threads = C3_POA_THREADS;
+    const int rpb = threads / 32;                                     // reads per block
     int bps = 4;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_kernel, C3_POA_THREADS, 0) != cudaSuccess || bps < 1) bps = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_kernel, threads, 0) != cudaSuccess || bps < 1) bps = 4;
     int grid = h->sm_count * bps;
-    grid = std::max(1, std::min(grid, (A.n_items + wpb - 1) / wpb));
+    grid = std::max(1, std::min(grid, (A.n_items + rpb - 1) / rpb));
     size_t free_b = 0, tot_b = 0;
     CK(cudaMemGetInfo(&free_b, &tot_b));
     int64_t budget = (int64_t)((double)(free_b + h->d_ws.cap) * 0.8);
-    int64_t max_warps = budget / ws_bytes;
-    if (max_warps < 1) return fail(h, -6, "POA workspace of %lld bytes per warp does not fit", (long long)ws_bytes);
-    if ((int64_t)grid * wpb > max_warps) grid = (int)std::max<int64_t>(1, max_warps / wpb);
-    CK(h->d_ws.ensure((size_t)grid * wpb * ws_bytes));
+    int64_t max_slots = budget / ws_bytes;
+    if (max_slots < rpb) return fail(h, -6, "POA workspace of %lld bytes per read does not fit", (long long)ws_bytes);
+    if ((int64_t)grid * rpb > max_slots) grid = (int)std::max<int64_t>(1, max_slots / rpb);
+    CK(h->d_ws.ensure((size_t)grid * rpb * ws_bytes));
     CK(h->d_counter.ensure(64));
     CK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
     A.ws = h->d_ws.as<uint8_t>(); A.ws_stride = ws_bytes;
     A.node_cap = (int)node_cap; A.pool_cap = pool_cap; A.cell_cap = (int)cell_cap; A.cigar_cap = cigar_cap; A.qp_stride = qp_stride;
     A.counter = h->d_counter.as<unsigned>();
-    c3_poa_kernel<<<grid, C3_POA_THREADS, 0, h->stream>>>(A);
+    c3_poa_kernel<<<grid, threads, 0, h->stream>>>(A);
     CK(cudaGetLastError());
     h->tim.kernel_launches++;
     return 0;
