@@ -62,14 +62,16 @@
 #define C3_E_BEST (-210)
 
 struct __align__(16) c3_pnode {
+    // first 16 bytes: everything a DP row needs (one 128-bit load)
     uint16_t next, prev;          // maintained topological list order
-    uint16_t in0, out0;           // first in / out neighbour (C3_NONE when absent)
-    uint16_t w0, in_more;         // weight of out0; pool index of the 2nd in edge
-    uint16_t out_more, mpl;       // pool index of the 2nd out edge; max_pos_left
-    uint16_t mpr, aln0;           // max_pos_right; aligned node ids (insertion order)
+    uint16_t in0, in_more;        // first in neighbour (C3_NONE when absent); pool index of the 2nd in edge
+    uint8_t base, in_n, out_n, aln_n;
+    uint16_t out0, w0;            // first out neighbour and its weight
+    // second 16 bytes: graph mutation / consensus
+    uint16_t out_more, mpl;       // pool index of the 2nd out edge; mpl: bit r set = read r passes here (r < 16)
+    uint16_t mpr, aln0;           // (spare); aligned node ids (insertion order)
     uint16_t aln1, aln2;
     uint16_t aln3, max_out;       // heaviest-bundling successor
-    uint8_t base, in_n, out_n, aln_n;
 };
 static_assert(sizeof(c3_pnode) == 32, "node record must be 32 bytes");
 
@@ -84,23 +86,21 @@ struct __align__(16) c3_prow { int32_t off; uint16_t beg, end; uint16_t mp, in0;
 static_assert(sizeof(c3_prow) == 16, "row record must be 16 bytes");
 __device__ __forceinline__ int c3_row_ng(const c3_prow &r) { return ((int)r.end - (int)r.beg + 4) >> 2; }
 
-// node record as two 128-bit loads + field decode (avoids a local-memory struct copy)
-struct c3_nrec { uint4 a, b; };
+// first half of a node record as one 128-bit load + field decode (avoids a local-memory struct copy)
+struct c3_nrec { uint4 a; };
 __device__ __forceinline__ c3_nrec c3_ld_node(const c3_pnode *p)
 {
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    c3_nrec r; r.a = q[0]; r.b = q[1]; return r;
+    c3_nrec r; r.a = *reinterpret_cast<const uint4 *>(p); return r;
 }
 #define C3_N_NEXT(r) ((int)((r).a.x & 0xffffu))
 #define C3_N_PREV(r) ((int)((r).a.x >> 16))
 #define C3_N_IN0(r) ((int)((r).a.y & 0xffffu))
-#define C3_N_OUT0(r) ((int)((r).a.y >> 16))
-#define C3_N_W0(r) ((int)((r).a.z & 0xffffu))
-#define C3_N_INMORE(r) ((int)((r).a.z >> 16))
-#define C3_N_OUTMORE(r) ((int)((r).a.w & 0xffffu))
-#define C3_N_BASE(r) ((int)((r).b.w & 0xffu))
-#define C3_N_INN(r) ((int)(((r).b.w >> 8) & 0xffu))
-#define C3_N_OUTN(r) ((int)(((r).b.w >> 16) & 0xffu))
+#define C3_N_INMORE(r) ((int)((r).a.y >> 16))
+#define C3_N_BASE(r) ((int)((r).a.z & 0xffu))
+#define C3_N_INN(r) ((int)(((r).a.z >> 8) & 0xffu))
+#define C3_N_OUTN(r) ((int)(((r).a.z >> 16) & 0xffu))
+#define C3_N_OUT0(r) ((int)((r).a.w & 0xffffu))
+#define C3_N_W0(r) ((int)((r).a.w >> 16))
 
 struct c3_poa_para_dev {
     int match, mismatch, o1, e1, o2, e2, wb, simd_bits;
