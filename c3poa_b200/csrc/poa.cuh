@@ -34,7 +34,9 @@
 #define C3_NEG_INF (-(1 << 29))
 #define C3_NEG_HALF (-(1 << 28))
 #define C3_MAXPRE 48
-#define C3_RING 4            // recent DP rows kept in shared memory per warp (rows of <= 128 columns)
+#ifndef C3_RING
+#define C3_RING 4            // recent DP rows kept in shared memory per warp (rows of <= 128 columns); 1, 2 or 4
+#endif
 
 #define C3_OP_M 0x1
 #define C3_OP_E1 0x2
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
 {
     __shared__ int4 s_ring[C3_POA_THREADS / 32][C3_RING][3 * 32];   // H,E1,E2 of recent rows: 32 groups each
     __shared__ c3_prow s_rrec[C3_POA_THREADS / 32][C3_RING];
-    __shared__ int s_rid[C3_POA_THREADS / 32][C3_RING];              // node id held by each ring slot (-1: none)
+    __shared__ int s_rid[C3_POA_THREADS / 32][4];                    // node id held by each ring slot (-1: none)
     __shared__ const int4 *s_pptr[C3_POA_THREADS / 32][C3_MAXPRE];   // predecessors 1..: row base (ring or HBM)
     __shared__ int s_pstr[C3_POA_THREADS / 32][C3_MAXPRE];           // array stride in groups
     __shared__ int s_pbe[C3_POA_THREADS / 32][C3_MAXPRE];            // beg | end << 16
@@ -799,7 +801,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     rrec[0] = ri; rid[0] = in_ring ? C3_SRC : -1;
                     ri.mp = C3_NONE;
                     W.ord[0] = ri;                                   // link = node id of the source = 0; no predecessor
-                    for (int t = 1; t < C3_RING; ++t) rid[t] = -1;
+                    for (int t = 1; t < 4; ++t) rid[t] = -1;
                 }
                 int32_t *H = W.cells, *E1 = H + 4 * ng, *E2 = E1 + 4 * ng;
                 int32_t *rg = reinterpret_cast<int32_t *>(&ring[0][0]);
@@ -871,6 +873,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                 const int8_t *qprow = W.qp + (nbase < 4 ? nbase : 0) * A.qp_stride;
                 const int p0b = r0.beg, p0e = r0.end, p0ng = (p0e - p0b + 4) >> 2;
                 int carry1 = C3_NEG_INF, carry2 = C3_NEG_INF;      // F entering lane 0 of the pass
+                const bool partial_row = (wd & 3) != 0;
                 int bestv = C3_NEG_INF; unsigned bestp = 0;
                 for (int g00 = 0; g00 < ng; g00 += 32) {
                     const int gl = g00 + lane;                     // group index within the row
@@ -911,13 +914,19 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     // scores of the 4 columns (int8 profile; g0 is a multiple of 4)
                     int sw = 0;
                     if (gact && nbase < 4) sw = *reinterpret_cast<const int *>(qprow + g0);
+                    // Cells past `end` exist only in the last group of a row whose band stops at qlen (the
+                    // band end is a multiple of 4 otherwise): those rows mask explicitly; on all other rows
+                    // inactive lanes carry exact NEG_INF inputs and a zero score, so no per-cell masking is needed.
                     const int nact = gact ? min(4, end - g0 + 1) : 0;      // active cells in this group
                     int hme[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int sc = (int)(int8_t)(sw >> (8 * k));
-                        const int hv_ = __vimax3_s32(m[k] + sc, x1[k], x2[k]);
-                        hme[k] = (k < nact) ? hv_ : C3_NEG_INF;
+                        hme[k] = __vimax3_s32(m[k] + sc, x1[k], x2[k]);
+                    }
+                    if (partial_row) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) hme[k] = (k < nact) ? hme[k] : C3_NEG_INF;
                     }
                     // F: in-lane recurrence, warp prefix-max of the lane aggregates, combine
                     int ga[4], gb[4];
@@ -931,8 +940,8 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     int t2 = __viaddmax_s32(gb[3], -e2, hme[3] - oe2) + 4 * e2 * lane;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
-                        const int u1 = __shfl_up_sync(C3_FULL, t1, d), u2 = __shfl_up_sync(C3_FULL, t2, d);
-                        if (lane >= d) { t1 = max(t1, u1); t2 = max(t2, u2); }
+                        // lanes below d get their own value back from shfl_up: max() leaves them unchanged
+                        t1 = max(t1, __shfl_up_sync(C3_FULL, t1, d)); t2 = max(t2, __shfl_up_sync(C3_FULL, t2, d));
                     }
                     int c1 = __shfl_up_sync(C3_FULL, t1, 1), c2 = __shfl_up_sync(C3_FULL, t2, 1);
                     const int tot1 = __shfl_sync(C3_FULL, t1, 31), tot2 = __shfl_sync(C3_FULL, t2, 31);
@@ -943,18 +952,21 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     carry1 = max(tot1 - 4 * e1 * 31, carry1 - 4 * e1 * 32);
                     carry2 = max(tot2 - 4 * e2 * 31, carry2 - 4 * e2 * 32);
                     int hh[4], n1v[4], n2v[4];
-                    int lmax = C3_NEG_INF;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int f1 = max(ga[k], c1 - k * e1), f2 = max(gb[k], c2 - k * e2);
-                        const int h = __vimax3_s32(hme[k], f1, f2);
-                        const int n1 = __viaddmax_s32(h, -oe1, x1[k] - e1), n2 = __viaddmax_s32(h, -oe2, x2[k] - e2);
-                        const bool cact = k < nact;
-                        hh[k] = cact ? h : C3_NEG_INF;
-                        n1v[k] = cact ? n1 : C3_NEG_INF;
-                        n2v[k] = cact ? n2 : C3_NEG_INF;
-                        lmax = max(lmax, hh[k]);
+                        hh[k] = __vimax3_s32(hme[k], f1, f2);
+                        n1v[k] = __viaddmax_s32(hh[k], -oe1, x1[k] - e1);
+                        n2v[k] = __viaddmax_s32(hh[k], -oe2, x2[k] - e2);
                     }
+                    if (partial_row) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const bool cact = k < nact;
+                            hh[k] = cact ? hh[k] : C3_NEG_INF; n1v[k] = cact ? n1v[k] : C3_NEG_INF; n2v[k] = cact ? n2v[k] : C3_NEG_INF;
+                        }
+                    }
+                    const int lmax = gact ? max(max(hh[0], hh[1]), max(hh[2], hh[3])) : C3_NEG_INF;
                     if (gact) {
                         const int4 vh = make_int4(hh[0], hh[1], hh[2], hh[3]);
                         const int4 v1 = make_int4(n1v[0], n1v[1], n1v[2], n1v[3]);
