@@ -195,6 +195,7 @@ static int launch_peaks(c3_handle *h, const int32_t *d_prof, const int64_t *d_of
     if (want_median) CK(h->d_median.ensure((size_t)n * 8 + 16));
     CK(h->d_counter.ensure(64));
     CK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
+    CK(cudaMemsetAsync(h->d_peaks.p, 0, (size_t)n * max_peaks * 4, h->stream));
     c3_peaks_args A;
     A.prof = d_prof; A.off = d_off; A.n = n; A.coef = h->d_coef.as<double>(); A.window = window; A.iters = iters;
     A.min_dist = min_dist; A.height_mult = hm; A.gate_mult = gm; A.scratch = h->d_pk_scratch.as<double>();
@@ -426,6 +427,7 @@ extern "C" int c3_poa_batch(c3_handle *h, int32_t n_groups, const char *seqs, co
     CK(cudaMemsetAsync(h->d_clen.p, 0, (size_t)n_groups * 4, h->stream));
     CK(cudaMemsetAsync(h->d_nodes.p, 0, (size_t)n_groups * 4, h->stream));
     CK(cudaMemsetAsync(h->d_cells.p, 0, (size_t)n_groups * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_cons.p, 0, (size_t)n_groups * cons_cap, h->stream));
     h->tim = c3_timings{};
     CK(cudaEventRecord(h->ev[0], h->stream));
     int rc = launch_encode(h, h->d_ascii.p, h->d_codes.p, total);
@@ -509,6 +511,9 @@ extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t
     CK(h->d_stats.ensure(64));
     CK(h->d_cons.ensure((size_t)n * cons_cap + 16));
     CK(cudaMemsetAsync(h->d_stats.p, 0, 64, h->stream));
+    // outputs are only partly written by the kernels (first n_peaks / n_sub / cons_len entries): define the rest
+    CK(cudaMemsetAsync(h->d_sub.p, 0, (size_t)n * max_peaks * 2 * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_cons.p, 0, (size_t)n * cons_cap, h->stream));
     int rc;
     CK(cudaEventRecord(h->ev[0], h->stream));
     if ((rc = encode_staged(h))) return rc;

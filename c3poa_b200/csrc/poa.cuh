@@ -831,7 +831,11 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                 const int npre = C3_N_INN(nd), nbase = C3_N_BASE(nd);
                 if (npre > C3_MAXPRE) { err = C3_E_PRE; break; }
                 // predecessors (in-edge order): recent rows come from the shared-memory ring, others from HBM
-                const int rid0 = rid[0], rid1 = rid[1], rid2 = rid[2], rid3 = rid[3];
+                // the slot this row is about to overwrite is not a valid source (a predecessor C3_RING rows back
+                // would be read while other lanes already store the new row there): such rows come from HBM
+                const int slot = rcount & (C3_RING - 1);
+                const int rid0 = slot == 0 ? -1 : rid[0], rid1 = slot == 1 ? -1 : rid[1];
+                const int rid2 = slot == 2 ? -1 : rid[2], rid3 = slot == 3 ? -1 : rid[3];
                 c3_prow r0; const int4 *p0ptr; int p0str;
                 {
                     const int p = C3_N_IN0(nd);
@@ -866,7 +870,6 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                 const int off = cell_used; cell_used += 12 * ng; cells_total += wd;
                 if (npre > 1) __syncwarp();
                 int4 *rowv = reinterpret_cast<int4 *>(W.cells + off);
-                const int slot = rcount & (C3_RING - 1);
                 C3_STAT(4, ng); C3_STAT(5, ng > 32); C3_STAT(6, wd);
                 const bool to_ring = ng <= 32;
                 int4 *ringv = &ring[slot][0];
