@@ -5,8 +5,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "c3poa_gpu.cu")
+SRC_HOST = os.path.join(HERE, "csrc", "ingest.cpp")
 OUT = os.path.join(HERE, "libc3poa_gpu.so")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "conk.cuh", "peaks.cuh", "poa.cuh")] + [
+DEPS = [SRC, SRC_HOST] + [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "conk.cuh", "peaks.cuh", "poa.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "c3poa_gpu.h")]
 
 
@@ -21,7 +22,7 @@ def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
         return out
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-o", out, SRC]
+           "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-o", out, SRC, SRC_HOST, "-lz"]
     cmd += [f"-D{d}" for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]

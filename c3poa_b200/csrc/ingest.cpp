@@ -1,0 +1,178 @@
+// ingest.cpp -- FASTQ/FASTA reader + length filter + batcher.
+//
+// Replaces the reference's use of mappy for I/O (mm.fastx_read, /root/reference/C3POa.py:201-206,239-254):
+// records shorter than --lencutoff are counted and skipped, the rest land back to back in caller-owned
+// (ideally pinned) buffers in exactly the layout c3_stage() consumes, plus the per-read Phred sum the
+// header needs (C3POa.py:168).  Host code only; plain or gzip input through zlib.
+#include "../../include/c3poa_gpu.h"
+#include <zlib.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+struct c3_fastq {
+    gzFile f = nullptr;             // gzip input
+    FILE *fp = nullptr;             // plain input: own buffered line reader (memchr), ~10x faster than gzgets
+    std::string buf; size_t bpos = 0, blen = 0;
+    std::string line, name, seq, qual;
+    bool have_pending = false;      // a parsed record that did not fit the previous batch
+    bool eof = false;
+    std::string carry;              // a header line read ahead (FASTA)
+};
+
+static bool read_line_plain(c3_fastq *q, std::string &out)
+{
+    out.clear();
+    for (;;) {
+        if (q->bpos == q->blen) {
+            q->blen = fread(&q->buf[0], 1, q->buf.size(), q->fp);
+            q->bpos = 0;
+            if (q->blen == 0) return !out.empty();
+        }
+        const char *p = &q->buf[q->bpos];
+        const char *nl = (const char *)memchr(p, '\n', q->blen - q->bpos);
+        if (nl) {
+            size_t n = (size_t)(nl - p);
+            out.append(p, n);
+            q->bpos += n + 1;
+            if (!out.empty() && out.back() == '\r') out.pop_back();
+            return true;
+        }
+        out.append(p, q->blen - q->bpos);
+        q->bpos = q->blen;
+    }
+}
+
+static bool read_line(c3_fastq *q, std::string &out)
+{
+    if (q->fp) return read_line_plain(q, out);
+    out.clear();
+    char buf[65536];
+    for (;;) {
+        if (!gzgets(q->f, buf, (int)sizeof(buf))) return !out.empty();
+        size_t n = strlen(buf);
+        if (n && buf[n - 1] == '\n') {
+            --n;
+            if (n && buf[n - 1] == '\r') --n;
+            out.append(buf, n);
+            return true;
+        }
+        out.append(buf, n);
+    }
+}
+
+static void set_name(c3_fastq *q, const std::string &hdr)
+{
+    size_t e = 1;
+    while (e < hdr.size() && hdr[e] != ' ' && hdr[e] != '\t') ++e;
+    q->name.assign(hdr, 1, e - 1);
+}
+
+// parse the next record into q->name/seq/qual; returns false at EOF
+static bool next_record(c3_fastq *q)
+{
+    std::string &ln = q->line;
+    for (;;) {
+        if (!q->carry.empty()) { ln.swap(q->carry); q->carry.clear(); }
+        else if (!read_line(q, ln)) return false;
+        if (ln.empty()) continue;
+        if (ln[0] == '@') {
+            set_name(q, ln);
+            if (!read_line(q, q->seq)) return false;
+            std::string plus;
+            if (!read_line(q, plus)) return false;
+            if (!read_line(q, q->qual)) q->qual.clear();
+            return true;
+        }
+        if (ln[0] == '>') {
+            set_name(q, ln);
+            q->seq.clear(); q->qual.clear();
+            std::string nx;
+            while (read_line(q, nx)) {
+                if (!nx.empty() && nx[0] == '>') { q->carry.swap(nx); break; }
+                q->seq += nx;
+            }
+            return true;
+        }
+    }
+}
+
+extern "C" int c3_fastq_open(const char *path, c3_fastq **out)
+{
+    if (!path || !out) return -1;
+    *out = nullptr;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return -2;
+    unsigned char magic[2] = {0, 0};
+    const size_t got = fread(magic, 1, 2, fp);
+    c3_fastq *q = new c3_fastq();
+    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+        fclose(fp);
+        q->f = gzopen(path, "rb");
+        if (!q->f) { delete q; return -2; }
+        gzbuffer(q->f, 1 << 20);
+    } else {
+        rewind(fp);
+        q->fp = fp;
+        q->buf.resize(4 << 20);
+    }
+    *out = q;
+    return 0;
+}
+
+extern "C" void c3_fastq_close(c3_fastq *q)
+{
+    if (!q) return;
+    if (q->f) gzclose(q->f);
+    if (q->fp) fclose(q->fp);
+    delete q;
+}
+
+extern "C" int c3_fastq_next(c3_fastq *q, int32_t max_reads, int64_t max_bases, int32_t min_len,
+                             char *seq, char *qual, int64_t *off, char *names, int64_t names_cap,
+                             int64_t *name_off, int64_t *qual_sum, int64_t *n_short)
+{
+    if (!q || !seq || !off || !names || !name_off || max_reads <= 0 || max_bases <= 0) return -1;
+    int n = 0;
+    int64_t bases = 0, nb = 0;
+    off[0] = 0; name_off[0] = 0;
+    while (n < max_reads) {
+        if (!q->have_pending) {
+            if (q->eof || !next_record(q)) { q->eof = true; break; }
+            if ((int64_t)q->seq.size() < (int64_t)min_len) { if (n_short) ++*n_short; continue; }
+        }
+        const int64_t L = (int64_t)q->seq.size(), NL = (int64_t)q->name.size() + 1;
+        if (bases + L > max_bases || nb + NL > names_cap) {
+            if (n == 0) return -3;                 // a single record larger than the buffers
+            q->have_pending = true;
+            break;
+        }
+        q->have_pending = false;
+        memcpy(seq + bases, q->seq.data(), (size_t)L);
+        long long qs = 0;
+        if (qual) {
+            const size_t QL = q->qual.size();
+            if ((int64_t)QL >= L) {
+                memcpy(qual + bases, q->qual.data(), (size_t)L);
+                const unsigned char *p = (const unsigned char *)q->qual.data();
+                unsigned long long acc = 0;
+                for (int64_t i = 0; i < L; ++i) acc += p[i];
+                qs = (long long)acc - 33ll * L;
+            } else {
+                for (int64_t i = 0; i < L; ++i) {
+                    const char c = (size_t)i < QL ? q->qual[(size_t)i] : 'I';  // FASTA: constant quality
+                    qual[bases + i] = c;
+                    qs += (unsigned char)c - 33;
+                }
+            }
+        } else {
+            for (char c : q->qual) qs += (unsigned char)c - 33;
+        }
+        if (qual_sum) qual_sum[n] = qs;
+        memcpy(names + nb, q->name.c_str(), (size_t)NL);
+        bases += L; nb += NL; ++n;
+        off[n] = bases; name_off[n] = nb;
+    }
+    return n;
+}

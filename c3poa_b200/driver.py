@@ -21,6 +21,7 @@ import numpy as np
 
 from .api import GpuConsensus, ReadBatch, pairwise_rows
 from .fastx import fastx_read, revcomp
+from .ingest import FastqBatches
 from .pairwise import pairwise_consensus  # noqa: F401  (2-repeat path, host side)
 
 VERSION = "v2.2.3-b200"
@@ -99,57 +100,62 @@ def run_blat(blat, reads_fastq, splint_file, tmp_dir, lencutoff):
 
 
 def header(name, qual, seq_len, repeats, cons_len):
-    """C3POa.py:168-171."""
-    avg_qual = round(sum(ord(x) - 33 for x in qual) / seq_len, 2)
+    """C3POa.py:168-171.  qual: the quality string, or its Phred sum (int) as the C++ ingest returns it."""
+    qsum = qual if isinstance(qual, (int, np.integer)) else sum(ord(x) - 33 for x in qual)
+    avg_qual = round(int(qsum) / seq_len, 2)
     return ">" + name + "_" + "_".join(str(x) for x in (avg_qual, seq_len, repeats, cons_len))
 
 
-def process_batch(gpu, reads, splint_dict, adapter_dict, mdist, handles):
-    """reads: list of (name, seq, qual) that have a splint.  Writes consensus FASTA + subread FASTQ."""
+def process_batch(gpu, names, blob, off, qual, qual_sum, splint_dict, adapter_dict, mdist, handles):
+    """One GPU batch on packed arrays (names[i], blob[off[i]:off[i+1]], qual likewise, Phred sums); every read
+    has a splint.  Writes consensus FASTA + subread FASTQ exactly as analyze_reads / determine_consensus do."""
     sp_names = sorted(splint_dict)
     splints = []
     for n in sp_names:
         splints += splint_dict[n]
-    idx = np.array([2 * sp_names.index(adapter_dict[r[0]][0]) + (1 if adapter_dict[r[0]][1] == "-" else 0)
-                    for r in reads], dtype=np.int32)
-    batch = ReadBatch.from_strings([r[1] for r in reads], splints, idx)
-    max_len = int(np.diff(batch.off).max())
-    out = gpu.consensus_batch(batch, min_dist=mdist, max_peaks=128, cons_cap=min(max_len, 65536))
+    idx = np.array([2 * sp_names.index(adapter_dict[n][0]) + (1 if adapter_dict[n][1] == "-" else 0) for n in names],
+                   dtype=np.int32)
+    sp_blob = np.frombuffer("".join(splints).encode(), dtype=np.uint8).copy()
+    sp_off = np.zeros(len(splints) + 1, dtype=np.int32)
+    sp_off[1:] = np.cumsum([len(s) for s in splints])
+    batch = ReadBatch(np.ascontiguousarray(blob), np.ascontiguousarray(off, dtype=np.int64), sp_blob, sp_off, idx)
+    max_len = int(np.diff(off).max())
+    out = gpu.consensus_batch(batch, min_dist=mdist, max_peaks=128, cons_cap=min(2 * max_len, 131072))
     R = out["results"]
     stats = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)     # pairwise: subset of consensus (2 repeats)
-    for i, (name, seq, qual) in enumerate(reads):
+    for i, name in enumerate(names):
         st = int(R["status"][i])
-        adapter = adapter_dict[name][0]
-        cons_fh, sub_fh = handles[adapter]
+        cons_fh, sub_fh = handles[adapter_dict[name][0]]
         if st == 1:
             stats["no_peaks"] += 1
             continue
         if st < 0:
             stats["errors"] += 1
             continue
+        a0, a1 = int(off[i]), int(off[i + 1])
+        seq = blob[a0:a1].tobytes().decode()
+        q = qual[a0:a1].tobytes().decode()
         ns, nd = int(R["n_sub"][i]), int(R["n_dang"][i])
         sb, db = out["sub_bounds"][i, :ns], out["dang_bounds"][i, :nd]
-        qual = qual if qual is not None else "I" * len(seq)
         if st == 2 and ns == 2 and R["cons_len"][i] > 0:
             # 2-repeat path: abPOA pairwise MSA rows from the GPU + quality-aware consensus
             # (bin/determine_consensus.py:33-41, bin/consensus.py)
             rows = pairwise_rows(out, i)
-            subs = [seq[a:b] for a, b in sb]
-            cons = pairwise_consensus(rows, subs, [qual[a:b] for a, b in sb])
+            cons = pairwise_consensus(rows, [seq[a:b] for a, b in sb], [q[a:b] for a, b in sb])
             stats["pairwise"] += 1
         elif st == 2:                       # 0-repeat path (mappy overlap of the dangling halves): not produced
             stats["zero"] = stats.get("zero", 0) + 1
             continue
         else:
             cons = out["cons"][i, :R["cons_len"][i]].tobytes().decode()
-        print(header(name, qual, len(seq), ns, len(cons)), file=cons_fh)
+        print(header(name, int(qual_sum[i]), len(seq), ns, len(cons)), file=cons_fh)
         print(cons, file=cons_fh)
         # subreads: @name_1..n, dangling @name_0 / @name_{n+1}  (bin/determine_consensus.py:57-77)
         for k, (a, b) in enumerate(sb):
-            print(f"@{name}_{k + 1}\n{seq[a:b]}\n+\n{qual[a:b]}", file=sub_fh)
+            print(f"@{name}_{k + 1}\n{seq[a:b]}\n+\n{q[a:b]}", file=sub_fh)
         for k, (a, b) in enumerate(db):
             tag = 0 if k == 0 else ns + 1
-            print(f"@{name}_{tag}\n{seq[a:b]}\n+\n{qual[a:b]}", file=sub_fh)
+            print(f"@{name}_{tag}\n{seq[a:b]}\n+\n{q[a:b]}", file=sub_fh)
         stats["consensus"] += 1
     return stats
 
@@ -161,12 +167,12 @@ def main(args):
     progs = config_reader(args.config) if args.config else {"racon": "racon", "blat": "blat"}
     tmp_dir = args.out_path + "tmp/"
     os.makedirs(tmp_dir, exist_ok=True)
-    names, short_reads = [], 0
-    for name, seq, _ in fastx_read(args.reads):
-        if len(seq) < args.lencutoff:
-            short_reads += 1
-        else:
-            names.append(name)
+    names = []
+    scan = FastqBatches(args.reads, min_len=args.lencutoff, max_reads=args.batch, pinned=False)
+    for b in scan:                              # pass 1: names of the reads >= --lencutoff (C3POa.py:200-206)
+        names += b["names"]
+    short_reads = int(scan.n_short.value)
+    scan.close()
     align_psl = tmp_dir + "splint_to_read_alignments.psl"
     if not os.path.exists(align_psl) or os.stat(align_psl).st_size == 0:
         print("Aligning splints to reads with blat", file=sys.stderr)
@@ -231,23 +237,36 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
     mod = int(os.environ.get("C3POA_DEVICE_MODULO", "0"))      # tests: fold ranks onto fewer GPUs
     gpu = GpuConsensus(device % mod if mod > 0 else device)
     totals = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)
-    buf, k = [], 0
-    for read in fastx_read(args.reads):
-        if len(read[1]) < args.lencutoff or read[0] not in adapter_dict:
+    k = 0
+    reader = FastqBatches(args.reads, min_len=args.lencutoff, max_reads=args.batch)
+    for b in reader:
+        # keep the reads that have a splint and belong to this rank (round-robin over the kept reads)
+        sel = []
+        for i, name in enumerate(b["names"]):
+            if name in adapter_dict:
+                if k % world == rank:
+                    sel.append(i)
+                k += 1
+        if not sel:
             continue
-        k += 1
-        if (k - 1) % world != rank:
-            continue
-        buf.append(read)
-        if len(buf) == args.batch:
-            for key, v in process_batch(gpu, buf, splint_dict, adapter_dict, args.mdistcutoff, handles).items():
-                totals[key] = totals.get(key, 0) + v
-            buf = []
-    if buf:
-        for key, v in process_batch(gpu, buf, splint_dict, adapter_dict, args.mdistcutoff, handles).items():
+        names, off = b["names"], b["off"]
+        if len(sel) == b["n"]:
+            blob, qual, qsum = b["blob"], b["qual"], b["qual_sum"]
+        else:
+            idx = np.asarray(sel)
+            lens = (off[idx + 1] - off[idx])
+            blob = np.concatenate([b["blob"][off[i]:off[i + 1]] for i in sel])
+            qual = np.concatenate([b["qual"][off[i]:off[i + 1]] for i in sel])
+            qsum = b["qual_sum"][idx]
+            names = [names[i] for i in sel]
+            off = np.zeros(len(sel) + 1, dtype=np.int64)
+            off[1:] = np.cumsum(lens)
+        for key, v in process_batch(gpu, names, blob, off, qual, qsum, splint_dict, adapter_dict, args.mdistcutoff,
+                                    handles).items():
             totals[key] = totals.get(key, 0) + v
-    for a, b in handles.values():
-        a.close(); b.close()
+    reader.close()
+    for a, b2 in handles.values():
+        a.close(); b2.close()
     gpu.close()
     return totals
 

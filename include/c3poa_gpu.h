@@ -126,6 +126,18 @@ int c3_consensus_batch(c3_handle *h, int32_t n_reads, const char *reads, const i
 void *c3_host_alloc(size_t bytes);
 void  c3_host_free(void *p);
 
+/* Ingest: FASTQ/FASTA (plain or gzip) -> length filter -> packed batch in the layout c3_stage()
+ * takes; replaces the reference's mappy.fastx_read passes (C3POa.py:201-206,239-254).  c3_fastq_next fills up to
+ * max_reads reads / max_bases bases: seq (and qual if non-NULL) concatenated with off[n+1], NUL-terminated names
+ * with name_off[n+1], per-read Phred sums (header quality, C3POa.py:168); reads shorter than min_len are skipped
+ * and counted in *n_short.  Returns the number of reads (0 at end of file) or <0.                              */
+typedef struct c3_fastq c3_fastq;
+int  c3_fastq_open(const char *path, c3_fastq **out);
+int  c3_fastq_next(c3_fastq *fq, int32_t max_reads, int64_t max_bases, int32_t min_len, char *seq, char *qual,
+                   int64_t *off, char *names, int64_t names_cap, int64_t *name_off, int64_t *qual_sum,
+                   int64_t *n_short);
+void c3_fastq_close(c3_fastq *fq);
+
 /* Micro-benchmark used for the integer-pipe roofline denominator: independent
  * VIADDMNMX chains on every SM, CUDA-event timed.  Returns int-ops/s.        */
 int c3_measure_int_peak(c3_handle *h, double *out_ops_per_s);

@@ -98,3 +98,36 @@ def test_shard_range_covers_everything():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_cxx_ingest_matches_python_reader(tmp_path):
+    """f-2: the library's FASTQ/FASTA reader (plain + gzip) against the pure-Python reader."""
+    import gzip
+    import shutil
+    from c3poa_b200 import synth
+    from c3poa_b200.fastx import fastx_read
+    from c3poa_b200.ingest import FastqBatches
+    d = synth.make_reads(37, insert_len=250, repeat_range=(1, 4), seed=3)
+    short = synth.make_reads(5, insert_len=100, repeats=1, seed=4, flank=(10, 20))
+    names = d["names"] + [f"short{i} extra comment" for i in range(5)]
+    fq = tmp_path / "r.fastq"
+    synth.write_fastq(fq, names, d["seqs"] + short["seqs"], d["quals"] + short["quals"])
+    with open(fq, "rb") as f, gzip.open(str(fq) + ".gz", "wb") as g:
+        shutil.copyfileobj(f, g)
+    ref = [r for r in fastx_read(str(fq))]
+    for path in (str(fq), str(fq) + ".gz"):
+        for min_len in (0, 700):
+            fb = FastqBatches(path, min_len=min_len, max_reads=8, max_bases=40000, pinned=False)
+            got = []
+            for b in fb:
+                assert b["n"] <= 8 and b["off"][-1] <= 40000
+                for i in range(b["n"]):
+                    a, e = b["off"][i], b["off"][i + 1]
+                    got.append((b["names"][i], b["blob"][a:e].tobytes().decode(), b["qual"][a:e].tobytes().decode()))
+                    assert b["qual_sum"][i] == sum(ord(c) - 33 for c in got[-1][2])
+            exp = [r for r in ref if len(r[1]) >= min_len]
+            assert got == exp and fb.n_short.value == len(ref) - len(exp)
+    fa = tmp_path / "s.fasta"
+    fa.write_text(">A desc\nACGT\nAC\n>B\nTTTT\n")
+    b = next(FastqBatches(str(fa), pinned=False))
+    assert b["names"] == ["A", "B"] and b["blob"].tobytes() == b"ACGTACTTTT" and b["off"].tolist() == [0, 6, 10]
