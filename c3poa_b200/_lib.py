@@ -17,7 +17,7 @@ EXPORTS = [
     "c3_version", "c3_device_count", "c3_init", "c3_destroy", "c3_last_error", "c3_default_poa_params",
     "c3_get_timings", "c3_conk_batch", "c3_peaks_batch", "c3_poa_batch", "c3_stage", "c3_run", "c3_fetch",
     "c3_consensus_batch", "c3_measure_int_peak", "c3_host_alloc", "c3_host_free",
-    "c3_fastq_open", "c3_fastq_next", "c3_fastq_close",
+    "c3_fastq_open", "c3_fastq_next", "c3_fastq_close", "c3_assign_splints",
 ]
 
 
@@ -77,6 +77,7 @@ def load():
     L.c3_host_alloc.restype = vp
     L.c3_host_free.argtypes = [vp]
     L.c3_host_free.restype = None
+    L.c3_assign_splints.argtypes = [vp, i32, vp, i64p, i32, vp, vp, i32, vp, vp]
     L.c3_fastq_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.c3_fastq_next.argtypes = [vp, i32, C.c_int64, i32, vp, vp, vp, vp, C.c_int64, vp, vp, vp]
     L.c3_fastq_close.argtypes = [vp]

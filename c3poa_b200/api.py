@@ -140,6 +140,21 @@ class GpuConsensus:
                                        batch.sp_idx.ctypes.data, penalty, prof.ctypes.data), "c3_conk_batch")
         return prof
 
+    # ---- f-3: splint assignment ----
+    def assign_splints(self, blob: np.ndarray, off: np.ndarray, candidates, penalty: int = 20):
+        """candidates: list[str] (every splint in both orientations).  Returns (best int32[n], scores int32[c, n])."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        n = off.size - 1
+        cb, coff = _pack(candidates)
+        coff = coff.astype(np.int32)
+        best = np.zeros(n, dtype=np.int32)
+        scores = np.zeros((len(candidates), n), dtype=np.int32)
+        self._ck(self._L.c3_assign_splints(self._h, n, blob.ctypes.data, off.ctypes.data, len(candidates),
+                                           cb.ctypes.data, coff.ctypes.data, penalty, best.ctypes.data,
+                                           scores.ctypes.data), "c3_assign_splints")
+        return best, scores
+
     # ---- B2 ----
     def peaks_batch(self, prof: np.ndarray, off: np.ndarray, min_dist=500, iters=3, window=41, order=2,
                     coef=None, want_smoothed=False, max_peaks=64, height_mult=3.0, gate_mult=6.0):

@@ -334,6 +334,65 @@ extern "C" int c3_conk_batch(c3_handle *h, int32_t n_reads, const char *reads, c
 }
 
 // ---------------------------------------------------------------------------
+// f-3: splint assignment (replaces the BLAT pre-step, bin/preprocess.py:12-45,74-76, with the conk kernel)
+// ---------------------------------------------------------------------------
+__global__ void c3_profile_max_kernel(int n, const int32_t *__restrict__ prof, const int64_t *__restrict__ off,
+                                      int32_t *__restrict__ out)
+{
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const int64_t a = off[r], b = off[r + 1];
+    int m = 0;
+    for (int64_t i = a + lane; i < b; i += 32) m = max(m, prof[i]);
+    m = __reduce_max_sync(C3_FULL, m);
+    if (lane == 0) out[r] = m;
+}
+
+__global__ void c3_fill_i32_kernel(int32_t *p, int n, int v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+extern "C" int c3_assign_splints(c3_handle *h, int32_t n_reads, const char *reads, const int64_t *read_off,
+                                 int32_t n_cands, const char *cands, const int32_t *cand_off, int32_t penalty,
+                                 int32_t *out_best, int32_t *out_scores)
+{
+    if (!h) return -1;
+    if (n_cands <= 0 || !out_best) return fail(h, -5, "bad arguments");
+    std::vector<int32_t> zero((size_t)std::max(n_reads, 1), 0);
+    int rc = stage_reads(h, n_reads, reads, read_off, n_cands, cands, cand_off, zero.data());
+    if (rc) return rc;
+    h->tim = c3_timings{};
+    CK(h->d_status.ensure((size_t)n_cands * n_reads * 4));          // scores [n_cands][n_reads]
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = encode_staged(h))) return rc;
+    for (int c = 0; c < n_cands; ++c) {
+        c3_fill_i32_kernel<<<(n_reads + 255) / 256, 256, 0, h->stream>>>(h->d_sp_idx.as<int32_t>(), n_reads, c);
+        CK(cudaGetLastError());
+        if ((rc = launch_conk(h, penalty))) return rc;
+        c3_profile_max_kernel<<<(n_reads + 3) / 4, 128, 0, h->stream>>>(n_reads, h->d_prof.as<int32_t>(), h->d_off.as<int64_t>(),
+                                                                        h->d_status.as<int32_t>() + (size_t)c * n_reads);
+        CK(cudaGetLastError());
+        h->tim.kernel_launches += 2;
+    }
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    std::vector<int32_t> sc((size_t)n_cands * n_reads);
+    CK(cudaMemcpyAsync(sc.data(), h->d_status.p, sc.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->tim.conk_ms, h->ev[0], h->ev[1]);
+    h->tim.total_ms = h->tim.conk_ms;
+    for (int r = 0; r < n_reads; ++r) {
+        int best = 0, bv = sc[r];
+        for (int c = 1; c < n_cands; ++c) { const int v = sc[(size_t)c * n_reads + r]; if (v > bv) { bv = v; best = c; } }
+        out_best[r] = best;
+    }
+    if (out_scores) memcpy(out_scores, sc.data(), sc.size() * 4);
+    h->staged = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // B2
 // ---------------------------------------------------------------------------
 extern "C" int c3_peaks_batch(c3_handle *h, int32_t n, const int32_t *profile, const int64_t *off,

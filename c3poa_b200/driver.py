@@ -44,6 +44,11 @@ def parse_args(argv=None):
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     p.add_argument("--batch", type=int, default=50000, help="reads per GPU batch")
     p.add_argument("--gpus", type=int, default=1, help="GPUs of this node to shard the reads over (one process each)")
+    p.add_argument("--assign", choices=["psl", "gpu"], default="psl",
+                   help="splint/strand per read: 'psl' = BLAT PSL as the reference (default); 'gpu' = conk profile of "
+                        "every splint x strand on the GPU (no BLAT; not BLAT-equivalent)")
+    p.add_argument("--assign_min_frac", type=float, default=0.05,
+                   help="--assign gpu: accept the best splint if its profile maximum reaches this fraction of a perfect match")
     return p.parse_args(argv)
 
 
@@ -173,14 +178,20 @@ def main(args):
         names += b["names"]
     short_reads = int(scan.n_short.value)
     scan.close()
-    align_psl = tmp_dir + "splint_to_read_alignments.psl"
-    if not os.path.exists(align_psl) or os.stat(align_psl).st_size == 0:
-        print("Aligning splints to reads with blat", file=sys.stderr)
-        run_blat(progs["blat"], args.reads, args.splint_file, tmp_dir, args.lencutoff)
+    splint_dict = {n: [s, revcomp(s)] for n, s, _ in fastx_read(args.splint_file)}
+    if args.assign == "gpu":
+        adapter_dict, adapter_set, no_splint = None, set(splint_dict), 0       # assigned per batch on the GPU
     else:
-        print("Reading existing psl file", file=sys.stderr)
-    adapter_dict, adapter_set, no_splint = read_psl(align_psl, names)
+        align_psl = tmp_dir + "splint_to_read_alignments.psl"
+        if not os.path.exists(align_psl) or os.stat(align_psl).st_size == 0:
+            print("Aligning splints to reads with blat", file=sys.stderr)
+            run_blat(progs["blat"], args.reads, args.splint_file, tmp_dir, args.lencutoff)
+        else:
+            print("Reading existing psl file", file=sys.stderr)
+        adapter_dict, adapter_set, no_splint = read_psl(align_psl, names)
     all_reads = len(names) + short_reads
+    totals = _run_all(args, adapter_dict, splint_dict, adapter_set)
+    no_splint += totals.pop("no_splint", 0)
     with open(args.out_path + "c3poa.log", "w") as log:     # C3POa.py:214-229
         print("C3POa version:", VERSION, file=log)
         print("Total reads:", all_reads, file=log)
@@ -189,32 +200,34 @@ def main(args):
         print("Total thrown away reads:", short_reads + no_splint,
               "({:.2f}%)".format((short_reads + no_splint) / max(all_reads, 1) * 100), file=log)
         print("Reads after preprocessing:", all_reads - (short_reads + no_splint), file=log)
-    splint_dict = {n: [s, revcomp(s)] for n, s, _ in fastx_read(args.splint_file)}
+    print("GPU consensus:", totals, file=sys.stderr)
+    return totals
+
+
+def _run_all(args, adapter_dict, splint_dict, adapter_set):
     for adapter in adapter_set:
         os.makedirs(args.out_path + adapter, exist_ok=True)
     if args.gpus <= 1:
-        totals = _consume(args, args.device, 0, 1, adapter_dict, splint_dict, adapter_set, final=True)
-    else:
-        # one process per GPU (spawn, like the reference's pool: C3POa.py:236,279); reads are sharded by
-        # index, every rank writes <splint>/tmp<rank>/ and the parent concatenates (cat_files, C3POa.py:259-271)
-        import multiprocessing as mp
-        ctx = mp.get_context("spawn")
-        with ctx.Pool(args.gpus) as pool:
-            parts = pool.starmap(_consume, [(args, r, r, args.gpus, adapter_dict, splint_dict, adapter_set, False)
-                                            for r in range(args.gpus)])
-        totals = {k: sum(p.get(k, 0) for p in parts) for k in set().union(*parts)}
-        for adapter in adapter_set:
-            base = args.out_path + adapter
-            for fn in ("R2C2_Consensus.fasta", "R2C2_Subreads.fastq"):
-                with _opener(args)(base + "/" + fn) as fh:
-                    for r in range(args.gpus):
-                        part = f"{base}/tmp{r}/{fn}"
-                        if os.path.exists(part):
-                            with open(part) as src:
-                                shutil.copyfileobj(src, fh)
-            for r in range(args.gpus):
-                shutil.rmtree(f"{base}/tmp{r}", ignore_errors=True)
-    print("GPU consensus:", totals, file=sys.stderr)
+        return _consume(args, args.device, 0, 1, adapter_dict, splint_dict, adapter_set, final=True)
+    # one process per GPU (spawn, like the reference's pool: C3POa.py:236,279); reads are sharded by index, every
+    # rank writes <splint>/tmp<rank>/ and the parent concatenates (cat_files, C3POa.py:259-271)
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(args.gpus) as pool:
+        parts = pool.starmap(_consume, [(args, r, r, args.gpus, adapter_dict, splint_dict, adapter_set, False)
+                                        for r in range(args.gpus)])
+    totals = {k: sum(p.get(k, 0) for p in parts) for k in set().union(*parts)}
+    for adapter in adapter_set:
+        base = args.out_path + adapter
+        for fn in ("R2C2_Consensus.fasta", "R2C2_Subreads.fastq"):
+            with _opener(args)(base + "/" + fn) as fh:
+                for r in range(args.gpus):
+                    part = f"{base}/tmp{r}/{fn}"
+                    if os.path.exists(part):
+                        with open(part) as src:
+                            shutil.copyfileobj(src, fh)
+        for r in range(args.gpus):
+            shutil.rmtree(f"{base}/tmp{r}", ignore_errors=True)
     return totals
 
 
@@ -239,14 +252,36 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
     totals = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)
     k = 0
     reader = FastqBatches(args.reads, min_len=args.lencutoff, max_reads=args.batch)
+    gpu_assign = adapter_dict is None
+    if gpu_assign:
+        sp_names = sorted(splint_dict)
+        cands = [s for n in sp_names for s in splint_dict[n]]
+        perfect = np.array([5 * len(s) * (len(s) + 1) // 2 for s in cands], dtype=np.float64)
     for b in reader:
         # keep the reads that have a splint and belong to this rank (round-robin over the kept reads)
         sel = []
-        for i, name in enumerate(b["names"]):
-            if name in adapter_dict:
-                if k % world == rank:
-                    sel.append(i)
-                k += 1
+        if gpu_assign:
+            mine = [i for i in range(b["n"]) if (k + i) % world == rank]
+            k += b["n"]
+            adapter_dict = {}
+            if mine:
+                m_off = np.zeros(len(mine) + 1, dtype=np.int64)
+                m_off[1:] = np.cumsum([b["off"][i + 1] - b["off"][i] for i in mine])
+                m_blob = b["blob"] if len(mine) == b["n"] else np.concatenate([b["blob"][b["off"][i]:b["off"][i + 1]] for i in mine])
+                best, scores = gpu.assign_splints(m_blob, m_off, cands)
+                for t, i in enumerate(mine):
+                    c = int(best[t])
+                    if scores[c, t] >= args.assign_min_frac * perfect[c]:
+                        adapter_dict[b["names"][i]] = (sp_names[c // 2], "-" if c % 2 else "+")
+                        sel.append(i)
+                    else:
+                        totals["no_splint"] = totals.get("no_splint", 0) + 1
+        else:
+            for i, name in enumerate(b["names"]):
+                if name in adapter_dict:
+                    if k % world == rank:
+                        sel.append(i)
+                    k += 1
         if not sel:
             continue
         names, off = b["names"], b["off"]

@@ -126,6 +126,15 @@ int c3_consensus_batch(c3_handle *h, int32_t n_reads, const char *reads, const i
 void *c3_host_alloc(size_t bytes);
 void  c3_host_free(void *p);
 
+/* Splint assignment on the GPU: the conk profile of every candidate (splint x strand,
+ * concatenated ASCII with cand_off[n_cands+1]) against every read; a candidate's score is the maximum of its
+ * raw profile, out_best[r] the arg-max (lowest index on ties), out_scores (optional) is [n_cands][n_reads].
+ * Stands in for the BLAT pre-step (bin/preprocess.py:12-45,74-76); it is NOT BLAT-equivalent: the acceptance
+ * criterion is agreement with the known splint/strand of synthetic reads (tests), thresholding is the caller's. */
+int c3_assign_splints(c3_handle *h, int32_t n_reads, const char *reads, const int64_t *read_off,
+                      int32_t n_cands, const char *cands, const int32_t *cand_off, int32_t penalty,
+                      int32_t *out_best, int32_t *out_scores);
+
 /* Ingest: FASTQ/FASTA (plain or gzip) -> length filter -> packed batch in the layout c3_stage()
  * takes; replaces the reference's mappy.fastx_read passes (C3POa.py:201-206,239-254).  c3_fastq_next fills up to
  * max_reads reads / max_bases bases: seq (and qual if non-NULL) concatenated with off[n+1], NUL-terminated names

@@ -398,3 +398,42 @@ def test_driver_multi_process_sharding(gpu, tmp_path):
     b = {n: s for n, s, _ in fastx_read(str(tmp_path / "b" / "Splint1" / "R2C2_Consensus.fasta"))}
     assert a == b and len(a) == 40                   # output order is unspecified in the reference: compare as sets
     assert not any(p.name.startswith("tmp") for p in (tmp_path / "b" / "Splint1").iterdir())
+
+
+def test_splint_assignment_on_gpu(gpu, tmp_path):
+    """f-3: the conk kernel over every splint x strand finds the known splint and strand of synthetic reads;
+    reads without a splint stay below the acceptance fraction; the driver gives the same consensi with
+    --assign gpu as with the PSL."""
+    from c3poa_b200 import driver
+    from c3poa_b200.fastx import fastx_read
+    rng = np.random.default_rng(71)
+    splints = {"Splint1": synth.SPLINT1}
+    for k in range(2, 5):
+        splints[f"Splint{k}"] = synth.random_seq(rng, 284).tobytes().decode()
+    d = synth.make_reads(160, insert_choices=[500, 1000, 2000], repeat_range=(1, 6), seed=72, splints=splints)
+    sp_names = sorted(splints)
+    cands = [s for n in sp_names for s in (splints[n], synth.revcomp(splints[n]))]
+    truth = np.array([2 * sp_names.index(s) + (1 if st == "-" else 0) for s, st in zip(d["splint_name"], d["strand"])])
+    junk = [synth.random_seq(rng, 3000).tobytes().decode() for _ in range(10)]
+    b = ReadBatch.from_strings(d["seqs"] + junk, cands, np.zeros(170, dtype=np.int32))
+    best, scores = gpu.assign_splints(b.blob, b.off, cands)
+    assert np.array_equal(best[:160], truth)
+    perfect = 5 * 284 * 285 // 2
+    top = scores[best, np.arange(170)]
+    assert top[:160].min() > 0.05 * perfect > top[160:].max(), (top[:160].min(), top[160:].max())
+    second = np.sort(scores[:, :160], axis=0)[-2]
+    assert np.all(top[:160] > 3 * second)                       # clear margin over every other candidate
+    # driver: --assign gpu reproduces the PSL-driven run
+    for o in ("psl", "gpu"):
+        (tmp_path / o / "tmp").mkdir(parents=True)
+    synth.write_fastq(tmp_path / "reads.fastq", d["names"], d["seqs"], d["quals"])
+    (tmp_path / "splint.fasta").write_text("".join(f">{n}\n{s}\n" for n, s in splints.items()))
+    synth.write_psl(tmp_path / "psl" / "tmp" / "splint_to_read_alignments.psl", d["names"], d["splint_name"], d["strand"])
+    base = ["-r", str(tmp_path / "reads.fastq"), "-s", str(tmp_path / "splint.fasta")]
+    driver.main(driver.parse_args(base + ["-o", str(tmp_path / "psl")]))
+    driver.main(driver.parse_args(base + ["-o", str(tmp_path / "gpu"), "--assign", "gpu"]))
+    for n in sp_names:
+        a = {x: s for x, s, _ in fastx_read(str(tmp_path / "psl" / n / "R2C2_Consensus.fasta"))}
+        g = {x: s for x, s, _ in fastx_read(str(tmp_path / "gpu" / n / "R2C2_Consensus.fasta"))}
+        assert a == g and len(a) > 10, n
+    assert "No splint reads: 0" in (tmp_path / "gpu" / "c3poa.log").read_text()
