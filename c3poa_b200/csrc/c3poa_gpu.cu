@@ -6,6 +6,7 @@
 #include "peaks.cuh"
 #include "poa.cuh"
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -44,7 +45,7 @@ struct c3_handle {
     DevBuf d_prof, d_brow, d_counter, d_coef, d_pk_scratch, d_smoothed, d_median;
     DevBuf d_peaks, d_npk, d_sub, d_dang, d_res, d_stats, d_cons, d_ws;
     // B3 staging
-    DevBuf d_item_base, d_bounds, d_nseq, d_status, d_clen, d_nodes, d_cells;
+    DevBuf d_item_base, d_bounds, d_nseq, d_status, d_clen, d_nodes, d_cells, d_order;
 };
 
 static int fail(c3_handle *h, int code, const char *fmt, ...)
@@ -101,7 +102,7 @@ extern "C" void c3_destroy(c3_handle *h)
     DevBuf *bufs[] = {&h->d_ascii, &h->d_codes, &h->d_off, &h->d_sp_ascii, &h->d_sp_codes, &h->d_sp_off, &h->d_sp_idx,
                       &h->d_prof, &h->d_brow, &h->d_counter, &h->d_coef, &h->d_pk_scratch, &h->d_smoothed, &h->d_median,
                       &h->d_peaks, &h->d_npk, &h->d_sub, &h->d_dang, &h->d_res, &h->d_stats, &h->d_cons, &h->d_ws,
-                      &h->d_item_base, &h->d_bounds, &h->d_nseq, &h->d_status, &h->d_clen, &h->d_nodes, &h->d_cells};
+                      &h->d_item_base, &h->d_bounds, &h->d_nseq, &h->d_status, &h->d_clen, &h->d_nodes, &h->d_cells, &h->d_order};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -214,6 +215,37 @@ static void to_dev_para(const c3_poa_params *p, c3_poa_para_dev *d)
     d->o2 = p->gap_open2; d->e2 = p->gap_ext2; d->wb = p->wb; d->simd_bits = p->simd_bits; d->wf = p->wf;
 }
 
+// Work order for the persistent POA grid: items with >= min_seqs sequences, largest estimated DP cost first
+// (LPT scheduling: the longest reads start first, so a batch ends with short ones).  cost ~ alignments x
+// mean length x band width.  O(n) bucket sort on 1/16-octave cost classes.
+static int upload_poa_order(c3_handle *h, c3_poa_args &A, const std::vector<int32_t> &nseq, const std::vector<int64_t> &total,
+                            int min_seqs, const c3_poa_params *pp)
+{
+    const int n = (int)nseq.size();
+    std::vector<int32_t> cls((size_t)n, -1);
+    const int NB = 64 * 16;
+    std::vector<int32_t> cnt(NB + 1, 0);
+    int n_work = 0;
+    for (int i = 0; i < n; ++i) {
+        if (nseq[i] < min_seqs) continue;
+        const double L = (double)total[i] / nseq[i];
+        const double cost = (double)std::max(nseq[i] - 1, 1) * L * (2.0 * (pp->wb + pp->wf * L) + 48.0) + 1.0;
+        int e; const double m = frexp(cost, &e);                  // cost = m * 2^e, m in [0.5, 1)
+        int b = e * 16 + (int)((m - 0.5) * 32.0);
+        b = std::max(0, std::min(NB - 1, b));
+        cls[i] = b; ++cnt[b]; ++n_work;
+    }
+    std::vector<int32_t> start(NB + 1, 0);
+    for (int b = NB - 1, acc = 0; b >= 0; --b) { start[b] = acc; acc += cnt[b]; }   // descending classes
+    std::vector<int32_t> order((size_t)std::max(n_work, 1));
+    for (int i = 0; i < n; ++i) if (cls[i] >= 0) order[start[cls[i]]++] = i;
+    CK(h->d_order.ensure((size_t)std::max(n_work, 1) * 4));
+    CK(cudaMemcpyAsync(h->d_order.p, order.data(), (size_t)n_work * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));                          // `order` is a local
+    A.order = h->d_order.as<int32_t>(); A.n_work = n_work;
+    return 0;
+}
+
 // workspace sizing from the batch maxima (longest sequence, most sequences, largest total)
 static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int64_t max_total, const c3_poa_params *pp)
 {
@@ -238,7 +270,8 @@ static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int
     int bps = 4;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_kernel, threads, 0) != cudaSuccess || bps < 1) bps = 4;
     int grid = h->sm_count * bps;
-    grid = std::max(1, std::min(grid, (A.n_items + rpb - 1) / rpb));
+    if (!A.order) A.n_work = A.n_items;
+    grid = std::max(1, std::min(grid, (A.n_work + rpb - 1) / rpb));
     size_t free_b = 0, tot_b = 0;
     CK(cudaMemGetInfo(&free_b, &tot_b));
     int64_t budget = (int64_t)((double)(free_b + h->d_ws.cap) * 0.8);
@@ -499,6 +532,11 @@ extern "C" int c3_poa_batch(c3_handle *h, int32_t n_groups, const char *seqs, co
     A.cons = h->d_cons.as<char>(); A.cons_cap = cons_cap; A.status = h->d_status.as<int32_t>();
     A.cons_len = h->d_clen.as<int32_t>(); A.nodes_out = h->d_nodes.as<int32_t>(); A.cells_out = h->d_cells.as<long long>();
     A.out_stride = 1; A.cells_stride = 2; A.msa2 = want_msa ? 1 : 0; A.ok_status = 0;
+    {
+        std::vector<int64_t> tot((size_t)n_groups);
+        for (int g = 0; g < n_groups; ++g) tot[g] = seq_off[group_off[g + 1]] - seq_off[group_off[g]];
+        if ((rc = upload_poa_order(h, A, nseq, tot, 1, params))) return rc;
+    }
     if ((rc = launch_poa(h, A, max_q, max_nseq, max_total, params))) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));
     CK(cudaMemcpyAsync(out_cons, h->d_cons.p, (size_t)n_groups * cons_cap, cudaMemcpyDeviceToHost, h->stream));
@@ -605,6 +643,17 @@ extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t
         A.codes = h->d_codes.as<uint8_t>(); A.item_base = h->d_off.as<int64_t>(); A.bounds = h->d_sub.as<int32_t>();
         A.n_seqs = &res->n_sub; A.n_seqs_stride = sizeof(c3_read_result) / 4; A.n_items = n; A.max_seqs = max_peaks; A.min_seqs = 2;
         A.msa2 = 1; A.ok_status = 2;    // 2-repeat reads: [row0 | row1] of the pairwise MSA in the consensus slot
+        {   // per-read repeat count and subread bases (left in poa_cells by the split kernel) -> work order
+            std::vector<c3_read_result> hr((size_t)n);
+            CK(cudaMemcpyAsync(hr.data(), h->d_res.p, (size_t)n * sizeof(c3_read_result), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            std::vector<int32_t> ns((size_t)n); std::vector<int64_t> tot((size_t)n);
+            for (int i = 0; i < n; ++i) {
+                ns[i] = hr[i].status >= 0 ? hr[i].n_sub : 0;
+                tot[i] = ns[i] >= 2 ? hr[i].poa_cells : 0;
+            }
+            if ((rc = upload_poa_order(h, A, ns, tot, 2, params))) return rc;
+        }
         A.cons = h->d_cons.as<char>(); A.cons_cap = cons_cap; A.status = &res->status; A.cons_len = &res->cons_len;
         A.nodes_out = &res->poa_nodes; A.cells_out = (long long *)&res->poa_cells;
         A.out_stride = sizeof(c3_read_result) / 4; A.cells_stride = sizeof(c3_read_result) / 4;

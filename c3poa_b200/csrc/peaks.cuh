@@ -306,6 +306,8 @@ __global__ void c3_split_kernel(int n_reads, const int64_t *__restrict__ read_of
         if (lr - pk[np - 1] > 100) { db[2 * nd] = pk[np - 1]; db[2 * nd + 1] = lr; ++nd; }
         out.n_dang = nd;
         if (ns >= 2) {                                     // POA work: consensus (>=3) or the two MSA rows (==2)
+            out.poa_cells = tot;                           // subread bases, for the host's work ordering; the POA
+                                                           // kernel overwrites it with the DP cell count
             atomicMax(&stats[0], mq); atomicMax(&stats[1], ns); atomicMax(&stats[2], tot); atomicAdd(&stats[3], 1);
         }
         if (ns == 2 || ns == 0) out.status = 2;            // pairwise / zero-repeat paths

@@ -134,6 +134,8 @@ struct c3_poa_args {
     int32_t *status; int32_t *cons_len; int32_t *nodes_out; long long *cells_out;
     int out_stride, cells_stride;  // strides of the int32 outputs / of cells_out, in int32 units
     unsigned *counter;
+    const int32_t *order;          // optional work order (largest estimated cost first); n_work entries
+    int n_work;                    // number of work items handed out (== n_items when order is null)
 };
 
 struct c3_poa_ws {
@@ -686,7 +688,8 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
         int item = 0;
         if (lane == 0) item = (int)atomicAdd(A.counter, 1u);
         item = __shfl_sync(C3_FULL, item, 0);
-        if (item >= A.n_items) break;
+        if (item >= A.n_work) break;
+        if (A.order) item = A.order[item];
         const int nseq = A.n_seqs[(int64_t)item * A.n_seqs_stride];
         if (nseq < A.min_seqs || nseq > A.max_seqs) continue;
         const uint8_t *ibase = A.codes + A.item_base[item];
