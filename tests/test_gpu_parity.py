@@ -437,3 +437,16 @@ def test_splint_assignment_on_gpu(gpu, tmp_path):
         g = {x: s for x, s, _ in fastx_read(str(tmp_path / "gpu" / n / "R2C2_Consensus.fasta"))}
         assert a == g and len(a) > 10, n
     assert "No splint reads: 0" in (tmp_path / "gpu" / "c3poa.log").read_text()
+
+
+def test_fused_very_long_reads(gpu, oracle):
+    """cfg 4 upper end: 30-55 kb concatemers (5 kb inserts x 5-9), plus a read whose single subread is too long for
+    the graph (> 65 000 columns is rejected loudly, not mis-computed)."""
+    d = synth.make_reads(4, insert_len=5000, repeat_range=(5, 9), seed=81, flank=(500, 3000))
+    out = _check_fused(gpu, oracle, d, cons_cap=16384)
+    assert np.all(out["results"]["status"] == 0) and out["results"]["cons_len"].min() > 5000
+    rng = np.random.default_rng(82)
+    a = synth.random_seq(rng, 70000).tobytes().decode()
+    from c3poa_b200.api import GpuError
+    with pytest.raises(GpuError, match="too long"):
+        gpu.poa_batch([[a, a[:69000], a]], cons_cap=80000)
