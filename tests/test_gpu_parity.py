@@ -450,3 +450,27 @@ def test_fused_very_long_reads(gpu, oracle):
     from c3poa_b200.api import GpuError
     with pytest.raises(GpuError, match="too long"):
         gpu.poa_batch([[a, a[:69000], a]], cons_cap=80000)
+
+
+def test_drop_in_shims(gpu, oracle):
+    """The per-call drop-ins keep the reference's signatures and return types:
+    conk.conk(splint, seq, penalty), call_peaks(scores, min_dist, iters, window, order),
+    pyabpoa.msa_aligner(match=5).msa(seqs, out_cons, out_msa)."""
+    from c3poa_b200.shims.conk import conk
+    from c3poa_b200.shims.call_peaks import call_peaks
+    import c3poa_b200.shims.pyabpoa as poa
+    d = synth.make_reads(3, insert_len=400, repeats=4, seed=91, both_strands=False)
+    seq = d["seqs"][0]
+    scores = conk.conk(synth.SPLINT1, seq, 20)
+    assert np.array_equal(np.asarray(scores), oracle.conk(synth.SPLINT1, seq, 20))
+    peaks = call_peaks(scores, 500, 3, 41, 2)
+    ref_peaks, _, _ = oracle.call_peaks(np.asarray(scores), 500)
+    assert isinstance(peaks, np.ndarray) and peaks.dtype == np.int64 and np.array_equal(peaks, ref_peaks)
+    assert list(peaks + len(synth.SPLINT1) // 2)                       # usable as C3POa.py:125-127 uses it
+    assert call_peaks(np.full(800, 3), 500, 3, 41, 2) == []            # gate not passed -> [] like the reference
+    _, pk, sb, _ = oracle.split(ref_peaks, len(synth.SPLINT1), len(seq))
+    subs = [seq[a:b] for a, b in sb]
+    res = poa.msa_aligner(match=5).msa(subs, out_cons=True, out_msa=True)
+    assert res.cons_seq[0] == oracle.poa_msa(subs)["cons"] and res.n_seq == len(subs)
+    res2 = poa.msa_aligner(match=5).msa(subs[:2], out_cons=False, out_msa=True)
+    assert res2.msa_seq == oracle.poa_msa(subs[:2], out_cons=False, out_msa=True)["msa"] and not res2.cons_seq
