@@ -4,21 +4,27 @@
 // Replaces poa.msa_aligner(match=5).msa(subreads, out_cons=True, out_msa=True)
 //   (/root/reference/bin/determine_consensus.py:30-47).
 //
-// One warp per read (persistent grid, atomic work counter).  Per added subread:
-//   prepare   (warp-parallel)  reset band bookkeeping, heaviest successor per node,
-//                              "remaining path length" by pointer jumping
-//   DP        (warp-parallel)  rows = graph nodes in a maintained topological list
-//                              order, lanes = band columns; the horizontal (F) gap
-//                              dependency is a warp prefix-max over H+e*j
-//   backtrack (lane 0)         value-based, abPOA's M -> E1 -> E2 -> F1 -> F2 order with
-//                              the op-mask state machine
-//   merge     (lane 0)         graph update; new nodes are spliced into the list so that
-//                              aligned groups stay contiguous (a valid topological
-//                              order of the graph without re-sorting; every quantity
-//                              the DP derives is order-independent)
-// then heaviest bundling (lane 0) and the consensus walk.
+// One warp per read (persistent grid, atomic work counter, largest reads first).  Per added subread:
+//   prepare   (lanes over nodes)  heaviest successor per node, then abPOA's "remaining path length"
+//                                 by in-place pointer jumping on packed (hops, next) words
+//   profile   (lanes over cols)   int8 substitution scores of the subread against A/C/G/T
+//   DP        (lanes over cols)   rows = graph nodes in a maintained topological list order; each lane owns
+//                                 4 consecutive band columns (128 per pass); predecessor rows come as 128-bit
+//                                 loads from a shared-memory ring of recent rows (else HBM); the horizontal
+//                                 (F) gap is an in-lane recurrence + one warp prefix-max of lane aggregates;
+//                                 row arg-max by two REDUX; band anchors are pulled from predecessor records
+//   backtrack (all lanes)         c3_bt_merge: the first-predecessor chain inside a 32-row window is resolved
+//                                 by pointer doubling and up to 31 match/mismatch moves are verified at once;
+//                                 other moves take the generic step (abPOA's M -> E1 -> E2 -> F1 -> F2 order and
+//                                 op-mask state machine); F is rebuilt along one row when an insertion is traced
+//   merge     (all lanes)         32 cigar ops at a time: weight bumps of existing edges in parallel, new nodes
+//                                 and edges through lane 0 in order; new nodes are spliced into the list next to
+//                                 their aligned group (a valid topological order without re-sorting; every
+//                                 quantity the DP derives is order-independent)
+// then either the two MSA rows (2-sequence groups, c3_emit_msa) or heaviest bundling and the
+// consensus walk (c3_consensus, single thread).
 //
-// The graph, DP rows and cigar live in a per-warp HBM workspace (L1/L2 cached).
+// The graph, DP rows, row records and cigar live in a per-warp HBM workspace (L1/L2 cached).
 #pragma once
 #include "common.cuh"
 
@@ -70,8 +76,8 @@ struct __align__(16) c3_pnode {
     uint8_t base, in_n, out_n, aln_n;
     uint16_t out0, w0;            // first out neighbour and its weight
     // second 16 bytes: graph mutation / consensus
-    uint16_t out_more, mpl;       // pool index of the 2nd out edge; mpl: bit r set = read r passes here (r < 16)
-    uint16_t mpr, aln0;           // (spare); aligned node ids (insertion order)
+    uint16_t out_more, rmask;     // pool index of the 2nd out edge; rmask: bit r set = read r passes here (r < 16)
+    uint16_t spare, aln0;         // aligned node ids (insertion order)
     uint16_t aln1, aln2;
     uint16_t aln3, max_out;       // heaviest-bundling successor
 };
@@ -195,7 +201,7 @@ __device__ __forceinline__ int c3_g_add_node(c3_graph &g, uint8_t base)
     if (g.node_n >= g.node_cap) { g.err = C3_E_NODES; return 0; }
     c3_pnode n;
     n.next = n.prev = n.in0 = n.out0 = n.in_more = n.out_more = C3_NONE;
-    n.w0 = 0; n.mpl = 0; n.mpr = 0; n.aln0 = n.aln1 = n.aln2 = n.aln3 = C3_NONE; n.max_out = C3_NONE;
+    n.w0 = 0; n.rmask = 0; n.spare = 0; n.aln0 = n.aln1 = n.aln2 = n.aln3 = C3_NONE; n.max_out = C3_NONE;
     n.base = base; n.in_n = n.out_n = n.aln_n = 0;
     g.nodes[g.node_n] = n;
     return g.node_n++;
@@ -467,7 +473,7 @@ __device__ __forceinline__ int c3_bt_merge(const c3_poa_args &A, const c3_poa_pa
             const bool is_match = have && kind == (int)C3_CG_MATCH;
             bool eq = false;
             if (is_match) eq = W.nodes[node_id].base == q[qpos];
-            if (eq && sq < 16) W.nodes[node_id].mpl |= (uint16_t)(1u << sq);
+            if (eq && sq < 16) W.nodes[node_id].rmask |= (uint16_t)(1u << sq);
             const unsigned m_nondel = __ballot_sync(C3_FULL, have && kind != (int)C3_CG_DEL);
             const unsigned m_eq = __ballot_sync(C3_FULL, eq);
             const unsigned lower = m_nondel & ((1u << lane) - 1u);
@@ -514,14 +520,14 @@ __device__ __forceinline__ int c3_bt_merge(const c3_poa_args &A, const c3_poa_pa
                                 if (al != -1) {
                                     c3_g_add_edge(g, last_id, al, 1 - last_new);
                                     last_id = al; last_new = 0;
-                                    if (sq < 16) g.nodes[al].mpl |= (uint16_t)(1u << sq);
+                                    if (sq < 16) g.nodes[al].rmask |= (uint16_t)(1u << sq);
                                 } else {
                                     const int id = c3_g_add_node(g, bq);
                                     if (g.err) break;
                                     c3_list_insert_before(g, id, nid);
                                     c3_g_add_edge(g, last_id, id, 0);
                                     last_id = id; last_new = 1;
-                                    if (sq < 16) g.nodes[id].mpl = (uint16_t)(1u << sq);
+                                    if (sq < 16) g.nodes[id].rmask = (uint16_t)(1u << sq);
                                     for (int k = 0; k < nm.aln_n; ++k) {     // abpoa_add_graph_aligned_node
                                         const int a = c3_aln_get(nm, k);
                                         c3_aln_push(&g.nodes[a], (uint16_t)id);
@@ -540,7 +546,7 @@ __device__ __forceinline__ int c3_bt_merge(const c3_poa_args &A, const c3_poa_pa
                             c3_list_insert_after(g, id, c3_group_tail(g, last_id));
                             c3_g_add_edge(g, last_id, id, 0);
                             last_id = id; last_new = 1;
-                            if (sq < 16) g.nodes[id].mpl = (uint16_t)(1u << sq);
+                            if (sq < 16) g.nodes[id].rmask = (uint16_t)(1u << sq);
                         }
                     }
                 }
@@ -614,8 +620,8 @@ __device__ __forceinline__ int c3_emit_msa(const c3_poa_args &A, const c3_poa_ws
             int rk = rank[v];
             for (int k = 0; k < nd.aln_n; ++k) rk = max(rk, rank[c3_aln_get(nd, k)]);
             const char ch = "ACGTN"[nd.base];
-            if (nd.mpl & 1) co[rk - 1] = ch;
-            if (nd.mpl & 2) co[msa_len + rk - 1] = ch;
+            if (nd.rmask & 1) co[rk - 1] = ch;
+            if (nd.rmask & 2) co[msa_len + rk - 1] = ch;
         }
     }
     return msa_len;
@@ -706,7 +712,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
             else {
                 for (int i = lane; i < L + 2; i += 32) {
                     c3_pnode n;
-                    n.in_more = n.out_more = C3_NONE; n.mpl = 1; n.mpr = 0;    // mpl: bit r set = read r passes here (r < 16)
+                    n.in_more = n.out_more = C3_NONE; n.rmask = 1; n.spare = 0;     // the first sequence (read 0) passes through every initial node
                     n.aln0 = n.aln1 = n.aln2 = n.aln3 = C3_NONE; n.max_out = C3_NONE; n.aln_n = 0;
                     if (i == C3_SRC) {
                         n.base = 4; n.in_n = 0; n.out_n = 1; n.in0 = C3_NONE; n.out0 = 2; n.w0 = 1;
