@@ -44,6 +44,7 @@ def parse_args(argv=None):
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     p.add_argument("--batch", type=int, default=50000, help="reads per GPU batch")
     p.add_argument("--gpus", type=int, default=1, help="GPUs of this node to shard the reads over (one process each)")
+    p.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (handles + host threads)")
     p.add_argument("--assign", choices=["psl", "gpu"], default="psl",
                    help="splint/strand per read: 'psl' = BLAT PSL as the reference (default); 'gpu' = conk profile of "
                         "every splint x strand on the GPU (no BLAT; not BLAT-equivalent)")
@@ -111,9 +112,8 @@ def header(name, qual, seq_len, repeats, cons_len):
     return ">" + name + "_" + "_".join(str(x) for x in (avg_qual, seq_len, repeats, cons_len))
 
 
-def process_batch(gpu, names, blob, off, qual, qual_sum, splint_dict, adapter_dict, mdist, handles):
-    """One GPU batch on packed arrays (names[i], blob[off[i]:off[i+1]], qual likewise, Phred sums); every read
-    has a splint.  Writes consensus FASTA + subread FASTQ exactly as analyze_reads / determine_consensus do."""
+def compute_batch(gpu, names, blob, off, splint_dict, adapter_dict, mdist):
+    """The GPU part of one batch (packed arrays; every read has a splint): returns the fused-path outputs."""
     sp_names = sorted(splint_dict)
     splints = []
     for n in sp_names:
@@ -125,7 +125,11 @@ def process_batch(gpu, names, blob, off, qual, qual_sum, splint_dict, adapter_di
     sp_off[1:] = np.cumsum([len(s) for s in splints])
     batch = ReadBatch(np.ascontiguousarray(blob), np.ascontiguousarray(off, dtype=np.int64), sp_blob, sp_off, idx)
     max_len = int(np.diff(off).max())
-    out = gpu.consensus_batch(batch, min_dist=mdist, max_peaks=128, cons_cap=min(2 * max_len, 131072))
+    return gpu.consensus_batch(batch, min_dist=mdist, max_peaks=128, cons_cap=min(2 * max_len, 131072))
+
+
+def write_batch(out, names, blob, off, qual, qual_sum, adapter_dict, handles):
+    """The host part: consensus FASTA + subread FASTQ exactly as analyze_reads / determine_consensus write them."""
     R = out["results"]
     stats = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)     # pairwise: subset of consensus (2 repeats)
     for i, name in enumerate(names):
@@ -231,6 +235,13 @@ def _run_all(args, adapter_dict, splint_dict, adapter_set):
     return totals
 
 
+def _drain_one(pending, handles, totals):
+    fut, names, blob, off, qual, qsum, ad = pending.pop(0)
+    out = fut.result()
+    for key, v in write_batch(out, names, blob, off, qual, qsum, ad, handles).items():
+        totals[key] = totals.get(key, 0) + v
+
+
 def _opener(args):
     return (lambda p: gzip.open(p + ".gz", "wt")) if args.compress_output else (lambda p: open(p, "w"))
 
@@ -251,8 +262,27 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
     gpu = GpuConsensus(device % mod if mod > 0 else device)
     totals = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)
     k = 0
-    reader = FastqBatches(args.reads, min_len=args.lencutoff, max_reads=args.batch)
+    import queue
+    from concurrent.futures import ThreadPoolExecutor
+    n_inflight = max(1, int(getattr(args, "inflight", 2)))
+    gpus = [gpu] + [GpuConsensus(gpu.device) for _ in range(n_inflight - 1)]
+    free_gpus = queue.Queue()
+    for g2 in gpus:
+        free_gpus.put(g2)
+
+    def run_on_free_handle(*a):
+        g3 = free_gpus.get()                # a handle is not thread-safe: one batch per handle at a time
+        try:
+            return compute_batch(g3, *a)
+        finally:
+            free_gpus.put(g3)
+
+    pool = ThreadPoolExecutor(max_workers=n_inflight)
+    pending = []
+    reader = FastqBatches(args.reads, min_len=args.lencutoff, max_reads=args.batch,
+                          max_bases=min(1 << 29, max(1 << 22, args.batch * 12000)), nbuf=n_inflight + 2)
     gpu_assign = adapter_dict is None
+    assign_gpu = GpuConsensus(gpu.device) if gpu_assign else None
     if gpu_assign:
         sp_names = sorted(splint_dict)
         cands = [s for n in sp_names for s in splint_dict[n]]
@@ -268,7 +298,7 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
                 m_off = np.zeros(len(mine) + 1, dtype=np.int64)
                 m_off[1:] = np.cumsum([b["off"][i + 1] - b["off"][i] for i in mine])
                 m_blob = b["blob"] if len(mine) == b["n"] else np.concatenate([b["blob"][b["off"][i]:b["off"][i + 1]] for i in mine])
-                best, scores = gpu.assign_splints(m_blob, m_off, cands)
+                best, scores = assign_gpu.assign_splints(m_blob, m_off, cands)
                 for t, i in enumerate(mine):
                     c = int(best[t])
                     if scores[c, t] >= args.assign_min_frac * perfect[c]:
@@ -296,9 +326,20 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
             names = [names[i] for i in sel]
             off = np.zeros(len(sel) + 1, dtype=np.int64)
             off[1:] = np.cumsum(lens)
-        for key, v in process_batch(gpu, names, blob, off, qual, qsum, splint_dict, adapter_dict, args.mdistcutoff,
-                                    handles).items():
-            totals[key] = totals.get(key, 0) + v
+        # two batches in flight per GPU (one handle + host thread each): the next batch's copies and kernels
+        # overlap the tail of the previous persistent POA grid and the Python-side output writing
+        ad = dict(adapter_dict) if gpu_assign else adapter_dict
+        fut = pool.submit(run_on_free_handle, names, blob, off, splint_dict, ad, args.mdistcutoff)
+        pending.append((fut, names, blob, off, qual, qsum, ad))
+        while len(pending) >= len(gpus) + 1 or (pending and pending[0][0].done()):
+            _drain_one(pending, handles, totals)
+    while pending:
+        _drain_one(pending, handles, totals)
+    pool.shutdown()
+    for g2 in gpus[1:]:
+        g2.close()
+    if assign_gpu is not None:
+        assign_gpu.close()
     reader.close()
     for a, b2 in handles.values():
         a.close(); b2.close()

@@ -391,12 +391,17 @@ def test_driver_multi_process_sharding(gpu, tmp_path):
     ngpu = _lib.load().c3_device_count()
     os.environ["C3POA_DEVICE_MODULO"] = str(ngpu)
     try:
-        driver.main(driver.parse_args(base + ["-o", str(tmp_path / "b"), "--gpus", "2"]))
+        driver.main(driver.parse_args(base + ["-o", str(tmp_path / "b"), "--gpus", "2", "--batch", "7"]))
     finally:
         del os.environ["C3POA_DEVICE_MODULO"]
+    # many small batches, three in flight on one GPU
+    (tmp_path / "c" / "tmp").mkdir(parents=True)
+    synth.write_psl(tmp_path / "c" / "tmp" / "splint_to_read_alignments.psl", d["names"], d["splint_name"], d["strand"])
+    driver.main(driver.parse_args(base + ["-o", str(tmp_path / "c"), "--batch", "9", "--inflight", "3"]))
+    c = {n: s for n, s, _ in fastx_read(str(tmp_path / "c" / "Splint1" / "R2C2_Consensus.fasta"))}
     a = {n: s for n, s, _ in fastx_read(str(tmp_path / "a" / "Splint1" / "R2C2_Consensus.fasta"))}
     b = {n: s for n, s, _ in fastx_read(str(tmp_path / "b" / "Splint1" / "R2C2_Consensus.fasta"))}
-    assert a == b and len(a) == 40                   # output order is unspecified in the reference: compare as sets
+    assert a == b == c and len(a) == 40              # output order is unspecified in the reference: compare as sets
     assert not any(p.name.startswith("tmp") for p in (tmp_path / "b" / "Splint1").iterdir())
 
 
