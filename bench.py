@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--config", default="cfg2_1kb_x5", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--poa-mode", default="auto", choices=["auto", "warp", "lane"],
+                    help="POA kernel: auto = thread-per-read lane kernel for large batches, warp-per-read otherwise")
     return ap.parse_args()
 
 
@@ -159,7 +161,7 @@ def main():
     from c3poa_b200.dist import Group
     grp = Group("nccl")
 
-    gpu = GpuConsensus(local_rank)
+    gpu = GpuConsensus(local_rank, poa_mode=a.poa_mode)
     blob, off, sp_idx, splints = make_workload(a.config, a.reads, SEED + 1000 * rank)
     n = off.size - 1
     # pinned host staging of the inputs (e2e copies come from here)
@@ -197,6 +199,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     res = gpu.fetch(out)["results"]
+    lane_given, lane_done = gpu.lane_counts()
     dev_ms_max = allmax(dev_ms)
     wall_max = allmax(wall_s)
     n_ok = int((res["status"] == 0).sum())
@@ -279,6 +282,7 @@ def main():
             "poa_gcups": poa_cells / poa_s / 1e9 * world if poa_s > 0 else None,
             "conk_gcups": conk_cells / conk_s / 1e9 * world if conk_s > 0 else None,
             "reads_ok_rank0": n_ok, "reads_err_rank0": n_err,
+            "poa_kernel": {"mode": a.poa_mode, "lane_reads_rank0": lane_given, "lane_done_rank0": lane_done},
             "e2e": {"value": total_reads / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,

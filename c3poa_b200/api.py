@@ -96,7 +96,9 @@ class GpuError(RuntimeError):
 class GpuConsensus:
     """One handle per device (not thread-safe; use one per host thread/GPU)."""
 
-    def __init__(self, device: int = 0):
+    POA_MODES = {"auto": 0, "warp": 1, "lane": 2}
+
+    def __init__(self, device: int = 0, poa_mode: str = "auto"):
         self._L = _lib.load()
         h = C.c_void_p()
         rc = self._L.c3_init(device, C.byref(h))
@@ -105,6 +107,19 @@ class GpuConsensus:
                            "(the GPU stages have no CPU fallback)")
         self._h = h
         self.device = device
+        if poa_mode != "auto":
+            self.set_poa_mode(poa_mode)
+
+    def set_poa_mode(self, mode: str):
+        """POA kernel choice: 'auto' (thread-per-read kernel for batches of >= 8192 eligible reads), 'warp'
+        (warp-per-read kernel only), 'lane' (thread-per-read kernel whenever eligible).  Same results."""
+        self._ck(self._L.c3_set_poa_mode(self._h, self.POA_MODES[mode]), "c3_set_poa_mode")
+
+    def lane_counts(self):
+        """(reads given to the lane kernel, reads it finished) of the last poa_batch / run."""
+        a, b = C.c_int32(), C.c_int32()
+        self._ck(self._L.c3_lane_counts(self._h, C.byref(a), C.byref(b)), "c3_lane_counts")
+        return a.value, b.value
 
     def close(self):
         if getattr(self, "_h", None):

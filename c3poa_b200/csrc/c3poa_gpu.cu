@@ -5,6 +5,7 @@
 #include "conk.cuh"
 #include "peaks.cuh"
 #include "poa.cuh"
+#include "poa_lane.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -46,6 +47,11 @@ struct c3_handle {
     DevBuf d_peaks, d_npk, d_sub, d_dang, d_res, d_stats, d_cons, d_ws;
     // B3 staging
     DevBuf d_item_base, d_bounds, d_nseq, d_status, d_clen, d_nodes, d_cells, d_order;
+    // POA kernel choice: 0 auto (lane kernel for large batches), 1 warp kernel only, 2 lane kernel whenever eligible
+    int poa_mode = 0;
+    DevBuf d_order_lane, d_done;
+    int n_work_lane = 0, lane_items = 0, lane_n_items = 0;
+    int64_t lane_max_total = 0; int lane_max_nseq = 0, lane_max_q = 0;
 };
 
 static int fail(c3_handle *h, int code, const char *fmt, ...)
@@ -102,7 +108,8 @@ extern "C" void c3_destroy(c3_handle *h)
     DevBuf *bufs[] = {&h->d_ascii, &h->d_codes, &h->d_off, &h->d_sp_ascii, &h->d_sp_codes, &h->d_sp_off, &h->d_sp_idx,
                       &h->d_prof, &h->d_brow, &h->d_counter, &h->d_coef, &h->d_pk_scratch, &h->d_smoothed, &h->d_median,
                       &h->d_peaks, &h->d_npk, &h->d_sub, &h->d_dang, &h->d_res, &h->d_stats, &h->d_cons, &h->d_ws,
-                      &h->d_item_base, &h->d_bounds, &h->d_nseq, &h->d_status, &h->d_clen, &h->d_nodes, &h->d_cells, &h->d_order};
+                      &h->d_item_base, &h->d_bounds, &h->d_nseq, &h->d_status, &h->d_clen, &h->d_nodes, &h->d_cells, &h->d_order,
+                      &h->d_order_lane, &h->d_done};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -119,6 +126,30 @@ extern "C" void *c3_host_alloc(size_t bytes)
 extern "C" void c3_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" const char *c3_last_error(const c3_handle *h) { return h ? h->err : "null handle"; }
+
+extern "C" int c3_set_poa_mode(c3_handle *h, int32_t mode)
+{
+    if (!h) return -1;
+    if (mode < 0 || mode > 2) return fail(h, -5, "poa mode must be 0 (auto), 1 (warp kernel) or 2 (lane kernel)");
+    h->poa_mode = mode;
+    return 0;
+}
+
+// reads of the last B3/B4 call that the lane kernel was given / finished (the rest went to the warp kernel)
+extern "C" int c3_lane_counts(c3_handle *h, int32_t *out_given, int32_t *out_done)
+{
+    if (!h || !out_given || !out_done) return -1;
+    *out_given = h->lane_items; *out_done = 0;
+    if (h->lane_items <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    std::vector<int32_t> d(h->d_done.cap / 4);
+    const size_t n = std::min(d.size(), (size_t)h->lane_n_items);
+    CK(cudaMemcpy(d.data(), h->d_done.p, n * 4, cudaMemcpyDeviceToHost));
+    int c = 0;
+    for (size_t i = 0; i < n; ++i) c += d[i] != 0;
+    *out_done = c;
+    return 0;
+}
 
 extern "C" int c3_get_timings(const c3_handle *h, c3_timings *out)
 {
@@ -241,8 +272,89 @@ static int upload_poa_order(c3_handle *h, c3_poa_args &A, const std::vector<int3
     for (int i = 0; i < n; ++i) if (cls[i] >= 0) order[start[cls[i]]++] = i;
     CK(h->d_order.ensure((size_t)std::max(n_work, 1) * 4));
     CK(cudaMemcpyAsync(h->d_order.p, order.data(), (size_t)n_work * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));                          // `order` is a local
+    // the lane kernel's share (poa_lane.cuh): same order, items it covers; neighbours in this order become the
+    // 32 threads of a warp, so they are of similar size.  Its workspace is sized from these items alone.
+    std::vector<int32_t> lane((size_t)std::max(n_work, 1));
+    int nl = 0;
+    h->lane_max_total = 0; h->lane_max_nseq = 0; h->lane_max_q = 0;
+    if (pp->simd_bits == 256 && pp->wb >= 0) {
+        for (int k = 0; k < n_work; ++k) {
+            const int i = order[k];
+            if (A.msa2 && nseq[i] == 2) continue;
+            const int64_t L = total[i] / nseq[i];
+            if (L > 5000 || nseq[i] > 40) continue;                // long / deep reads: per-thread arenas would not fit
+            lane[nl++] = i;
+            h->lane_max_total = std::max(h->lane_max_total, total[i]);
+            h->lane_max_nseq = std::max(h->lane_max_nseq, nseq[i]);
+        }
+    }
+    CK(h->d_order_lane.ensure((size_t)std::max(nl, 1) * 4));
+    CK(cudaMemcpyAsync(h->d_order_lane.p, lane.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));                          // `order` and `lane` are locals
     A.order = h->d_order.as<int32_t>(); A.n_work = n_work;
+    h->n_work_lane = nl;
+    return 0;
+}
+
+// Lane kernel pass (poa_lane.cuh) ahead of the warp kernel: covers the bulk of a large batch; whatever it
+// declines or cannot fit stays not-done and is picked up by c3_poa_kernel afterwards.
+static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_params *pp)
+{
+    h->lane_items = 0;
+    A.done = nullptr;
+    const int nl = h->n_work_lane;
+    const bool want = h->poa_mode == 2 || (h->poa_mode == 0 && nl >= 8192);
+    if (!want || nl <= 0) return 0;
+    const int max_nseq = h->lane_max_nseq;
+    const int64_t max_total = h->lane_max_total;
+    max_q = (int)std::min<int64_t>(max_q, max_total);
+    // per-thread graph workspace: same node estimate as the warp kernel
+    int64_t est = 2 + (int64_t)max_q + (int64_t)(max_nseq - 1) * ((int64_t)max_q * 35 / 100 + 16);
+    int64_t node_cap = std::min<int64_t>(std::min<int64_t>(est, max_total + 2), 65504);
+    node_cap = std::max<int64_t>((node_cap + 31) & ~31ll, 64);
+    const int pool_cap = (int)node_cap;
+    const int cigar_cap = (int)((max_q + node_cap + 64 + 1) & ~1ll);
+    const int qp_stride = (max_q + 48) & ~15;
+    const int64_t ws_bytes = c3_poa_ws_bytes((int)node_cap, pool_cap, 0, cigar_cap, qp_stride);
+    // per-warp DP arena: rows of one alignment x vectors per row step (the widest band among 32 threads).
+    // Sized for the usual case, not the worst: an overflow only sends those reads to the warp kernel.
+    const int w = pp->wb + (int)(pp->wf * max_q);
+    const int64_t rows_est = 2 + (int64_t)max_q + (int64_t)(max_nseq - 1) * ((int64_t)max_q * 20 / 100 + 16);
+    const int64_t vec_est = (2 * w + 48) / 16 + 1;
+    int64_t arena4 = std::min<int64_t>(rows_est, node_cap) * vec_est * C3L_VSTRIDE;
+    if (arena4 > 0x7fffff00ll / 4) return 0;                       // int32 cell indices
+    const int64_t warp_bytes = 32 * ws_bytes + arena4 * 16;
+    const int wpb = C3L_THREADS / 32;
+    int bps = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_lane_kernel, C3L_THREADS, 0) != cudaSuccess || bps < 1) bps = 4;
+    bps = std::min(bps, C3L_MINB);
+    int64_t warps = (int64_t)h->sm_count * bps * wpb;
+    warps = std::min<int64_t>(warps, ((int64_t)nl + 31) / 32);
+    size_t free_b = 0, tot_b = 0;
+    CK(cudaMemGetInfo(&free_b, &tot_b));
+    const int64_t budget = (int64_t)((double)(free_b + h->d_ws.cap) * 0.8);
+    warps = std::min<int64_t>(warps, budget / warp_bytes);
+    warps = warps / wpb * wpb;
+    if (warps < wpb) return 0;                                     // does not fit: the warp kernel takes everything
+    CK(h->d_ws.ensure((size_t)(warps * warp_bytes)));
+    CK(h->d_done.ensure((size_t)A.n_items * 4));
+    CK(cudaMemsetAsync(h->d_done.p, 0, (size_t)A.n_items * 4, h->stream));
+    CK(h->d_counter.ensure(64));
+    CK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
+    c3_lane_args L;
+    L.A = A;
+    L.A.ws = h->d_ws.as<uint8_t>(); L.A.ws_stride = ws_bytes;
+    L.A.node_cap = (int)node_cap; L.A.pool_cap = pool_cap; L.A.cell_cap = 0; L.A.cigar_cap = cigar_cap; L.A.qp_stride = qp_stride;
+    L.A.counter = h->d_counter.as<unsigned>();
+    L.A.order = h->d_order_lane.as<int32_t>(); L.A.n_work = nl;
+    L.arena = reinterpret_cast<int4 *>(h->d_ws.as<uint8_t>() + warps * 32 * ws_bytes);
+    L.arena_stride4 = arena4; L.arena_cap4 = (int)arena4;
+    L.done = h->d_done.as<int32_t>();
+    c3_poa_lane_kernel<<<(int)(warps / wpb), C3L_THREADS, 0, h->stream>>>(L);
+    CK(cudaGetLastError());
+    h->tim.kernel_launches++;
+    h->lane_items = nl; h->lane_n_items = A.n_items;
+    A.done = h->d_done.as<int32_t>();
     return 0;
 }
 
@@ -251,6 +363,11 @@ static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int
 {
     to_dev_para(pp, &A.P);
     if (A.P.simd_bits != 128 && A.P.simd_bits != 256 && A.P.simd_bits != 512) return fail(h, -5, "simd_bits must be 128/256/512");
+    if (!A.order) h->n_work_lane = 0;
+    {
+        const int rc = launch_poa_lane(h, A, max_q, pp);
+        if (rc) return rc;
+    }
     int64_t est = 2 + (int64_t)max_q + (int64_t)(max_nseq - 1) * ((int64_t)max_q * 35 / 100 + 16);
     int64_t node_cap = std::min<int64_t>(std::min<int64_t>(est, max_total + 2), 65534);
     node_cap = std::max<int64_t>((node_cap + 31) & ~31ll, 64);

@@ -34,6 +34,7 @@
 #ifndef C3_POA_MINB
 #define C3_POA_MINB 5       // resident CTAs per SM the register allocation is bounded for (<= 102 regs; measured best)
 #endif
+#define C3_HD __host__ __device__
 #define C3_NONE 0xffffu
 #define C3_SRC 0
 #define C3_SINK 1
@@ -93,11 +94,11 @@ struct c3_pedge { uint16_t id, w, next, pad; };              // overflow edge (i
 // ord[k]  (by position): link = node id, mp = position of in0 (the first predecessor's row).
 struct __align__(16) c3_prow { int32_t off; uint16_t beg, end; uint16_t mp, in0; uint16_t link; uint8_t base, npre; };
 static_assert(sizeof(c3_prow) == 16, "row record must be 16 bytes");
-__device__ __forceinline__ int c3_row_ng(const c3_prow &r) { return ((int)r.end - (int)r.beg + 4) >> 2; }
+C3_HD __forceinline__ int c3_row_ng(const c3_prow &r) { return ((int)r.end - (int)r.beg + 4) >> 2; }
 
 // first half of a node record as one 128-bit load + field decode (avoids a local-memory struct copy)
 struct c3_nrec { uint4 a; };
-__device__ __forceinline__ c3_nrec c3_ld_node(const c3_pnode *p)
+C3_HD __forceinline__ c3_nrec c3_ld_node(const c3_pnode *p)
 {
     c3_nrec r; r.a = *reinterpret_cast<const uint4 *>(p); return r;
 }
@@ -143,6 +144,7 @@ struct c3_poa_args {
     unsigned *counter;
     const int32_t *order;          // optional work order (largest estimated cost first); n_work entries
     int n_work;                    // number of work items handed out (== n_items when order is null)
+    const int32_t *done;           // optional [n_items]: 1 = already finished by c3_poa_lane_kernel, skip
 };
 
 struct c3_poa_ws {
@@ -159,7 +161,7 @@ __host__ __device__ inline int64_t c3_poa_ws_bytes(int node_cap, int pool_cap, i
     return (b + 255) & ~(int64_t)255;
 }
 
-__device__ __forceinline__ c3_poa_ws c3_poa_ws_carve(uint8_t *base, int node_cap, int pool_cap, int cell_cap, int cigar_cap)
+C3_HD __forceinline__ c3_poa_ws c3_poa_ws_carve(uint8_t *base, int node_cap, int pool_cap, int cell_cap, int cigar_cap)
 {
     c3_poa_ws w;
     w.nodes = (c3_pnode *)base; base += (int64_t)node_cap * 32;
@@ -178,16 +180,16 @@ __device__ __forceinline__ long long c3_mkkey(int v, unsigned prio)
     return (long long)(((unsigned long long)(unsigned)v << 32) | (unsigned long long)prio);
 }
 
-__device__ __forceinline__ int c3_score(const c3_poa_para_dev &P, int a, int b)
+C3_HD __forceinline__ int c3_score(const c3_poa_para_dev &P, int a, int b)
 {
     return (a >= 4 || b >= 4) ? 0 : (a == b ? P.match : -P.mismatch);
 }
 
-__device__ __forceinline__ uint16_t c3_aln_get(const c3_pnode &n, int k)
+C3_HD __forceinline__ uint16_t c3_aln_get(const c3_pnode &n, int k)
 {
     return k == 0 ? n.aln0 : k == 1 ? n.aln1 : k == 2 ? n.aln2 : n.aln3;
 }
-__device__ __forceinline__ void c3_aln_push(c3_pnode *n, uint16_t id)
+C3_HD __forceinline__ void c3_aln_push(c3_pnode *n, uint16_t id)
 {
     const int k = n->aln_n;
     if (k == 0) n->aln0 = id; else if (k == 1) n->aln1 = id; else if (k == 2) n->aln2 = id; else if (k == 3) n->aln3 = id; else return;
@@ -197,7 +199,7 @@ __device__ __forceinline__ void c3_aln_push(c3_pnode *n, uint16_t id)
 // ---------------- graph mutation (lane 0 only) ----------------
 struct c3_graph { c3_pnode *nodes; c3_pedge *pool; int node_n, pool_n, node_cap, pool_cap, err; };
 
-__device__ __forceinline__ int c3_g_add_node(c3_graph &g, uint8_t base)
+C3_HD __forceinline__ int c3_g_add_node(c3_graph &g, uint8_t base)
 {
     if (g.node_n >= g.node_cap) { g.err = C3_E_NODES; return 0; }
     c3_pnode n;
@@ -209,7 +211,7 @@ __device__ __forceinline__ int c3_g_add_node(c3_graph &g, uint8_t base)
 }
 
 // abpoa_add_graph_edge: find (optional) else append at the END of both lists
-__device__ void c3_g_add_edge(c3_graph &g, int from, int to, int check)
+C3_HD inline void c3_g_add_edge(c3_graph &g, int from, int to, int check)
 {
     c3_pnode *f = &g.nodes[from], *t = &g.nodes[to];
     const int fo = f->out_n;
@@ -241,20 +243,20 @@ __device__ void c3_g_add_edge(c3_graph &g, int from, int to, int check)
     f->out_n = (uint8_t)(fo + 1);
 }
 
-__device__ __forceinline__ void c3_list_insert_before(c3_graph &g, int x, int y)
+C3_HD __forceinline__ void c3_list_insert_before(c3_graph &g, int x, int y)
 {
     const uint16_t p = g.nodes[y].prev;
     g.nodes[x].prev = p; g.nodes[x].next = (uint16_t)y;
     g.nodes[p].next = (uint16_t)x; g.nodes[y].prev = (uint16_t)x;
 }
-__device__ __forceinline__ void c3_list_insert_after(c3_graph &g, int x, int a)
+C3_HD __forceinline__ void c3_list_insert_after(c3_graph &g, int x, int a)
 {
     const uint16_t nx = g.nodes[a].next;
     g.nodes[x].prev = (uint16_t)a; g.nodes[x].next = nx;
     g.nodes[a].next = (uint16_t)x; g.nodes[nx].prev = (uint16_t)x;
 }
 // last list element of the contiguous aligned block that contains `a`, looking forward
-__device__ int c3_group_tail(const c3_graph &g, int a)
+C3_HD inline int c3_group_tail(const c3_graph &g, int a)
 {
     const c3_pnode na = g.nodes[a];
     int e = a;
@@ -630,7 +632,7 @@ __device__ __forceinline__ int c3_emit_msa(const c3_poa_args &A, const c3_poa_ws
 
 // Heaviest bundling (abpoa_heaviest_bundling) + consensus walk.  Single-thread routine: called by
 // one lane per graph; returns the consensus length or a C3_E_* code.
-__device__ __forceinline__ int c3_consensus(const c3_poa_args &A, const c3_poa_ws &W, char *co)
+C3_HD __forceinline__ int c3_consensus(const c3_poa_args &A, const c3_poa_ws &W, char *co)
 {
     int cons_len = 0;
     int32_t *score = (int32_t *)W.hr;
@@ -697,6 +699,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
         item = __shfl_sync(C3_FULL, item, 0);
         if (item >= A.n_work) break;
         if (A.order) item = A.order[item];
+        if (A.done && A.done[item]) continue;
         const int nseq = A.n_seqs[(int64_t)item * A.n_seqs_stride];
         if (nseq < A.min_seqs || nseq > A.max_seqs) continue;
         const uint8_t *ibase = A.codes + A.item_base[item];

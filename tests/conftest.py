@@ -12,11 +12,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-@pytest.fixture(scope="session")
-def gpu():
-    """The CUDA handle.  No skip: on a GPU box a missing library/device must FAIL the test."""
+@pytest.fixture(scope="session", params=["auto", "lane"])
+def gpu(request):
+    """The CUDA handle.  No skip: on a GPU box a missing library/device must FAIL the test.
+    Every GPU test runs twice: POA through the warp-per-read kernel ("auto" picks it for small batches) and
+    through the thread-per-read lane kernel (with the warp kernel as its fallback)."""
     from c3poa_b200.api import GpuConsensus
-    h = GpuConsensus(0)
+    h = GpuConsensus(0, poa_mode=request.param)
+    h.poa_mode = request.param
     yield h
     h.close()
 

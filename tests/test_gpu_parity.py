@@ -120,6 +120,24 @@ def test_poa_parity(gpu, oracle):
     assert not bad, f"poa mismatches (group, status, |cons| gpu/oracle, cells gpu/oracle, nodes gpu/oracle): {bad}"
 
 
+def test_lane_kernel_serves_what_it_covers(gpu, oracle):
+    """In lane mode the thread-per-read kernel finishes every plain consensus group itself (no silent fallback)."""
+    rng = np.random.default_rng(12)
+    groups = []
+    for L in rng.integers(40, 1500, size=100):
+        a = synth.random_seq(rng, int(L))
+        groups.append([synth.mutate(rng, a).tobytes().decode() for _ in range(int(rng.integers(3, 8)))])
+    r = gpu.poa_batch(groups)
+    given, done = gpu.lane_counts()
+    if gpu.poa_mode == "lane":
+        assert (given, done) == (len(groups), len(groups))
+    else:
+        assert given == 0
+    for i in range(0, len(groups), 7):
+        o = oracle.poa_msa(groups[i])
+        assert r["status"][i] == 0 and r["cons"][i] == o["cons"] and r["cells"][i] == o["cells"] and r["nodes"][i] == o["node_n"], i
+
+
 def test_poa_pairwise_msa(gpu, oracle):
     """2-repeat path: the two MSA rows (abpoa_generate_rc_msa order) and the reference's pairwise consensus."""
     import json

@@ -35,7 +35,7 @@ def main():
     ci = {h: i for i, h in enumerate(hdr)}
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=td, capture_output=True)
-        cub = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
+        cub = max((f for f in os.listdir(td) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(td, f)))
         dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout
     lines, in_fn, cur_line = [], False, None
     for ln in dis.splitlines():
