@@ -846,6 +846,15 @@ extern "C" int c3_debug_stats(unsigned long long *out16, int reset)
 }
 #endif
 
+#ifdef C3L_PROF
+extern "C" int c3_debug_lane_prof(unsigned long long *out16, int reset)
+{
+    if (out16) cudaMemcpyFromSymbol(out16, c3l_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(c3l_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 extern "C" int c3_measure_int_peak(c3_handle *h, double *out_ops_per_s)
 {
     if (!h || !out_ops_per_s) return -1;

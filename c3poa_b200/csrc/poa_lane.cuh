@@ -54,6 +54,20 @@ static inline int c3l_hmax(int a, int b) { return a > b ? a : b; }
 #define C3L_MAX3(a, b, c) c3l_hmax(c3l_hmax((a), (b)), (c))
 #endif
 
+// -DC3L_PROF: per-phase cycle counters (lane 0 of every warp adds clock64() deltas); read with c3_debug_lane_prof
+#if defined(C3L_PROF) && defined(__CUDACC__)
+__device__ unsigned long long c3l_prof[16];
+#endif
+#if defined(C3L_PROF) && defined(__CUDA_ARCH__)
+#define C3L_TICK(id) do { const long long t1_ = clock64(); if (lane == 0) atomicAdd(&c3l_prof[id], (unsigned long long)(t1_ - tprof_)); tprof_ = clock64(); } while (0)
+#define C3L_TICK_INIT long long tprof_ = clock64()
+#define C3L_COUNT(id, v) do { if (lane == 0) atomicAdd(&c3l_prof[id], (unsigned long long)(v)); } while (0)
+#else
+#define C3L_TICK(id) do { } while (0)
+#define C3L_TICK_INIT do { } while (0)
+#define C3L_COUNT(id, v) do { } while (0)
+#endif
+
 struct c3l_state {
     int item, on, err, nseq;
     const uint8_t *ibase; const int32_t *bnd;
@@ -389,6 +403,7 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
 {
     bool run = S.aligning && !S.err;
     S.aligning = 0;
+    C3L_TICK_INIT;
     const int e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const uint8_t *q = S.q; const int qlen = S.qlen;
     unsigned long long *cg = W.cigar;
@@ -418,6 +433,7 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
     }
     int cur_op = C3_OP_ALL;
     while (C3L_ANY(run && rt.link != C3_SRC && j > 0)) {
+        C3L_COUNT(11, 1);
         if (!(run && rt.link != C3_SRC && j > 0)) continue;
         const int i = rt.link;
         const int b = rt.beg;
@@ -475,6 +491,7 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
             if (!hit && (cur_op & C3_OP_F) && j - 1 >= b) {
                 // F is not stored: rebuild F[j] and F[j-1] of this row from its H
                 int f1 = C3_NEG_INF, f2 = C3_NEG_INF, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
+                C3L_COUNT(12, 1); C3L_COUNT(13, j - b);
                 for (int c = 0; c < j - b; ++c) {
                     hl = ar[c3l_ci(rt.off, 0, c, lane)];
                     f1l = f1; f2l = f2;
@@ -509,6 +526,7 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
         nc += j;
     } else nc = 0;
 
+    C3L_TICK(6);
     // ---- merge: the cigar is walked from its tail = forward order ----
     c3_graph g; g.nodes = W.nodes; g.pool = W.pool; g.node_n = S.node_n; g.pool_n = S.pool_n;
     g.node_cap = A.node_cap; g.pool_cap = A.pool_cap; g.err = 0;
@@ -562,6 +580,7 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
             }
         }
     }
+    C3L_TICK(7);
     if (run) {
         if (!g.err) c3_g_add_edge(g, last_id, C3_SINK, 1 - last_new);
         if (g.err) S.err = C3L_E_RETRY;
@@ -644,6 +663,7 @@ __global__ void __launch_bounds__(C3L_THREADS, C3L_MINB) c3_poa_lane_kernel(c3_l
     int32_t *ar = reinterpret_cast<int32_t *>(L.arena + (int64_t)gwarp * L.arena_stride4);
     const c3_poa_para_dev P = A.P;
     c3l_state S;
+    C3L_TICK_INIT;
     for (;;) {
         int first = 0;
         if (lane == 0) first = (int)atomicAdd(A.counter, 32u);
@@ -653,31 +673,39 @@ __global__ void __launch_bounds__(C3L_THREADS, C3L_MINB) c3_poa_lane_kernel(c3_l
         const int item = have ? (A.order ? A.order[first + lane] : first + lane) : 0;
         c3l_item_begin(S, A, W, item, have);
         __syncwarp();
+        C3L_TICK(0);
         const int max_nseq = __reduce_max_sync(C3_FULL, (S.on && !S.err) ? S.nseq : 0);
         for (int sq = 1; sq < max_nseq; ++sq) {
             int nv = c3l_align_begin(S, A, P, W, sq);
             __syncwarp();
             int mv = __reduce_max_sync(C3_FULL, nv);
+            C3L_TICK(1);
             if (mv == 0) continue;
             int used4 = mv * C3L_VSTRIDE;
             if (used4 > L.arena_cap4) { if (S.aligning) { S.err = C3L_E_RETRY; S.aligning = 0; } continue; }
             c3l_source_row(S, P, W, ar, lane);
             __syncwarp();
+            C3L_TICK(2);
             for (;;) {
                 nv = c3l_row_setup(S, A, W);
                 __syncwarp();
                 mv = __reduce_max_sync(C3_FULL, nv);
+                C3L_TICK(3);
                 if (mv == 0) break;
                 if (used4 + mv * C3L_VSTRIDE > L.arena_cap4) { if (S.aligning) S.err = C3L_E_RETRY; break; }
                 c3l_row_compute(S, A, P, W, ar, used4, lane);
                 used4 += mv * C3L_VSTRIDE;
                 __syncwarp();
+                C3L_TICK(4);
+                C3L_COUNT(9, 1); C3L_COUNT(10, mv);
             }
             c3l_align_end(S, A, P, W, ar, lane, sq);
             __syncwarp();
+            C3L_TICK(5);
         }
         c3l_item_end(S, A, W, L.done);
         __syncwarp();
+        C3L_TICK(8);
     }
 }
 #endif
