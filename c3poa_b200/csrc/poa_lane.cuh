@@ -27,7 +27,10 @@
 #include "poa.cuh"
 
 #define C3L_E_RETRY (-299)
-#define C3L_VSTRIDE 384            // int4 per 16-column vector of one warp step: 3 arrays x 4 quarters x 32 lanes
+#define C3L_VSTRIDE 400            // int4 per 16-column vector of one warp step: 3 arrays x 4 quarters x 32 lanes + 32 x (F1,F2) carry-in
+#ifndef C3L_NC
+#define C3L_NC 8                   // columns per software-pipeline step of the row loop (8 or 16)
+#endif
 #ifndef C3L_THREADS
 #define C3L_THREADS 64
 #endif
@@ -74,8 +77,12 @@ struct c3l_state {
     int node_n, pool_n;
     long long cells_total;
     const uint8_t *q; int qlen, n, w, aligning;
-    int v, rcount; c3_nrec nd; uint32_t hrv;          // row walk: current node, rows done, prefetched records
-    int beg, end, nvec, beg_sn, end_sn; c3_prow r0;   // the row between setup and compute
+    int v, rcount;                                    // row walk: current node, rows done
+    c3_nrec nd, nd1, nd2; uint32_t hrv, hr1, hr2;     // look-ahead: records of v and of the next two nodes of the list
+    uint2 pe, pe1;                                    // first overflow in-edge of v / next(v) (in_n > 1)
+    c3_prow ra, rb;                                   // row records of v's first two predecessors (unless == vlast)
+    c3_prow last; int vlast;                          // the row just computed
+    int beg, end, nvec, beg_sn, end_sn; c3_prow r0, r1;   // the row between setup and compute
 };
 
 // int32 index of column c (relative to the row's band start) of array a in the row stored at off4
@@ -83,6 +90,9 @@ C3_HD __forceinline__ int c3l_ci(int off4, int a, int c, int lane)
 {
     return ((off4 + (c >> 4) * C3L_VSTRIDE + ((a << 2) + ((c >> 2) & 3)) * 32 + lane) << 2) + (c & 3);
 }
+
+// int32 index of the (F1, F2) pair entering vector vi of the row stored at off4
+C3_HD __forceinline__ int c3l_fi(int off4, int vi, int lane) { return ((off4 + vi * C3L_VSTRIDE + 384) << 2) + 2 * lane; }
 
 // ---------------------------------------------------------------------------
 // item start: first sequence -> linear graph
@@ -200,7 +210,15 @@ C3_HD __forceinline__ int c3l_align_begin(c3l_state &S, const c3_poa_args &A, co
     return S.nvec;
 }
 
-// source row cells + records; positions the row walk on the first node after the source
+// node / edge / row records by index, with the list terminator (C3_NONE) mapped to the sink so that the
+// look-ahead past the end of the walk stays inside the workspace
+C3_HD __forceinline__ int c3l_cl(const int v) { return v == (int)C3_NONE ? C3_SINK : v; }
+C3_HD __forceinline__ uint2 c3l_ld_edge(const c3_pedge *p) { return *reinterpret_cast<const uint2 *>(p); }
+#define C3L_E_ID(e) ((int)((e).x & 0xffffu))
+#define C3L_E_NEXT(e) ((int)((e).y & 0xffffu))
+
+// source row cells + records; positions the row walk on the first node after the source and fills the
+// look-ahead (records of the next two nodes, first overflow in-edges, predecessor row records)
 C3_HD __forceinline__ void c3l_source_row(c3l_state &S, const c3_poa_para_dev &P, const c3_poa_ws &W, int32_t *ar, const int lane)
 {
     if (!S.aligning) return;
@@ -209,8 +227,11 @@ C3_HD __forceinline__ void c3l_source_row(c3l_state &S, const c3_poa_para_dev &P
     c3_prow ri; ri.off = 0; ri.beg = (uint16_t)b0; ri.end = (uint16_t)S.end; ri.mp = 1;   // successors of the source start at column 1
     ri.in0 = C3_NONE; ri.base = 4; ri.npre = 0; ri.link = 0;
     W.rows[C3_SRC] = ri;
+    S.last = ri; S.vlast = C3_SRC;
     ri.mp = C3_NONE;
     W.ord[0] = ri;
+    for (int vi = 0; vi < S.nvec; ++vi)
+        *reinterpret_cast<int2 *>(ar + c3l_fi(0, vi, lane)) = make_int2(C3_NEG_INF, C3_NEG_INF);
     for (int c = 0; c < 16 * S.nvec; ++c) {
         int h = C3_NEG_INF, x1 = C3_NEG_INF, x2 = C3_NEG_INF;
         if (b0 == 0 && c < wd) {
@@ -221,11 +242,23 @@ C3_HD __forceinline__ void c3l_source_row(c3l_state &S, const c3_poa_para_dev &P
     }
     S.v = W.nodes[C3_SRC].next; S.rcount = 1;
     S.nd = c3_ld_node(&W.nodes[S.v]); S.hrv = W.hr[S.v];
+    const int v1 = c3l_cl(C3_N_NEXT(S.nd));
+    S.nd1 = c3_ld_node(&W.nodes[v1]); S.hr1 = W.hr[v1];
+    const int v2 = c3l_cl(C3_N_NEXT(S.nd1));
+    S.nd2 = c3_ld_node(&W.nodes[v2]); S.hr2 = W.hr[v2];
+    S.pe = make_uint2(0u, 0u); S.pe1 = make_uint2(0u, 0u);
+    if (C3_N_INN(S.nd) > 1) S.pe = c3l_ld_edge(&W.pool[C3_N_INMORE(S.nd)]);
+    if (C3_N_INN(S.nd1) > 1) S.pe1 = c3l_ld_edge(&W.pool[C3_N_INMORE(S.nd1)]);
+    S.ra = ri; S.rb = ri;
+    if (C3_N_IN0(S.nd) != C3_SRC) S.ra = W.rows[c3l_cl(C3_N_IN0(S.nd))];
+    if (C3_N_INN(S.nd) > 1 && C3L_E_ID(S.pe) != C3_SRC) S.rb = W.rows[C3L_E_ID(S.pe)];
     S.nvec = 0;
 }
 
 // ---------------------------------------------------------------------------
 // row setup: adaptive band of the current node's row.  Returns its number of vectors (0: no row).
+// The records of the first two predecessors were requested while the previous row was computed (S.ra, S.rb);
+// a predecessor that IS the previous row comes from S.last.
 // ---------------------------------------------------------------------------
 C3_HD __forceinline__ int c3l_row_setup(c3l_state &S, const c3_poa_args &A, const c3_poa_ws &W)
 {
@@ -236,11 +269,14 @@ C3_HD __forceinline__ int c3l_row_setup(c3l_state &S, const c3_poa_args &A, cons
     const int rr = qlen - rem;
     const int npre = C3_N_INN(S.nd);
     if (npre > C3_MAXPRE) { S.err = C3L_E_RETRY; return 0; }       // c3_poa_kernel's limit: let it report
-    const c3_prow r0 = W.rows[C3_N_IN0(S.nd)];
+    const c3_prow r0 = (C3_N_IN0(S.nd) == S.vlast) ? S.last : S.ra;
     int mpl = min(S.n, (int)r0.mp), mpr = r0.mp, min_pre_beg = r0.beg;
+    c3_prow r1; r1.off = 0; r1.beg = 16; r1.end = 0; r1.mp = 0; r1.in0 = C3_NONE; r1.link = 0; r1.base = 4; r1.npre = 0;   // empty band
     if (npre > 1) {
-        int e = C3_N_INMORE(S.nd);
-        for (int k = 1; k < npre; ++k) {
+        r1 = (C3L_E_ID(S.pe) == S.vlast) ? S.last : S.rb;
+        mpl = min(mpl, (int)r1.mp); mpr = max(mpr, (int)r1.mp); min_pre_beg = min(min_pre_beg, (int)r1.beg);
+        int e = C3L_E_NEXT(S.pe);
+        for (int k = 2; k < npre; ++k) {
             const c3_pedge pe = W.pool[e]; e = pe.next;
             const c3_prow ri = W.rows[pe.id];
             mpl = min(mpl, (int)ri.mp); mpr = max(mpr, (int)ri.mp); min_pre_beg = min(min_pre_beg, (int)ri.beg);
@@ -252,20 +288,21 @@ C3_HD __forceinline__ int c3l_row_setup(c3l_state &S, const c3_poa_args &A, cons
     const int end_sn = max(end >> 4, beg_sn);
     beg = beg_sn << 4; end = min(qlen, ((end_sn + 1) << 4) - 1);
     if (end - beg + 1 <= 0) { S.err = C3L_E_RETRY; return 0; }
-    S.beg = beg; S.end = end; S.beg_sn = beg_sn; S.end_sn = end_sn; S.r0 = r0;
+    S.beg = beg; S.end = end; S.beg_sn = beg_sn; S.end_sn = end_sn; S.r0 = r0; S.r1 = r1;
     S.nvec = end_sn - beg_sn + 1;
     return S.nvec;
 }
 
-// one predecessor's vector (16 columns from j0) of H, E1, E2, or NEG_INF when outside its band
-C3_HD __forceinline__ void c3l_load_vec(const int4 *ar4, const c3_prow &rp, const int j0, const int lane,
-                                        int (&hv)[16], int (&v1)[16], int (&v2)[16])
+// C3L_NC columns (from j0, a multiple of C3L_NC) of one predecessor's H, E1, E2, or NEG_INF outside its band
+C3_HD __forceinline__ void c3l_load_part(const int4 *ar4, const c3_prow &rp, const int j0, const int lane,
+                                         int (&hv)[C3L_NC], int (&v1)[C3L_NC], int (&v2)[C3L_NC])
 {
     const int pb = rp.beg, pe = rp.end;
     if (j0 >= pb && j0 <= pe) {
-        const int4 *src = ar4 + rp.off + ((j0 - pb) >> 4) * C3L_VSTRIDE + lane;
+        const int c = j0 - pb;
+        const int4 *src = ar4 + rp.off + (c >> 4) * C3L_VSTRIDE + ((c >> 2) & 3) * 32 + lane;
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
+        for (int qd = 0; qd < C3L_NC / 4; ++qd) {
             const int4 a = C3L_LDCS4(src + qd * 32), b = C3L_LDCS4(src + (4 + qd) * 32), c = C3L_LDCS4(src + (8 + qd) * 32);
             hv[4 * qd] = a.x; hv[4 * qd + 1] = a.y; hv[4 * qd + 2] = a.z; hv[4 * qd + 3] = a.w;
             v1[4 * qd] = b.x; v1[4 * qd + 1] = b.y; v1[4 * qd + 2] = b.z; v1[4 * qd + 3] = b.w;
@@ -273,12 +310,14 @@ C3_HD __forceinline__ void c3l_load_vec(const int4 *ar4, const c3_prow &rp, cons
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { hv[k] = C3_NEG_INF; v1[k] = C3_NEG_INF; v2[k] = C3_NEG_INF; }
+        for (int k = 0; k < C3L_NC; ++k) { hv[k] = C3_NEG_INF; v1[k] = C3_NEG_INF; v2[k] = C3_NEG_INF; }
     }
 }
 
 // ---------------------------------------------------------------------------
-// row compute: all vectors of the row set up by c3l_row_setup, row record, advance to the next node
+// row compute: all columns of the row set up by c3l_row_setup in steps of C3L_NC, row record, advance to the
+// next node.  While the cells are computed, everything the NEXT row's setup reads is requested: the row
+// records of its first two predecessors, the node record two rows ahead and that node's first overflow edge.
 // ---------------------------------------------------------------------------
 C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, const c3_poa_para_dev &P, const c3_poa_ws &W,
                                            int32_t *ar, const int base4, const int lane)
@@ -286,82 +325,107 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
     if (S.nvec <= 0) return;
     const int e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const int v = S.v;
-    const int vnext = C3_N_NEXT(S.nd);
-    const c3_nrec nd_next = c3_ld_node(&W.nodes[vnext]);       // prefetch the next row's records
-    const uint32_t hr_next = W.hr[vnext];
+    // ---- look-ahead for the next row (v1) and the one after (v2) ----
+    const int v1 = c3l_cl(C3_N_NEXT(S.nd)), v2 = c3l_cl(C3_N_NEXT(S.nd1)), v3 = c3l_cl(C3_N_NEXT(S.nd2));
+    const c3_nrec nd3 = c3_ld_node(&W.nodes[v3]);
+    const uint32_t hr3 = W.hr[v3];
+    uint2 pe2 = make_uint2(0u, 0u);
+    if (C3_N_INN(S.nd2) > 1) pe2 = c3l_ld_edge(&W.pool[C3_N_INMORE(S.nd2)]);
+    c3_prow ra_n = S.last, rb_n = S.last;
+    {
+        const int in0n = c3l_cl(C3_N_IN0(S.nd1));
+        if (in0n != v) ra_n = W.rows[in0n];
+        if (C3_N_INN(S.nd1) > 1 && C3L_E_ID(S.pe1) != v) rb_n = W.rows[C3L_E_ID(S.pe1)];
+    }
+    (void)v2;
     const int npre = C3_N_INN(S.nd), nbase = C3_N_BASE(S.nd);
     const int beg = S.beg, end = S.end, nvec = S.nvec;
-    const c3_prow r0 = S.r0;
+    const c3_prow r0 = S.r0, r1 = S.r1;
     const int4 *ar4 = reinterpret_cast<const int4 *>(ar);
     int4 *out4 = reinterpret_cast<int4 *>(ar) + base4 + lane;
     const int8_t *qprow = W.qp + (nbase < 4 ? nbase : 0) * A.qp_stride;
-    int f1 = C3_NEG_INF, f2 = C3_NEG_INF, carry0 = C3_NEG_INF;
+    int f1 = C3_NEG_INF, f2 = C3_NEG_INF, carry0 = C3_NEG_INF, carry1 = C3_NEG_INF;
     int bestkey = -0x7fffffff - 1;
-    // software pipeline: the first predecessor's vector and the profile words of vector vi+1 are requested
-    // before vector vi is computed
-    int nh[16], nx1[16], nx2[16];
-    uint4 nsw = make_uint4(0u, 0u, 0u, 0u);
-    c3l_load_vec(ar4, r0, beg, lane, nh, nx1, nx2);
-    if (nbase < 4) nsw = *reinterpret_cast<const uint4 *>(qprow + beg);
-    for (int vi = 0; vi < nvec; ++vi) {
-        const int j0 = beg + 16 * vi;
-        int m[16], x1[16], x2[16];
-        const uint4 sw = nsw;
-        m[0] = carry0;
+    // software pipeline: both predecessors' cells and the profile words of step h+1 are requested before
+    // step h is computed
+    int nh[C3L_NC], nx1[C3L_NC], nx2[C3L_NC], ph[C3L_NC], px1[C3L_NC], px2[C3L_NC];
+    uint32_t nsw[C3L_NC / 4];
 #pragma unroll
-        for (int k = 1; k < 16; ++k) m[k] = nh[k - 1];
-        carry0 = nh[15];
+    for (int t = 0; t < C3L_NC / 4; ++t) nsw[t] = 0u;
+    c3l_load_part(ar4, r0, beg, lane, nh, nx1, nx2);
+    c3l_load_part(ar4, r1, beg, lane, ph, px1, px2);
+    if (nbase < 4) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { x1[k] = nx1[k]; x2[k] = nx2[k]; }
-        if (vi + 1 < nvec) {
-            c3l_load_vec(ar4, r0, j0 + 16, lane, nh, nx1, nx2);
-            if (nbase < 4) nsw = *reinterpret_cast<const uint4 *>(qprow + j0 + 16);
-        }
-        if (npre > 1) {
-            int e = C3_N_INMORE(S.nd);
-            for (int k = 1; k < npre; ++k) {
-                const c3_pedge pe = W.pool[e]; e = pe.next;
-                const c3_prow rp = W.rows[pe.id];
-                int hv[16], v1[16], v2[16];
-                c3l_load_vec(ar4, rp, j0, lane, hv, v1, v2);
-                const int jc = j0 - 1;
-                int prev = C3_NEG_INF;
-                if (vi > 0 && jc >= (int)rp.beg && jc <= (int)rp.end) prev = C3L_LDCS1(ar + c3l_ci(rp.off, 0, jc - rp.beg, lane));
-                m[0] = max(m[0], prev);
+        for (int t = 0; t < C3L_NC / 4; ++t) nsw[t] = *reinterpret_cast<const uint32_t *>(qprow + beg + 4 * t);
+    }
+    const int nstep = nvec * (16 / C3L_NC);
+    for (int h = 0; h < nstep; ++h) {
+        const int j0 = beg + C3L_NC * h;
+        int m[C3L_NC], x1[C3L_NC], x2[C3L_NC];
+        uint32_t swv[C3L_NC / 4];
 #pragma unroll
-                for (int t = 1; t < 16; ++t) m[t] = max(m[t], hv[t - 1]);
+        for (int t = 0; t < C3L_NC / 4; ++t) swv[t] = nsw[t];
+        m[0] = max(carry0, carry1);
 #pragma unroll
-                for (int t = 0; t < 16; ++t) { x1[t] = max(x1[t], v1[t]); x2[t] = max(x2[t], v2[t]); }
+        for (int k = 1; k < C3L_NC; ++k) m[k] = max(nh[k - 1], ph[k - 1]);
+        carry0 = nh[C3L_NC - 1]; carry1 = ph[C3L_NC - 1];
+#pragma unroll
+        for (int k = 0; k < C3L_NC; ++k) { x1[k] = max(nx1[k], px1[k]); x2[k] = max(nx2[k], px2[k]); }
+        if (h + 1 < nstep) {
+            c3l_load_part(ar4, r0, j0 + C3L_NC, lane, nh, nx1, nx2);
+            c3l_load_part(ar4, r1, j0 + C3L_NC, lane, ph, px1, px2);
+            if (nbase < 4) {
+#pragma unroll
+                for (int t = 0; t < C3L_NC / 4; ++t) nsw[t] = *reinterpret_cast<const uint32_t *>(qprow + j0 + C3L_NC + 4 * t);
             }
         }
-        const uint32_t swv[4] = {sw.x, sw.y, sw.z, sw.w};
-        int hme[16];
+        if (npre > 2) {                                  // third and further predecessors: rare, not pipelined
+            int e = C3L_E_NEXT(S.pe);
+            for (int k = 2; k < npre; ++k) {
+                const c3_pedge pe = W.pool[e]; e = pe.next;
+                const c3_prow rp = W.rows[pe.id];
+                int hv[C3L_NC], v1[C3L_NC], v2[C3L_NC];
+                c3l_load_part(ar4, rp, j0, lane, hv, v1, v2);
+                const int jc = j0 - 1;
+                int prev = C3_NEG_INF;
+                if (h > 0 && jc >= (int)rp.beg && jc <= (int)rp.end) prev = C3L_LDCS1(ar + c3l_ci(rp.off, 0, jc - rp.beg, lane));
+                m[0] = max(m[0], prev);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+                for (int t = 1; t < C3L_NC; ++t) m[t] = max(m[t], hv[t - 1]);
+#pragma unroll
+                for (int t = 0; t < C3L_NC; ++t) { x1[t] = max(x1[t], v1[t]); x2[t] = max(x2[t], v2[t]); }
+            }
+        }
+        const int vi = (C3L_NC * h) >> 4;
+        if (((C3L_NC * h) & 15) == 0)                   // F entering this 16-column vector: the backtrack restarts from it
+            *reinterpret_cast<int2 *>(ar + c3l_fi(base4, vi, lane)) = make_int2(f1, f2);
+        int hme[C3L_NC];
+#pragma unroll
+        for (int k = 0; k < C3L_NC; ++k) {
             const int sc = (int)(int8_t)(swv[k >> 2] >> (8 * (k & 3)));
             hme[k] = C3L_MAX3(m[k] + sc, x1[k], x2[k]);
         }
-        const int lim = end - j0;                       // last active column of this vector (>= 15: all)
-        if (lim < 15) {
+        const int lim = end - j0;                       // last active column of this step (>= C3L_NC - 1: all)
+        if (lim < C3L_NC - 1) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) if (k > lim) hme[k] = C3_NEG_INF;
+            for (int k = 0; k < C3L_NC; ++k) if (k > lim) hme[k] = C3_NEG_INF;
         }
-        int hh[16], n1[16], n2[16];
+        int hh[C3L_NC], n1[C3L_NC], n2[C3L_NC];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < C3L_NC; ++k) {
             hh[k] = C3L_MAX3(hme[k], f1, f2);
             f1 = C3L_ADDMAX(f1, -e1, hme[k] - oe1);
             f2 = C3L_ADDMAX(f2, -e2, hme[k] - oe2);
             n1[k] = C3L_ADDMAX(hh[k], -oe1, x1[k] - e1);
             n2[k] = C3L_ADDMAX(hh[k], -oe2, x2[k] - e2);
         }
-        if (lim < 15) {
+        if (lim < C3L_NC - 1) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) if (k > lim) { hh[k] = C3_NEG_INF; n1[k] = C3_NEG_INF; n2[k] = C3_NEG_INF; }
+            for (int k = 0; k < C3L_NC; ++k) if (k > lim) { hh[k] = C3_NEG_INF; n1[k] = C3_NEG_INF; n2[k] = C3_NEG_INF; }
         }
-        int4 *dst = out4 + vi * C3L_VSTRIDE;
+        int4 *dst = out4 + vi * C3L_VSTRIDE + (((C3L_NC * h) >> 2) & 3) * 32;
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
+        for (int qd = 0; qd < C3L_NC / 4; ++qd) {
             dst[qd * 32] = make_int4(hh[4 * qd], hh[4 * qd + 1], hh[4 * qd + 2], hh[4 * qd + 3]);
             dst[(4 + qd) * 32] = make_int4(n1[4 * qd], n1[4 * qd + 1], n1[4 * qd + 2], n1[4 * qd + 3]);
             dst[(8 + qd) * 32] = make_int4(n2[4 * qd], n2[4 * qd + 1], n2[4 * qd + 2], n2[4 * qd + 3]);
@@ -369,10 +433,11 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
         // simd_abpoa_ada_max_i as one packed max: value in the high half, tie-break priority in the low half
         // (lowest SIMD lane, then the last vector, then the earliest vector)
         const int vp = (vi == nvec - 1) ? 0xfff : (0xffe - vi);
+        const int k16 = (C3L_NC * h) & 15;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < C3L_NC; ++k) {
             const int hc = max(hh[k], -32768);
-            bestkey = C3L_ADDMAX((int)((unsigned)hc << 16) + vp, (15 - k) << 12, bestkey);
+            bestkey = C3L_ADDMAX((int)((unsigned)hc << 16) + vp, (15 - k16 - k) << 12, bestkey);
         }
     }
     int best_i = -1;
@@ -386,11 +451,13 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
     ri.in0 = (uint16_t)C3_N_IN0(S.nd); ri.base = (uint8_t)nbase; ri.npre = (uint8_t)npre;
     ri.link = (uint16_t)S.rcount;
     W.rows[v] = ri;
+    S.last = ri; S.vlast = v;
     ri.link = (uint16_t)v; ri.mp = r0.link;
     W.ord[S.rcount] = ri;
     S.cells_total += end - beg + 1;
     ++S.rcount;
-    S.v = vnext; S.nd = nd_next; S.hrv = hr_next;
+    S.v = v1; S.nd = S.nd1; S.hrv = S.hr1; S.nd1 = S.nd2; S.hr1 = S.hr2; S.nd2 = nd3; S.hr2 = hr3;
+    S.pe = S.pe1; S.pe1 = pe2; S.ra = ra_n; S.rb = rb_n;
     S.nvec = 0;
 }
 
@@ -489,13 +556,25 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
                 }
             }
             if (!hit && (cur_op & C3_OP_F) && j - 1 >= b) {
-                // F is not stored: rebuild F[j] and F[j-1] of this row from its H
-                int f1 = C3_NEG_INF, f2 = C3_NEG_INF, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
-                C3L_COUNT(12, 1); C3L_COUNT(13, j - b);
-                for (int c = 0; c < j - b; ++c) {
-                    hl = ar[c3l_ci(rt.off, 0, c, lane)];
-                    f1l = f1; f2l = f2;
-                    f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
+                // F is stored only where it enters a 16-column vector: rebuild F[j-1] and F[j] from there
+                const int cm = j - 1 - b, vs = cm >> 4, tm = cm & 15;
+                const int2 fin = *reinterpret_cast<const int2 *>(ar + c3l_fi(rt.off, vs, lane));
+                const int4 *hp = reinterpret_cast<const int4 *>(ar) + rt.off + vs * C3L_VSTRIDE + lane;
+                int hq[16];
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const int4 a4 = hp[qd * 32];
+                    hq[4 * qd] = a4.x; hq[4 * qd + 1] = a4.y; hq[4 * qd + 2] = a4.z; hq[4 * qd + 3] = a4.w;
+                }
+                int f1 = fin.x, f2 = fin.y, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
+                C3L_COUNT(12, 1);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c <= tm) {
+                        hl = hq[c];
+                        f1l = f1; f2l = f2;
+                        f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
+                    }
                 }
                 if (cur_op & C3_OP_F1) {
                     if (!(cur_op & C3_OP_M) || hij == f1) {

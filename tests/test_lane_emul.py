@@ -65,7 +65,7 @@ def run_emul(lib, groups, para=None, msa2=0, min_seqs=1, node_cap=None, arena_ca
     qp_stride = (max_q + 48) & ~15
     if arena_cap4 is None:
         w = p["wb"] + int(p["wf"] * max_q)
-        arena_cap4 = node_cap * ((2 * w + 64 + 16) // 16 + 2) * 384
+        arena_cap4 = node_cap * ((2 * w + 64 + 16) // 16 + 2) * 400
     cons_cap = max_q * 2 + 64
     cons = np.zeros((n, cons_cap), dtype=np.uint8)
     status = np.full(n, -1, dtype=np.int32)
@@ -158,5 +158,5 @@ def test_lane_declines_what_it_does_not_cover(emul):
     assert not run_emul(emul, [g], para=dict(simd_bits=128))["done"][0]
     assert not run_emul(emul, [g], para=dict(wb=-1))["done"][0]
     # arena / node capacity overflow -> not done, nothing reported
-    assert not run_emul(emul, [g], arena_cap4=384 * 40)["done"][0]
+    assert not run_emul(emul, [g], arena_cap4=400 * 40)["done"][0]
     assert not run_emul(emul, [g], node_cap=320)["done"][0]

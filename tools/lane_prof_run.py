@@ -7,7 +7,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, '.')
-os.environ['C3POA_GPU_LIB'] = 'build/variants/lib_lprof.so'
+os.environ.setdefault('C3POA_GPU_LIB', 'build/variants/lib_lprof.so')
 from c3poa_b200 import synth, _lib  # noqa: E402
 from c3poa_b200.api import GpuConsensus, ReadBatch  # noqa: E402
 
@@ -19,12 +19,14 @@ b = ReadBatch(blob, off, np.frombuffer(sp.encode(), dtype=np.uint8).copy(), np.a
 g = GpuConsensus(0, poa_mode="lane")
 z = (C.c_ulonglong * 16)()
 g.consensus_batch(b, max_peaks=16, cons_cap=2048)
-L.c3_debug_lane_prof(z, 1)
+if hasattr(L, 'c3_debug_lane_prof'):
+    L.c3_debug_lane_prof(z, 1)
 out = g.consensus_batch(b, max_peaks=16, cons_cap=2048)
-L.c3_debug_lane_prof(z, 0)
+if hasattr(L, 'c3_debug_lane_prof'):
+    L.c3_debug_lane_prof(z, 0)
 v = list(z)
 names = ['item_begin', 'align_begin', 'source_row', 'row_setup', 'row_compute', 'align_end(rest)', 'backtrack', 'merge', 'item_end']
-tot = sum(v[:9])
+tot = max(sum(v[:9]), 1)
 for i, nm in enumerate(names):
     print(f'{nm:18s} {v[i]/1e9:10.3f} Gcycles {100*v[i]/tot:6.2f} %')
 print('warp row steps', v[9], 'mean mv', v[10] / max(v[9], 1), 'cycles/row-step compute', v[4] / max(v[9], 1), 'setup', v[3] / max(v[9], 1))
