@@ -325,8 +325,17 @@ static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa
     if (arena4 > 0x7fffff00ll / 4) return 0;                       // int32 cell indices
     const int64_t warp_bytes = 32 * ws_bytes + arena4 * 16;
     const int wpb = C3L_THREADS / 32;
+    // shared-memory ring of the row just computed: vec_est slots of 3 KB per warp, cut down if C3L_MINB CTAs
+    // would not fit the SM (rows wider than the ring are simply not mirrored)
+    int sm_vec = (int)vec_est;
+    {
+        const int per_cta_max = (C3L_SMEM_KB * 1024) / C3L_MINB;
+        sm_vec = std::max(1, std::min(sm_vec, per_cta_max / (wpb * 3072)));
+    }
+    const size_t sm_bytes = (size_t)wpb * sm_vec * 3072;
+    CK(cudaFuncSetAttribute(c3_poa_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_bytes));
     int bps = 4;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_lane_kernel, C3L_THREADS, 0) != cudaSuccess || bps < 1) bps = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_lane_kernel, C3L_THREADS, sm_bytes) != cudaSuccess || bps < 1) bps = 4;
     bps = std::min(bps, C3L_MINB);
     int64_t warps = (int64_t)h->sm_count * bps * wpb;
     warps = std::min<int64_t>(warps, ((int64_t)nl + 31) / 32);
@@ -348,9 +357,9 @@ static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa
     L.A.counter = h->d_counter.as<unsigned>();
     L.A.order = h->d_order_lane.as<int32_t>(); L.A.n_work = nl;
     L.arena = reinterpret_cast<int4 *>(h->d_ws.as<uint8_t>() + warps * 32 * ws_bytes);
-    L.arena_stride4 = arena4; L.arena_cap4 = (int)arena4;
+    L.arena_stride4 = arena4; L.arena_cap4 = (int)arena4; L.sm_vec = sm_vec;
     L.done = h->d_done.as<int32_t>();
-    c3_poa_lane_kernel<<<(int)(warps / wpb), C3L_THREADS, 0, h->stream>>>(L);
+    c3_poa_lane_kernel<<<(int)(warps / wpb), C3L_THREADS, sm_bytes, h->stream>>>(L);
     CK(cudaGetLastError());
     h->tim.kernel_launches++;
     h->lane_items = nl; h->lane_n_items = A.n_items;

@@ -10,12 +10,18 @@
 //                 horizontal (F) gap is a plain in-thread recurrence (no warp scan), the row arg-max is one
 //                 packed max per cell (no REDUX), and backtrack / merge / consensus run 32 at a time.
 //
-// DP rows live in a per-warp arena, interleaved by lane so that the warp's loads and stores are coalesced:
-// the s-th row step of a warp owns `mv` vectors (mv = widest band among the 32 threads, in 16-column
-// vectors = abPOA's int16 SIMD granule); vector vi holds H, E1, E2 as 3 x 4 int4 per lane at
-//     int4 index  base4 + vi*384 + (array*4 + quarter)*32 + lane.
-// Columns past a row's band end inside its last vector hold NEG_INF, so successors load whole vectors.
-// Graph, row records, cigar and the int8 query profile are thread-private (c3_poa_ws without cells).
+// DP rows live in a per-warp arena, interleaved by lane so that the warp's loads and stores are coalesced.
+// Cells are STORED as int16 (abPOA's own lane width in this score mode; arithmetic stays int32 in registers):
+// the s-th row step of a warp owns `mv` vectors (mv = widest band among the 32 threads, in 16-column vectors
+// = abPOA's int16 SIMD granule); vector vi holds, per lane, H / E1 / E2 as 3 x 2 uint4 (8 columns each) and the
+// (F1, F2) pair entering the vector:
+//     uint4 index  base4 + vi*208 + (array*2 + half)*32 + lane,       F pair: int2 at uint4 index base4 + vi*208 + 192
+// Values below -32768 are stored as -32768; a loaded H of -32768 reads back as NEG_INF.  That is exact as long
+// as every reachable cell stays above -32768+64, which the row loop checks (else the read goes to the warp
+// kernel).  Columns past a row's band end inside its last vector hold -32768, so successors load whole vectors.
+// The row just computed is also kept in shared memory (same packed form, ring of `smR` vector slots per lane,
+// slot = absolute vector index mod smR): the usual first predecessor -- the previous row -- never comes from L2.
+// Graph, row records, cigar and the column codes of the query are thread-private (c3_poa_ws without cells).
 //
 // Scope: int16-lane score mode with the 256-bit granule (pn = 16), banded (wb >= 0), consensus output
 // (2-sequence MSA rows stay with poa.cuh).  Anything else -- and any capacity overflow -- leaves the item
@@ -27,10 +33,11 @@
 #include "poa.cuh"
 
 #define C3L_E_RETRY (-299)
-#define C3L_VSTRIDE 400            // int4 per 16-column vector of one warp step: 3 arrays x 4 quarters x 32 lanes + 32 x (F1,F2) carry-in
-#ifndef C3L_NC
-#define C3L_NC 8                   // columns per software-pipeline step of the row loop (8 or 16)
+#define C3L_VSTRIDE 208            // uint4 per 16-column vector of one warp step: 3 arrays x 2 halves x 32 lanes + 32 x (F1,F2) carry-in
+#ifndef C3L_SMEM_KB
+#define C3L_SMEM_KB 200            // shared memory per SM the rings may take (the rest of the 228 KB stays L1)
 #endif
+#define C3L_LOW_GUARD 64           // reachable cells must stay above -32768 + C3L_LOW_GUARD
 #ifndef C3L_THREADS
 #define C3L_THREADS 64
 #endif
@@ -46,12 +53,34 @@
 #define C3L_ADDMAX(a, b, c) __viaddmax_s32((a), (b), (c))
 #define C3L_MAX3(a, b, c) __vimax3_s32((a), (b), (c))
 #define C3L_ANY(x) __any_sync(C3_FULL, (x))
+#ifdef C3L_EXP_PLAINLD
+#define C3L_LDCS4(p) (*(p))
+#else
 #define C3L_LDCS4(p) __ldcs(p)           // DP rows are read once by the successor row: stream them (evict-first)
-#define C3L_LDCS1(p) __ldcs(p)
+#endif
+#define C3L_UMIN(a, b) min((unsigned)(a), (unsigned)(b))
+#define C3L_PACK2(lo, hi) __byte_perm((unsigned)(lo), (unsigned)(hi), 0x5410)
+#define C3L_VMAX2(a, b) __vmaxs2((a), (b))          // per-halfword signed max: VIMNMX.S16x2
+#define C3L_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#ifdef C3L_PF2
+#define C3L_PREFETCH2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#else
+#define C3L_PREFETCH2(p) do { } while (0)
+#endif
 #else
 #define C3L_ANY(x) (x)
 #define C3L_LDCS4(p) (*(p))
-#define C3L_LDCS1(p) (*(p))
+static inline unsigned c3l_humin(unsigned a, unsigned b) { return a < b ? a : b; }
+#define C3L_UMIN(a, b) c3l_humin((unsigned)(a), (unsigned)(b))
+#define C3L_PACK2(lo, hi) (((unsigned)(lo) & 0xffffu) | ((unsigned)(hi) << 16))
+static inline unsigned c3l_hvmax2(unsigned a, unsigned b)
+{
+    const int al = (int16_t)(a & 0xffffu), ah = (int16_t)(a >> 16), bl = (int16_t)(b & 0xffffu), bh = (int16_t)(b >> 16);
+    return ((unsigned)(al > bl ? al : bl) & 0xffffu) | ((unsigned)(ah > bh ? ah : bh) << 16);
+}
+#define C3L_VMAX2(a, b) c3l_hvmax2((a), (b))
+#define C3L_PREFETCH(p) do { } while (0)
+#define C3L_PREFETCH2(p) do { } while (0)
 static inline int c3l_hmax(int a, int b) { return a > b ? a : b; }
 #define C3L_ADDMAX(a, b, c) c3l_hmax((a) + (b), (c))
 #define C3L_MAX3(a, b, c) c3l_hmax(c3l_hmax((a), (b)), (c))
@@ -81,24 +110,55 @@ struct c3l_state {
     c3_nrec nd, nd1, nd2; uint32_t hrv, hr1, hr2;     // look-ahead: records of v and of the next two nodes of the list
     uint2 pe, pe1;                                    // first overflow in-edge of v / next(v) (in_n > 1)
     c3_prow ra, rb;                                   // row records of v's first two predecessors (unless == vlast)
-    c3_prow last; int vlast;                          // the row just computed
+    c3_prow last; int vlast, last_sm;                 // the row just computed; last_sm: it is in the shared-memory ring
     int beg, end, nvec, beg_sn, end_sn; c3_prow r0, r1;   // the row between setup and compute
 };
 
-// int32 index of column c (relative to the row's band start) of array a in the row stored at off4
+// int16 index of column c (relative to the row's band start) of array a in the row stored at off4
 C3_HD __forceinline__ int c3l_ci(int off4, int a, int c, int lane)
 {
-    return ((off4 + (c >> 4) * C3L_VSTRIDE + ((a << 2) + ((c >> 2) & 3)) * 32 + lane) << 2) + (c & 3);
+    return ((off4 + (c >> 4) * C3L_VSTRIDE + ((a << 1) + ((c >> 3) & 1)) * 32 + lane) << 3) + (c & 7);
 }
+// stored cells: H reads -32768 back as NEG_INF; E1 / E2 stay as stored (they only feed max() and inequalities)
+C3_HD __forceinline__ int c3l_map(const int v) { return v == -32768 ? C3_NEG_INF : v; }
+C3_HD __forceinline__ int c3l_ld_h(const int32_t *ar, const int idx16) { return c3l_map((int)reinterpret_cast<const int16_t *>(ar)[idx16]); }
+C3_HD __forceinline__ int c3l_ld_e(const int32_t *ar, const int idx16) { return (int)reinterpret_cast<const int16_t *>(ar)[idx16]; }
+
+// node / edge / row records by index, with the list terminator (C3_NONE) mapped to the sink so that the
+// look-ahead past the end of the walk stays inside the workspace
+C3_HD __forceinline__ int c3l_cl(const int v) { return v == (int)C3_NONE ? C3_SINK : v; }
+C3_HD __forceinline__ uint2 c3l_ld_edge(const c3_pedge *p) { return *reinterpret_cast<const uint2 *>(p); }
+#define C3L_E_ID(e) ((int)((e).x & 0xffffu))
+#define C3L_E_NEXT(e) ((int)((e).y & 0xffffu))
 
 // int32 index of the (F1, F2) pair entering vector vi of the row stored at off4
-C3_HD __forceinline__ int c3l_fi(int off4, int vi, int lane) { return ((off4 + vi * C3L_VSTRIDE + 384) << 2) + 2 * lane; }
+C3_HD __forceinline__ int c3l_fi(int off4, int vi, int lane) { return ((off4 + vi * C3L_VSTRIDE + 192) << 2) + 2 * lane; }
+
+C3_HD __forceinline__ void c3l_unpack8(const uint4 w, int (&o)[8])
+{
+    o[0] = (int)(int16_t)(w.x & 0xffffu); o[1] = (int)w.x >> 16;
+    o[2] = (int)(int16_t)(w.y & 0xffffu); o[3] = (int)w.y >> 16;
+    o[4] = (int)(int16_t)(w.z & 0xffffu); o[5] = (int)w.z >> 16;
+    o[6] = (int)(int16_t)(w.w & 0xffffu); o[7] = (int)w.w >> 16;
+}
+C3_HD __forceinline__ uint4 c3l_vmax8(const uint4 a, const uint4 b)
+{
+    return make_uint4(C3L_VMAX2(a.x, b.x), C3L_VMAX2(a.y, b.y), C3L_VMAX2(a.z, b.z), C3L_VMAX2(a.w, b.w));
+}
+C3_HD __forceinline__ uint4 c3l_pack8(const int (&v)[8])
+{
+    int c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = max(v[k], -32768);
+    return make_uint4(C3L_PACK2(c[0], c[1]), C3L_PACK2(c[2], c[3]), C3L_PACK2(c[4], c[5]), C3L_PACK2(c[6], c[7]));
+}
 
 // ---------------------------------------------------------------------------
 // item start: first sequence -> linear graph
 // ---------------------------------------------------------------------------
 C3_HD __forceinline__ void c3l_item_begin(c3l_state &S, const c3_poa_args &A, const c3_poa_ws &W, const int item, const bool have)
 {
+    const int P_ms = A.P.match + A.P.mismatch;
     S.item = item; S.on = 0; S.err = 0; S.nseq = 0; S.node_n = 0; S.pool_n = 0; S.cells_total = 0; S.aligning = 0;
     S.v = C3_SINK; S.nvec = 0;
     const uint8_t *q = nullptr;
@@ -111,7 +171,7 @@ C3_HD __forceinline__ void c3l_item_begin(c3l_state &S, const c3_poa_args &A, co
             S.on = 1; S.nseq = nseq;
             q = S.ibase + S.bnd[0];
             L = S.bnd[1] - S.bnd[0];
-            if (L <= 0 || L > 65000 || L + 2 > A.node_cap) S.err = C3L_E_RETRY;
+            if (L <= 0 || L > 65000 || L + 2 > A.node_cap || P_ms > 255) S.err = C3L_E_RETRY;
             else cnt = L + 2;
         }
     }
@@ -128,6 +188,7 @@ C3_HD __forceinline__ void c3l_item_begin(c3l_state &S, const c3_poa_args &A, co
             n.prev = (uint16_t)(L + 1); n.next = C3_NONE;
         } else {
             n.base = q[i - 2]; n.in_n = 1; n.out_n = 1; n.w0 = 1;
+            if (n.base >= 4) S.err = C3L_E_RETRY;           // N: scored 0 against everything -- the warp kernel's business
             n.in0 = (uint16_t)(i == 2 ? C3_SRC : i - 1);
             n.out0 = (uint16_t)(i == L + 1 ? C3_SINK : i + 1);
             n.prev = n.in0; n.next = n.out0;
@@ -158,45 +219,47 @@ C3_HD __forceinline__ int c3l_align_begin(c3l_state &S, const c3_poa_args &A, co
         else { S.q = q; S.qlen = qlen; S.n = n; S.w = P.wb + (int)(P.wf * (double)qlen); }
     }
     // remaining path length along the heaviest out-edges: hops(v -> sink), reverse list walk
+    // (the next node's record is requested before this node's hops are resolved: one load latency per node)
     int v = C3_NONE;
     if (act) { W.hr[C3_SINK] = C3_SINK; v = W.nodes[C3_SINK].prev; }
+    c3_nrec cur = c3_ld_node(&W.nodes[c3l_cl(v)]);
+    int cur_om = W.nodes[c3l_cl(v)].out_more;
     while (C3L_ANY(v != C3_NONE)) {
         if (v == C3_NONE) continue;
-        const c3_pnode *nd = &W.nodes[v];
-        int best_w = nd->w0, best = nd->out0;
-        uint16_t e = nd->out_more;
-        while (e != C3_NONE) {
+        const int pv = C3_N_PREV(cur);
+        const c3_nrec nxt = c3_ld_node(&W.nodes[c3l_cl(pv)]);
+        const int nxt_om = W.nodes[c3l_cl(pv)].out_more;
+        int best_w = C3_N_W0(cur), best = C3_N_OUT0(cur);
+        int e = cur_om;
+        while (e != (int)C3_NONE) {
             const c3_pedge pe = W.pool[e];
             if ((int)pe.w > best_w) { best_w = pe.w; best = pe.id; }
             e = pe.next;
         }
         W.hr[v] = ((W.hr[best] >> 16) + 1u) << 16;
-        v = nd->prev;
+        v = pv; cur = nxt; cur_om = nxt_om;
     }
-    // query profile: int8 scores per node base, 16 columns per store; column j scores q[j-1], j = 0 scores 0
+    // column codes: qa[j] = base code of column j (= q[j-1]), 16 columns per store; j = 0 and the padding hold 4.
+    // The row loop scores 4 columns per word against the node base on the fly (no per-base profile in memory: with
+    // 256 threads per SM a 4-row profile does not stay in L1).  A sequence with an N is not handled here.
     {
-        const int qs = A.qp_stride, jmax = act ? ((qlen + 16) & ~15) : 0;   // the DP reads vectors up to column qlen | 15
+        const int jmax = act ? ((qlen + 16) & ~15) : 0;   // the DP reads vectors up to column qlen | 15
+        bool has_n = false;
         for (int j0 = 0; C3L_ANY(j0 < jmax); j0 += 16) {
             if (j0 >= jmax) continue;
-            uint32_t wv[4][4];
-#pragma unroll
-            for (int b4 = 0; b4 < 4; ++b4)
-#pragma unroll
-                for (int t = 0; t < 4; ++t) wv[b4][t] = 0;
+            uint32_t wv[4] = {0x04040404u, 0x04040404u, 0x04040404u, 0x04040404u};
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int j = j0 + k;
                 if (j >= 1 && j <= qlen) {
-                    const int qc = q[j - 1];
-#pragma unroll
-                    for (int b4 = 0; b4 < 4; ++b4)
-                        wv[b4][k >> 2] |= (uint32_t)(uint8_t)(int8_t)c3_score(P, b4, qc) << (8 * (k & 3));
+                    const uint32_t qc = q[j - 1];
+                    has_n |= qc >= 4;
+                    wv[k >> 2] = (wv[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (qc << (8 * (k & 3)));
                 }
             }
-#pragma unroll
-            for (int b4 = 0; b4 < 4; ++b4)
-                *reinterpret_cast<uint4 *>(W.qp + b4 * qs + j0) = make_uint4(wv[b4][0], wv[b4][1], wv[b4][2], wv[b4][3]);
+            *reinterpret_cast<uint4 *>(W.qp + j0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
+        if (has_n) { S.err = C3L_E_RETRY; act = false; }
     }
     if (!act) return 0;
     // source row band
@@ -209,13 +272,6 @@ C3_HD __forceinline__ int c3l_align_begin(c3l_state &S, const c3_poa_args &A, co
     S.aligning = 1;
     return S.nvec;
 }
-
-// node / edge / row records by index, with the list terminator (C3_NONE) mapped to the sink so that the
-// look-ahead past the end of the walk stays inside the workspace
-C3_HD __forceinline__ int c3l_cl(const int v) { return v == (int)C3_NONE ? C3_SINK : v; }
-C3_HD __forceinline__ uint2 c3l_ld_edge(const c3_pedge *p) { return *reinterpret_cast<const uint2 *>(p); }
-#define C3L_E_ID(e) ((int)((e).x & 0xffffu))
-#define C3L_E_NEXT(e) ((int)((e).y & 0xffffu))
 
 // source row cells + records; positions the row walk on the first node after the source and fills the
 // look-ahead (records of the next two nodes, first overflow in-edges, predecessor row records)
@@ -230,16 +286,19 @@ C3_HD __forceinline__ void c3l_source_row(c3l_state &S, const c3_poa_para_dev &P
     S.last = ri; S.vlast = C3_SRC;
     ri.mp = C3_NONE;
     W.ord[0] = ri;
+    int16_t *ar16 = reinterpret_cast<int16_t *>(ar);
     for (int vi = 0; vi < S.nvec; ++vi)
         *reinterpret_cast<int2 *>(ar + c3l_fi(0, vi, lane)) = make_int2(C3_NEG_INF, C3_NEG_INF);
     for (int c = 0; c < 16 * S.nvec; ++c) {
-        int h = C3_NEG_INF, x1 = C3_NEG_INF, x2 = C3_NEG_INF;
+        int h = -32768, x1 = -32768, x2 = -32768;
         if (b0 == 0 && c < wd) {
             if (c == 0) { h = 0; x1 = -oe1; x2 = -oe2; }
             else h = max(-(P.o1 + P.e1 * c), -(P.o2 + P.e2 * c));
+            if (h < -32768 + C3L_LOW_GUARD) S.err = C3L_E_RETRY;
         }
-        ar[c3l_ci(0, 0, c, lane)] = h; ar[c3l_ci(0, 1, c, lane)] = x1; ar[c3l_ci(0, 2, c, lane)] = x2;
+        ar16[c3l_ci(0, 0, c, lane)] = (int16_t)h; ar16[c3l_ci(0, 1, c, lane)] = (int16_t)x1; ar16[c3l_ci(0, 2, c, lane)] = (int16_t)x2;
     }
+    S.last_sm = 0;
     S.v = W.nodes[C3_SRC].next; S.rcount = 1;
     S.nd = c3_ld_node(&W.nodes[S.v]); S.hrv = W.hr[S.v];
     const int v1 = c3l_cl(C3_N_NEXT(S.nd));
@@ -268,7 +327,7 @@ C3_HD __forceinline__ int c3l_row_setup(c3l_state &S, const c3_poa_args &A, cons
     const int rem = (int)(S.hrv >> 16) - 1;
     const int rr = qlen - rem;
     const int npre = C3_N_INN(S.nd);
-    if (npre > C3_MAXPRE) { S.err = C3L_E_RETRY; return 0; }       // c3_poa_kernel's limit: let it report
+    if (npre > C3_MAXPRE || C3_N_BASE(S.nd) >= 4) { S.err = C3L_E_RETRY; return 0; }   // c3_poa_kernel's limit / an N node: let it handle
     const c3_prow r0 = (C3_N_IN0(S.nd) == S.vlast) ? S.last : S.ra;
     int mpl = min(S.n, (int)r0.mp), mpr = r0.mp, min_pre_beg = r0.beg;
     c3_prow r1; r1.off = 0; r1.beg = 16; r1.end = 0; r1.mp = 0; r1.in0 = C3_NONE; r1.link = 0; r1.base = 4; r1.npre = 0;   // empty band
@@ -293,40 +352,39 @@ C3_HD __forceinline__ int c3l_row_setup(c3l_state &S, const c3_poa_args &A, cons
     return S.nvec;
 }
 
-// C3L_NC columns (from j0, a multiple of C3L_NC) of one predecessor's H, E1, E2, or NEG_INF outside its band
-C3_HD __forceinline__ void c3l_load_part(const int4 *ar4, const c3_prow &rp, const int j0, const int lane,
-                                         int (&hv)[C3L_NC], int (&v1)[C3L_NC], int (&v2)[C3L_NC])
+// 8 columns (from j0, a multiple of 8) of one predecessor's packed H, E1, E2 -- from the arena, or from the
+// shared-memory ring when the predecessor is the row just computed; outside its band: all -32768
+C3_HD __forceinline__ void c3l_load8(const uint4 *ar4, const uint4 *sm, const bool from_sm, const int slot,
+                                     const c3_prow &rp, const int j0, const int lane, uint4 &a, uint4 &b, uint4 &c)
 {
-    const int pb = rp.beg, pe = rp.end;
-    if (j0 >= pb && j0 <= pe) {
-        const int c = j0 - pb;
-        const int4 *src = ar4 + rp.off + (c >> 4) * C3L_VSTRIDE + ((c >> 2) & 3) * 32 + lane;
-#pragma unroll
-        for (int qd = 0; qd < C3L_NC / 4; ++qd) {
-            const int4 a = C3L_LDCS4(src + qd * 32), b = C3L_LDCS4(src + (4 + qd) * 32), c = C3L_LDCS4(src + (8 + qd) * 32);
-            hv[4 * qd] = a.x; hv[4 * qd + 1] = a.y; hv[4 * qd + 2] = a.z; hv[4 * qd + 3] = a.w;
-            v1[4 * qd] = b.x; v1[4 * qd + 1] = b.y; v1[4 * qd + 2] = b.z; v1[4 * qd + 3] = b.w;
-            v2[4 * qd] = c.x; v2[4 * qd + 1] = c.y; v2[4 * qd + 2] = c.z; v2[4 * qd + 3] = c.w;
+    if (j0 >= (int)rp.beg && j0 <= (int)rp.end) {
+        if (from_sm) {
+            const uint4 *src = sm + (slot * 6 + ((j0 >> 3) & 1)) * 32 + lane;
+            a = src[0]; b = src[64]; c = src[128];
+        } else {
+            const int cc = j0 - rp.beg;
+            const uint4 *src = ar4 + rp.off + (cc >> 4) * C3L_VSTRIDE + ((cc >> 3) & 1) * 32 + lane;
+            a = C3L_LDCS4(src); b = C3L_LDCS4(src + 64); c = C3L_LDCS4(src + 128);
         }
     } else {
-#pragma unroll
-        for (int k = 0; k < C3L_NC; ++k) { hv[k] = C3_NEG_INF; v1[k] = C3_NEG_INF; v2[k] = C3_NEG_INF; }
+        a = b = c = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
     }
 }
 
 // ---------------------------------------------------------------------------
-// row compute: all columns of the row set up by c3l_row_setup in steps of C3L_NC, row record, advance to the
+// row compute: all columns of the row set up by c3l_row_setup in steps of 8, row record, advance to the
 // next node.  While the cells are computed, everything the NEXT row's setup reads is requested: the row
 // records of its first two predecessors, the node record two rows ahead and that node's first overflow edge.
+// sm: this warp's shared-memory ring (smR vector slots per lane; smR = 0: none).
 // ---------------------------------------------------------------------------
 C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, const c3_poa_para_dev &P, const c3_poa_ws &W,
-                                           int32_t *ar, const int base4, const int lane)
+                                           int32_t *ar, const int base4, const int lane, uint4 *sm, const int smR)
 {
     if (S.nvec <= 0) return;
     const int e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const int v = S.v;
-    // ---- look-ahead for the next row (v1) and the one after (v2) ----
-    const int v1 = c3l_cl(C3_N_NEXT(S.nd)), v2 = c3l_cl(C3_N_NEXT(S.nd1)), v3 = c3l_cl(C3_N_NEXT(S.nd2));
+    // ---- look-ahead for the next row (v1) and the one after ----
+    const int v1 = c3l_cl(C3_N_NEXT(S.nd)), v3 = c3l_cl(C3_N_NEXT(S.nd2));
     const c3_nrec nd3 = c3_ld_node(&W.nodes[v3]);
     const uint32_t hr3 = W.hr[v3];
     uint2 pe2 = make_uint2(0u, 0u);
@@ -337,109 +395,172 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
         if (in0n != v) ra_n = W.rows[in0n];
         if (C3_N_INN(S.nd1) > 1 && C3L_E_ID(S.pe1) != v) rb_n = W.rows[C3L_E_ID(S.pe1)];
     }
-    (void)v2;
     const int npre = C3_N_INN(S.nd), nbase = C3_N_BASE(S.nd);
     const int beg = S.beg, end = S.end, nvec = S.nvec;
     const c3_prow r0 = S.r0, r1 = S.r1;
-    const int4 *ar4 = reinterpret_cast<const int4 *>(ar);
-    int4 *out4 = reinterpret_cast<int4 *>(ar) + base4 + lane;
-    const int8_t *qprow = W.qp + (nbase < 4 ? nbase : 0) * A.qp_stride;
-    int f1 = C3_NEG_INF, f2 = C3_NEG_INF, carry0 = C3_NEG_INF, carry1 = C3_NEG_INF;
-    int bestkey = -0x7fffffff - 1;
-    // software pipeline: both predecessors' cells and the profile words of step h+1 are requested before
-    // step h is computed
-    int nh[C3L_NC], nx1[C3L_NC], nx2[C3L_NC], ph[C3L_NC], px1[C3L_NC], px2[C3L_NC];
-    uint32_t nsw[C3L_NC / 4];
-#pragma unroll
-    for (int t = 0; t < C3L_NC / 4; ++t) nsw[t] = 0u;
-    c3l_load_part(ar4, r0, beg, lane, nh, nx1, nx2);
-    c3l_load_part(ar4, r1, beg, lane, ph, px1, px2);
-    if (nbase < 4) {
-#pragma unroll
-        for (int t = 0; t < C3L_NC / 4; ++t) nsw[t] = *reinterpret_cast<const uint32_t *>(qprow + beg + 4 * t);
-    }
-    const int nstep = nvec * (16 / C3L_NC);
-    for (int h = 0; h < nstep; ++h) {
-        const int j0 = beg + C3L_NC * h;
-        int m[C3L_NC], x1[C3L_NC], x2[C3L_NC];
-        uint32_t swv[C3L_NC / 4];
-#pragma unroll
-        for (int t = 0; t < C3L_NC / 4; ++t) swv[t] = nsw[t];
-        m[0] = max(carry0, carry1);
-#pragma unroll
-        for (int k = 1; k < C3L_NC; ++k) m[k] = max(nh[k - 1], ph[k - 1]);
-        carry0 = nh[C3L_NC - 1]; carry1 = ph[C3L_NC - 1];
-#pragma unroll
-        for (int k = 0; k < C3L_NC; ++k) { x1[k] = max(nx1[k], px1[k]); x2[k] = max(nx2[k], px2[k]); }
-        if (h + 1 < nstep) {
-            c3l_load_part(ar4, r0, j0 + C3L_NC, lane, nh, nx1, nx2);
-            c3l_load_part(ar4, r1, j0 + C3L_NC, lane, ph, px1, px2);
-            if (nbase < 4) {
-#pragma unroll
-                for (int t = 0; t < C3L_NC / 4; ++t) nsw[t] = *reinterpret_cast<const uint32_t *>(qprow + j0 + C3L_NC + 4 * t);
+    // the first predecessor comes from the ring when it is the row just computed and this band does not start
+    // left of it (then no slot is overwritten before it is read); this row goes into the ring if it fits
+    const bool p0_sm = S.last_sm && C3_N_IN0(S.nd) == S.vlast && beg >= (int)r0.beg;
+    const bool keep_sm = nvec <= smR;
+    int slot = smR > 0 ? S.beg_sn % smR : 0;
+    const uint4 *ar4 = reinterpret_cast<const uint4 *>(ar);
+    const int nstep = nvec * 2;
+    // three or more predecessors (rare per thread, frequent per warp): the first and the third.. are folded into
+    // the ring before the row loop -- per-halfword max on the packed cells, one walk of the edge list, loads of all
+    // steps independent -- so the row loop itself never follows an edge chain.  The second one stays in the loop.
+    bool p0_ring = p0_sm;
+    c3_prow r0e = r0;
+    const bool fold = npre > 2 && keep_sm;              // (a row wider than the ring takes the slow in-loop path below)
+    if (fold) {
+        const int slot0 = slot;
+        if (!p0_sm || beg < (int)r0.beg || end > (int)r0.end) {
+            int sl = slot0;
+            for (int h = 0; h < nstep; ++h) {
+                const int j0 = beg + 8 * h;
+                if (!(p0_sm && j0 >= (int)r0.beg && j0 <= (int)r0.end)) {
+                    uint4 a, b, c;
+                    c3l_load8(ar4, sm, false, 0, r0, j0, lane, a, b, c);
+                    uint4 *d2 = sm + (sl * 6 + (h & 1)) * 32 + lane;
+                    d2[0] = a; d2[64] = b; d2[128] = c;
+                }
+                if (h & 1) { ++sl; if (sl >= smR) sl = 0; }
             }
         }
-        if (npre > 2) {                                  // third and further predecessors: rare, not pipelined
+        int e = C3L_E_NEXT(S.pe);
+        for (int k = 2; k < npre; ++k) {
+            const c3_pedge pe = W.pool[e]; e = pe.next;
+            const c3_prow rp = W.rows[pe.id];
+            int sl = slot0;
+            for (int h = 0; h < nstep; ++h) {
+                const int j0 = beg + 8 * h;
+                if (j0 >= (int)rp.beg && j0 <= (int)rp.end) {
+                    uint4 a, b, c;
+                    c3l_load8(ar4, sm, false, 0, rp, j0, lane, a, b, c);
+                    uint4 *d2 = sm + (sl * 6 + (h & 1)) * 32 + lane;
+                    d2[0] = c3l_vmax8(d2[0], a); d2[64] = c3l_vmax8(d2[64], b); d2[128] = c3l_vmax8(d2[128], c);
+                }
+                if (h & 1) { ++sl; if (sl >= smR) sl = 0; }
+            }
+        }
+        p0_ring = true;
+        r0e.beg = (uint16_t)beg; r0e.end = (uint16_t)(beg + 16 * nvec - 1);
+    }
+    uint4 *out4 = reinterpret_cast<uint4 *>(ar) + base4 + lane;
+    const int8_t *qprow = W.qp;                         // column codes
+    const uint32_t nb4 = (uint32_t)nbase * 0x01010101u, ms = (uint32_t)(P.match + P.mismatch), ms4 = ms * 0x01010101u;
+    const int mism = P.mismatch;
+    int f1 = C3_NEG_INF, f2 = C3_NEG_INF, carry0 = C3_NEG_INF, carry1 = C3_NEG_INF;
+    int bestkey = -0x7fffffff - 1;
+    unsigned lowest = 0xffffffffu;                      // min over cells of (unsigned)(H + 32767): reachable cells only count
+    // software pipeline: both predecessors' cells and the profile words of step h+1 are requested before
+    // step h is computed
+    uint4 na, nb, nc, pa, pb, pc;
+    uint2 nsw = make_uint2(0u, 0u);
+    c3l_load8(ar4, sm, p0_ring, slot, r0e, beg, lane, na, nb, nc);
+    c3l_load8(ar4, sm, false, 0, r1, beg, lane, pa, pb, pc);
+    nsw = *reinterpret_cast<const uint2 *>(qprow + beg);
+    for (int h = 0; h < nstep; ++h) {
+        const int j0 = beg + 8 * h;
+        int m[8], x1[8], x2[8];
+        const uint2 sw = nsw;
+        {
+            int t0[8], t1[8];
+            c3l_unpack8(na, t0); c3l_unpack8(pa, t1);
+            m[0] = max(carry0, carry1);
+#pragma unroll
+            for (int k = 1; k < 8; ++k) m[k] = max(t0[k - 1], t1[k - 1]);   // -32768 (unreachable) is NOT mapped back here:
+            carry0 = t0[7]; carry1 = t1[7];                                  // if it ever wins a cell, `lowest` sends the read away
+            c3l_unpack8(nb, t0); c3l_unpack8(pb, t1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x1[k] = max(t0[k], t1[k]);
+            c3l_unpack8(nc, t0); c3l_unpack8(pc, t1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x2[k] = max(t0[k], t1[k]);
+        }
+        const int wslot = slot;
+        if (h & 1) { ++slot; if (slot >= smR) slot = 0; }
+        if (h + 1 < nstep) {
+            c3l_load8(ar4, sm, p0_ring, slot, r0e, j0 + 8, lane, na, nb, nc);
+            c3l_load8(ar4, sm, false, 0, r1, j0 + 8, lane, pa, pb, pc);
+            nsw = *reinterpret_cast<const uint2 *>(qprow + j0 + 8);
+        }
+        if (npre > 2 && !fold) {                         // wider than the ring: follow the edge chain per step
             int e = C3L_E_NEXT(S.pe);
             for (int k = 2; k < npre; ++k) {
                 const c3_pedge pe = W.pool[e]; e = pe.next;
                 const c3_prow rp = W.rows[pe.id];
-                int hv[C3L_NC], v1[C3L_NC], v2[C3L_NC];
-                c3l_load_part(ar4, rp, j0, lane, hv, v1, v2);
+                uint4 qa, qb, qc;
+                c3l_load8(ar4, sm, false, 0, rp, j0, lane, qa, qb, qc);
                 const int jc = j0 - 1;
                 int prev = C3_NEG_INF;
-                if (h > 0 && jc >= (int)rp.beg && jc <= (int)rp.end) prev = C3L_LDCS1(ar + c3l_ci(rp.off, 0, jc - rp.beg, lane));
+                if (h > 0 && jc >= (int)rp.beg && jc <= (int)rp.end) prev = c3l_ld_e(ar, c3l_ci(rp.off, 0, jc - rp.beg, lane));
                 m[0] = max(m[0], prev);
+                int t0[8];
+                c3l_unpack8(qa, t0);
 #pragma unroll
-                for (int t = 1; t < C3L_NC; ++t) m[t] = max(m[t], hv[t - 1]);
+                for (int t = 1; t < 8; ++t) m[t] = max(m[t], t0[t - 1]);
+                c3l_unpack8(qb, t0);
 #pragma unroll
-                for (int t = 0; t < C3L_NC; ++t) { x1[t] = max(x1[t], v1[t]); x2[t] = max(x2[t], v2[t]); }
+                for (int t = 0; t < 8; ++t) x1[t] = max(x1[t], t0[t]);
+                c3l_unpack8(qc, t0);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) x2[t] = max(x2[t], t0[t]);
             }
         }
-        const int vi = (C3L_NC * h) >> 4;
-        if (((C3L_NC * h) & 15) == 0)                   // F entering this 16-column vector: the backtrack restarts from it
+        const int vi = h >> 1;
+        if (!(h & 1))                                   // F entering this 16-column vector: the backtrack restarts from it
             *reinterpret_cast<int2 *>(ar + c3l_fi(base4, vi, lane)) = make_int2(f1, f2);
-        int hme[C3L_NC];
+        int hme[8];
+        // 4 columns per word: byte = match + mismatch where the column's base equals the node's, else 0
+        uint32_t swv[2] = {sw.x ^ nb4, sw.y ^ nb4};
 #pragma unroll
-        for (int k = 0; k < C3L_NC; ++k) {
-            const int sc = (int)(int8_t)(swv[k >> 2] >> (8 * (k & 3)));
+        for (int t = 0; t < 2; ++t) swv[t] = ms4 - (((swv[t] + 0x7f7f7f7fu) >> 7) & 0x01010101u) * ms;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int sc = (int)((swv[k >> 2] >> (8 * (k & 3))) & 0xffu) - mism;
             hme[k] = C3L_MAX3(m[k] + sc, x1[k], x2[k]);
         }
-        const int lim = end - j0;                       // last active column of this step (>= C3L_NC - 1: all)
-        if (lim < C3L_NC - 1) {
+        const int lim = end - j0;                       // last active column of this step (>= 7: all)
+        if (lim < 7) {
 #pragma unroll
-            for (int k = 0; k < C3L_NC; ++k) if (k > lim) hme[k] = C3_NEG_INF;
+            for (int k = 0; k < 8; ++k) if (k > lim) hme[k] = C3_NEG_INF;
         }
-        int hh[C3L_NC], n1[C3L_NC], n2[C3L_NC];
+        int hh[8], n1[8], n2[8];
 #pragma unroll
-        for (int k = 0; k < C3L_NC; ++k) {
+        for (int k = 0; k < 8; ++k) {
             hh[k] = C3L_MAX3(hme[k], f1, f2);
             f1 = C3L_ADDMAX(f1, -e1, hme[k] - oe1);
             f2 = C3L_ADDMAX(f2, -e2, hme[k] - oe2);
             n1[k] = C3L_ADDMAX(hh[k], -oe1, x1[k] - e1);
             n2[k] = C3L_ADDMAX(hh[k], -oe2, x2[k] - e2);
+            lowest = C3L_UMIN(lowest, hh[k] + 32767);
         }
-        if (lim < C3L_NC - 1) {
+        if (lim < 7) {
 #pragma unroll
-            for (int k = 0; k < C3L_NC; ++k) if (k > lim) { hh[k] = C3_NEG_INF; n1[k] = C3_NEG_INF; n2[k] = C3_NEG_INF; }
+            for (int k = 0; k < 8; ++k) if (k > lim) { hh[k] = C3_NEG_INF; n1[k] = C3_NEG_INF; n2[k] = C3_NEG_INF; }
         }
-        int4 *dst = out4 + vi * C3L_VSTRIDE + (((C3L_NC * h) >> 2) & 3) * 32;
-#pragma unroll
-        for (int qd = 0; qd < C3L_NC / 4; ++qd) {
-            dst[qd * 32] = make_int4(hh[4 * qd], hh[4 * qd + 1], hh[4 * qd + 2], hh[4 * qd + 3]);
-            dst[(4 + qd) * 32] = make_int4(n1[4 * qd], n1[4 * qd + 1], n1[4 * qd + 2], n1[4 * qd + 3]);
-            dst[(8 + qd) * 32] = make_int4(n2[4 * qd], n2[4 * qd + 1], n2[4 * qd + 2], n2[4 * qd + 3]);
+        const uint4 oa = c3l_pack8(hh), ob = c3l_pack8(n1), oc = c3l_pack8(n2);
+        uint4 *dst = out4 + vi * C3L_VSTRIDE + (h & 1) * 32;
+#ifndef C3L_EXP_NOSTORE
+        dst[0] = oa; dst[64] = ob; dst[128] = oc;
+#else
+        if (lowest == 12345u) { dst[0] = oa; dst[64] = ob; dst[128] = oc; }
+#endif
+        if (keep_sm) {
+            uint4 *d2 = sm + (wslot * 6 + (h & 1)) * 32 + lane;
+            d2[0] = oa; d2[64] = ob; d2[128] = oc;
         }
         // simd_abpoa_ada_max_i as one packed max: value in the high half, tie-break priority in the low half
         // (lowest SIMD lane, then the last vector, then the earliest vector)
         const int vp = (vi == nvec - 1) ? 0xfff : (0xffe - vi);
-        const int k16 = (C3L_NC * h) & 15;
+        const int k16 = (h & 1) * 8;
 #pragma unroll
-        for (int k = 0; k < C3L_NC; ++k) {
+        for (int k = 0; k < 8; ++k) {
             const int hc = max(hh[k], -32768);
             bestkey = C3L_ADDMAX((int)((unsigned)hc << 16) + vp, (15 - k16 - k) << 12, bestkey);
         }
     }
+    if (lowest < (unsigned)C3L_LOW_GUARD) S.err = C3L_E_RETRY;   // a reachable cell came too close to the int16 floor
     int best_i = -1;
     if ((bestkey >> 16) > -32768) {
         const int sl = 15 - ((bestkey >> 12) & 15);
@@ -451,11 +572,31 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
     ri.in0 = (uint16_t)C3_N_IN0(S.nd); ri.base = (uint8_t)nbase; ri.npre = (uint8_t)npre;
     ri.link = (uint16_t)S.rcount;
     W.rows[v] = ri;
-    S.last = ri; S.vlast = v;
+    S.last = ri; S.vlast = v; S.last_sm = keep_sm ? 1 : 0;
     ri.link = (uint16_t)v; ri.mp = r0.link;
     W.ord[S.rcount] = ri;
     S.cells_total += end - beg + 1;
     ++S.rcount;
+    // the next row's predecessors that will come from the arena (an old row as first predecessor, any second one):
+    // start their lines towards L2 now, over the columns this row covered (the next band is about the same)
+    {
+        const int in0n = c3l_cl(C3_N_IN0(S.nd1));
+        if (in0n != v || !keep_sm) {
+            const c3_prow rq = (in0n != v) ? ra_n : ri;
+            for (int j0 = max(beg, (int)rq.beg); j0 <= min(end + 16, (int)rq.end); j0 += 8) {
+                const int cc = j0 - rq.beg;
+                const uint4 *src = ar4 + rq.off + (cc >> 4) * C3L_VSTRIDE + ((cc >> 3) & 1) * 32 + lane;
+                C3L_PREFETCH2(src); C3L_PREFETCH2(src + 64); C3L_PREFETCH2(src + 128);
+            }
+        }
+        if (C3_N_INN(S.nd1) > 1 && C3L_E_ID(S.pe1) != v) {
+            for (int j0 = max(beg, (int)rb_n.beg); j0 <= min(end + 16, (int)rb_n.end); j0 += 8) {
+                const int cc = j0 - rb_n.beg;
+                const uint4 *src = ar4 + rb_n.off + (cc >> 4) * C3L_VSTRIDE + ((cc >> 3) & 1) * 32 + lane;
+                C3L_PREFETCH2(src); C3L_PREFETCH2(src + 64); C3L_PREFETCH2(src + 128);
+            }
+        }
+    }
     S.v = v1; S.nd = S.nd1; S.hrv = S.hr1; S.nd1 = S.nd2; S.hr1 = S.hr2; S.nd2 = nd3; S.hr2 = hr3;
     S.pe = S.pe1; S.pe1 = pe2; S.ra = ra_n; S.rb = rb_n;
     S.nvec = 0;
@@ -486,7 +627,7 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
             if (k == 0) p = C3_N_IN0(sk); else { const c3_pedge pe = W.pool[e]; p = pe.id; e = pe.next; }
             const c3_prow rp = W.rows[p];
             const int en = min(qlen, (int)rp.end);
-            const int val = ar[c3l_ci(rp.off, 0, en - rp.beg, lane)];
+            const int val = c3l_ld_h(ar, c3l_ci(rp.off, 0, en - rp.beg, lane));
             if (val > best_score) { best_score = val; bj = en; bk = rp.link; }
         }
         if (bk < 0 || qlen - bj + 8 > A.cigar_cap) { S.err = C3L_E_RETRY; run = false; }
@@ -495,13 +636,16 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
             for (int t = qlen; t > bj; --t)
                 cg[qlen - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
             nc = qlen - bj;
-            hij = ar[c3l_ci(rt.off, 0, j - rt.beg, lane)];
+            hij = c3l_ld_h(ar, c3l_ci(rt.off, 0, j - rt.beg, lane));
         }
     }
     int cur_op = C3_OP_ALL;
+    // the record of the current row's first predecessor is requested as soon as the row is known (one step ahead)
+    c3_prow pr0 = W.ord[rt.mp == C3_NONE ? 0 : rt.mp];
     while (C3L_ANY(run && rt.link != C3_SRC && j > 0)) {
         C3L_COUNT(11, 1);
         if (!(run && rt.link != C3_SRC && j > 0)) continue;
+        const int row_before = rt.link;
         const int i = rt.link;
         const int b = rt.beg;
         int hit = 0;
@@ -513,11 +657,10 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
             if (cur_op & C3_OP_M) {
                 int e = in_more;
                 for (int k = 0; k < npre; ++k) {
-                    int pk;
-                    if (k == 0) pk = rt.mp; else { const c3_pedge pe = W.pool[e]; pk = W.rows[pe.id].link; e = pe.next; }
-                    const c3_prow pr = W.ord[pk];
+                    c3_prow pr = pr0;
+                    if (k > 0) { const c3_pedge pe = W.pool[e]; pr = W.ord[W.rows[pe.id].link]; e = pe.next; }
                     if (j - 1 < max((int)pr.beg, b) || j - 1 > (int)pr.end) continue;
-                    const int ph = ar[c3l_ci(pr.off, 0, j - 1 - pr.beg, lane)];
+                    const int ph = c3l_ld_h(ar, c3l_ci(pr.off, 0, j - 1 - pr.beg, lane));
                     if (ph + s == hij) {
                         opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
                         rt = pr; --j; hit = 1; cur_op = C3_OP_ALL; hij = ph;
@@ -528,23 +671,22 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
             if (!hit && (cur_op & C3_OP_E)) {
                 int e = in_more;
                 for (int k = 0; k < npre; ++k) {
-                    int pk;
-                    if (k == 0) pk = rt.mp; else { const c3_pedge pe = W.pool[e]; pk = W.rows[pe.id].link; e = pe.next; }
-                    const c3_prow pr = W.ord[pk];
+                    c3_prow pr = pr0;
+                    if (k > 0) { const c3_pedge pe = W.pool[e]; pr = W.ord[W.rows[pe.id].link]; e = pe.next; }
                     if (j < (int)pr.beg || j > (int)pr.end) continue;
                     const int pc = j - pr.beg;
-                    const int ph = ar[c3l_ci(pr.off, 0, pc, lane)], pe1 = ar[c3l_ci(pr.off, 1, pc, lane)], pe2 = ar[c3l_ci(pr.off, 2, pc, lane)];
+                    const int ph = c3l_ld_h(ar, c3l_ci(pr.off, 0, pc, lane)), pe1 = c3l_ld_e(ar, c3l_ci(pr.off, 1, pc, lane)), pe2 = c3l_ld_e(ar, c3l_ci(pr.off, 2, pc, lane));
                     if (cur_op & C3_OP_E1) {
                         if (cur_op & C3_OP_M) {
                             if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
-                        } else if (ar[c3l_ci(rt.off, 1, j - b, lane)] == pe1 - e1) {
+                        } else if (c3l_ld_e(ar, c3l_ci(rt.off, 1, j - b, lane)) == pe1 - e1) {
                             cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1;
                         }
                     }
                     if (!hit && (cur_op & C3_OP_E2)) {
                         if (cur_op & C3_OP_M) {
                             if (hij == pe2) { cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1; }
-                        } else if (ar[c3l_ci(rt.off, 2, j - b, lane)] == pe2 - e2) {
+                        } else if (c3l_ld_e(ar, c3l_ci(rt.off, 2, j - b, lane)) == pe2 - e2) {
                             cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1;
                         }
                     }
@@ -559,12 +701,16 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
                 // F is stored only where it enters a 16-column vector: rebuild F[j-1] and F[j] from there
                 const int cm = j - 1 - b, vs = cm >> 4, tm = cm & 15;
                 const int2 fin = *reinterpret_cast<const int2 *>(ar + c3l_fi(rt.off, vs, lane));
-                const int4 *hp = reinterpret_cast<const int4 *>(ar) + rt.off + vs * C3L_VSTRIDE + lane;
+                const uint4 *hp = reinterpret_cast<const uint4 *>(ar) + rt.off + vs * C3L_VSTRIDE + lane;
                 int hq[16];
+                {
+                    int t0[8];
+                    c3l_unpack8(hp[0], t0);
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const int4 a4 = hp[qd * 32];
-                    hq[4 * qd] = a4.x; hq[4 * qd + 1] = a4.y; hq[4 * qd + 2] = a4.z; hq[4 * qd + 3] = a4.w;
+                    for (int k = 0; k < 8; ++k) hq[k] = c3l_map(t0[k]);
+                    c3l_unpack8(hp[32], t0);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) hq[8 + k] = c3l_map(t0[k]);
                 }
                 int f1 = fin.x, f2 = fin.y, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
                 C3L_COUNT(12, 1);
@@ -595,6 +741,7 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
             }
         }
         if (!hit) { S.err = C3L_E_RETRY; run = false; continue; }
+        if ((int)rt.link != row_before) pr0 = W.ord[rt.mp == C3_NONE ? 0 : rt.mp];
         cg[nc] = opw;
         ++nc;
         if (nc + j + 8 > A.cigar_cap) { S.err = C3L_E_RETRY; run = false; }
@@ -610,9 +757,15 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
     c3_graph g; g.nodes = W.nodes; g.pool = W.pool; g.node_n = S.node_n; g.pool_n = S.pool_n;
     g.node_cap = A.node_cap; g.pool_cap = A.pool_cap; g.err = 0;
     int last_id = C3_SRC, last_new = 0;
+    unsigned long long opn = nc > 0 ? cg[nc - 1] : 0ull;
     for (int t = nc - 1; C3L_ANY(t >= 0 && !g.err); --t) {
         if (!(t >= 0 && !g.err)) continue;
-        const unsigned long long opc = cg[t];
+        const unsigned long long opc = opn;
+        if (t > 0) {                                       // next op now, and its node record on the way into L1
+            opn = cg[t - 1];
+            const int nn = (int)((opn >> 8) & 0xffff);
+            if (nn != (int)C3_NONE) C3L_PREFETCH(&g.nodes[nn]);
+        }
         const int kc = (int)(opc & 0xff), nid = (int)((opc >> 8) & 0xffff), qp = (int)(opc >> 32);
         if (kc == (int)C3_CG_DEL) continue;
         if (kc == (int)C3_CG_MATCH) {
@@ -730,6 +883,7 @@ struct c3_lane_args {
     c3_poa_args A;                 // ws / ws_stride: per-THREAD workspace (cell_cap = 0); order / n_work: eligible items
     int4 *arena; long long arena_stride4;   // per-warp DP arena, in int4
     int arena_cap4;                // int4 per warp
+    int sm_vec;                    // shared-memory ring: vector slots per lane (dynamic shared memory = warps x sm_vec x 3 KB)
     int32_t *done;                 // [n_items] 1 = finished here
 };
 
@@ -741,6 +895,9 @@ __global__ void __launch_bounds__(C3L_THREADS, C3L_MINB) c3_poa_lane_kernel(c3_l
     const c3_poa_ws W = c3_poa_ws_carve(A.ws + ((int64_t)gwarp * 32 + lane) * A.ws_stride, A.node_cap, A.pool_cap, 0, A.cigar_cap);
     int32_t *ar = reinterpret_cast<int32_t *>(L.arena + (int64_t)gwarp * L.arena_stride4);
     const c3_poa_para_dev P = A.P;
+    extern __shared__ uint4 c3l_smem[];
+    uint4 *sm = c3l_smem + (size_t)(threadIdx.x >> 5) * L.sm_vec * 192;
+    const int smR = L.sm_vec;
     c3l_state S;
     C3L_TICK_INIT;
     for (;;) {
@@ -772,7 +929,7 @@ __global__ void __launch_bounds__(C3L_THREADS, C3L_MINB) c3_poa_lane_kernel(c3_l
                 C3L_TICK(3);
                 if (mv == 0) break;
                 if (used4 + mv * C3L_VSTRIDE > L.arena_cap4) { if (S.aligning) S.err = C3L_E_RETRY; break; }
-                c3l_row_compute(S, A, P, W, ar, used4, lane);
+                c3l_row_compute(S, A, P, W, ar, used4, lane, sm, smR);
                 used4 += mv * C3L_VSTRIDE;
                 __syncwarp();
                 C3L_TICK(4);

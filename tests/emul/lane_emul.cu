@@ -10,7 +10,7 @@
 extern "C" int c3l_emul_batch(int n_items, const uint8_t *codes, const int64_t *item_base, const int32_t *bounds,
                               const int32_t *n_seqs, int max_seqs, int min_seqs, int msa2,
                               int match, int mismatch, int o1, int e1, int o2, int e2, int wb, double wf, int simd_bits,
-                              int node_cap, int cigar_cap, int qp_stride, int arena_cap4,
+                              int node_cap, int cigar_cap, int qp_stride, int arena_cap4, int sm_vec,
                               char *cons, int cons_cap, int32_t *status, int32_t *cons_len, int32_t *nodes_out,
                               long long *cells_out, int32_t *done)
 {
@@ -27,6 +27,8 @@ extern "C" int c3l_emul_batch(int n_items, const uint8_t *codes, const int64_t *
     const int64_t ws_bytes = c3_poa_ws_bytes(node_cap, node_cap, 0, cigar_cap, qp_stride);
     uint8_t *ws = (uint8_t *)aligned_alloc(256, (size_t)ws_bytes * 32);
     int32_t *ar = (int32_t *)aligned_alloc(256, (size_t)arena_cap4 * 16);
+    std::vector<uint4> smbuf((size_t)(sm_vec > 0 ? sm_vec : 1) * 192);
+    uint4 *sm = smbuf.data();
     if (!ws || !ar) return -1;
     memset(ws, 0, (size_t)ws_bytes * 32);
     A.ws = ws; A.ws_stride = ws_bytes;
@@ -53,7 +55,7 @@ extern "C" int c3l_emul_batch(int n_items, const uint8_t *codes, const int64_t *
                 for (int l = 0; l < 32; ++l) { const int nv = c3l_row_setup(S[l], A, W[l]); if (nv > mv) mv = nv; }
                 if (mv == 0) break;
                 if (used4 + mv * C3L_VSTRIDE > arena_cap4) { for (int l = 0; l < 32; ++l) if (S[l].aligning) S[l].err = C3L_E_RETRY; break; }
-                for (int l = 0; l < 32; ++l) c3l_row_compute(S[l], A, P, W[l], ar, used4, l);
+                for (int l = 0; l < 32; ++l) c3l_row_compute(S[l], A, P, W[l], ar, used4, l, sm, sm_vec);
                 used4 += mv * C3L_VSTRIDE;
             }
             for (int l = 0; l < 32; ++l) c3l_align_end(S[l], A, P, W[l], ar, l, sq);
