@@ -325,14 +325,14 @@ static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa
     if (arena4 > 0x7fffff00ll / 4) return 0;                       // int32 cell indices
     const int64_t warp_bytes = 32 * ws_bytes + arena4 * 16;
     const int wpb = C3L_THREADS / 32;
-    // shared-memory ring of the row just computed: vec_est slots of 3 KB per warp, cut down if C3L_MINB CTAs
+    // shared-memory ring of the row just computed: vec_est slots of 3.5 KB per warp, cut down if C3L_MINB CTAs
     // would not fit the SM (rows wider than the ring are simply not mirrored)
     int sm_vec = (int)vec_est;
     {
         const int per_cta_max = (C3L_SMEM_KB * 1024) / C3L_MINB;
-        sm_vec = std::max(1, std::min(sm_vec, per_cta_max / (wpb * 3072)));
+        sm_vec = std::max(1, std::min(sm_vec, per_cta_max / (wpb * C3L_RSLOT * 512)));
     }
-    const size_t sm_bytes = (size_t)wpb * sm_vec * 3072;
+    const size_t sm_bytes = (size_t)wpb * sm_vec * C3L_RSLOT * 512;
     CK(cudaFuncSetAttribute(c3_poa_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_bytes));
     int bps = 4;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_lane_kernel, C3L_THREADS, sm_bytes) != cudaSuccess || bps < 1) bps = 4;
@@ -856,10 +856,10 @@ extern "C" int c3_debug_stats(unsigned long long *out16, int reset)
 #endif
 
 #ifdef C3L_PROF
-extern "C" int c3_debug_lane_prof(unsigned long long *out16, int reset)
+extern "C" int c3_debug_lane_prof(unsigned long long *out24, int reset)
 {
-    if (out16) cudaMemcpyFromSymbol(out16, c3l_prof, sizeof(unsigned long long) * 16);
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(c3l_prof, z, sizeof(z)); }
+    if (out24) cudaMemcpyFromSymbol(out24, c3l_prof, sizeof(unsigned long long) * 24);
+    if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(c3l_prof, z, sizeof(z)); }
     return 0;
 }
 #endif

@@ -16,9 +16,10 @@
 // = abPOA's int16 SIMD granule); vector vi holds, per lane, H / E1 / E2 as 3 x 2 uint4 (8 columns each) and the
 // (F1, F2) pair entering the vector:
 //     uint4 index  base4 + vi*208 + (array*2 + half)*32 + lane,       F pair: int2 at uint4 index base4 + vi*208 + 192
-// Values below -32768 are stored as -32768; a loaded H of -32768 reads back as NEG_INF.  That is exact as long
-// as every reachable cell stays above -32768+64, which the row loop checks (else the read goes to the warp
-// kernel).  Columns past a row's band end inside its last vector hold -32768, so successors load whole vectors.
+// "Unreachable" is stored as C3L_FLOOR (-30720): every packed operation clamps there, and a loaded H at the floor
+// reads back as NEG_INF in the backtrack.  That is exact as long as every reachable cell of a row stays well above
+// the floor, which the row loop checks from the row's first cell (else the read goes to the warp kernel).
+// Columns past a row's band end inside its last vector hold the floor, so successors load whole vectors.
 // The row just computed is also kept in shared memory (same packed form, ring of `smR` vector slots per lane,
 // slot = absolute vector index mod smR): the usual first predecessor -- the previous row -- never comes from L2.
 // Graph, row records, cigar and the column codes of the query are thread-private (c3_poa_ws without cells).
@@ -37,13 +38,20 @@
 #ifndef C3L_SMEM_KB
 #define C3L_SMEM_KB 200            // shared memory per SM the rings may take (the rest of the 228 KB stays L1)
 #endif
-#define C3L_LOW_GUARD 64           // reachable cells must stay above -32768 + C3L_LOW_GUARD
+#ifdef C3L_CODES_RING
+#define C3L_RSLOT 7                // uint4 per lane and ring slot: H, E1, E2 x 2 halves + the 16 column codes of that vector
+#else
+#define C3L_RSLOT 6                // uint4 per lane and ring slot: H, E1, E2 x 2 halves
+#endif
+#define C3L_FLOOR (-30720)         // stored "unreachable"; every packed operation clamps here, 2048 above the int16 wrap
+#define C3L_FLOOR2 0x88008800u
+#define C3L_LOW_GUARD 64           // reachable cells must stay above C3L_FLOOR + C3L_LOW_GUARD
 #ifndef C3L_THREADS
 #define C3L_THREADS 64
 #endif
 #ifndef C3L_MINB
-#define C3L_MINB 4
-#endif
+#define C3L_MINB 6                 // CTAs per SM the registers are bounded for (168): 12 warps per SM.  Measured on B200 per 100k
+#endif                             // cfg2 reads: 4 -> 393 ms, 6 -> 374 ms, 8 (128 registers, spills, ring too small) -> 610 ms
 
 // The serial per-thread phases (graph walks, backtrack, merge, consensus) loop under warp-uniform control:
 // `while (C3L_ANY(cond)) { if (cond) { one step } }` -- every thread of the warp makes the same number of
@@ -61,11 +69,20 @@
 #define C3L_UMIN(a, b) min((unsigned)(a), (unsigned)(b))
 #define C3L_PACK2(lo, hi) __byte_perm((unsigned)(lo), (unsigned)(hi), 0x5410)
 #define C3L_VMAX2(a, b) __vmaxs2((a), (b))          // per-halfword signed max: VIMNMX.S16x2
+#define C3L_VADDMAX2(a, b, c) __viaddmax_s16x2((a), (b), (c))   // per-halfword max(a + b, c): VIADDMNMX.S16x2
+#define C3L_VMAX3_2(a, b, c) __vimax3_s16x2((a), (b), (c))      // VIMNMX3.S16x2
+__device__ __forceinline__ unsigned c3l_prmt(unsigned a, unsigned b, unsigned sel)
+{
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));   // generic mode: selector bit 3 = replicate the byte's sign
+    return d;
+}
+#define C3L_PRMT(a, b, sel) c3l_prmt((a), (b), (sel))
 #define C3L_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
-#ifdef C3L_PF2
+#ifndef C3L_NO_PF2
 #define C3L_PREFETCH2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #else
-#define C3L_PREFETCH2(p) do { } while (0)
+#define C3L_PREFETCH2(p) do { (void)(p); } while (0)
 #endif
 #else
 #define C3L_ANY(x) (x)
@@ -79,8 +96,29 @@ static inline unsigned c3l_hvmax2(unsigned a, unsigned b)
     return ((unsigned)(al > bl ? al : bl) & 0xffffu) | ((unsigned)(ah > bh ? ah : bh) << 16);
 }
 #define C3L_VMAX2(a, b) c3l_hvmax2((a), (b))
-#define C3L_PREFETCH(p) do { } while (0)
-#define C3L_PREFETCH2(p) do { } while (0)
+static inline unsigned c3l_hvaddmax2(unsigned a, unsigned b, unsigned c)
+{
+    const int16_t sl = (int16_t)(uint16_t)((a & 0xffffu) + (b & 0xffffu)), sh = (int16_t)(uint16_t)((a >> 16) + (b >> 16));
+    const int16_t cl = (int16_t)(c & 0xffffu), ch = (int16_t)(c >> 16);
+    return ((unsigned)(uint16_t)(sl > cl ? sl : cl)) | ((unsigned)(uint16_t)(sh > ch ? sh : ch) << 16);
+}
+static inline unsigned c3l_hprmt(unsigned a, unsigned b, unsigned sel)
+{
+    const unsigned long long v = ((unsigned long long)b << 32) | a;
+    unsigned d = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned n = (sel >> (4 * i)) & 0xfu;
+        unsigned byte = (unsigned)(v >> (8 * (n & 7u))) & 0xffu;
+        if (n & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;
+        d |= byte << (8 * i);
+    }
+    return d;
+}
+#define C3L_VADDMAX2(a, b, c) c3l_hvaddmax2((a), (b), (c))
+#define C3L_VMAX3_2(a, b, c) c3l_hvmax2(c3l_hvmax2((a), (b)), (c))
+#define C3L_PRMT(a, b, sel) c3l_hprmt((a), (b), (sel))
+#define C3L_PREFETCH(p) do { (void)(p); } while (0)
+#define C3L_PREFETCH2(p) do { (void)(p); } while (0)
 static inline int c3l_hmax(int a, int b) { return a > b ? a : b; }
 #define C3L_ADDMAX(a, b, c) c3l_hmax((a) + (b), (c))
 #define C3L_MAX3(a, b, c) c3l_hmax(c3l_hmax((a), (b)), (c))
@@ -88,13 +126,19 @@ static inline int c3l_hmax(int a, int b) { return a > b ? a : b; }
 
 // -DC3L_PROF: per-phase cycle counters (lane 0 of every warp adds clock64() deltas); read with c3_debug_lane_prof
 #if defined(C3L_PROF) && defined(__CUDACC__)
-__device__ unsigned long long c3l_prof[16];
+__device__ unsigned long long c3l_prof[24];
 #endif
 #if defined(C3L_PROF) && defined(__CUDA_ARCH__)
 #define C3L_TICK(id) do { const long long t1_ = clock64(); if (lane == 0) atomicAdd(&c3l_prof[id], (unsigned long long)(t1_ - tprof_)); tprof_ = clock64(); } while (0)
 #define C3L_TICK_INIT long long tprof_ = clock64()
 #define C3L_COUNT(id, v) do { if (lane == 0) atomicAdd(&c3l_prof[id], (unsigned long long)(v)); } while (0)
+// inside the row loop: `dep` makes the clock read wait for the values it names
+#define C3L_TICK2_INIT long long tp2_ = clock64()
+#define C3L_TICK2(id, dep) do { long long t1_; asm volatile("{ .reg .b32 t; mov.b32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(t1_) : "r"((unsigned)(dep)) : "memory"); \
+    if (lane == 0) atomicAdd(&c3l_prof[id], (unsigned long long)(t1_ - tp2_)); tp2_ = clock64(); } while (0)
 #else
+#define C3L_TICK2_INIT do { } while (0)
+#define C3L_TICK2(id, dep) do { } while (0)
 #define C3L_TICK(id) do { } while (0)
 #define C3L_TICK_INIT do { } while (0)
 #define C3L_COUNT(id, v) do { } while (0)
@@ -107,9 +151,12 @@ struct c3l_state {
     long long cells_total;
     const uint8_t *q; int qlen, n, w, aligning;
     int v, rcount;                                    // row walk: current node, rows done
-    c3_nrec nd, nd1, nd2; uint32_t hrv, hr1, hr2;     // look-ahead: records of v and of the next two nodes of the list
-    uint2 pe, pe1;                                    // first overflow in-edge of v / next(v) (in_n > 1)
-    c3_prow ra, rb;                                   // row records of v's first two predecessors (unless == vlast)
+    c3_nrec nd, nd1, nd2, nd3; uint32_t hrv, hr1, hr2, hr3;   // look-ahead: records of v and of the next three nodes of the list
+    uint2 pe, pe1, pe2;                               // first overflow in-edge of v, v+1, v+2 (in_n > 1)
+    c3_prow ra, rb, ra1, rb1;                         // row records of the first two predecessors of v and of v+1 (unless among
+                                                      // the two rows computed last when they were requested)
+    c3_prow last2; int vlast2;                        // the row before the one just computed
+    int code_lo, code_hi;                             // vectors whose column codes are in the ring (code_lo > code_hi: none)
     c3_prow last; int vlast, last_sm;                 // the row just computed; last_sm: it is in the shared-memory ring
     int beg, end, nvec, beg_sn, end_sn; c3_prow r0, r1;   // the row between setup and compute
 };
@@ -119,8 +166,8 @@ C3_HD __forceinline__ int c3l_ci(int off4, int a, int c, int lane)
 {
     return ((off4 + (c >> 4) * C3L_VSTRIDE + ((a << 1) + ((c >> 3) & 1)) * 32 + lane) << 3) + (c & 7);
 }
-// stored cells: H reads -32768 back as NEG_INF; E1 / E2 stay as stored (they only feed max() and inequalities)
-C3_HD __forceinline__ int c3l_map(const int v) { return v == -32768 ? C3_NEG_INF : v; }
+// stored cells: H at the floor reads back as NEG_INF; E1 / E2 stay as stored (they only feed max() and inequalities)
+C3_HD __forceinline__ int c3l_map(const int v) { return v <= C3L_FLOOR ? C3_NEG_INF : v; }
 C3_HD __forceinline__ int c3l_ld_h(const int32_t *ar, const int idx16) { return c3l_map((int)reinterpret_cast<const int16_t *>(ar)[idx16]); }
 C3_HD __forceinline__ int c3l_ld_e(const int32_t *ar, const int idx16) { return (int)reinterpret_cast<const int16_t *>(ar)[idx16]; }
 
@@ -144,13 +191,6 @@ C3_HD __forceinline__ void c3l_unpack8(const uint4 w, int (&o)[8])
 C3_HD __forceinline__ uint4 c3l_vmax8(const uint4 a, const uint4 b)
 {
     return make_uint4(C3L_VMAX2(a.x, b.x), C3L_VMAX2(a.y, b.y), C3L_VMAX2(a.z, b.z), C3L_VMAX2(a.w, b.w));
-}
-C3_HD __forceinline__ uint4 c3l_pack8(const int (&v)[8])
-{
-    int c[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) c[k] = max(v[k], -32768);
-    return make_uint4(C3L_PACK2(c[0], c[1]), C3L_PACK2(c[2], c[3]), C3L_PACK2(c[4], c[5]), C3L_PACK2(c[6], c[7]));
 }
 
 // ---------------------------------------------------------------------------
@@ -290,34 +330,36 @@ C3_HD __forceinline__ void c3l_source_row(c3l_state &S, const c3_poa_para_dev &P
     for (int vi = 0; vi < S.nvec; ++vi)
         *reinterpret_cast<int2 *>(ar + c3l_fi(0, vi, lane)) = make_int2(C3_NEG_INF, C3_NEG_INF);
     for (int c = 0; c < 16 * S.nvec; ++c) {
-        int h = -32768, x1 = -32768, x2 = -32768;
+        int h = C3L_FLOOR, x1 = C3L_FLOOR, x2 = C3L_FLOOR;
         if (b0 == 0 && c < wd) {
             if (c == 0) { h = 0; x1 = -oe1; x2 = -oe2; }
             else h = max(-(P.o1 + P.e1 * c), -(P.o2 + P.e2 * c));
-            if (h < -32768 + C3L_LOW_GUARD) S.err = C3L_E_RETRY;
+            if (h < C3L_FLOOR + 1024) S.err = C3L_E_RETRY;
         }
         ar16[c3l_ci(0, 0, c, lane)] = (int16_t)h; ar16[c3l_ci(0, 1, c, lane)] = (int16_t)x1; ar16[c3l_ci(0, 2, c, lane)] = (int16_t)x2;
     }
-    S.last_sm = 0;
+    S.last_sm = 0; S.code_lo = 1; S.code_hi = 0;
     S.v = W.nodes[C3_SRC].next; S.rcount = 1;
     S.nd = c3_ld_node(&W.nodes[S.v]); S.hrv = W.hr[S.v];
     const int v1 = c3l_cl(C3_N_NEXT(S.nd));
     S.nd1 = c3_ld_node(&W.nodes[v1]); S.hr1 = W.hr[v1];
     const int v2 = c3l_cl(C3_N_NEXT(S.nd1));
     S.nd2 = c3_ld_node(&W.nodes[v2]); S.hr2 = W.hr[v2];
-    S.pe = make_uint2(0u, 0u); S.pe1 = make_uint2(0u, 0u);
+    const int v3 = c3l_cl(C3_N_NEXT(S.nd2));
+    S.nd3 = c3_ld_node(&W.nodes[v3]); S.hr3 = W.hr[v3];
+    S.pe = S.pe1 = S.pe2 = make_uint2(0u, 0u);
     if (C3_N_INN(S.nd) > 1) S.pe = c3l_ld_edge(&W.pool[C3_N_INMORE(S.nd)]);
     if (C3_N_INN(S.nd1) > 1) S.pe1 = c3l_ld_edge(&W.pool[C3_N_INMORE(S.nd1)]);
-    S.ra = ri; S.rb = ri;
-    if (C3_N_IN0(S.nd) != C3_SRC) S.ra = W.rows[c3l_cl(C3_N_IN0(S.nd))];
-    if (C3_N_INN(S.nd) > 1 && C3L_E_ID(S.pe) != C3_SRC) S.rb = W.rows[C3L_E_ID(S.pe)];
+    if (C3_N_INN(S.nd2) > 1) S.pe2 = c3l_ld_edge(&W.pool[C3_N_INMORE(S.nd2)]);
+    // the first two nodes after the source can only have the source / the first node as predecessors: S.last, S.last2
+    S.ra = S.rb = S.ra1 = S.rb1 = ri; S.last2 = ri; S.vlast2 = -1;
     S.nvec = 0;
 }
 
 // ---------------------------------------------------------------------------
 // row setup: adaptive band of the current node's row.  Returns its number of vectors (0: no row).
-// The records of the first two predecessors were requested while the previous row was computed (S.ra, S.rb);
-// a predecessor that IS the previous row comes from S.last.
+// The records of the first two predecessors were requested two rows ago (S.ra, S.rb); a predecessor that is one of
+// the two rows computed since comes from S.last / S.last2.
 // ---------------------------------------------------------------------------
 C3_HD __forceinline__ int c3l_row_setup(c3l_state &S, const c3_poa_args &A, const c3_poa_ws &W)
 {
@@ -328,11 +370,11 @@ C3_HD __forceinline__ int c3l_row_setup(c3l_state &S, const c3_poa_args &A, cons
     const int rr = qlen - rem;
     const int npre = C3_N_INN(S.nd);
     if (npre > C3_MAXPRE || C3_N_BASE(S.nd) >= 4) { S.err = C3L_E_RETRY; return 0; }   // c3_poa_kernel's limit / an N node: let it handle
-    const c3_prow r0 = (C3_N_IN0(S.nd) == S.vlast) ? S.last : S.ra;
+    const c3_prow r0 = (C3_N_IN0(S.nd) == S.vlast) ? S.last : (C3_N_IN0(S.nd) == S.vlast2) ? S.last2 : S.ra;
     int mpl = min(S.n, (int)r0.mp), mpr = r0.mp, min_pre_beg = r0.beg;
     c3_prow r1; r1.off = 0; r1.beg = 16; r1.end = 0; r1.mp = 0; r1.in0 = C3_NONE; r1.link = 0; r1.base = 4; r1.npre = 0;   // empty band
     if (npre > 1) {
-        r1 = (C3L_E_ID(S.pe) == S.vlast) ? S.last : S.rb;
+        r1 = (C3L_E_ID(S.pe) == S.vlast) ? S.last : (C3L_E_ID(S.pe) == S.vlast2) ? S.last2 : S.rb;
         mpl = min(mpl, (int)r1.mp); mpr = max(mpr, (int)r1.mp); min_pre_beg = min(min_pre_beg, (int)r1.beg);
         int e = C3L_E_NEXT(S.pe);
         for (int k = 2; k < npre; ++k) {
@@ -353,13 +395,13 @@ C3_HD __forceinline__ int c3l_row_setup(c3l_state &S, const c3_poa_args &A, cons
 }
 
 // 8 columns (from j0, a multiple of 8) of one predecessor's packed H, E1, E2 -- from the arena, or from the
-// shared-memory ring when the predecessor is the row just computed; outside its band: all -32768
+// shared-memory ring when the predecessor is the row just computed; outside its band: all C3L_FLOOR
 C3_HD __forceinline__ void c3l_load8(const uint4 *ar4, const uint4 *sm, const bool from_sm, const int slot,
                                      const c3_prow &rp, const int j0, const int lane, uint4 &a, uint4 &b, uint4 &c)
 {
     if (j0 >= (int)rp.beg && j0 <= (int)rp.end) {
         if (from_sm) {
-            const uint4 *src = sm + (slot * 6 + ((j0 >> 3) & 1)) * 32 + lane;
+            const uint4 *src = sm + (slot * C3L_RSLOT + ((j0 >> 3) & 1)) * 32 + lane;
             a = src[0]; b = src[64]; c = src[128];
         } else {
             const int cc = j0 - rp.beg;
@@ -367,7 +409,42 @@ C3_HD __forceinline__ void c3l_load8(const uint4 *ar4, const uint4 *sm, const bo
             a = C3L_LDCS4(src); b = C3L_LDCS4(src + 64); c = C3L_LDCS4(src + 128);
         }
     } else {
-        a = b = c = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
+        a = b = c = make_uint4(C3L_FLOOR2, C3L_FLOOR2, C3L_FLOOR2, C3L_FLOOR2);
+    }
+}
+
+// Folds one predecessor row into the ring over the band [beg, beg + 8 nstep): mode 1 = the ring becomes that row
+// (floor outside its band), mode 2 = the row is in the ring already, only the steps outside its band are set to the
+// floor, mode 0 = per-halfword max with what the ring holds.  4 steps of arena loads are in flight at a time.
+C3_HD __forceinline__ void c3l_fold_pred(const uint4 *ar4, uint4 *sm, const int smR, const int slot0, const c3_prow &rp,
+                                         const int beg, const int nstep, const int lane, const int mode)
+{
+    for (int h0 = 0; h0 < nstep; h0 += 4) {
+        uint4 a[4], b[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j0 = beg + 8 * (h0 + u);
+            const bool inb = h0 + u < nstep && j0 >= (int)rp.beg && j0 <= (int)rp.end;
+            a[u] = b[u] = c[u] = make_uint4(C3L_FLOOR2, C3L_FLOOR2, C3L_FLOOR2, C3L_FLOOR2);
+            if (inb && mode != 2) {
+                const int cc = j0 - rp.beg;
+                const uint4 *src = ar4 + rp.off + (cc >> 4) * C3L_VSTRIDE + ((cc >> 3) & 1) * 32 + lane;
+                a[u] = C3L_LDCS4(src); b[u] = C3L_LDCS4(src + 64); c[u] = C3L_LDCS4(src + 128);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int h = h0 + u, j0 = beg + 8 * h;
+            if (h >= nstep) continue;
+            const bool inb = j0 >= (int)rp.beg && j0 <= (int)rp.end;
+            int sl = slot0 + (h >> 1); if (sl >= smR) sl -= smR;
+            uint4 *d2 = sm + (sl * C3L_RSLOT + (h & 1)) * 32 + lane;
+            if (mode == 0) {
+                if (inb) { d2[0] = c3l_vmax8(d2[0], a[u]); d2[64] = c3l_vmax8(d2[64], b[u]); d2[128] = c3l_vmax8(d2[128], c[u]); }
+            } else if (mode == 1 || !inb) {
+                d2[0] = a[u]; d2[64] = b[u]; d2[128] = c[u];
+            }
+        }
     }
 }
 
@@ -384,20 +461,46 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
     const int e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const int v = S.v;
     // ---- look-ahead for the next row (v1) and the one after ----
-    const int v1 = c3l_cl(C3_N_NEXT(S.nd)), v3 = c3l_cl(C3_N_NEXT(S.nd2));
-    const c3_nrec nd3 = c3_ld_node(&W.nodes[v3]);
-    const uint32_t hr3 = W.hr[v3];
-    uint2 pe2 = make_uint2(0u, 0u);
-    if (C3_N_INN(S.nd2) > 1) pe2 = c3l_ld_edge(&W.pool[C3_N_INMORE(S.nd2)]);
-    c3_prow ra_n = S.last, rb_n = S.last;
+    const int v1 = c3l_cl(C3_N_NEXT(S.nd)), v4 = c3l_cl(C3_N_NEXT(S.nd3));
+    const c3_nrec nd4 = c3_ld_node(&W.nodes[v4]);
+    const uint32_t hr4 = W.hr[v4];
+    uint2 pe3 = make_uint2(0u, 0u);
+    if (C3_N_INN(S.nd3) > 1) pe3 = c3l_ld_edge(&W.pool[C3_N_INMORE(S.nd3)]);
+    c3_prow ra2 = S.last, rb2 = S.last;                 // predecessors of v+2 (rows v and v+1 do not exist yet: last / last2 then)
     {
-        const int in0n = c3l_cl(C3_N_IN0(S.nd1));
-        if (in0n != v) ra_n = W.rows[in0n];
-        if (C3_N_INN(S.nd1) > 1 && C3L_E_ID(S.pe1) != v) rb_n = W.rows[C3L_E_ID(S.pe1)];
+        const int p0 = c3l_cl(C3_N_IN0(S.nd2)), p1 = C3L_E_ID(S.pe2);
+        if (p0 != v && p0 != v1) ra2 = W.rows[p0];
+        if (C3_N_INN(S.nd2) > 1 && p1 != v && p1 != v1) rb2 = W.rows[p1];
+    }
+    // cells of the NEXT row's predecessors that will come from the arena: start their lines towards L2 a whole row
+    // ahead, over the columns of this row's band (the next band is about the same)
+    {
+        const int p0 = c3l_cl(C3_N_IN0(S.nd1)), p1 = C3L_E_ID(S.pe1);
+        const int lo = S.beg, hi = S.end + 16;
+        if (p0 != v) {
+            const c3_prow rq = (p0 == S.vlast) ? S.last : S.ra1;
+            const uint4 *a4 = reinterpret_cast<const uint4 *>(ar);
+            for (int j0 = max(lo, (int)rq.beg); j0 <= min(hi, (int)rq.end); j0 += 8) {
+                const int cc = j0 - rq.beg;
+                const uint4 *src = a4 + rq.off + (cc >> 4) * C3L_VSTRIDE + ((cc >> 3) & 1) * 32 + lane;
+                C3L_PREFETCH2(src); C3L_PREFETCH2(src + 64); C3L_PREFETCH2(src + 128);
+            }
+        }
+        if (C3_N_INN(S.nd1) > 1 && p1 != v) {
+            const c3_prow rq = (p1 == S.vlast) ? S.last : S.rb1;
+            const uint4 *a4 = reinterpret_cast<const uint4 *>(ar);
+            for (int j0 = max(lo, (int)rq.beg); j0 <= min(hi, (int)rq.end); j0 += 8) {
+                const int cc = j0 - rq.beg;
+                const uint4 *src = a4 + rq.off + (cc >> 4) * C3L_VSTRIDE + ((cc >> 3) & 1) * 32 + lane;
+                C3L_PREFETCH2(src); C3L_PREFETCH2(src + 64); C3L_PREFETCH2(src + 128);
+            }
+        }
     }
     const int npre = C3_N_INN(S.nd), nbase = C3_N_BASE(S.nd);
     const int beg = S.beg, end = S.end, nvec = S.nvec;
     const c3_prow r0 = S.r0, r1 = S.r1;
+    C3L_TICK2_INIT;
+    C3L_TICK2(16, r0.off + r1.off + beg);
     // the first predecessor comes from the ring when it is the row just computed and this band does not start
     // left of it (then no slot is overwritten before it is read); this row goes into the ring if it fits
     const bool p0_sm = S.last_sm && C3_N_IN0(S.nd) == S.vlast && beg >= (int)r0.beg;
@@ -405,84 +508,91 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
     int slot = smR > 0 ? S.beg_sn % smR : 0;
     const uint4 *ar4 = reinterpret_cast<const uint4 *>(ar);
     const int nstep = nvec * 2;
-    // three or more predecessors (rare per thread, frequent per warp): the first and the third.. are folded into
-    // the ring before the row loop -- per-halfword max on the packed cells, one walk of the edge list, loads of all
-    // steps independent -- so the row loop itself never follows an edge chain.  The second one stays in the loop.
+    // Anything but "one predecessor, and it is in the ring" is first FOLDED into the ring: a per-halfword max over all
+    // predecessor rows on the packed cells, with one walk of the edge list and the loads of 4 steps in flight
+    // at a time.  The row loop below then reads nothing but the ring (no arena load sits on its critical path).
+    // A row wider than the ring takes the slow path: cells of the first two predecessors straight from the arena,
+    // further ones along the edge chain per step.
     bool p0_ring = p0_sm;
-    c3_prow r0e = r0;
-    const bool fold = npre > 2 && keep_sm;              // (a row wider than the ring takes the slow in-loop path below)
+    c3_prow r0e = r0, r1e = r1;
+    // (-DC3L_FOLD_ALL folds the second predecessor as well: measured slower, 392 vs 374 ms per 100k reads -- the fold's
+    // loads are exposed once per row, the in-loop register prefetch overlaps them with the arithmetic.  -DC3L_CODES_RING
+    // keeps the column codes in the ring too: slower as well, 398 ms, the larger ring costs L1.)
+#ifdef C3L_FOLD_ALL
+    const bool fold = keep_sm && !(p0_sm && npre == 1);
+    const bool fold1 = true;                            // the second predecessor is folded too
+#else
+    const bool fold = keep_sm && npre > 2;              // the second predecessor stays in the row loop (register prefetch)
+    const bool fold1 = false;
+#endif
     if (fold) {
-        const int slot0 = slot;
-        if (!p0_sm || beg < (int)r0.beg || end > (int)r0.end) {
-            int sl = slot0;
-            for (int h = 0; h < nstep; ++h) {
-                const int j0 = beg + 8 * h;
-                if (!(p0_sm && j0 >= (int)r0.beg && j0 <= (int)r0.end)) {
-                    uint4 a, b, c;
-                    c3l_load8(ar4, sm, false, 0, r0, j0, lane, a, b, c);
-                    uint4 *d2 = sm + (sl * 6 + (h & 1)) * 32 + lane;
-                    d2[0] = a; d2[64] = b; d2[128] = c;
-                }
-                if (h & 1) { ++sl; if (sl >= smR) sl = 0; }
-            }
-        }
-        int e = C3L_E_NEXT(S.pe);
-        for (int k = 2; k < npre; ++k) {
-            const c3_pedge pe = W.pool[e]; e = pe.next;
-            const c3_prow rp = W.rows[pe.id];
-            int sl = slot0;
-            for (int h = 0; h < nstep; ++h) {
-                const int j0 = beg + 8 * h;
-                if (j0 >= (int)rp.beg && j0 <= (int)rp.end) {
-                    uint4 a, b, c;
-                    c3l_load8(ar4, sm, false, 0, rp, j0, lane, a, b, c);
-                    uint4 *d2 = sm + (sl * 6 + (h & 1)) * 32 + lane;
-                    d2[0] = c3l_vmax8(d2[0], a); d2[64] = c3l_vmax8(d2[64], b); d2[128] = c3l_vmax8(d2[128], c);
-                }
-                if (h & 1) { ++sl; if (sl >= smR) sl = 0; }
+        const bool have0 = p0_sm && beg >= (int)r0.beg;
+        if (!have0) c3l_fold_pred(ar4, sm, smR, slot, r0, beg, nstep, lane, 1);
+        else if (end > (int)r0.end) c3l_fold_pred(ar4, sm, smR, slot, r0, beg, nstep, lane, 2);
+        if (npre > 1) {
+            if (fold1) c3l_fold_pred(ar4, sm, smR, slot, r1, beg, nstep, lane, 0);
+            int e = C3L_E_NEXT(S.pe);
+            for (int k = 2; k < npre; ++k) {
+                const c3_pedge pe = W.pool[e]; e = pe.next;
+                const c3_prow rp = W.rows[pe.id];
+                c3l_fold_pred(ar4, sm, smR, slot, rp, beg, nstep, lane, 0);
             }
         }
         p0_ring = true;
         r0e.beg = (uint16_t)beg; r0e.end = (uint16_t)(beg + 16 * nvec - 1);
+        if (fold1) { r1e.beg = 16; r1e.end = 0; }       // nothing left for the in-loop second predecessor
     }
+    C3L_TICK2(17, sm[lane].x);
     uint4 *out4 = reinterpret_cast<uint4 *>(ar) + base4 + lane;
     const int8_t *qprow = W.qp;                         // column codes
-    const uint32_t nb4 = (uint32_t)nbase * 0x01010101u, ms = (uint32_t)(P.match + P.mismatch), ms4 = ms * 0x01010101u;
-    const int mism = P.mismatch;
-    int f1 = C3_NEG_INF, f2 = C3_NEG_INF, carry0 = C3_NEG_INF, carry1 = C3_NEG_INF;
-    int bestkey = -0x7fffffff - 1;
-    unsigned lowest = 0xffffffffu;                      // min over cells of (unsigned)(H + 32767): reachable cells only count
-    // software pipeline: both predecessors' cells and the profile words of step h+1 are requested before
-    // step h is computed
+    // column codes of the band's vectors: in the ring next to the cells (thread-private global data does not stay in
+    // L1 with 256 threads per SM); the band moves right about one column per row, so this loads one vector per ~16 rows
+#ifdef C3L_CODES_RING
+    const bool codes_sm = keep_sm;
+#else
+    const bool codes_sm = false;
+#endif
+    if (codes_sm) {
+        if (S.code_lo > S.code_hi || S.beg_sn < S.code_lo || S.beg_sn > S.code_hi + 1) { S.code_lo = S.beg_sn; S.code_hi = S.beg_sn - 1; }
+        for (int vv = S.code_hi + 1; vv <= S.end_sn; ++vv) {
+            int sl = slot + (vv - S.beg_sn); if (sl >= smR) sl -= smR;
+            sm[(sl * C3L_RSLOT + 6) * 32 + lane] = *reinterpret_cast<const uint4 *>(qprow + 16 * vv);
+        }
+        S.code_hi = max(S.code_hi, S.end_sn);
+        S.code_lo = max(S.code_lo, S.code_hi - smR + 1);
+    }
+    // The row loop works on the packed cells, two columns per 32-bit word (VIADDMNMX.S16x2 / VIMNMX3.S16x2); only the
+    // horizontal gap F, a strictly sequential recurrence, and the row arg-max run per column in int32.
+    const uint32_t nb4 = (uint32_t)nbase * 0x01010101u, m4 = (uint32_t)P.match * 0x01010101u;
+    const uint32_t dms = (uint32_t)(256 - (P.match + P.mismatch));      // byte: match  ->  match - (match + mismatch)
+    const uint32_t ne1 = C3L_PACK2(-e1, -e1), ne2 = C3L_PACK2(-e2, -e2), noe1 = C3L_PACK2(-oe1, -oe1), noe2 = C3L_PACK2(-oe2, -oe2);
+    int g1 = C3_NEG_INF + oe1, g2 = C3_NEG_INF + oe2;   // F1 + (o1 + e1), F2 + (o2 + e2): one add-max per column and gap type
+    uint32_t carry = C3L_FLOOR2;                        // high half: merged predecessor H at column j0 - 1
+    int bestkey = -0x7fffffff - 1, h_first = 0;
+    // software pipeline: both predecessors' cells and the column codes of step h+1 are requested before step h
     uint4 na, nb, nc, pa, pb, pc;
     uint2 nsw = make_uint2(0u, 0u);
     c3l_load8(ar4, sm, p0_ring, slot, r0e, beg, lane, na, nb, nc);
-    c3l_load8(ar4, sm, false, 0, r1, beg, lane, pa, pb, pc);
-    nsw = *reinterpret_cast<const uint2 *>(qprow + beg);
+    c3l_load8(ar4, sm, false, 0, r1e, beg, lane, pa, pb, pc);
+    uint4 cw = make_uint4(0u, 0u, 0u, 0u);              // codes of the current vector when they come from the ring
+    if (codes_sm) { cw = sm[(slot * C3L_RSLOT + 6) * 32 + lane]; nsw = make_uint2(cw.x, cw.y); }
+    else nsw = *reinterpret_cast<const uint2 *>(qprow + beg);
+    C3L_TICK2(18, nsw.x + na.x + pa.x);
     for (int h = 0; h < nstep; ++h) {
         const int j0 = beg + 8 * h;
-        int m[8], x1[8], x2[8];
+        uint32_t hv[4] = {C3L_VMAX2(na.x, pa.x), C3L_VMAX2(na.y, pa.y), C3L_VMAX2(na.z, pa.z), C3L_VMAX2(na.w, pa.w)};
+        uint32_t x1[4] = {C3L_VMAX2(nb.x, pb.x), C3L_VMAX2(nb.y, pb.y), C3L_VMAX2(nb.z, pb.z), C3L_VMAX2(nb.w, pb.w)};
+        uint32_t x2[4] = {C3L_VMAX2(nc.x, pc.x), C3L_VMAX2(nc.y, pc.y), C3L_VMAX2(nc.z, pc.z), C3L_VMAX2(nc.w, pc.w)};
         const uint2 sw = nsw;
-        {
-            int t0[8], t1[8];
-            c3l_unpack8(na, t0); c3l_unpack8(pa, t1);
-            m[0] = max(carry0, carry1);
-#pragma unroll
-            for (int k = 1; k < 8; ++k) m[k] = max(t0[k - 1], t1[k - 1]);   // -32768 (unreachable) is NOT mapped back here:
-            carry0 = t0[7]; carry1 = t1[7];                                  // if it ever wins a cell, `lowest` sends the read away
-            c3l_unpack8(nb, t0); c3l_unpack8(pb, t1);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x1[k] = max(t0[k], t1[k]);
-            c3l_unpack8(nc, t0); c3l_unpack8(pc, t1);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x2[k] = max(t0[k], t1[k]);
-        }
+        C3L_TICK2(13, hv[0] + x1[1] + x2[2] + sw.x);     // waited for the loads of this step
         const int wslot = slot;
         if (h & 1) { ++slot; if (slot >= smR) slot = 0; }
         if (h + 1 < nstep) {
             c3l_load8(ar4, sm, p0_ring, slot, r0e, j0 + 8, lane, na, nb, nc);
-            c3l_load8(ar4, sm, false, 0, r1, j0 + 8, lane, pa, pb, pc);
-            nsw = *reinterpret_cast<const uint2 *>(qprow + j0 + 8);
+            c3l_load8(ar4, sm, false, 0, r1e, j0 + 8, lane, pa, pb, pc);
+            if (!codes_sm) nsw = *reinterpret_cast<const uint2 *>(qprow + j0 + 8);
+            else if (h & 1) { cw = sm[(slot * C3L_RSLOT + 6) * 32 + lane]; nsw = make_uint2(cw.x, cw.y); }
+            else nsw = make_uint2(cw.z, cw.w);
         }
         if (npre > 2 && !fold) {                         // wider than the ring: follow the edge chain per step
             int e = C3L_E_NEXT(S.pe);
@@ -492,62 +602,78 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
                 uint4 qa, qb, qc;
                 c3l_load8(ar4, sm, false, 0, rp, j0, lane, qa, qb, qc);
                 const int jc = j0 - 1;
-                int prev = C3_NEG_INF;
-                if (h > 0 && jc >= (int)rp.beg && jc <= (int)rp.end) prev = c3l_ld_e(ar, c3l_ci(rp.off, 0, jc - rp.beg, lane));
-                m[0] = max(m[0], prev);
-                int t0[8];
-                c3l_unpack8(qa, t0);
-#pragma unroll
-                for (int t = 1; t < 8; ++t) m[t] = max(m[t], t0[t - 1]);
-                c3l_unpack8(qb, t0);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) x1[t] = max(x1[t], t0[t]);
-                c3l_unpack8(qc, t0);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) x2[t] = max(x2[t], t0[t]);
+                if (h > 0 && jc >= (int)rp.beg && jc <= (int)rp.end) {
+                    const int prev = c3l_ld_e(ar, c3l_ci(rp.off, 0, jc - rp.beg, lane));
+                    carry = C3L_VMAX2(carry, C3L_PACK2(C3L_FLOOR, prev));
+                }
+                hv[0] = C3L_VMAX2(hv[0], qa.x); hv[1] = C3L_VMAX2(hv[1], qa.y); hv[2] = C3L_VMAX2(hv[2], qa.z); hv[3] = C3L_VMAX2(hv[3], qa.w);
+                x1[0] = C3L_VMAX2(x1[0], qb.x); x1[1] = C3L_VMAX2(x1[1], qb.y); x1[2] = C3L_VMAX2(x1[2], qb.z); x1[3] = C3L_VMAX2(x1[3], qb.w);
+                x2[0] = C3L_VMAX2(x2[0], qc.x); x2[1] = C3L_VMAX2(x2[1], qc.y); x2[2] = C3L_VMAX2(x2[2], qc.z); x2[3] = C3L_VMAX2(x2[3], qc.w);
             }
         }
         const int vi = h >> 1;
         if (!(h & 1))                                   // F entering this 16-column vector: the backtrack restarts from it
-            *reinterpret_cast<int2 *>(ar + c3l_fi(base4, vi, lane)) = make_int2(f1, f2);
-        int hme[8];
-        // 4 columns per word: byte = match + mismatch where the column's base equals the node's, else 0
-        uint32_t swv[2] = {sw.x ^ nb4, sw.y ^ nb4};
+            *reinterpret_cast<int2 *>(ar + c3l_fi(base4, vi, lane)) = make_int2(g1 - oe1, g2 - oe2);
+        // M: merged predecessor H one column to the left
+        uint32_t mw[4];
+        mw[0] = C3L_PRMT(carry, hv[0], 0x5432u);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) swv[t] = ms4 - (((swv[t] + 0x7f7f7f7fu) >> 7) & 0x01010101u) * ms;
+        for (int t = 1; t < 4; ++t) mw[t] = C3L_PRMT(hv[t - 1], hv[t], 0x5432u);
+        carry = hv[3];
+        // scores: 4 columns per word, byte = match where the column's base equals the node's, else -mismatch;
+        // sign-extended to halfwords
+        uint32_t sb[2] = {sw.x ^ nb4, sw.y ^ nb4};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int sc = (int)((swv[k >> 2] >> (8 * (k & 3))) & 0xffu) - mism;
-            hme[k] = C3L_MAX3(m[k] + sc, x1[k], x2[k]);
-        }
+        for (int t = 0; t < 2; ++t) sb[t] = m4 + (((sb[t] + 0x7f7f7f7fu) >> 7) & 0x01010101u) * dms;
+        const uint32_t sc[4] = {C3L_PRMT(sb[0], 0u, 0x9180u), C3L_PRMT(sb[0], 0u, 0xb3a2u), C3L_PRMT(sb[1], 0u, 0x9180u), C3L_PRMT(sb[1], 0u, 0xb3a2u)};
+        uint32_t hme[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) hme[t] = C3L_VMAX3_2(C3L_VADDMAX2(mw[t], sc[t], C3L_FLOOR2), x1[t], x2[t]);
         const int lim = end - j0;                       // last active column of this step (>= 7: all)
         if (lim < 7) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) if (k > lim) hme[k] = C3_NEG_INF;
+            for (int t = 0; t < 4; ++t) {
+                if (2 * t > lim) hme[t] = C3L_FLOOR2;
+                else if (2 * t + 1 > lim) hme[t] = (hme[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
+            }
         }
-        int hh[8], n1[8], n2[8];
+        int hk[8], fm[8], hhk[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { hk[2 * t] = (int)(int16_t)(hme[t] & 0xffffu); hk[2 * t + 1] = (int)hme[t] >> 16; }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            hh[k] = C3L_MAX3(hme[k], f1, f2);
-            f1 = C3L_ADDMAX(f1, -e1, hme[k] - oe1);
-            f2 = C3L_ADDMAX(f2, -e2, hme[k] - oe2);
-            n1[k] = C3L_ADDMAX(hh[k], -oe1, x1[k] - e1);
-            n2[k] = C3L_ADDMAX(hh[k], -oe2, x2[k] - e2);
-            lowest = C3L_UMIN(lowest, hh[k] + 32767);
+            fm[k] = C3L_MAX3(g1 - oe1, g2 - oe2, C3L_FLOOR);
+            hhk[k] = max(hk[k], fm[k]);
+            g1 = C3L_ADDMAX(g1, -e1, hk[k]);
+            g2 = C3L_ADDMAX(g2, -e2, hk[k]);
+        }
+        if (h == 0) h_first = hhk[0];
+        uint32_t hh2[4], n1[4], n2[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            hh2[t] = C3L_VMAX2(hme[t], C3L_PACK2(fm[2 * t], fm[2 * t + 1]));
+            n1[t] = C3L_VADDMAX2(x1[t], ne1, C3L_VADDMAX2(hh2[t], noe1, C3L_FLOOR2));
+            n2[t] = C3L_VADDMAX2(x2[t], ne2, C3L_VADDMAX2(hh2[t], noe2, C3L_FLOOR2));
         }
         if (lim < 7) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) if (k > lim) { hh[k] = C3_NEG_INF; n1[k] = C3_NEG_INF; n2[k] = C3_NEG_INF; }
+            for (int t = 0; t < 4; ++t) {
+                if (2 * t > lim) { hh2[t] = n1[t] = n2[t] = C3L_FLOOR2; hhk[2 * t] = hhk[2 * t + 1] = C3L_FLOOR; }
+                else if (2 * t + 1 > lim) {
+                    hh2[t] = (hh2[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
+                    n1[t] = (n1[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
+                    n2[t] = (n2[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
+                    hhk[2 * t + 1] = C3L_FLOOR;
+                }
+            }
         }
-        const uint4 oa = c3l_pack8(hh), ob = c3l_pack8(n1), oc = c3l_pack8(n2);
+        const uint4 oa = make_uint4(hh2[0], hh2[1], hh2[2], hh2[3]), ob = make_uint4(n1[0], n1[1], n1[2], n1[3]),
+                    oc = make_uint4(n2[0], n2[1], n2[2], n2[3]);
+        C3L_TICK2(14, oa.x + ob.y + oc.z);               // arithmetic
         uint4 *dst = out4 + vi * C3L_VSTRIDE + (h & 1) * 32;
-#ifndef C3L_EXP_NOSTORE
         dst[0] = oa; dst[64] = ob; dst[128] = oc;
-#else
-        if (lowest == 12345u) { dst[0] = oa; dst[64] = ob; dst[128] = oc; }
-#endif
         if (keep_sm) {
-            uint4 *d2 = sm + (wslot * 6 + (h & 1)) * 32 + lane;
+            uint4 *d2 = sm + (wslot * C3L_RSLOT + (h & 1)) * 32 + lane;
             d2[0] = oa; d2[64] = ob; d2[128] = oc;
         }
         // simd_abpoa_ada_max_i as one packed max: value in the high half, tie-break priority in the low half
@@ -555,14 +681,19 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
         const int vp = (vi == nvec - 1) ? 0xfff : (0xffe - vi);
         const int k16 = (h & 1) * 8;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int hc = max(hh[k], -32768);
-            bestkey = C3L_ADDMAX((int)((unsigned)hc << 16) + vp, (15 - k16 - k) << 12, bestkey);
-        }
+        for (int k = 0; k < 8; ++k)
+            bestkey = C3L_ADDMAX(hhk[k] * 65536 + vp, (15 - k16 - k) << 12, bestkey);
+        C3L_TICK2(15, bestkey);                          // stores issued + arg-max
     }
-    if (lowest < (unsigned)C3L_LOW_GUARD) S.err = C3L_E_RETRY;   // a reachable cell came too close to the int16 floor
+    // Exactness of the int16 form: a cell can lose at most D per column to its left neighbour (gap open / extend),
+    // so a first band cell comfortably above the floor means that every cell of the row is reachable and was never
+    // clamped.  Anything else leaves the read to the warp kernel.
+    {
+        const int D = max(min(oe1, oe2), max(e1, e2));
+        if (h_first < C3L_FLOOR + C3L_LOW_GUARD + oe2 + D * (end - beg + 1)) S.err = C3L_E_RETRY;
+    }
     int best_i = -1;
-    if ((bestkey >> 16) > -32768) {
+    if ((bestkey >> 16) > C3L_FLOOR) {
         const int sl = 15 - ((bestkey >> 12) & 15);
         const int vp = bestkey & 0xfff;
         const int sn = (vp == 0xfff) ? S.end_sn : S.beg_sn + (0xffe - vp);
@@ -572,34 +703,16 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
     ri.in0 = (uint16_t)C3_N_IN0(S.nd); ri.base = (uint8_t)nbase; ri.npre = (uint8_t)npre;
     ri.link = (uint16_t)S.rcount;
     W.rows[v] = ri;
+    S.last2 = S.last; S.vlast2 = S.vlast;
     S.last = ri; S.vlast = v; S.last_sm = keep_sm ? 1 : 0;
     ri.link = (uint16_t)v; ri.mp = r0.link;
     W.ord[S.rcount] = ri;
     S.cells_total += end - beg + 1;
     ++S.rcount;
-    // the next row's predecessors that will come from the arena (an old row as first predecessor, any second one):
-    // start their lines towards L2 now, over the columns this row covered (the next band is about the same)
-    {
-        const int in0n = c3l_cl(C3_N_IN0(S.nd1));
-        if (in0n != v || !keep_sm) {
-            const c3_prow rq = (in0n != v) ? ra_n : ri;
-            for (int j0 = max(beg, (int)rq.beg); j0 <= min(end + 16, (int)rq.end); j0 += 8) {
-                const int cc = j0 - rq.beg;
-                const uint4 *src = ar4 + rq.off + (cc >> 4) * C3L_VSTRIDE + ((cc >> 3) & 1) * 32 + lane;
-                C3L_PREFETCH2(src); C3L_PREFETCH2(src + 64); C3L_PREFETCH2(src + 128);
-            }
-        }
-        if (C3_N_INN(S.nd1) > 1 && C3L_E_ID(S.pe1) != v) {
-            for (int j0 = max(beg, (int)rb_n.beg); j0 <= min(end + 16, (int)rb_n.end); j0 += 8) {
-                const int cc = j0 - rb_n.beg;
-                const uint4 *src = ar4 + rb_n.off + (cc >> 4) * C3L_VSTRIDE + ((cc >> 3) & 1) * 32 + lane;
-                C3L_PREFETCH2(src); C3L_PREFETCH2(src + 64); C3L_PREFETCH2(src + 128);
-            }
-        }
-    }
-    S.v = v1; S.nd = S.nd1; S.hrv = S.hr1; S.nd1 = S.nd2; S.hr1 = S.hr2; S.nd2 = nd3; S.hr2 = hr3;
-    S.pe = S.pe1; S.pe1 = pe2; S.ra = ra_n; S.rb = rb_n;
+    S.v = v1; S.nd = S.nd1; S.hrv = S.hr1; S.nd1 = S.nd2; S.hr1 = S.hr2; S.nd2 = S.nd3; S.hr2 = S.hr3; S.nd3 = nd4; S.hr3 = hr4;
+    S.pe = S.pe1; S.pe1 = S.pe2; S.pe2 = pe3; S.ra = S.ra1; S.rb = S.rb1; S.ra1 = ra2; S.rb1 = rb2;
     S.nvec = 0;
+    C3L_TICK2(19, S.nd3.a.x + S.hr3 + S.pe2.x + S.ra1.off + S.rb1.off);
 }
 
 // ---------------------------------------------------------------------------
@@ -883,7 +996,7 @@ struct c3_lane_args {
     c3_poa_args A;                 // ws / ws_stride: per-THREAD workspace (cell_cap = 0); order / n_work: eligible items
     int4 *arena; long long arena_stride4;   // per-warp DP arena, in int4
     int arena_cap4;                // int4 per warp
-    int sm_vec;                    // shared-memory ring: vector slots per lane (dynamic shared memory = warps x sm_vec x 3 KB)
+    int sm_vec;                    // shared-memory ring: vector slots per lane (dynamic shared memory = warps x sm_vec x 3.5 KB)
     int32_t *done;                 // [n_items] 1 = finished here
 };
 
@@ -896,7 +1009,7 @@ __global__ void __launch_bounds__(C3L_THREADS, C3L_MINB) c3_poa_lane_kernel(c3_l
     int32_t *ar = reinterpret_cast<int32_t *>(L.arena + (int64_t)gwarp * L.arena_stride4);
     const c3_poa_para_dev P = A.P;
     extern __shared__ uint4 c3l_smem[];
-    uint4 *sm = c3l_smem + (size_t)(threadIdx.x >> 5) * L.sm_vec * 192;
+    uint4 *sm = c3l_smem + (size_t)(threadIdx.x >> 5) * L.sm_vec * (C3L_RSLOT * 32);
     const int smR = L.sm_vec;
     c3l_state S;
     C3L_TICK_INIT;

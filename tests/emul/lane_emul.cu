@@ -27,7 +27,7 @@ extern "C" int c3l_emul_batch(int n_items, const uint8_t *codes, const int64_t *
     const int64_t ws_bytes = c3_poa_ws_bytes(node_cap, node_cap, 0, cigar_cap, qp_stride);
     uint8_t *ws = (uint8_t *)aligned_alloc(256, (size_t)ws_bytes * 32);
     int32_t *ar = (int32_t *)aligned_alloc(256, (size_t)arena_cap4 * 16);
-    std::vector<uint4> smbuf((size_t)(sm_vec > 0 ? sm_vec : 1) * 192);
+    std::vector<uint4> smbuf((size_t)(sm_vec > 0 ? sm_vec : 1) * C3L_RSLOT * 32);
     uint4 *sm = smbuf.data();
     if (!ws || !ar) return -1;
     memset(ws, 0, (size_t)ws_bytes * 32);
