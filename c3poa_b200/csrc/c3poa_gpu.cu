@@ -52,6 +52,7 @@ struct c3_handle {
     DevBuf d_order_lane, d_done;
     int n_work_lane = 0, lane_items = 0, lane_n_items = 0;
     int64_t lane_max_total = 0; int lane_max_nseq = 0, lane_max_q = 0;
+    double lane_cost_spread = 1.0;       // estimated cost of the largest lane item / of the median one
 };
 
 static int fail(c3_handle *h, int code, const char *fmt, ...)
@@ -288,6 +289,7 @@ static int upload_poa_order(c3_handle *h, c3_poa_args &A, const std::vector<int3
             h->lane_max_nseq = std::max(h->lane_max_nseq, nseq[i]);
         }
     }
+    h->lane_cost_spread = nl > 0 ? exp2((double)(cls[lane[0]] - cls[lane[nl / 2]]) / 16.0) : 1.0;
     CK(h->d_order_lane.ensure((size_t)std::max(nl, 1) * 4));
     CK(cudaMemcpyAsync(h->d_order_lane.p, lane.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));                          // `order` and `lane` are locals
@@ -303,8 +305,7 @@ static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa
     h->lane_items = 0;
     A.done = nullptr;
     const int nl = h->n_work_lane;
-    const bool want = h->poa_mode == 2 || (h->poa_mode == 0 && nl >= 8192);
-    if (!want || nl <= 0) return 0;
+    if (h->poa_mode == 1 || nl <= 0) return 0;
     const int max_nseq = h->lane_max_nseq;
     const int64_t max_total = h->lane_max_total;
     max_q = (int)std::min<int64_t>(max_q, max_total);
@@ -338,6 +339,10 @@ static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_lane_kernel, C3L_THREADS, sm_bytes) != cudaSuccess || bps < 1) bps = 4;
     bps = std::min(bps, C3L_MINB);
     int64_t warps = (int64_t)h->sm_count * bps * wpb;
+    // auto mode: 32 reads advance in lockstep per warp, so one warp item takes as long as ~20 reads in the warp kernel;
+    // that pays only when the batch fills most of the grid (measured break-even: about half a wave) and the reads are
+    // of similar size (the largest items set the latency of the whole launch).  Otherwise the warp kernel is faster.
+    if (h->poa_mode == 0 && ((int64_t)nl * 4 < warps * 32 * 3 || h->lane_cost_spread > 4.0)) return 0;
     warps = std::min<int64_t>(warps, ((int64_t)nl + 31) / 32);
     size_t free_b = 0, tot_b = 0;
     CK(cudaMemGetInfo(&free_b, &tot_b));

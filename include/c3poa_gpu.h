@@ -71,9 +71,10 @@ void c3_destroy(c3_handle *h);
 const char *c3_last_error(const c3_handle *h);
 void c3_default_poa_params(c3_poa_params *p);
 int  c3_get_timings(const c3_handle *h, c3_timings *out);
-/* Which POA kernel serves B3/B4: 0 = auto (thread-per-read "lane" kernel for batches of >= 8192 eligible
- * reads, warp-per-read kernel otherwise and for everything the lane kernel declines), 1 = warp kernel only,
- * 2 = lane kernel whenever a read is eligible.  Results are identical in every mode.                        */
+/* Which POA kernel serves B3/B4: 0 = auto (thread-per-read "lane" kernel when the eligible reads fill at least
+ * three quarters of its grid -- 56 832 reads on a B200 -- and are of similar size; warp-per-read kernel otherwise and
+ * for everything the lane kernel declines), 1 = warp kernel only, 2 = lane kernel whenever a read is eligible.
+ * Results are identical in every mode.                                                                        */
 int  c3_set_poa_mode(c3_handle *h, int32_t mode);
 /* Reads of the last B3/B4 call handed to the lane kernel, and how many of them it finished.                */
 int  c3_lane_counts(c3_handle *h, int32_t *out_given, int32_t *out_done);

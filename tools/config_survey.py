@@ -11,7 +11,9 @@ def resolve(d):
     idx = [2 * names.index(s) + (1 if st == "-" else 0) for s, st in zip(d["splint_name"], d["strand"])]
     return sp, np.array(idx, dtype=np.int32)
 
-g = GpuConsensus(0)
+mode = sys.argv[1] if len(sys.argv) > 1 else "auto"
+scale = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+g = GpuConsensus(0, poa_mode=mode)
 rng = np.random.default_rng(4)
 sp4 = {"Splint1": synth.SPLINT1, **{f"Splint{k}": synth.random_seq(rng, 284).tobytes().decode() for k in range(2, 5)}}
 cfgs = {
@@ -21,6 +23,7 @@ cfgs = {
     "cfg5 mixed 4 splints": dict(n_reads=4000, insert_choices=[500, 1000, 2000, 4000], repeat_range=(2, 10), seed=5, splints=sp4),
 }
 for name, kw in cfgs.items():
+    kw = dict(kw); kw["n_reads"] *= scale
     d = synth.make_reads(**kw)
     sp, idx = resolve(d)
     b = ReadBatch.from_strings(d["seqs"], sp, idx)
@@ -32,4 +35,4 @@ for name, kw in cfgs.items():
     cells = int(R["poa_cells"].sum())
     print(f"{name:22s} reads {b.n:5d} bases {int(b.off[-1])/1e6:7.1f}M status {dict(zip(map(int,u),map(int,c)))} "
           f"total {t['total_ms']:8.1f} ms ({b.n/t['total_ms']*1e3:9.0f} reads/s) conk {t['conk_ms']:7.1f} peaks {t['peaks_ms']:6.1f} "
-          f"poa {t['poa_ms']:8.1f} ms  POA {cells/t['poa_ms']/1e6:6.1f} GCUPS  max nodes {int(R['poa_nodes'].max())}")
+          f"poa {t['poa_ms']:8.1f} ms  POA {cells/t['poa_ms']/1e6:6.1f} GCUPS  max nodes {int(R['poa_nodes'].max())}  lane given/done {g.lane_counts()}")
