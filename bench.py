@@ -232,12 +232,13 @@ def main():
             pass
     poa_s = stage_ms["poa_ms"] * 1e-3 / a.steps
     conk_s = stage_ms["conk_ms"] * 1e-3 / a.steps
-    dominant = "c3_poa_kernel" if poa_s >= conk_s else "c3_conk_kernel"
+    poa_kernel_name = "c3_poa_lane_kernel" if lane_done * 2 >= n else "c3_poa_kernel"
+    dominant = poa_kernel_name if poa_s >= conk_s else "c3_conk_kernel"
     sb = out["sub_bounds"]
     ns = res["n_sub"]
     in_poa = ns >= 3
     sub_bases = int(((sb[:, :, 1] - sb[:, :, 0]) * (np.arange(max_peaks)[None, :] < ns[:, None]))[in_poa].sum())
-    if dominant == "c3_poa_kernel":
+    if dominant != "c3_conk_kernel":
         # 2-bit bases in + consensus out + 1 B/cell backtrack written and read once
         alg_bytes = sub_bases / 4 + int(res["cons_len"][in_poa].sum()) + 2 * poa_cells
         k_s, int_ops = poa_s, OPS_PER_POA_CELL * poa_cells
@@ -246,8 +247,8 @@ def main():
         k_s, int_ops = conk_s, OPS_PER_CONK_CELL * conk_cells
     achieved = alg_bytes / k_s / 1e9 if k_s > 0 else 0.0
     traffic = None
-    tf = os.path.join(ROOT, "profiles", "r01_poa_traffic.json")
-    if dominant == "c3_poa_kernel" and os.path.exists(tf):      # from one `ncu --set full` capture, per launch
+    tf = os.path.join(ROOT, "profiles", "r01_poa_lane_traffic.json" if dominant == "c3_poa_lane_kernel" else "r01_poa_traffic.json")
+    if dominant != "c3_conk_kernel" and os.path.exists(tf):      # from one `ncu --set full` capture, per launch
         try:
             t = json.load(open(tf))
             traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * (n / t["reads_per_launch"])
@@ -255,10 +256,13 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": hbm_src,
-                "note": "integer-ALU bound kernel: see roofline_int for the binding resource"}
+                "note": ("thread-per-read kernel: bound by memory latency at 12 warps/SM (ncu: issue slots 24 % busy, DRAM 29 % of "
+                         "peak, long-scoreboard stalls); traffic is 9x the algorithmic bytes because H/E1/E2 are kept as int16 "
+                         "per cell for the value-based backtrack" if dominant == "c3_poa_lane_kernel" else
+                         "integer-ALU bound kernel: see roofline_int for the binding resource")}
     roofline_int = {"kernel": dominant, "achieved_ops_per_s": int_ops / k_s if k_s > 0 else 0.0,
                     "peak_ops_per_s": int_peak, "frac": (int_ops / k_s / int_peak) if (k_s > 0 and int_peak > 0) else None,
-                    "ops_per_cell": OPS_PER_POA_CELL if dominant == "c3_poa_kernel" else OPS_PER_CONK_CELL,
+                    "ops_per_cell": OPS_PER_POA_CELL if dominant != "c3_conk_kernel" else OPS_PER_CONK_CELL,
                     "peak_source": "measured live: independent VIADDMNMX chains on all SMs (c3_measure_int_peak)"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
