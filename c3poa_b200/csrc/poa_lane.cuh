@@ -264,6 +264,7 @@ C3_HD __forceinline__ int c3l_align_begin(c3l_state &S, const c3_poa_args &A, co
     if (act) { W.hr[C3_SINK] = C3_SINK; v = W.nodes[C3_SINK].prev; }
     c3_nrec cur = c3_ld_node(&W.nodes[c3l_cl(v)]);
     int cur_om = W.nodes[c3l_cl(v)].out_more;
+    int vdone = C3_SINK; uint32_t hdone = C3_SINK;
     while (C3L_ANY(v != C3_NONE)) {
         if (v == C3_NONE) continue;
         const int pv = C3_N_PREV(cur);
@@ -276,7 +277,10 @@ C3_HD __forceinline__ int c3l_align_begin(c3l_state &S, const c3_poa_args &A, co
             if ((int)pe.w > best_w) { best_w = pe.w; best = pe.id; }
             e = pe.next;
         }
-        W.hr[v] = ((W.hr[best] >> 16) + 1u) << 16;
+        // (the heaviest successor is usually the node handled one trip earlier: its word is still in a register)
+        const uint32_t hb = (best == vdone) ? hdone : W.hr[best];
+        hdone = ((hb >> 16) + 1u) << 16; vdone = v;
+        W.hr[v] = hdone;
         v = pv; cur = nxt; cur_om = nxt_om;
     }
     // column codes: qa[j] = base code of column j (= q[j-1]), 16 columns per store; j = 0 and the padding hold 4.
@@ -706,6 +710,7 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
     S.last2 = S.last; S.vlast2 = S.vlast;
     S.last = ri; S.vlast = v; S.last_sm = keep_sm ? 1 : 0;
     ri.link = (uint16_t)v; ri.mp = r0.link;
+    ri.in0 = npre > 1 ? r1.link : (uint16_t)C3_NONE;   // by position: in0 = position of the SECOND predecessor's row
     W.ord[S.rcount] = ri;
     S.cells_total += end - beg + 1;
     ++S.rcount;
@@ -755,6 +760,7 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
     int cur_op = C3_OP_ALL;
     // the record of the current row's first predecessor is requested as soon as the row is known (one step ahead)
     c3_prow pr0 = W.ord[rt.mp == C3_NONE ? 0 : rt.mp];
+    c3_prow pr1 = W.ord[rt.in0 == C3_NONE ? 0 : rt.in0];        // second predecessor likewise (rows with two or more)
     while (C3L_ANY(run && rt.link != C3_SRC && j > 0)) {
         C3L_COUNT(11, 1);
         if (!(run && rt.link != C3_SRC && j > 0)) continue;
@@ -766,26 +772,42 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
         if (j >= b && j <= (int)rt.end) {
             const int s = c3_score(P, rt.base, q[j - 1]);
             const int npre = rt.npre;
-            const int in_more = npre > 1 ? (int)W.nodes[i].in_more : (int)C3_NONE;
+            // third and further predecessors follow the edge list (rare); the first two come from pr0 / pr1
             if (cur_op & C3_OP_M) {
-                int e = in_more;
-                for (int k = 0; k < npre; ++k) {
-                    c3_prow pr = pr0;
-                    if (k > 0) { const c3_pedge pe = W.pool[e]; pr = W.ord[W.rows[pe.id].link]; e = pe.next; }
-                    if (j - 1 < max((int)pr.beg, b) || j - 1 > (int)pr.end) continue;
-                    const int ph = c3l_ld_h(ar, c3l_ci(pr.off, 0, j - 1 - pr.beg, lane));
-                    if (ph + s == hij) {
-                        opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                        rt = pr; --j; hit = 1; cur_op = C3_OP_ALL; hij = ph;
-                        break;
+                const bool ok0 = !(j - 1 < max((int)pr0.beg, b) || j - 1 > (int)pr0.end);
+                const bool ok1 = npre > 1 && !(j - 1 < max((int)pr1.beg, b) || j - 1 > (int)pr1.end);
+                int ph0 = 0, ph1 = 0;                  // both cells requested before either is compared
+                if (ok0) ph0 = c3l_ld_h(ar, c3l_ci(pr0.off, 0, j - 1 - pr0.beg, lane));
+                if (ok1) ph1 = c3l_ld_h(ar, c3l_ci(pr1.off, 0, j - 1 - pr1.beg, lane));
+                if (ok0 && ph0 + s == hij) {
+                    opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                    rt = pr0; --j; hit = 1; cur_op = C3_OP_ALL; hij = ph0;
+                } else if (ok1 && ph1 + s == hij) {
+                    opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                    rt = pr1; --j; hit = 1; cur_op = C3_OP_ALL; hij = ph1;
+                } else if (npre > 2) {
+                    int e = W.pool[W.nodes[i].in_more].next;
+                    for (int k = 2; k < npre; ++k) {
+                        const c3_pedge pe = W.pool[e]; e = pe.next;
+                        const c3_prow pr = W.ord[W.rows[pe.id].link];
+                        if (j - 1 < max((int)pr.beg, b) || j - 1 > (int)pr.end) continue;
+                        const int ph = c3l_ld_h(ar, c3l_ci(pr.off, 0, j - 1 - pr.beg, lane));
+                        if (ph + s == hij) {
+                            opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                            rt = pr; --j; hit = 1; cur_op = C3_OP_ALL; hij = ph;
+                            break;
+                        }
                     }
                 }
             }
             if (!hit && (cur_op & C3_OP_E)) {
-                int e = in_more;
+                int e = C3_NONE;
                 for (int k = 0; k < npre; ++k) {
-                    c3_prow pr = pr0;
-                    if (k > 0) { const c3_pedge pe = W.pool[e]; pr = W.ord[W.rows[pe.id].link]; e = pe.next; }
+                    c3_prow pr = k == 0 ? pr0 : pr1;
+                    if (k >= 2) {
+                        if (k == 2) e = W.pool[W.nodes[i].in_more].next;
+                        const c3_pedge pe = W.pool[e]; pr = W.ord[W.rows[pe.id].link]; e = pe.next;
+                    }
                     if (j < (int)pr.beg || j > (int)pr.end) continue;
                     const int pc = j - pr.beg;
                     const int ph = c3l_ld_h(ar, c3l_ci(pr.off, 0, pc, lane)), pe1 = c3l_ld_e(ar, c3l_ci(pr.off, 1, pc, lane)), pe2 = c3l_ld_e(ar, c3l_ci(pr.off, 2, pc, lane));
@@ -854,7 +876,10 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
             }
         }
         if (!hit) { S.err = C3L_E_RETRY; run = false; continue; }
-        if ((int)rt.link != row_before) pr0 = W.ord[rt.mp == C3_NONE ? 0 : rt.mp];
+        if ((int)rt.link != row_before) {
+            pr0 = W.ord[rt.mp == C3_NONE ? 0 : rt.mp];
+            pr1 = W.ord[rt.in0 == C3_NONE ? 0 : rt.in0];
+        }
         cg[nc] = opw;
         ++nc;
         if (nc + j + 8 > A.cigar_cap) { S.err = C3L_E_RETRY; run = false; }

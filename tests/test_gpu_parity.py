@@ -393,6 +393,34 @@ def test_cfg5_like_mixed_batch_properties(gpu, oracle):
         assert np.array_equal(ref["cons"][k, :L], out["cons"][i, :L]), i
 
 
+def test_lane_and_warp_kernels_agree_at_scale(gpu):
+    """45 000 cfg2 reads: `auto` hands a batch of this size to the thread-per-read lane kernel; the warp-per-read kernel
+    must return the same bytes for every read (status, peaks, bounds, consensus, DP cell counts, graph sizes)."""
+    if gpu.poa_mode != "auto":
+        pytest.skip("runs once, switching modes itself")
+    blob, off, strand = synth.make_batch(45000, insert_len=1000, repeats=5, seed=77)
+    sp = synth.SPLINT1 + synth.revcomp(synth.SPLINT1)
+    b = ReadBatch(blob, off, np.frombuffer(sp.encode(), dtype=np.uint8).copy(), np.array([0, 284, 568], dtype=np.int32),
+                  strand.astype(np.int32))
+    try:
+        a = gpu.consensus_batch(b, max_peaks=16, cons_cap=2048)
+        given, done = gpu.lane_counts()
+        assert given >= 44000 and done == given, (given, done)          # the lane kernel ran, and finished all it took
+        a = {k: np.array(v, copy=True) for k, v in a.items()}
+        gpu.set_poa_mode("warp")
+        w = gpu.consensus_batch(b, max_peaks=16, cons_cap=2048)
+        assert gpu.lane_counts()[0] == 0
+    finally:
+        gpu.set_poa_mode("auto")
+    for f in ("status", "n_peaks", "n_sub", "cons_len", "poa_cells", "poa_nodes"):
+        assert np.array_equal(a["results"][f], w["results"][f]), f
+    assert (a["results"]["status"] == 0).mean() > 0.95
+    assert np.array_equal(a["peaks"], w["peaks"]) and np.array_equal(a["sub_bounds"], w["sub_bounds"])
+    L = a["results"]["cons_len"]
+    mask = np.arange(a["cons"].shape[1])[None, :] < L[:, None]
+    assert np.array_equal(a["cons"][mask], w["cons"][mask])
+
+
 def test_driver_multi_process_sharding(gpu, tmp_path):
     """--gpus N: one process per GPU, reads sharded by index, per-rank tmp dirs concatenated (here both
     ranks are mapped onto the box's GPUs modulo the device count, so the path runs on a 1-GPU box too)."""
