@@ -52,9 +52,17 @@ __device__ double c3_radix_select(const double *buf, int n, int k, unsigned *his
     for (int shift = 56; shift >= 0; shift -= 8) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            unsigned long long kx = c3_dkey(buf[i]);
-            if ((kx & mask) == prefix) atomicAdd(&hist[(unsigned)(kx >> shift) & 255u], 1u);
+        // smoothed profiles share their leading bytes: without aggregation the first passes are n atomics on one
+        // address.  Lanes with the same digit elect one of them to add their count.
+        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+            const int i = i0 + threadIdx.x;
+            unsigned digit = 0xffffffffu;
+            if (i < n) {
+                const unsigned long long kx = c3_dkey(buf[i]);
+                if ((kx & mask) == prefix) digit = (unsigned)(kx >> shift) & 255u;
+            }
+            const unsigned peers = __match_any_sync(C3_FULL, digit);
+            if (digit != 0xffffffffu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[digit], (unsigned)__popc(peers));
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -74,7 +82,7 @@ __device__ double c3_radix_select(const double *buf, int n, int k, unsigned *his
 __global__ void __launch_bounds__(C3_PK_THREADS) c3_peaks_kernel(c3_peaks_args A)
 {
     __shared__ double s_coef[C3_PK_MAXWIN];
-    __shared__ double s_tile[C3_PK_TILE + C3_PK_MAXWIN - 1];
+    __shared__ __align__(16) double s_tile[C3_PK_TILE + C3_PK_MAXWIN + 3];
     __shared__ double s_pr[C3_PK_MAXC];
     __shared__ int s_pos[C3_PK_MAXC];
     __shared__ int s_order[C3_PK_MAXC];
@@ -134,11 +142,28 @@ __global__ void __launch_bounds__(C3_PK_THREADS) c3_peaks_kernel(c3_peaks_args A
                     }
                     s_tile[u] = v;
                 }
+                if (tid < 2) s_tile[need + tid] = 0.0;       // read (never used) by the second output of an odd-length tile
                 __syncthreads();
-                for (int u = tid; u < tn; u += blockDim.x) {
-                    double acc = 0.0;
-                    for (int k = 0; k < W; ++k) acc = __dadd_rn(acc, __dmul_rn(s_coef[k], s_tile[u + k]));
-                    dst[t0 + u] = acc;
+                // two consecutive outputs per thread: the window is read once as 16-byte words (the kernel is bound by
+                // shared-memory wavefronts, not by the fp64 pipe); summation order per output unchanged (k = 0..W-1)
+                for (int u = 2 * tid; u < tn; u += 2 * blockDim.x) {
+                    double a0 = 0.0, a1 = 0.0;
+                    const double2 *tp = reinterpret_cast<const double2 *>(s_tile + u);
+                    double2 w2 = tp[0];
+                    int k = 0;
+                    for (; k + 1 < W; k += 2) {
+                        const double2 nx = tp[(k >> 1) + 1];
+                        const double c0 = s_coef[k], c1 = s_coef[k + 1];
+                        a0 = __dadd_rn(a0, __dmul_rn(c0, w2.x)); a1 = __dadd_rn(a1, __dmul_rn(c0, w2.y));
+                        a0 = __dadd_rn(a0, __dmul_rn(c1, w2.y)); a1 = __dadd_rn(a1, __dmul_rn(c1, nx.x));
+                        w2 = nx;
+                    }
+                    if (k < W) {                         // odd window: last tap
+                        const double c0 = s_coef[k];
+                        a0 = __dadd_rn(a0, __dmul_rn(c0, w2.x)); a1 = __dadd_rn(a1, __dmul_rn(c0, w2.y));
+                    }
+                    dst[t0 + u] = a0;
+                    if (u + 1 < tn) dst[t0 + u + 1] = a1;
                 }
                 __syncthreads();
             }
@@ -156,8 +181,18 @@ __global__ void __launch_bounds__(C3_PK_THREADS) c3_peaks_kernel(c3_peaks_args A
         double med;
         if (n & 1) med = c3_radix_select(x, n, n / 2, s_hist, s_sh);
         else {
-            const double lo = c3_radix_select(x, n, n / 2 - 1, s_hist, s_sh);
+            // hi = element n/2 of the sorted profile; lo = element n/2 - 1 = hi itself when at most n/2 - 1 samples are
+            // smaller than hi, else the largest sample below hi: one pass instead of a second select
             const double hi = c3_radix_select(x, n, n / 2, s_hist, s_sh);
+            double below = -1.0e308; int nb = 0;
+            for (int i = tid; i < n; i += blockDim.x) { const double v = x[i]; if (v < hi) { ++nb; below = fmax(below, v); } }
+            for (int o = 16; o > 0; o >>= 1) { below = fmax(below, __shfl_xor_sync(C3_FULL, below, o)); nb += __shfl_xor_sync(C3_FULL, nb, o); }
+            if ((tid & 31) == 0) { s_red[tid >> 5] = below; s_cnt[tid >> 5] = nb; }
+            __syncthreads();
+            below = s_red[0]; nb = s_cnt[0];
+            for (int i = 1; i < C3_PK_THREADS / 32; ++i) { below = fmax(below, s_red[i]); nb += s_cnt[i]; }
+            __syncthreads();
+            const double lo = (nb > n / 2 - 1) ? below : hi;
             med = __ddiv_rn(__dadd_rn(lo, hi), 2.0);
         }
         double mx = -1.0e308;
