@@ -339,6 +339,10 @@ static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_lane_kernel, C3L_THREADS, sm_bytes) != cudaSuccess || bps < 1) bps = 4;
     bps = std::min(bps, C3L_MINB);
     int64_t warps = (int64_t)h->sm_count * bps * wpb;
+    if (const char *lim = getenv("C3POA_LANE_WARPS_PER_SM")) {       // tuning only: occupancy sweeps
+        const int w = atoi(lim);
+        if (w >= wpb) warps = std::min<int64_t>(warps, (int64_t)h->sm_count * (w / wpb) * wpb);
+    }
     // auto mode: 32 reads advance in lockstep per warp, so one warp item takes as long as ~20 reads in the warp kernel;
     // that pays only when the batch fills most of the grid (measured break-even: about half a wave) and the reads are
     // of similar size (the largest items set the latency of the whole launch).  Otherwise the warp kernel is faster.
