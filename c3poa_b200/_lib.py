@@ -18,6 +18,7 @@ EXPORTS = [
     "c3_get_timings", "c3_conk_batch", "c3_peaks_batch", "c3_poa_batch", "c3_stage", "c3_run", "c3_fetch",
     "c3_consensus_batch", "c3_measure_int_peak", "c3_host_alloc", "c3_host_free",
     "c3_fastq_open", "c3_fastq_next", "c3_fastq_close", "c3_assign_splints", "c3_set_poa_mode", "c3_lane_counts",
+    "c3_format_batch",
 ]
 
 
@@ -84,5 +85,7 @@ def load():
     L.c3_fastq_next.argtypes = [vp, i32, C.c_int64, i32, vp, vp, vp, vp, C.c_int64, vp, vp, vp]
     L.c3_fastq_close.argtypes = [vp]
     L.c3_fastq_close.restype = None
+    L.c3_format_batch.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, i32, vp, C.c_int64, vp, vp,
+                                  C.c_int64, vp, vp]
     _LIB = L
     return L

@@ -176,3 +176,83 @@ extern "C" int c3_fastq_next(c3_fastq *q, int32_t max_reads, int64_t max_bases, 
     }
     return n;
 }
+
+// ---------------------------------------------------------------------------
+// Output side: the consensus FASTA and subread FASTQ records of a batch, formatted
+// exactly as the reference writes them --
+//   >{name}_{avg_qual}_{len}_{repeats}_{cons_len}\n{cons}\n                      (C3POa.py:167-173)
+//   @{name}_{k}\n{subread}\n+\n{qual}\n   k = 1..repeats; dangling ends k = 0 and k = repeats + 1
+//                                                                                (bin/determine_consensus.py:57-77)
+// -- for the reads of one output group (splint directory).  Python formatting of 50 000 reads per batch was the
+// slowest stage of the driver by 10x; this is one pass of memcpy.
+// ---------------------------------------------------------------------------
+static char *put_int(char *p, long long v)
+{
+    char tmp[24]; int n = 0;
+    if (v < 0) { *p++ = '-'; v = -v; }
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+// str(round(x, 2)) of Python for x >= 0: two decimals correctly rounded, trailing zeros dropped, at least one kept
+static char *put_avg_qual(char *p, long long qsum, long long len)
+{
+    char tmp[64];
+    int n = snprintf(tmp, sizeof(tmp), "%.2f", (double)qsum / (double)len);
+    while (n > 0 && tmp[n - 1] == '0' && n >= 2 && tmp[n - 2] != '.') --n;
+    memcpy(p, tmp, (size_t)n);
+    return p + n;
+}
+
+extern "C" int c3_format_batch(int32_t n_reads, const char *names, const int64_t *name_off,
+                               const char *seq, const char *qual, const int64_t *off, const int64_t *qual_sum,
+                               const c3_read_result *res, const int32_t *sub_bounds, const int32_t *dang_bounds,
+                               int32_t max_peaks, const char *cons, int32_t cons_cap,
+                               const int32_t *group, int32_t which_group,
+                               char *out_cons, int64_t out_cons_cap, int64_t *out_cons_len,
+                               char *out_sub, int64_t out_sub_cap, int64_t *out_sub_len, int64_t *stats)
+{
+    if (n_reads < 0 || !names || !name_off || !seq || !off || !qual_sum || !res || !sub_bounds || !dang_bounds || !cons ||
+        !out_cons || !out_cons_len || !out_sub || !out_sub_len)
+        return -1;
+    char *pc = out_cons, *ps = out_sub;
+    long long n_cons = 0, n_nopeak = 0, n_left = 0, n_err = 0;
+    for (int32_t i = 0; i < n_reads; ++i) {
+        if (group && group[i] != which_group) continue;
+        const c3_read_result &r = res[i];
+        if (r.status == 1) { ++n_nopeak; continue; }
+        if (r.status < 0) { ++n_err; continue; }
+        if (r.status != 0) { ++n_left; continue; }                // 2-repeat / 0-repeat paths: the caller's
+        const char *nm = names + name_off[i];
+        const size_t nl = strlen(nm);
+        const int64_t a0 = off[i], len = off[i + 1] - off[i];
+        const int ns = r.n_sub, nd = r.n_dang, cl = r.cons_len;
+        if (ns < 0 || ns > max_peaks || nd < 0 || nd > 2 || cl < 0 || cl > cons_cap) return -3;
+        if (pc + nl + 96 + cl > out_cons + out_cons_cap) return -2;
+        *pc++ = '>'; memcpy(pc, nm, nl); pc += nl; *pc++ = '_';
+        pc = put_avg_qual(pc, qual_sum[i], len); *pc++ = '_';
+        pc = put_int(pc, len); *pc++ = '_';
+        pc = put_int(pc, ns); *pc++ = '_';
+        pc = put_int(pc, cl); *pc++ = '\n';
+        memcpy(pc, cons + (int64_t)i * cons_cap, (size_t)cl); pc += cl; *pc++ = '\n';
+        const int32_t *sb = sub_bounds + (int64_t)i * max_peaks * 2, *db = dang_bounds + (int64_t)i * 4;
+        for (int k = 0; k < ns + nd; ++k) {
+            const int32_t a = k < ns ? sb[2 * k] : db[2 * (k - ns)], b = k < ns ? sb[2 * k + 1] : db[2 * (k - ns) + 1];
+            const int tag = k < ns ? k + 1 : (k == ns ? 0 : ns + 1);
+            if (a < 0 || b < a || b > len) return -3;
+            const int64_t sl = b - a;
+            if (ps + nl + 32 + 2 * sl > out_sub + out_sub_cap) return -2;
+            *ps++ = '@'; memcpy(ps, nm, nl); ps += nl; *ps++ = '_';
+            ps = put_int(ps, tag); *ps++ = '\n';
+            memcpy(ps, seq + a0 + a, (size_t)sl); ps += sl;
+            *ps++ = '\n'; *ps++ = '+'; *ps++ = '\n';
+            if (qual) { memcpy(ps, qual + a0 + a, (size_t)sl); ps += sl; }
+            *ps++ = '\n';
+        }
+        ++n_cons;
+    }
+    *out_cons_len = pc - out_cons; *out_sub_len = ps - out_sub;
+    if (stats) { stats[0] = n_cons; stats[1] = n_nopeak; stats[2] = n_left; stats[3] = n_err; }
+    return 0;
+}

@@ -129,42 +129,43 @@ def compute_batch(gpu, names, blob, off, splint_dict, adapter_dict, mdist):
 
 
 def write_batch(out, names, blob, off, qual, qual_sum, adapter_dict, handles):
-    """The host part: consensus FASTA + subread FASTQ exactly as analyze_reads / determine_consensus write them."""
+    """The host part: consensus FASTA + subread FASTQ exactly as analyze_reads / determine_consensus write them.
+    Reads with a plain consensus (status 0) are formatted by the library in one pass per splint directory
+    (c3_format_batch); only the 2-repeat reads, whose quality-aware pairwise consensus is host-side Python
+    (bin/consensus.py), are still handled one by one."""
+    from .ingest import format_batch, pack_names
     R = out["results"]
     stats = dict(consensus=0, no_peaks=0, pairwise=0, errors=0)     # pairwise: subset of consensus (2 repeats)
-    for i, name in enumerate(names):
-        st = int(R["status"][i])
+    order = sorted(handles)
+    gidx = {a: k for k, a in enumerate(order)}
+    group = np.fromiter((gidx[adapter_dict[nm][0]] for nm in names), dtype=np.int32, count=len(names))
+    names_raw, name_off = pack_names(names)
+    for k, adapter in enumerate(order):
+        fa, fq, st = format_batch(out, names_raw, name_off, blob, qual, off, qual_sum, group, k)
+        cons_fh, sub_fh = handles[adapter]
+        cons_fh.write(fa); sub_fh.write(fq)
+        stats["consensus"] += st["consensus"]; stats["no_peaks"] += st["no_peaks"]; stats["errors"] += st["errors"]
+    for i in np.flatnonzero(R["status"] == 2):
+        name = names[i]
         cons_fh, sub_fh = handles[adapter_dict[name][0]]
-        if st == 1:
-            stats["no_peaks"] += 1
-            continue
-        if st < 0:
-            stats["errors"] += 1
+        ns, nd = int(R["n_sub"][i]), int(R["n_dang"][i])
+        if not (ns == 2 and R["cons_len"][i] > 0):
+            stats["zero"] = stats.get("zero", 0) + 1     # 0-repeat path (mappy overlap of the dangling halves): not produced
             continue
         a0, a1 = int(off[i]), int(off[i + 1])
         seq = blob[a0:a1].tobytes().decode()
         q = qual[a0:a1].tobytes().decode()
-        ns, nd = int(R["n_sub"][i]), int(R["n_dang"][i])
         sb, db = out["sub_bounds"][i, :ns], out["dang_bounds"][i, :nd]
-        if st == 2 and ns == 2 and R["cons_len"][i] > 0:
-            # 2-repeat path: abPOA pairwise MSA rows from the GPU + quality-aware consensus
-            # (bin/determine_consensus.py:33-41, bin/consensus.py)
-            rows = pairwise_rows(out, i)
-            cons = pairwise_consensus(rows, [seq[a:b] for a, b in sb], [q[a:b] for a, b in sb])
-            stats["pairwise"] += 1
-        elif st == 2:                       # 0-repeat path (mappy overlap of the dangling halves): not produced
-            stats["zero"] = stats.get("zero", 0) + 1
-            continue
-        else:
-            cons = out["cons"][i, :R["cons_len"][i]].tobytes().decode()
-        print(header(name, int(qual_sum[i]), len(seq), ns, len(cons)), file=cons_fh)
-        print(cons, file=cons_fh)
+        # 2-repeat path: abPOA pairwise MSA rows from the GPU + quality-aware consensus
+        # (bin/determine_consensus.py:33-41, bin/consensus.py)
+        rows = pairwise_rows(out, i)
+        cons = pairwise_consensus(rows, [seq[a:b] for a, b in sb], [q[a:b] for a, b in sb])
+        cons_fh.write((header(name, int(qual_sum[i]), len(seq), ns, len(cons)) + "\n" + cons + "\n").encode())
         # subreads: @name_1..n, dangling @name_0 / @name_{n+1}  (bin/determine_consensus.py:57-77)
-        for k, (a, b) in enumerate(sb):
-            print(f"@{name}_{k + 1}\n{seq[a:b]}\n+\n{q[a:b]}", file=sub_fh)
-        for k, (a, b) in enumerate(db):
-            tag = 0 if k == 0 else ns + 1
-            print(f"@{name}_{tag}\n{seq[a:b]}\n+\n{q[a:b]}", file=sub_fh)
+        recs = [f"@{name}_{k + 1}\n{seq[a:b]}\n+\n{q[a:b]}\n" for k, (a, b) in enumerate(sb)]
+        recs += [f"@{name}_{0 if k == 0 else ns + 1}\n{seq[a:b]}\n+\n{q[a:b]}\n" for k, (a, b) in enumerate(db)]
+        sub_fh.write("".join(recs).encode())
+        stats["pairwise"] += 1
         stats["consensus"] += 1
     return stats
 
@@ -228,7 +229,7 @@ def _run_all(args, adapter_dict, splint_dict, adapter_set):
                 for r in range(args.gpus):
                     part = f"{base}/tmp{r}/{fn}"
                     if os.path.exists(part):
-                        with open(part) as src:
+                        with open(part, "rb") as src:
                             shutil.copyfileobj(src, fh)
         for r in range(args.gpus):
             shutil.rmtree(f"{base}/tmp{r}", ignore_errors=True)
@@ -243,7 +244,7 @@ def _drain_one(pending, handles, totals):
 
 
 def _opener(args):
-    return (lambda p: gzip.open(p + ".gz", "wt")) if args.compress_output else (lambda p: open(p, "w"))
+    return (lambda p: gzip.open(p + ".gz", "wb")) if args.compress_output else (lambda p: open(p, "wb"))
 
 
 def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, final):
@@ -256,7 +257,7 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
         else:
             base += f"/tmp{rank}"
             os.makedirs(base, exist_ok=True)
-            op = lambda p: open(p, "w")      # noqa: E731
+            op = lambda p: open(p, "wb")     # noqa: E731
         handles[adapter] = (op(base + "/R2C2_Consensus.fasta"), op(base + "/R2C2_Subreads.fastq"))
     mod = int(os.environ.get("C3POA_DEVICE_MODULO", "0"))      # tests: fold ranks onto fewer GPUs
     gpu = GpuConsensus(device % mod if mod > 0 else device)

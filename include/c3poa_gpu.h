@@ -127,6 +127,20 @@ int c3_consensus_batch(c3_handle *h, int32_t n_reads, const char *reads, const i
                        int32_t *out_peaks, int32_t *out_sub_bounds, int32_t *out_dang_bounds,
                        char *out_cons, c3_read_result *out_results);
 
+/* Output records of a batch, host code: for the reads with group[i] == which_group (group may be NULL:
+ * all reads) and status 0, appends ">{name}_{avg_qual}_{len}_{repeats}_{cons_len}\n{cons}\n" to out_cons
+ * (/root/reference/C3POa.py:167-173; avg_qual formatted like Python's str(round(x, 2))) and the subread / dangling
+ * FASTQ records "@{name}_{k}\n{seq}\n+\n{qual}\n" to out_sub (/root/reference/bin/determine_consensus.py:57-77).
+ * names: NUL-terminated, name_off[i] = start of read i's name (as c3_fastq_next returns them); the other arrays are
+ * the inputs / outputs of c3_consensus_batch.  stats[4] (optional): records written, reads without peaks, reads left
+ * to the caller (status 2: pairwise / zero-repeat paths), reads with errors.  Returns 0, -2 if a buffer is too small
+ * (size them with 2 x bases + (repeats + 2) x (name + 32) per read), -3 on inconsistent bounds.                  */
+int c3_format_batch(int32_t n_reads, const char *names, const int64_t *name_off, const char *seq, const char *qual,
+                    const int64_t *off, const int64_t *qual_sum, const c3_read_result *res,
+                    const int32_t *sub_bounds, const int32_t *dang_bounds, int32_t max_peaks, const char *cons,
+                    int32_t cons_cap, const int32_t *group, int32_t which_group, char *out_cons, int64_t out_cons_cap,
+                    int64_t *out_cons_len, char *out_sub, int64_t out_sub_cap, int64_t *out_sub_len, int64_t *stats);
+
 /* Pinned (page-locked) host buffers for callers that want full-speed H2D/D2H
  * (any host pointer is accepted by the batch calls; pageable memory is staged
  * by the driver).  Returns NULL on failure.                                  */

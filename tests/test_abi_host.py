@@ -131,3 +131,85 @@ def test_cxx_ingest_matches_python_reader(tmp_path):
     fa.write_text(">A desc\nACGT\nAC\n>B\nTTTT\n")
     b = next(FastqBatches(str(fa), pinned=False))
     assert b["names"] == ["A", "B"] and b["blob"].tobytes() == b"ACGTACTTTT" and b["off"].tolist() == [0, 6, 10]
+
+
+def _fake_outputs(rng, n, max_peaks=8, cons_cap=96):
+    from c3poa_b200._lib import RESULT_DTYPE
+    names = [f"read{i}/ch{int(rng.integers(1, 512))}" for i in range(n)]
+    lens = rng.integers(60, 900, size=n)
+    off = np.zeros(n + 1, dtype=np.int64); off[1:] = np.cumsum(lens)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    blob = rng.choice(acgt, size=int(off[-1]))
+    qual = rng.integers(33 + 1, 33 + 45, size=int(off[-1])).astype(np.uint8)
+    qsum = np.array([int((qual[off[i]:off[i + 1]].astype(np.int64) - 33).sum()) for i in range(n)], dtype=np.int64)
+    R = np.zeros(n, dtype=RESULT_DTYPE)
+    sb = np.zeros((n, max_peaks, 2), dtype=np.int32); db = np.zeros((n, 2, 2), dtype=np.int32)
+    cons = rng.choice(acgt, size=(n, cons_cap))
+    for i in range(n):
+        R["status"][i] = rng.choice([0, 0, 0, 0, 1, 2, -203])
+        ns = int(rng.integers(0, max_peaks)); R["n_sub"][i] = ns
+        cuts = np.sort(rng.choice(np.arange(1, lens[i]), size=ns + 1, replace=False))
+        for k in range(ns):
+            sb[i, k] = (cuts[k], cuts[k + 1])
+        nd = int(rng.integers(0, 3)); R["n_dang"][i] = nd
+        if nd >= 1:
+            db[i, 0] = (0, cuts[0])
+        if nd == 2:
+            db[i, 1] = (cuts[-1], lens[i])
+        R["cons_len"][i] = rng.integers(0, cons_cap + 1)
+    return names, off, blob, qual, qsum, dict(results=R, sub_bounds=sb, dang_bounds=db, cons=cons)
+
+
+def test_format_batch_matches_reference_formatting():
+    """c3_format_batch (C++) against the Python statements of the reference: header with Python's str(round(x, 2))
+    (C3POa.py:167-173) and the subread / dangling FASTQ records (bin/determine_consensus.py:57-77), per output group."""
+    from c3poa_b200.driver import header
+    from c3poa_b200.ingest import format_batch, pack_names
+    rng = np.random.default_rng(11)
+    names, off, blob, qual, qsum, out = _fake_outputs(rng, 600)
+    R, sb, db, cons = out["results"], out["sub_bounds"], out["dang_bounds"], out["cons"]
+    group = rng.integers(0, 3, size=len(names)).astype(np.int32)
+    raw, noff = pack_names(names)
+    total = 0
+    for g in range(3):
+        fa, fq, st = format_batch(out, raw, noff, blob, qual, off, qsum, group, g)
+        efa, efq = [], []
+        for i, name in enumerate(names):
+            if group[i] != g or R["status"][i] != 0:
+                continue
+            seq = blob[off[i]:off[i + 1]].tobytes().decode(); q = qual[off[i]:off[i + 1]].tobytes().decode()
+            ns, nd = int(R["n_sub"][i]), int(R["n_dang"][i])
+            c = cons[i, :R["cons_len"][i]].tobytes().decode()
+            efa.append(header(name, int(qsum[i]), len(seq), ns, len(c)) + "\n" + c + "\n")
+            efq += [f"@{name}_{k + 1}\n{seq[a:b]}\n+\n{q[a:b]}\n" for k, (a, b) in enumerate(sb[i, :ns])]
+            efq += [f"@{name}_{0 if k == 0 else ns + 1}\n{seq[a:b]}\n+\n{q[a:b]}\n" for k, (a, b) in enumerate(db[i, :nd])]
+        assert fa.tobytes().decode() == "".join(efa) and fq.tobytes().decode() == "".join(efq), g
+        sel = group == g
+        assert st == dict(consensus=int((R["status"][sel] == 0).sum()), no_peaks=int((R["status"][sel] == 1).sum()),
+                          left=int((R["status"][sel] == 2).sum()), errors=int((R["status"][sel] < 0).sum()))
+        total += st["consensus"]
+    assert total == int((R["status"] == 0).sum())
+
+
+def test_format_batch_average_quality_like_python_round():
+    """The one float in the header: Python prints str(round(qsum / len, 2)) -- ties, trailing zeros, integers."""
+    from c3poa_b200._lib import RESULT_DTYPE
+    from c3poa_b200.driver import header
+    from c3poa_b200.ingest import format_batch, pack_names
+    rng = np.random.default_rng(3)
+    cases = [(1, 8), (3, 8), (5, 8), (7, 8), (20, 1), (200, 10), (465, 10), (4653, 100), (1, 3), (2, 3), (1005, 1000),
+             (5, 1000), (15, 1000), (25, 1000), (0, 7), (123456789, 1000)]
+    cases += [(int(a), int(b)) for a, b in zip(rng.integers(0, 10 ** 6, 3000), rng.integers(1, 60000, 3000))]
+    n = len(cases)
+    names = [f"r{i}" for i in range(n)]
+    lens = np.array([b for _, b in cases], dtype=np.int64)
+    off = np.zeros(n + 1, dtype=np.int64); off[1:] = np.cumsum(lens)
+    blob = np.full(int(off[-1]), ord("A"), dtype=np.uint8)
+    R = np.zeros(n, dtype=RESULT_DTYPE)
+    out = dict(results=R, sub_bounds=np.zeros((n, 1, 2), dtype=np.int32), dang_bounds=np.zeros((n, 2, 2), dtype=np.int32),
+               cons=np.zeros((n, 1), dtype=np.uint8))
+    raw, noff = pack_names(names)
+    fa, _, _ = format_batch(out, raw, noff, blob, None, off, np.array([a for a, _ in cases], dtype=np.int64))
+    got = fa.tobytes().decode().split("\n")[0::2][:n]
+    for i, (a, b) in enumerate(cases):
+        assert got[i] == header(names[i], a, b, 0, 0), (a, b, got[i])

@@ -18,8 +18,9 @@ os.makedirs(f"{tmp}/out/tmp")
 synth.write_psl(f"{tmp}/out/tmp/splint_to_read_alignments.psl", names, ["Splint1"] * n, ["-" if x else "+" for x in st])
 open(f"{tmp}/splint.fasta", "w").write(f">Splint1\n{synth.SPLINT1}\n")
 print("wrote fastq in", round(time.time() - t0, 1), "s", os.path.getsize(f"{tmp}/reads.fastq") / 1e6, "MB")
+batch = sys.argv[2] if len(sys.argv) > 2 else "10000"
 for infl in (1, 2):
     t0 = time.time()
-    tot = driver.main(driver.parse_args(["-r", f"{tmp}/reads.fastq", "-s", f"{tmp}/splint.fasta", "-o", f"{tmp}/out", "--batch", "10000", "--inflight", str(infl)]))
+    tot = driver.main(driver.parse_args(["-r", f"{tmp}/reads.fastq", "-s", f"{tmp}/splint.fasta", "-o", f"{tmp}/out", "--batch", batch, "--inflight", str(infl)]))
     dt = time.time() - t0
     print(f"inflight={infl}: driver {n} reads in {dt:.1f} s -> {n/dt:.0f} reads/s  {tot}")
