@@ -351,8 +351,9 @@ static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa
     size_t free_b = 0, tot_b = 0;
     CK(cudaMemGetInfo(&free_b, &tot_b));
     const int64_t budget = (int64_t)((double)(free_b + h->d_ws.cap) * 0.8);
-    warps = std::min<int64_t>(warps, budget / warp_bytes);
-    warps = warps / wpb * wpb;
+    const int64_t fit = budget / warp_bytes / wpb * wpb;
+    if (h->poa_mode == 0 && fit * 2 < warps) return 0;             // auto: not worth it with under half of the grid resident
+    warps = std::min<int64_t>(warps, fit);
     if (warps < wpb) return 0;                                     // does not fit: the warp kernel takes everything
     CK(h->d_ws.ensure((size_t)(warps * warp_bytes)));
     CK(h->d_done.ensure((size_t)A.n_items * 4));

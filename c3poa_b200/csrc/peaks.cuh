@@ -45,8 +45,12 @@ __device__ __forceinline__ double c3_dunkey(unsigned long long k)
     return __longlong_as_double((long long)u);
 }
 
-// k-th smallest (0-based) of buf[0..n): MSB-first radix select, 8 bits per pass
-__device__ double c3_radix_select(const double *buf, int n, int k, unsigned *hist, unsigned long long *sh)
+// k-th smallest (0-based) of buf[0..n): MSB-first radix select, 8 bits per pass; as soon as at most C3_PK_SMALL
+// candidates share the prefix (after 2-3 passes for a smoothed profile) they are gathered and the answer is the one
+// whose rank among them is k.  cand: C3_PK_SMALL keys of shared memory.
+#define C3_PK_SMALL 512
+__device__ double c3_radix_select(const double *buf, int n, int k, unsigned *hist, unsigned long long *sh,
+                                  unsigned long long *cand)
 {
     unsigned long long prefix = 0, mask = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
@@ -70,11 +74,31 @@ __device__ double c3_radix_select(const double *buf, int n, int k, unsigned *his
             for (; b < 256; ++b) { if (cum + hist[b] > (unsigned)k) break; cum += hist[b]; }
             sh[0] = prefix | ((unsigned long long)b << shift);
             sh[1] = (unsigned long long)(k - (int)cum);
+            sh[2] = (unsigned long long)hist[b];           // candidates left
+            sh[3] = 0;
         }
         __syncthreads();
         prefix = sh[0]; k = (int)sh[1];
+        const int left = (int)sh[2];
         mask |= 0xffull << shift;
         __syncthreads();
+        if (left <= C3_PK_SMALL && shift > 0) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const unsigned long long kx = c3_dkey(buf[i]);
+                if ((kx & mask) == prefix) cand[atomicAdd((unsigned *)&sh[3], 1u)] = kx;
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < left; t += blockDim.x) {
+                const unsigned long long kt = cand[t];
+                int rank = 0;
+                for (int u = 0; u < left; ++u) { const unsigned long long ku = cand[u]; rank += (ku < kt) || (ku == kt && u < t); }
+                if (rank == k) sh[0] = kt;
+            }
+            __syncthreads();
+            prefix = sh[0];
+            __syncthreads();
+            break;
+        }
     }
     return c3_dunkey(prefix);
 }
@@ -88,7 +112,7 @@ __global__ void __launch_bounds__(C3_PK_THREADS) c3_peaks_kernel(c3_peaks_args A
     __shared__ int s_order[C3_PK_MAXC];
     __shared__ unsigned char s_keep[C3_PK_MAXC];
     __shared__ unsigned s_hist[256];
-    __shared__ unsigned long long s_sh[2];
+    __shared__ unsigned long long s_sh[4];
     __shared__ double s_red[C3_PK_THREADS / 32];
     __shared__ int s_cnt[C3_PK_THREADS + 1];
     __shared__ int s_r;
@@ -179,11 +203,11 @@ __global__ void __launch_bounds__(C3_PK_THREADS) c3_peaks_kernel(c3_peaks_args A
             for (int i = tid; i < n; i += blockDim.x) A.out_smoothed[off + i] = x[i];
         // ---------------- median (np.median) and max ----------------
         double med;
-        if (n & 1) med = c3_radix_select(x, n, n / 2, s_hist, s_sh);
+        if (n & 1) med = c3_radix_select(x, n, n / 2, s_hist, s_sh, reinterpret_cast<unsigned long long *>(s_pr));
         else {
             // hi = element n/2 of the sorted profile; lo = element n/2 - 1 = hi itself when at most n/2 - 1 samples are
             // smaller than hi, else the largest sample below hi: one pass instead of a second select
-            const double hi = c3_radix_select(x, n, n / 2, s_hist, s_sh);
+            const double hi = c3_radix_select(x, n, n / 2, s_hist, s_sh, reinterpret_cast<unsigned long long *>(s_pr));
             double below = -1.0e308; int nb = 0;
             for (int i = tid; i < n; i += blockDim.x) { const double v = x[i]; if (v < hi) { ++nb; below = fmax(below, v); } }
             for (int o = 16; o > 0; o >>= 1) { below = fmax(below, __shfl_xor_sync(C3_FULL, below, o)); nb += __shfl_xor_sync(C3_FULL, nb, o); }
