@@ -38,11 +38,7 @@
 #ifndef C3L_SMEM_KB
 #define C3L_SMEM_KB 200            // shared memory per SM the rings may take (the rest of the 228 KB stays L1)
 #endif
-#ifdef C3L_CODES_RING
-#define C3L_RSLOT 7                // uint4 per lane and ring slot: H, E1, E2 x 2 halves + the 16 column codes of that vector
-#else
 #define C3L_RSLOT 6                // uint4 per lane and ring slot: H, E1, E2 x 2 halves
-#endif
 #define C3L_FLOOR (-30720)         // stored "unreachable"; every packed operation clamps here, 2048 above the int16 wrap
 #define C3L_FLOOR2 0x88008800u
 #define C3L_LOW_GUARD 64           // reachable cells must stay above C3L_FLOOR + C3L_LOW_GUARD
@@ -61,11 +57,7 @@
 #define C3L_ADDMAX(a, b, c) __viaddmax_s32((a), (b), (c))
 #define C3L_MAX3(a, b, c) __vimax3_s32((a), (b), (c))
 #define C3L_ANY(x) __any_sync(C3_FULL, (x))
-#ifdef C3L_EXP_PLAINLD
-#define C3L_LDCS4(p) (*(p))
-#else
 #define C3L_LDCS4(p) __ldcs(p)           // DP rows are read once by the successor row: stream them (evict-first)
-#endif
 #define C3L_UMIN(a, b) min((unsigned)(a), (unsigned)(b))
 #define C3L_PACK2(lo, hi) __byte_perm((unsigned)(lo), (unsigned)(hi), 0x5410)
 #define C3L_VMAX2(a, b) __vmaxs2((a), (b))          // per-halfword signed max: VIMNMX.S16x2
@@ -156,7 +148,6 @@ struct c3l_state {
     c3_prow ra, rb, ra1, rb1;                         // row records of the first two predecessors of v and of v+1 (unless among
                                                       // the two rows computed last when they were requested)
     c3_prow last2; int vlast2;                        // the row before the one just computed
-    int code_lo, code_hi;                             // vectors whose column codes are in the ring (code_lo > code_hi: none)
     c3_prow last; int vlast, last_sm;                 // the row just computed; last_sm: it is in the shared-memory ring
     int beg, end, nvec, beg_sn, end_sn; c3_prow r0, r1;   // the row between setup and compute
 };
@@ -342,7 +333,7 @@ C3_HD __forceinline__ void c3l_source_row(c3l_state &S, const c3_poa_para_dev &P
         }
         ar16[c3l_ci(0, 0, c, lane)] = (int16_t)h; ar16[c3l_ci(0, 1, c, lane)] = (int16_t)x1; ar16[c3l_ci(0, 2, c, lane)] = (int16_t)x2;
     }
-    S.last_sm = 0; S.code_lo = 1; S.code_hi = 0;
+    S.last_sm = 0;
     S.v = W.nodes[C3_SRC].next; S.rcount = 1;
     S.nd = c3_ld_node(&W.nodes[S.v]); S.hrv = W.hr[S.v];
     const int v1 = c3l_cl(C3_N_NEXT(S.nd));
@@ -519,22 +510,15 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
     // further ones along the edge chain per step.
     bool p0_ring = p0_sm;
     c3_prow r0e = r0, r1e = r1;
-    // (-DC3L_FOLD_ALL folds the second predecessor as well: measured slower, 392 vs 374 ms per 100k reads -- the fold's
-    // loads are exposed once per row, the in-loop register prefetch overlaps them with the arithmetic.  -DC3L_CODES_RING
-    // keeps the column codes in the ring too: slower as well, 398 ms, the larger ring costs L1.)
-#ifdef C3L_FOLD_ALL
-    const bool fold = keep_sm && !(p0_sm && npre == 1);
-    const bool fold1 = true;                            // the second predecessor is folded too
-#else
+    // (Measured and dropped: folding the second predecessor as well -- 392 vs 374 ms per 100k reads, the fold's loads are
+    // exposed once per row while the in-loop register prefetch overlaps them with the arithmetic; the column codes in
+    // the ring -- 398 ms, the larger ring costs L1.)
     const bool fold = keep_sm && npre > 2;              // the second predecessor stays in the row loop (register prefetch)
-    const bool fold1 = false;
-#endif
     if (fold) {
         const bool have0 = p0_sm && beg >= (int)r0.beg;
         if (!have0) c3l_fold_pred(ar4, sm, smR, slot, r0, beg, nstep, lane, 1);
         else if (end > (int)r0.end) c3l_fold_pred(ar4, sm, smR, slot, r0, beg, nstep, lane, 2);
         if (npre > 1) {
-            if (fold1) c3l_fold_pred(ar4, sm, smR, slot, r1, beg, nstep, lane, 0);
             int e = C3L_E_NEXT(S.pe);
             for (int k = 2; k < npre; ++k) {
                 const c3_pedge pe = W.pool[e]; e = pe.next;
@@ -544,27 +528,10 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
         }
         p0_ring = true;
         r0e.beg = (uint16_t)beg; r0e.end = (uint16_t)(beg + 16 * nvec - 1);
-        if (fold1) { r1e.beg = 16; r1e.end = 0; }       // nothing left for the in-loop second predecessor
     }
     C3L_TICK2(17, sm[lane].x);
     uint4 *out4 = reinterpret_cast<uint4 *>(ar) + base4 + lane;
     const int8_t *qprow = W.qp;                         // column codes
-    // column codes of the band's vectors: in the ring next to the cells (thread-private global data does not stay in
-    // L1 with 256 threads per SM); the band moves right about one column per row, so this loads one vector per ~16 rows
-#ifdef C3L_CODES_RING
-    const bool codes_sm = keep_sm;
-#else
-    const bool codes_sm = false;
-#endif
-    if (codes_sm) {
-        if (S.code_lo > S.code_hi || S.beg_sn < S.code_lo || S.beg_sn > S.code_hi + 1) { S.code_lo = S.beg_sn; S.code_hi = S.beg_sn - 1; }
-        for (int vv = S.code_hi + 1; vv <= S.end_sn; ++vv) {
-            int sl = slot + (vv - S.beg_sn); if (sl >= smR) sl -= smR;
-            sm[(sl * C3L_RSLOT + 6) * 32 + lane] = *reinterpret_cast<const uint4 *>(qprow + 16 * vv);
-        }
-        S.code_hi = max(S.code_hi, S.end_sn);
-        S.code_lo = max(S.code_lo, S.code_hi - smR + 1);
-    }
     // The row loop works on the packed cells, two columns per 32-bit word (VIADDMNMX.S16x2 / VIMNMX3.S16x2); only the
     // horizontal gap F, a strictly sequential recurrence, and the row arg-max run per column in int32.
     const uint32_t nb4 = (uint32_t)nbase * 0x01010101u, m4 = (uint32_t)P.match * 0x01010101u;
@@ -578,9 +545,7 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
     uint2 nsw = make_uint2(0u, 0u);
     c3l_load8(ar4, sm, p0_ring, slot, r0e, beg, lane, na, nb, nc);
     c3l_load8(ar4, sm, false, 0, r1e, beg, lane, pa, pb, pc);
-    uint4 cw = make_uint4(0u, 0u, 0u, 0u);              // codes of the current vector when they come from the ring
-    if (codes_sm) { cw = sm[(slot * C3L_RSLOT + 6) * 32 + lane]; nsw = make_uint2(cw.x, cw.y); }
-    else nsw = *reinterpret_cast<const uint2 *>(qprow + beg);
+    nsw = *reinterpret_cast<const uint2 *>(qprow + beg);
     C3L_TICK2(18, nsw.x + na.x + pa.x);
     // (#pragma unroll 2 here: measured 422 vs 371 ms -- spills at 168 registers)
     for (int h = 0; h < nstep; ++h) {
@@ -595,9 +560,7 @@ C3_HD __forceinline__ void c3l_row_compute(c3l_state &S, const c3_poa_args &A, c
         if (h + 1 < nstep) {
             c3l_load8(ar4, sm, p0_ring, slot, r0e, j0 + 8, lane, na, nb, nc);
             c3l_load8(ar4, sm, false, 0, r1e, j0 + 8, lane, pa, pb, pc);
-            if (!codes_sm) nsw = *reinterpret_cast<const uint2 *>(qprow + j0 + 8);
-            else if (h & 1) { cw = sm[(slot * C3L_RSLOT + 6) * 32 + lane]; nsw = make_uint2(cw.x, cw.y); }
-            else nsw = make_uint2(cw.z, cw.w);
+            nsw = *reinterpret_cast<const uint2 *>(qprow + j0 + 8);
         }
         if (npre > 2 && !fold) {                         // wider than the ring: follow the edge chain per step
             int e = C3L_E_NEXT(S.pe);
