@@ -183,3 +183,18 @@ def test_lane_declines_what_it_does_not_cover(emul):
     # arena / node capacity overflow -> not done, nothing reported
     assert not run_emul(emul, [g], arena_cap4=208 * 40)["done"][0]
     assert not run_emul(emul, [g], node_cap=320)["done"][0]
+
+
+def test_lane_phases_bench_shape(emul, oracle):
+    """The bench workload's shape (1 kb insert + 284 nt splint, 5 subreads, 4/3/3 % errors), 64 reads = two warp items in
+    lockstep: every read is finished by the lane phases (no exactness-guard or capacity fallback) and equals the oracle."""
+    rng = np.random.default_rng(2025)
+    groups = []
+    for _ in range(64):
+        a = synth.random_seq(rng, 1284)
+        groups.append([synth.mutate(rng, a).tobytes().decode() for _ in range(5)])
+    r = run_emul(emul, groups, sm_vec=5)
+    assert all(r["done"]) and not any(r["status"])
+    for i in range(0, 64, 3):
+        o = oracle.poa_msa(groups[i])
+        assert r["cons"][i] == o["cons"] and r["cells"][i] == o["cells"] and r["nodes"][i] == o["node_n"], i
