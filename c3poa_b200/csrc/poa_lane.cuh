@@ -764,78 +764,107 @@ C3_HD __forceinline__ void c3l_align_end(c3l_state &S, const c3_poa_args &A, con
                     }
                 }
             }
-            if (!hit && (cur_op & C3_OP_E)) {
-                int e = C3_NONE;
-                for (int k = 0; k < npre; ++k) {
-                    c3_prow pr = k == 0 ? pr0 : pr1;
-                    if (k >= 2) {
-                        if (k == 2) e = W.pool[W.nodes[i].in_more].next;
-                        const c3_pedge pe = W.pool[e]; pr = W.ord[W.rows[pe.id].link]; e = pe.next;
-                    }
-                    if (j < (int)pr.beg || j > (int)pr.end) continue;
-                    const int pc = j - pr.beg;
-                    const int ph = c3l_ld_h(ar, c3l_ci(pr.off, 0, pc, lane)), pe1 = c3l_ld_e(ar, c3l_ci(pr.off, 1, pc, lane)), pe2 = c3l_ld_e(ar, c3l_ci(pr.off, 2, pc, lane));
-                    if (cur_op & C3_OP_E1) {
-                        if (cur_op & C3_OP_M) {
-                            if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
-                        } else if (c3l_ld_e(ar, c3l_ci(rt.off, 1, j - b, lane)) == pe1 - e1) {
-                            cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1;
+            if (!hit && (cur_op & (C3_OP_E | C3_OP_F))) {
+                // No match / mismatch move from here.  Everything the gap tests of this cell can need -- the first two
+                // predecessors' H, E1, E2 at column j, this row's E1, E2, and the vector of this row that F is rebuilt
+                // from -- is requested at once, so the tests cost one memory round trip, not one per question.
+                const bool want_e = (cur_op & C3_OP_E) != 0, want_f = (cur_op & C3_OP_F) && j - 1 >= b;
+                const bool oke0 = want_e && j >= (int)pr0.beg && j <= (int)pr0.end;
+                const bool oke1 = want_e && npre > 1 && j >= (int)pr1.beg && j <= (int)pr1.end;
+                int eh0 = 0, e10 = 0, e20 = 0, eh1 = 0, e11 = 0, e21 = 0, ce1 = 0, ce2 = 0;
+                int2 fin = make_int2(0, 0);
+                uint4 hq0 = make_uint4(0u, 0u, 0u, 0u), hq1 = hq0;
+                const int cm = j - 1 - b, vs = cm >> 4, tm = cm & 15;
+                if (oke0) {
+                    const int pc = j - pr0.beg;
+                    eh0 = c3l_ld_h(ar, c3l_ci(pr0.off, 0, pc, lane)); e10 = c3l_ld_e(ar, c3l_ci(pr0.off, 1, pc, lane)); e20 = c3l_ld_e(ar, c3l_ci(pr0.off, 2, pc, lane));
+                }
+                if (oke1) {
+                    const int pc = j - pr1.beg;
+                    eh1 = c3l_ld_h(ar, c3l_ci(pr1.off, 0, pc, lane)); e11 = c3l_ld_e(ar, c3l_ci(pr1.off, 1, pc, lane)); e21 = c3l_ld_e(ar, c3l_ci(pr1.off, 2, pc, lane));
+                }
+                if (want_e && !(cur_op & C3_OP_M)) { ce1 = c3l_ld_e(ar, c3l_ci(rt.off, 1, j - b, lane)); ce2 = c3l_ld_e(ar, c3l_ci(rt.off, 2, j - b, lane)); }
+                if (want_f) {
+                    fin = *reinterpret_cast<const int2 *>(ar + c3l_fi(rt.off, vs, lane));
+                    const uint4 *hp = reinterpret_cast<const uint4 *>(ar) + rt.off + vs * C3L_VSTRIDE + lane;
+                    hq0 = hp[0]; hq1 = hp[32];
+                }
+                if (want_e) {
+                    int e = C3_NONE;
+                    for (int k = 0; k < npre; ++k) {
+                        c3_prow pr = k == 0 ? pr0 : pr1;
+                        int ph = k == 0 ? eh0 : eh1, pe1 = k == 0 ? e10 : e11, pe2 = k == 0 ? e20 : e21;
+                        bool inb = k == 0 ? oke0 : oke1;
+                        if (k >= 2) {
+                            if (k == 2) e = W.pool[W.nodes[i].in_more].next;
+                            const c3_pedge pe = W.pool[e]; pr = W.ord[W.rows[pe.id].link]; e = pe.next;
+                            inb = j >= (int)pr.beg && j <= (int)pr.end;
+                            if (inb) {
+                                const int pc = j - pr.beg;
+                                ph = c3l_ld_h(ar, c3l_ci(pr.off, 0, pc, lane)); pe1 = c3l_ld_e(ar, c3l_ci(pr.off, 1, pc, lane)); pe2 = c3l_ld_e(ar, c3l_ci(pr.off, 2, pc, lane));
+                            }
+                        }
+                        if (!inb) continue;
+                        if (cur_op & C3_OP_E1) {
+                            if (cur_op & C3_OP_M) {
+                                if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
+                            } else if (ce1 == pe1 - e1) {
+                                cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1;
+                            }
+                        }
+                        if (!hit && (cur_op & C3_OP_E2)) {
+                            if (cur_op & C3_OP_M) {
+                                if (hij == pe2) { cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1; }
+                            } else if (ce2 == pe2 - e2) {
+                                cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1;
+                            }
+                        }
+                        if (hit) {
+                            opw = C3_CG_DEL | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                            rt = pr; hij = ph;
+                            break;
                         }
                     }
-                    if (!hit && (cur_op & C3_OP_E2)) {
-                        if (cur_op & C3_OP_M) {
-                            if (hij == pe2) { cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1; }
-                        } else if (c3l_ld_e(ar, c3l_ci(rt.off, 2, j - b, lane)) == pe2 - e2) {
-                            cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1;
+                }
+                // (cur_op may just have been rewritten by an E hit; the F test only runs without one)
+                if (!hit && want_f && (cur_op & C3_OP_F)) {
+                    // F is stored only where it enters a 16-column vector: rebuild F[j-1] and F[j] from there
+                    int hq[16];
+                    {
+                        int t0[8];
+                        c3l_unpack8(hq0, t0);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) hq[k] = c3l_map(t0[k]);
+                        c3l_unpack8(hq1, t0);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) hq[8 + k] = c3l_map(t0[k]);
+                    }
+                    int f1 = fin.x, f2 = fin.y, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
+                    C3L_COUNT(12, 1);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        if (c <= tm) {
+                            hl = hq[c];
+                            f1l = f1; f2l = f2;
+                            f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
+                        }
+                    }
+                    if (cur_op & C3_OP_F1) {
+                        if (!(cur_op & C3_OP_M) || hij == f1) {
+                            if (hl - oe1 == f1) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                            else if (f1l - e1 == f1) { cur_op = C3_OP_F1; hit = 1; }
+                        }
+                    }
+                    if (!hit && (cur_op & C3_OP_F2)) {
+                        if (!(cur_op & C3_OP_M) || hij == f2) {
+                            if (hl - oe2 == f2) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                            else if (f2l - e2 == f2) { cur_op = C3_OP_F2; hit = 1; }
                         }
                     }
                     if (hit) {
-                        opw = C3_CG_DEL | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                        rt = pr; hij = ph;
-                        break;
+                        opw = C3_CG_INS | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                        --j; hij = hl;
                     }
-                }
-            }
-            if (!hit && (cur_op & C3_OP_F) && j - 1 >= b) {
-                // F is stored only where it enters a 16-column vector: rebuild F[j-1] and F[j] from there
-                const int cm = j - 1 - b, vs = cm >> 4, tm = cm & 15;
-                const int2 fin = *reinterpret_cast<const int2 *>(ar + c3l_fi(rt.off, vs, lane));
-                const uint4 *hp = reinterpret_cast<const uint4 *>(ar) + rt.off + vs * C3L_VSTRIDE + lane;
-                int hq[16];
-                {
-                    int t0[8];
-                    c3l_unpack8(hp[0], t0);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) hq[k] = c3l_map(t0[k]);
-                    c3l_unpack8(hp[32], t0);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) hq[8 + k] = c3l_map(t0[k]);
-                }
-                int f1 = fin.x, f2 = fin.y, f1l = C3_NEG_INF, f2l = C3_NEG_INF, hl = C3_NEG_INF;
-                C3L_COUNT(12, 1);
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    if (c <= tm) {
-                        hl = hq[c];
-                        f1l = f1; f2l = f2;
-                        f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
-                    }
-                }
-                if (cur_op & C3_OP_F1) {
-                    if (!(cur_op & C3_OP_M) || hij == f1) {
-                        if (hl - oe1 == f1) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
-                        else if (f1l - e1 == f1) { cur_op = C3_OP_F1; hit = 1; }
-                    }
-                }
-                if (!hit && (cur_op & C3_OP_F2)) {
-                    if (!(cur_op & C3_OP_M) || hij == f2) {
-                        if (hl - oe2 == f2) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
-                        else if (f2l - e2 == f2) { cur_op = C3_OP_F2; hit = 1; }
-                    }
-                }
-                if (hit) {
-                    opw = C3_CG_INS | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
-                    --j; hij = hl;
                 }
             }
         }
