@@ -111,8 +111,9 @@ class GpuConsensus:
             self.set_poa_mode(poa_mode)
 
     def set_poa_mode(self, mode: str):
-        """POA kernel choice: 'auto' (thread-per-read kernel for batches of >= 8192 eligible reads), 'warp'
-        (warp-per-read kernel only), 'lane' (thread-per-read kernel whenever eligible).  Same results."""
+        """POA kernel choice: 'auto' (thread-per-read kernel for batches whose eligible reads fill >= 3/4 of its grid
+        -- 42 624 reads on a B200 -- and are of similar size), 'warp' (warp-per-read kernel only), 'lane'
+        (thread-per-read kernel whenever eligible).  Same results."""
         self._ck(self._L.c3_set_poa_mode(self._h, self.POA_MODES[mode]), "c3_set_poa_mode")
 
     def lane_counts(self):
