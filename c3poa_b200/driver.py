@@ -45,6 +45,9 @@ def parse_args(argv=None):
     p.add_argument("--batch", type=int, default=50000, help="reads per GPU batch")
     p.add_argument("--gpus", type=int, default=1, help="GPUs of this node to shard the reads over (one process each)")
     p.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (handles + host threads)")
+    p.add_argument("--polish", action="store_true", default=False,
+                   help="polish each batch's consensi with ONE racon process (racon from the config file / PATH); the "
+                        "default output is the pre-polish abPOA consensus")
     p.add_argument("--assign", choices=["psl", "gpu"], default="psl",
                    help="splint/strand per read: 'psl' = BLAT PSL as the reference (default); 'gpu' = conk profile of "
                         "every splint x strand on the GPU (no BLAT; not BLAT-equivalent)")
@@ -128,7 +131,7 @@ def compute_batch(gpu, names, blob, off, splint_dict, adapter_dict, mdist):
     return gpu.consensus_batch(batch, min_dist=mdist, max_peaks=128, cons_cap=min(2 * max_len, 131072))
 
 
-def write_batch(out, names, blob, off, qual, qual_sum, adapter_dict, handles):
+def write_batch(out, names, blob, off, qual, qual_sum, adapter_dict, handles, polish=None):
     """The host part: consensus FASTA + subread FASTQ exactly as analyze_reads / determine_consensus write them.
     Reads with a plain consensus (status 0) are formatted by the library in one pass per splint directory
     (c3_format_batch); only the 2-repeat reads, whose quality-aware pairwise consensus is host-side Python
@@ -140,6 +143,13 @@ def write_batch(out, names, blob, off, qual, qual_sum, adapter_dict, handles):
     gidx = {a: k for k, a in enumerate(order)}
     group = np.fromiter((gidx[adapter_dict[nm][0]] for nm in names), dtype=np.int32, count=len(names))
     names_raw, name_off = pack_names(names)
+    if polish is not None:
+        # f-4: one racon process per batch on (all subreads, whole-length overlaps, all pre-polish consensi); the
+        # consensus records are then formatted from the polished sequences
+        from .polish import polish_batch
+        _, fq_all, _ = format_batch(out, names_raw, name_off, blob, qual, off, qual_sum)
+        stats["polished"] = polish_batch(polish["racon"], polish["tmp_dir"], names, out, off, fq_all.tobytes(),
+                                         threads=polish.get("threads", 1), tag=f"batch{polish.get('serial', 0)}")
     for k, adapter in enumerate(order):
         fa, fq, st = format_batch(out, names_raw, name_off, blob, qual, off, qual_sum, group, k)
         cons_fh, sub_fh = handles[adapter]
@@ -236,10 +246,13 @@ def _run_all(args, adapter_dict, splint_dict, adapter_set):
     return totals
 
 
-def _drain_one(pending, handles, totals):
+def _drain_one(pending, handles, totals, polish=None):
     fut, names, blob, off, qual, qsum, ad = pending.pop(0)
     out = fut.result()
-    for key, v in write_batch(out, names, blob, off, qual, qsum, ad, handles).items():
+    if polish is not None:
+        polish = dict(polish, serial=totals.get("batches", 0))
+    totals["batches"] = totals.get("batches", 0) + 1
+    for key, v in write_batch(out, names, blob, off, qual, qsum, ad, handles, polish).items():
         totals[key] = totals.get(key, 0) + v
 
 
@@ -280,6 +293,12 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
 
     pool = ThreadPoolExecutor(max_workers=n_inflight)
     pending = []
+    polish = None
+    if getattr(args, "polish", False):         # f-4: one racon process per batch (bin/determine_consensus.py:49-104 per read)
+        progs = config_reader(args.config) if args.config else {"racon": "racon"}
+        pdir = args.out_path + f"tmp/polish{rank}/"
+        os.makedirs(pdir, exist_ok=True)
+        polish = dict(racon=progs["racon"], tmp_dir=pdir, threads=max(1, args.numThreads))
     reader = FastqBatches(args.reads, min_len=args.lencutoff, max_reads=args.batch,
                           max_bases=min(1 << 29, max(1 << 22, args.batch * 12000)), nbuf=n_inflight + 2)
     gpu_assign = adapter_dict is None
@@ -333,9 +352,9 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
         fut = pool.submit(run_on_free_handle, names, blob, off, splint_dict, ad, args.mdistcutoff)
         pending.append((fut, names, blob, off, qual, qsum, ad))
         while len(pending) >= len(gpus) + 1 or (pending and pending[0][0].done()):
-            _drain_one(pending, handles, totals)
+            _drain_one(pending, handles, totals, polish)
     while pending:
-        _drain_one(pending, handles, totals)
+        _drain_one(pending, handles, totals, polish)
     pool.shutdown()
     for g2 in gpus[1:]:
         g2.close()

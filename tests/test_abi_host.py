@@ -213,3 +213,56 @@ def test_format_batch_average_quality_like_python_round():
     got = fa.tobytes().decode().split("\n")[0::2][:n]
     for i, (a, b) in enumerate(cases):
         assert got[i] == header(names[i], a, b, 0, 0), (a, b, got[i])
+
+
+def test_polish_handoff_files_and_roundtrip(tmp_path):
+    """f-4 plumbing: one 'racon' process per batch gets (subread FASTQ, whole-length PAF overlaps, pre-polish consensi);
+    its output replaces the consensi by name, targets it does not return keep theirs.  racon itself is external: a
+    stand-in script checks its three inputs and returns every second target with a marker appended."""
+    import stat
+    from c3poa_b200.ingest import format_batch, pack_names
+    from c3poa_b200.polish import polish_batch, write_polish_inputs
+    rng = np.random.default_rng(5)
+    names, off, blob, qual, qsum, out = _fake_outputs(rng, 40)
+    R = out["results"]
+    raw, noff = pack_names(names)
+    _, fq, _ = format_batch(out, raw, noff, blob, qual, off, qsum)
+    seq_p, paf_p, tgt_p, idx = write_polish_inputs(str(tmp_path), names, out, off, fq.tobytes(), tag="t")
+    assert list(idx) == list(np.flatnonzero(R["status"] == 0))
+    tg = open(tgt_p).read().split("\n")
+    assert tg[0::2][:len(idx)] == [">" + names[i] for i in idx]
+    assert tg[1::2][:len(idx)] == [out["cons"][i, :R["cons_len"][i]].tobytes().decode() for i in idx]
+    paf = [ln.split("\t") for ln in open(paf_p).read().splitlines()]
+    assert len(paf) == int(R["n_sub"][idx].sum()) and all(len(f) == 12 for f in paf)
+    k = 0
+    for i in idx:
+        for s in range(int(R["n_sub"][i])):
+            ql = int(out["sub_bounds"][i, s, 1] - out["sub_bounds"][i, s, 0]); cl = int(R["cons_len"][i])
+            assert paf[k] == [f"{names[i]}_{s + 1}", str(ql), "0", str(ql), "+", names[i], str(cl), "0", str(cl),
+                              str(min(ql, cl)), str(max(ql, cl)), "60"]
+            k += 1
+    fake = tmp_path / "fake_racon"
+    fake.write_text("#!/usr/bin/env python3\n"
+                    "import sys\n"
+                    "seqs, paf, tgt = sys.argv[1:4]\n"
+                    "assert sys.argv[4:] == ['-q', '5', '-t', '3', '-u'], sys.argv\n"
+                    "assert open(seqs).read().count('\\n+\\n') > 0 and open(paf).read().count('\\t') > 0\n"
+                    "recs = open(tgt).read().split('>')[1:]\n"
+                    "for n, r in enumerate(recs):\n"
+                    "    name, seq = r.split('\\n')[:2]\n"
+                    "    if n % 2 == 0:\n"
+                    "        print('>' + name + ' LN:i:1 RC:i:2 XC:f:1.0')\n"
+                    "        print(seq[:10]); print(seq[10:] + 'GATTACA')\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    before = [out["cons"][i, :R["cons_len"][i]].tobytes().decode() for i in range(len(names))]
+    cap = out["cons"].shape[1]
+    n = polish_batch(str(fake), str(tmp_path), names, out, off, fq.tobytes(), threads=3, tag="u")
+    expect = 0
+    for pos, i in enumerate(idx):
+        now = out["cons"][i, :R["cons_len"][i]].tobytes().decode()
+        if pos % 2 == 0 and len(before[i]) + 7 <= cap:
+            assert now == before[i] + "GATTACA", i
+            expect += 1
+        else:
+            assert now == before[i], i
+    assert n == expect and not os.path.exists(str(tmp_path / "u_overlaps.paf"))

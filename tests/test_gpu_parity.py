@@ -293,6 +293,37 @@ def test_driver_end_to_end(gpu, oracle, tmp_path):
     assert sum(1 for s in subs if s[0].endswith("_1")) == len(cons)
 
 
+def test_driver_polish_flag_runs_one_process_per_batch(gpu, tmp_path):
+    """--polish: the driver hands each batch to ONE polishing process and writes what comes back.  racon is
+    external; a stand-in appends a marker to every target, so every plain consensus in the output must carry it
+    (the 2-repeat pairwise consensi are not polished by this path) and the call count must equal the batch count."""
+    import stat
+    from c3poa_b200 import driver
+    from c3poa_b200.fastx import fastx_read
+    if gpu.poa_mode != "auto":
+        pytest.skip("one mode is enough for the plumbing")
+    d = synth.make_reads(50, insert_len=600, repeats=4, seed=41)
+    out = tmp_path / "out"
+    (out / "tmp").mkdir(parents=True)
+    synth.write_fastq(tmp_path / "reads.fastq", d["names"], d["seqs"], d["quals"])
+    (tmp_path / "splint.fasta").write_text(f">Splint1\n{synth.SPLINT1}\n")
+    synth.write_psl(out / "tmp" / "splint_to_read_alignments.psl", d["names"], d["splint_name"], d["strand"])
+    fake = tmp_path / "fake_racon"
+    fake.write_text("#!/usr/bin/env python3\nimport sys\nopen(sys.argv[3] + '.calls', 'a').write('x')\n"
+                    "open(%r, 'a').write('x')\n"
+                    "for r in open(sys.argv[3]).read().split('>')[1:]:\n"
+                    "    name, seq = r.split('\\n')[:2]\n    print('>' + name); print(seq + 'GATTACA')\n" % str(tmp_path / "calls"))
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    (tmp_path / "config").write_text(f"racon\t{fake}\nblat\tblat\n")
+    args = driver.parse_args(["-r", str(tmp_path / "reads.fastq"), "-s", str(tmp_path / "splint.fasta"), "-o", str(out),
+                              "-c", str(tmp_path / "config"), "--polish", "--batch", "20"])
+    totals = driver.main(args)
+    cons = list(fastx_read(str(out / "Splint1" / "R2C2_Consensus.fasta")))
+    assert totals["errors"] == 0 and totals["polished"] == len(cons) >= 40
+    assert all(s.endswith("GATTACA") and int(n.rsplit("_", 1)[1]) == len(s) for n, s, _ in cons)
+    assert len((tmp_path / "calls").read_text()) == 3                     # 50 reads in batches of 20
+
+
 def test_poa_parameter_sweep(gpu, oracle):
     """abPOA keyword arguments other than the reference's (match=5): scoring, band and SIMD-granule variants."""
     rng = np.random.default_rng(41)
