@@ -299,8 +299,11 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
         pdir = args.out_path + f"tmp/polish{rank}/"
         os.makedirs(pdir, exist_ok=True)
         polish = dict(racon=progs["racon"], tmp_dir=pdir, threads=max(1, args.numThreads))
+    # staging buffers are pinned (slow to allocate: ~0.2 s per GB): no larger than the input can fill
+    fsz = os.path.getsize(args.reads)
+    could_hold = fsz * (8 if args.reads.endswith(".gz") else 1) + (1 << 20)
     reader = FastqBatches(args.reads, min_len=args.lencutoff, max_reads=args.batch,
-                          max_bases=min(1 << 29, max(1 << 22, args.batch * 12000)), nbuf=n_inflight + 2)
+                          max_bases=min(1 << 29, max(1 << 22, min(args.batch * 12000, could_hold))), nbuf=n_inflight + 2)
     gpu_assign = adapter_dict is None
     assign_gpu = GpuConsensus(gpu.device) if gpu_assign else None
     if gpu_assign:
