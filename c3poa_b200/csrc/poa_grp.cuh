@@ -1,0 +1,1084 @@
+// poa_grp.cuh -- stage 3b, group kernel: 8 lanes per read, 4 reads per warp.
+//
+// Same algorithm and the same results as poa.cuh / poa_lane.cuh (abPOA 1.0.5 semantics; replaces
+// poa.msa_aligner(match=5).msa(...), /root/reference/bin/determine_consensus.py:30-47), third mapping:
+//
+//   poa.cuh       one warp per read: half the lanes idle on a ~70-column band and every row pays the warp-uniform
+//                 bookkeeping 32 times over.
+//   poa_lane.cuh  one thread per read: 240 KB of thread-private graph state per read and 6 B per DP cell; nothing
+//                 is cacheable, every pointer-chasing step costs a DRAM round trip.
+//   poa_grp.cuh   one 8-lane group per read.  Everything a read owns is laid out BY POSITION in the topological
+//                 order, so all accesses of the DP are sequential and coalesced:
+//     * order[] / posof[] arrays instead of a linked list; after a merge the new nodes (already sorted by the
+//       gap of the old order they fall into) are merged into the order in parallel;
+//     * `prepare` turns the graph into one 16-byte row descriptor per position (node id, base, positions of the
+//       first two predecessors, remaining path length along the heaviest out-edges);
+//     * DP: each lane owns one 16-column vector of the band (abPOA's int16 SIMD granule), lane = vector index
+//       mod 8, cells packed two per register (VIADDMNMX.S16x2 / VIMNMX3.S16x2); the horizontal gap is an
+//       in-lane chain plus a 3-step (max,+) scan over the 8 lanes; predecessor rows come from a 4-row
+//       shared-memory ring (H, E1, E2 as int16) or, further back, from the arena;
+//     * arena: 3 bytes per cell -- H as int16 plus one byte holding H-E1 (3 bits) and H-E2 (5 bits), stored
+//       complemented (that is what one packed add of ~H yields); both
+//       differences are bounded by the gap-open costs, so H, E1 and E2 are recovered exactly and the backtrack
+//       stays abPOA's value-based one (M -> E1 -> E2 -> F1 -> F2, op-mask state machine).  Rows have a fixed
+//       stride of VS vectors, vector v of a row at slot v mod VS: a cell's address needs no row record;
+//     * backtrack: runs of match/mismatch moves along consecutive rows are verified 7 at a time.
+//
+// Scope: int16 score mode with the 256-bit granule, banded, default-sized gap costs (o1+e1 <= 7, o2+e2 <= 31),
+// consensus output.  Anything else -- and any capacity overflow or a row that fails the int16 exactness guard --
+// leaves the item not-done; the caller then runs it through c3_poa_kernel, which owns all error reporting.
+//
+// With -DC3G_EMUL the kernel body is host code as well: tests/emul/grp_emul.cu runs it on the fiber warp
+// emulator (tests/emul/warp_emu.cpp) against the oracle, no GPU needed.
+#pragma once
+#include "poa_lane.cuh"
+
+#define C3G_R 4                       // ring slots (rows) per group
+#define C3G_GL 8                      // lanes per group
+#define C3G_E_RETRY (-298)
+#define C3G_HWIN 1024                 // window of remaining-length words kept in shared memory during prepare
+
+#if defined(C3G_EMUL) && !defined(__CUDA_ARCH__)
+extern "C" int c3emu_shfl(unsigned mask, int v, int src);
+extern "C" unsigned c3emu_ballot(unsigned mask, int pred);
+extern "C" void c3emu_sync(unsigned mask);
+#define C3G_SHFL(m, v, s) c3emu_shfl((m), (int)(v), (s))
+#define C3G_BALLOT(m, p) c3emu_ballot((m), (p))
+#define C3G_SYNC(m) c3emu_sync(m)
+#define C3G_ATOMIC_INC(p) ((*(p))++)
+#define C3G_FFS(x) __builtin_ffs((int)(x))
+#define C3G_CLZ(x) ((x) ? __builtin_clz((unsigned)(x)) : 32)
+#else
+#define C3G_SHFL(m, v, s) __shfl_sync((m), (int)(v), (s))
+#define C3G_BALLOT(m, p) __ballot_sync((m), (p))
+#define C3G_SYNC(m) __syncwarp(m)
+#define C3G_ATOMIC_INC(p) atomicAdd((p), 1u)
+#define C3G_FFS(x) __ffs((int)(x))
+#define C3G_CLZ(x) __clz((int)(x))
+#endif
+#ifdef C3G_EMUL
+#define C3G_FN __host__ __device__ inline
+#else
+#define C3G_FN __device__ __forceinline__
+#endif
+#define C3G_ANYG(m, p) (C3G_BALLOT((m), (p)) != 0u)
+#if defined(__CUDA_ARCH__)
+#define C3G_VADD2(a, b) __vadd2((a), (b))            // per-halfword add, no carry between the halves: VIADD.16x2
+#else
+#define C3G_VADD2(a, b) ((uint32_t)(((((uint32_t)(a)) & 0xffffu) + (((uint32_t)(b)) & 0xffffu)) & 0xffffu) | (uint32_t)(((((uint32_t)(a)) >> 16) + (((uint32_t)(b)) >> 16)) << 16))
+#endif
+#if defined(C3G_EMUL) && !defined(__CUDA_ARCH__)
+extern "C" void c3g_emul_note(int line);            // test hook: why an item was declined
+#define C3G_DECLINE() c3g_emul_note(__LINE__)
+#else
+#define C3G_DECLINE() do { } while (0)
+#endif
+
+struct c3g_args {
+    c3_poa_args A;                    // inputs / outputs / parameters; order + n_work: items this kernel covers;
+                                      // node_cap, pool_cap, cigar_cap, qp_stride: per-group capacities
+    uint8_t *ws; long long ws_stride; // per-group graph workspace
+    uint4 *arena; long long arena_stride4;   // per-group DP arena, in uint4: node_cap rows x VS vectors x 3
+    int vs_shift;                     // log2 VS: vectors per arena row
+    int rv_shift;                     // log2 RV: vectors per shared-memory ring slot (RV <= VS)
+    int32_t *done;                    // [n_items] 1 = finished here
+};
+
+// per-group workspace
+struct c3g_ws {
+    c3_pnode *nodes; c3_pedge *pool;
+    uint4 *desc;                      // by position: x = id | p0 << 16, y = p1 | hops << 16, z = base | npre << 8 | xofs << 16
+    uint2 *rowrec;                    // by position: x = beg_sn | end_sn << 16, y = mp (arg-max column + 1)
+    uint16_t *order[2];               // position -> node id (double buffered across merges)
+    uint16_t *posof;                  // node id -> position
+    uint16_t *xpred;                  // positions of the third and further predecessors (in-edge order)
+    uint16_t *gaps;                   // new nodes of the running merge: old position they are inserted before
+    unsigned long long *cigar;
+    int8_t *qp;                       // substitution scores: 4 rows (node base) x qp_stride, index = column
+};
+
+__host__ __device__ inline int64_t c3g_ws_bytes(int node_cap, int pool_cap, int cigar_cap, int qp_stride)
+{
+    int64_t b = 0;
+    b += (int64_t)node_cap * 32 + (int64_t)pool_cap * 8 + (int64_t)node_cap * 16 + (int64_t)node_cap * 8;
+    b += (int64_t)node_cap * 2 * 2 + (int64_t)node_cap * 2 + (int64_t)pool_cap * 2 + (int64_t)node_cap * 2;
+    b += (int64_t)cigar_cap * 8 + (int64_t)qp_stride * 4;
+    return (b + 255) & ~(int64_t)255;
+}
+
+C3_HD __forceinline__ c3g_ws c3g_ws_carve(uint8_t *p, int node_cap, int pool_cap, int cigar_cap)
+{
+    c3g_ws w;
+    w.nodes = (c3_pnode *)p; p += (int64_t)node_cap * 32;
+    w.desc = (uint4 *)p; p += (int64_t)node_cap * 16;
+    w.pool = (c3_pedge *)p; p += (int64_t)pool_cap * 8;
+    w.rowrec = (uint2 *)p; p += (int64_t)node_cap * 8;
+    w.cigar = (unsigned long long *)p; p += (int64_t)cigar_cap * 8;
+    w.order[0] = (uint16_t *)p; p += (int64_t)node_cap * 2;
+    w.order[1] = (uint16_t *)p; p += (int64_t)node_cap * 2;
+    w.posof = (uint16_t *)p; p += (int64_t)node_cap * 2;
+    w.gaps = (uint16_t *)p; p += (int64_t)node_cap * 2;
+    w.xpred = (uint16_t *)p; p += (int64_t)pool_cap * 2;
+    w.qp = (int8_t *)p;
+    return w;
+}
+
+// shared memory per group: ring cells, then C3G_R row records
+C3_HD __forceinline__ int c3g_smem_group_bytes(int rv_shift) { return (C3G_R * 6 * 16 << rv_shift) + C3G_R * 8 + 32; }
+
+struct c3g_grp {                       // group-uniform state (replicated in the 8 lanes)
+    int item, sq, nseq, node_n, pool_n, err, ob;
+    long long cells_total;
+    const uint8_t *ibase; const int32_t *bnd;
+    const uint8_t *q; int qlen, n, w;
+};
+
+#define C3G_D_ID(d) ((int)((d).x & 0xffffu))
+#define C3G_D_P0(d) ((int)((d).x >> 16))
+#define C3G_D_P1(d) ((int)((d).y & 0xffffu))
+#define C3G_D_HOPS(d) ((int)((d).y >> 16))
+#define C3G_D_BASE(d) ((int)((d).z & 0xffu))
+#define C3G_D_NPRE(d) ((int)(((d).z >> 8) & 0xffu))
+#define C3G_D_XOFS(d) ((int)((d).z >> 16))
+#define C3G_R_BEG(r) ((int)((r).x & 0xffffu))
+#define C3G_R_END(r) ((int)((r).x >> 16))
+#define C3G_R_MP(r) ((int)((r).y & 0xffffu))
+
+// ---------------------------------------------------------------------------
+// item start: first sequence -> linear graph, order = SRC, 2, 3, ..., L+1, SINK
+// ---------------------------------------------------------------------------
+C3G_FN void c3g_item_begin(c3g_grp &G, const c3_poa_args &A, const c3g_ws &W, const int item, const int li)
+{
+    G.item = item; G.sq = 1; G.err = 0; G.nseq = 0; G.node_n = 0; G.pool_n = 0; G.cells_total = 0; G.ob = 0;
+    const int nseq = A.n_seqs[(int64_t)item * A.n_seqs_stride];
+    if (nseq < A.min_seqs || nseq > A.max_seqs || nseq < 1 || (A.msa2 && nseq == 2)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+    G.ibase = A.codes + A.item_base[item];
+    G.bnd = A.bounds + (int64_t)item * A.max_seqs * 2;
+    G.nseq = nseq;
+    const uint8_t *q = G.ibase + G.bnd[0];
+    const int L = G.bnd[1] - G.bnd[0];
+    if (L <= 0 || L > 65000 || L + 2 > A.node_cap) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+    uint16_t *ord = W.order[0];
+    for (int i = li; i < L + 2; i += C3G_GL) {
+        c3_pnode n;
+        n.in_more = n.out_more = C3_NONE; n.rmask = 1; n.spare = 0;
+        n.aln0 = n.aln1 = n.aln2 = n.aln3 = C3_NONE; n.max_out = C3_NONE; n.aln_n = 0;
+        n.prev = n.next = C3_NONE;
+        int pos;
+        if (i == C3_SRC) {
+            n.base = 4; n.in_n = 0; n.out_n = 1; n.in0 = C3_NONE; n.out0 = 2; n.w0 = 1; pos = 0;
+        } else if (i == C3_SINK) {
+            n.base = 4; n.in_n = 1; n.out_n = 0; n.in0 = (uint16_t)(L + 1); n.out0 = C3_NONE; n.w0 = 0; pos = L + 1;
+        } else {
+            n.base = q[i - 2]; n.in_n = 1; n.out_n = 1; n.w0 = 1;
+            n.in0 = (uint16_t)(i == 2 ? C3_SRC : i - 1);
+            n.out0 = (uint16_t)(i == L + 1 ? C3_SINK : i + 1);
+            pos = i - 1;
+        }
+        W.nodes[i] = n;
+        ord[pos] = (uint16_t)i; W.posof[i] = (uint16_t)pos;
+    }
+    G.node_n = L + 2;
+}
+
+// ---------------------------------------------------------------------------
+// prepare: score mode, band half-width, score profile, row descriptors by position (reverse sweep, 8 positions
+// per step) with the remaining path length along the heaviest out-edges.  hw: shared-memory window of hop counts.
+// ---------------------------------------------------------------------------
+C3G_FN void c3g_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_para_dev &P, const c3g_ws &W, uint16_t *hw,
+                        const int li, const int gbase, const unsigned gmask)
+{
+    const int sq = G.sq;
+    const uint8_t *q = G.ibase + G.bnd[2 * sq];
+    const int qlen = G.bnd[2 * sq + 1] - G.bnd[2 * sq];
+    const int n = G.node_n;
+    {
+        const int len = qlen > n ? qlen : n;
+        const int max_score = max(qlen * 5, len * P.e1 + P.o1);
+        const int pn = (max_score <= 32767 - P.mismatch - P.o1 - P.e1) ? P.simd_bits / 16 : P.simd_bits / 32;
+        if (qlen <= 0 || qlen > 65000 || qlen + 32 > A.qp_stride || pn != 16 || P.wb < 0) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+    }
+    G.q = q; G.qlen = qlen; G.n = n; G.w = P.wb + (int)(P.wf * (double)qlen);
+    // profile: qp[b][j] = score of node base b against column j (= q[j-1]); j = 0 and the padding score 0
+    {
+        const int qs = A.qp_stride;
+        for (int j0 = 4 * li; j0 < qs; j0 += 4 * C3G_GL) {
+            uint32_t wv[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = j0 + k;
+                if (j >= 1 && j <= qlen) {
+                    const int qc = q[j - 1];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) wv[b] |= (uint32_t)(uint8_t)(int8_t)c3_score(P, b, qc) << (8 * k);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) *reinterpret_cast<uint32_t *>(W.qp + b * qs + j0) = wv[b];
+        }
+    }
+    const uint16_t *ord = W.order[G.ob];
+    int xbase = 0;
+    const int nb = (n + C3G_GL - 1) / C3G_GL;
+    for (int bi = nb - 1; bi >= 0; --bi) {
+        const int pb = bi * C3G_GL, p = pb + li;
+        const bool valid = p < n;
+        int id = C3_SINK, base = 4, in_n = 0, p0 = C3_NONE, p1 = C3_NONE, e_more = C3_NONE;
+        int tgt = p, hops = 0, fin = 1;
+        if (valid) {
+            id = ord[p];
+            const c3_nrec nd = c3_ld_node(&W.nodes[id]);
+            base = C3_N_BASE(nd); in_n = C3_N_INN(nd);
+            if (in_n > 0) p0 = W.posof[C3_N_IN0(nd)];
+            if (in_n > 1) {
+                const c3_pedge pe = W.pool[C3_N_INMORE(nd)];
+                p1 = W.posof[pe.id]; e_more = pe.next;
+            }
+            if (id != C3_SINK) {
+                int best_w = C3_N_W0(nd), best = C3_N_OUT0(nd);
+                if (C3_N_OUTN(nd) > 1) {
+                    int e = W.nodes[id].out_more;
+                    while (e != (int)C3_NONE) {
+                        const c3_pedge pe = W.pool[e];
+                        if ((int)pe.w > best_w) { best_w = pe.w; best = pe.id; }
+                        e = pe.next;
+                    }
+                }
+                tgt = W.posof[best]; hops = 1; fin = 0;
+            }
+        }
+        // third and further predecessors: positions appended to xpred (exclusive scan of the counts over the group)
+        const int nx = in_n > 2 ? in_n - 2 : 0;
+        int incl = nx;
+#pragma unroll
+        for (int d = 1; d < C3G_GL; d <<= 1) {
+            const int v = C3G_SHFL(gmask, incl, gbase + ((li - d) & 7));
+            if (li >= d) incl += v;
+        }
+        const int xo = xbase + incl - nx;
+        xbase += C3G_SHFL(gmask, incl, gbase + 7);
+        if (xbase > A.pool_cap) { C3G_DECLINE(); G.err = C3G_E_RETRY; }          // uniform
+        if (nx > 0 && !G.err) {
+            int e = e_more;
+            for (int k = 0; k < nx && e != (int)C3_NONE; ++k) {
+                const c3_pedge pe = W.pool[e];
+                W.xpred[xo + k] = W.posof[pe.id]; e = pe.next;
+            }
+        }
+        // hops to the sink: pointer doubling inside the batch, then one look-up above it
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int src = gbase + ((tgt - pb) & 7);
+            const int t2 = C3G_SHFL(gmask, tgt, src), h2 = C3G_SHFL(gmask, hops, src), f2 = C3G_SHFL(gmask, fin, src);
+            if (!fin && tgt >= pb && tgt < pb + C3G_GL) { hops += h2; if (f2) fin = 1; else tgt = t2; }
+        }
+        if (!fin) {
+            if (tgt - pb < C3G_HWIN - C3G_GL) hops += hw[tgt & (C3G_HWIN - 1)];
+            else hops += C3G_D_HOPS(W.desc[tgt]);
+        }
+        C3G_SYNC(gmask);
+        if (valid) {
+            hw[p & (C3G_HWIN - 1)] = (uint16_t)hops;
+            if (in_n > C3_MAXPRE || hops > 65535) { C3G_DECLINE(); G.err = C3G_E_RETRY; }
+            W.desc[p] = make_uint4((uint32_t)id | ((uint32_t)p0 << 16), (uint32_t)p1 | ((uint32_t)hops << 16),
+                                   (uint32_t)base | ((uint32_t)in_n << 8) | ((uint32_t)xo << 16), 0u);
+        }
+        G.err = C3G_ANYG(gmask, G.err != 0) ? C3G_E_RETRY : 0;
+        C3G_SYNC(gmask);
+        if (G.err) return;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// DP
+// ---------------------------------------------------------------------------
+struct c3g_cells { uint32_t h[8], x1[8], x2[8]; };
+
+// this lane's vector `sn` of the row at position pk (record rk): packed H, E1, E2.  Outside the row's band:
+// floor.  Rows not older than C3G_R positions whose band fits a ring slot come from shared memory, the others from
+// the arena (E1 = H - d1, E2 = H - d2; the source row keeps E only at column 0).
+C3G_FN void c3g_load_pred(c3g_cells &c, const uint4 *ring, const int rv_shift, const uint4 *arena, const int vs_shift,
+                          const int pos, const int pk, const uint2 rk, const int sn, const int ring_delta)
+{
+    const int pb = C3G_R_BEG(rk), pe = C3G_R_END(rk);
+    if (sn < pb || sn > pe) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) c.h[t] = c.x1[t] = c.x2[t] = C3L_FLOOR2;
+        return;
+    }
+    if (pos - pk <= ring_delta && pe - pb < (1 << rv_shift)) {
+        const uint4 *s = ring + (((pk & (C3G_R - 1)) * 6) << rv_shift) + (sn & ((1 << rv_shift) - 1));
+        const int st = 1 << rv_shift;
+        const uint4 a0 = s[0], a1 = s[st], b0 = s[2 * st], b1 = s[3 * st], c0 = s[4 * st], c1 = s[5 * st];
+        c.h[0] = a0.x; c.h[1] = a0.y; c.h[2] = a0.z; c.h[3] = a0.w; c.h[4] = a1.x; c.h[5] = a1.y; c.h[6] = a1.z; c.h[7] = a1.w;
+        c.x1[0] = b0.x; c.x1[1] = b0.y; c.x1[2] = b0.z; c.x1[3] = b0.w; c.x1[4] = b1.x; c.x1[5] = b1.y; c.x1[6] = b1.z; c.x1[7] = b1.w;
+        c.x2[0] = c0.x; c.x2[1] = c0.y; c.x2[2] = c0.z; c.x2[3] = c0.w; c.x2[4] = c1.x; c.x2[5] = c1.y; c.x2[6] = c1.z; c.x2[7] = c1.w;
+        return;
+    }
+    const uint4 *s = arena + (((int64_t)pk << vs_shift) + (sn & ((1 << vs_shift) - 1))) * 3;
+    const uint4 a0 = s[0], a1 = s[1], eb = s[2];
+    c.h[0] = a0.x; c.h[1] = a0.y; c.h[2] = a0.z; c.h[3] = a0.w; c.h[4] = a1.x; c.h[5] = a1.y; c.h[6] = a1.z; c.h[7] = a1.w;
+    if (pk == 0) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) c.x1[t] = c.x2[t] = C3L_FLOOR2;
+        if (sn == 0) {
+            const uint32_t b0 = ~eb.x & 0xffu;
+            c.x1[0] = C3L_PACK2((int)(int16_t)(c.h[0] & 0xffffu) - (int)(b0 & 7u), C3L_FLOOR);
+            c.x2[0] = C3L_PACK2((int)(int16_t)(c.h[0] & 0xffffu) - (int)(b0 >> 3), C3L_FLOOR);
+        }
+        return;
+    }
+    // byte = ~(d1 | d2 << 3): (byte & 7) - 7 = -d1, ((byte >> 3) & 31) - 31 = -d2, added per halfword
+    const uint32_t ew[4] = {eb.x, eb.y, eb.z, eb.w};
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const uint32_t two = C3L_PRMT(ew[t >> 1], 0u, (t & 1) ? 0x4342u : 0x4140u);    // bytes -> halfwords
+        c.x1[t] = C3G_VADD2(c.h[t], C3G_VADD2(two & 0x00070007u, 0xfff9fff9u));
+        c.x2[t] = C3G_VADD2(c.h[t], C3G_VADD2((two >> 3) & 0x001f001fu, 0xffe1ffe1u));
+    }
+}
+
+C3G_FN uint2 c3g_get_rowrec(const uint2 *srr, const uint2 *rowrec, const int pos, const int pk)
+{
+    return (pos - pk <= C3G_R) ? srr[pk & (C3G_R - 1)] : rowrec[pk];
+}
+
+// source row: cells, ring slot 0, arena, record
+C3G_FN void c3g_source_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, uint4 *ring, uint2 *srr,
+                           uint4 *arena, const int li, const unsigned gmask)
+{
+    const int oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
+    const int qlen = G.qlen;
+    const int rem = C3G_D_HOPS(W.desc[0]) - 1;
+    const int rr = qlen - rem;
+    const int end = min(qlen, max(0, rr) + G.w);
+    const int end_sn = end >> 4, e0 = min(qlen, end_sn * 16 + 15);
+    const int nvec = end_sn + 1;
+    if (nvec > (1 << L.vs_shift)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+    const int rvm = (1 << L.rv_shift) - 1, vsm = (1 << L.vs_shift) - 1;
+    bool low = false;
+    for (int sn = li; sn <= end_sn; sn += C3G_GL) {
+        uint32_t h[8], x1[8], x2[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            int hv[2], a1[2], a2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int c = sn * 16 + 2 * t + u;
+                hv[u] = a1[u] = a2[u] = C3L_FLOOR;
+                if (c <= e0) {
+                    if (c == 0) { hv[u] = 0; a1[u] = -oe1; a2[u] = -oe2; }
+                    else hv[u] = max(-(P.o1 + P.e1 * c), -(P.o2 + P.e2 * c));
+                    if (hv[u] < C3L_FLOOR + 1024) low = true;
+                }
+            }
+            h[t] = C3L_PACK2(hv[0], hv[1]); x1[t] = C3L_PACK2(a1[0], a1[1]); x2[t] = C3L_PACK2(a2[0], a2[1]);
+        }
+        if (nvec <= rvm + 1) {
+            uint4 *s = ring + (sn & rvm);
+            const int st = rvm + 1;
+            s[0] = make_uint4(h[0], h[1], h[2], h[3]); s[st] = make_uint4(h[4], h[5], h[6], h[7]);
+            s[2 * st] = make_uint4(x1[0], x1[1], x1[2], x1[3]); s[3 * st] = make_uint4(x1[4], x1[5], x1[6], x1[7]);
+            s[4 * st] = make_uint4(x2[0], x2[1], x2[2], x2[3]); s[5 * st] = make_uint4(x2[4], x2[5], x2[6], x2[7]);
+        }
+        uint4 *d = arena + (int64_t)(sn & vsm) * 3;
+        d[0] = make_uint4(h[0], h[1], h[2], h[3]); d[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        d[2] = make_uint4(sn == 0 ? ~(uint32_t)(oe1 | (oe2 << 3)) : ~0u, ~0u, ~0u, ~0u);
+    }
+    if (C3G_ANYG(gmask, low)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+    const uint2 rec = make_uint2((uint32_t)end_sn << 16, 1u);      // successors of the source start at column 1
+    if (li == 0) { W.rowrec[0] = rec; srr[0] = rec; }
+}
+
+// one DP row (position pos, descriptor d).  Returns the band width in columns, 0 after an error.
+C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, uint4 *ring, uint2 *srr,
+                   uint4 *arena, const int pos, const uint4 d, const int li, const int gbase, const unsigned gmask)
+{
+    const int e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
+    const int qlen = G.qlen, w = G.w, n = G.n;
+    const int npre = C3G_D_NPRE(d), nbase = C3G_D_BASE(d);
+    const int p0 = C3G_D_P0(d), p1 = C3G_D_P1(d);
+    const uint2 r0 = c3g_get_rowrec(srr, W.rowrec, pos, p0);
+    uint2 r1 = make_uint2(1u, 0u);                                // empty band
+    int mpl = min(n, C3G_R_MP(r0)), mpr = C3G_R_MP(r0), minb = C3G_R_BEG(r0);
+    if (npre > 1) {
+        r1 = c3g_get_rowrec(srr, W.rowrec, pos, p1);
+        mpl = min(mpl, C3G_R_MP(r1)); mpr = max(mpr, C3G_R_MP(r1)); minb = min(minb, C3G_R_BEG(r1));
+        for (int k = 2; k < npre; ++k) {
+            const int pk = W.xpred[C3G_D_XOFS(d) + k - 2];
+            const uint2 rk = c3g_get_rowrec(srr, W.rowrec, pos, pk);
+            mpl = min(mpl, C3G_R_MP(rk)); mpr = max(mpr, C3G_R_MP(rk)); minb = min(minb, C3G_R_BEG(rk));
+        }
+    }
+    const int rr = qlen - (C3G_D_HOPS(d) - 1);
+    const int beg_sn = max(max(0, min(mpl, rr) - w) >> 4, minb);
+    const int end_sn = max(min(qlen, max(mpr, rr) + w) >> 4, beg_sn);
+    const int beg = beg_sn << 4, end = min(qlen, end_sn * 16 + 15);
+    const int nvec = end_sn - beg_sn + 1;
+    if (nvec > (1 << L.vs_shift)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return 0; }
+    const bool to_ring = nvec <= (1 << L.rv_shift);
+    const int rvm = (1 << L.rv_shift) - 1, vsm = (1 << L.vs_shift) - 1;
+    const uint32_t ne1 = C3L_PACK2(-e1, -e1), ne2 = C3L_PACK2(-e2, -e2), noe1 = C3L_PACK2(-oe1, -oe1), noe2 = C3L_PACK2(-oe2, -oe2);
+    int pc1 = C3L_FLOOR, pc2 = C3L_FLOOR;                          // F1, F2' entering the pass (chain domain, see below)
+    uint32_t mcarry = C3L_FLOOR2;                                  // merged predecessor H of the vector before the pass
+    int bestkey = -0x7fffffff - 1, h_first = 0;
+    // everything read from the ring must be in registers before any lane overwrites the slot of row pos - C3G_R:
+    // a row of several passes stores its first vectors before it has read the last ones, so it does not use that slot
+    const int ring_delta = nvec <= C3G_GL ? C3G_R : C3G_R - 1;
+    for (int sn0 = beg_sn; sn0 <= end_sn; sn0 += C3G_GL) {
+        const int l = (li - sn0) & 7, sn = sn0 + l;
+        const bool act = sn <= end_sn;
+        const int j0 = sn << 4;
+        c3g_cells c;
+        if (act) {
+            c3g_load_pred(c, ring, L.rv_shift, arena, L.vs_shift, pos, p0, r0, sn, ring_delta);
+            if (npre > 1) {
+                c3g_cells t;
+                c3g_load_pred(t, ring, L.rv_shift, arena, L.vs_shift, pos, p1, r1, sn, ring_delta);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { c.h[u] = C3L_VMAX2(c.h[u], t.h[u]); c.x1[u] = C3L_VMAX2(c.x1[u], t.x1[u]); c.x2[u] = C3L_VMAX2(c.x2[u], t.x2[u]); }
+                for (int k = 2; k < npre; ++k) {
+                    const int pk = W.xpred[C3G_D_XOFS(d) + k - 2];
+                    const uint2 rk = c3g_get_rowrec(srr, W.rowrec, pos, pk);
+                    c3g_load_pred(t, ring, L.rv_shift, arena, L.vs_shift, pos, pk, rk, sn, ring_delta);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { c.h[u] = C3L_VMAX2(c.h[u], t.h[u]); c.x1[u] = C3L_VMAX2(c.x1[u], t.x1[u]); c.x2[u] = C3L_VMAX2(c.x2[u], t.x2[u]); }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) c.h[u] = c.x1[u] = c.x2[u] = C3L_FLOOR2;
+        }
+        // M: merged predecessor H one column to the left (the first cell of the band never takes M)
+        uint32_t top = (uint32_t)C3G_SHFL(gmask, c.h[7], gbase + ((li - 1) & 7));
+        if (l == 0) top = mcarry;
+        mcarry = (uint32_t)C3G_SHFL(gmask, c.h[7], gbase + ((sn0 + 7) & 7));
+        uint32_t mw[8];
+        mw[0] = C3L_PRMT(top, c.h[0], 0x5432u);
+#pragma unroll
+        for (int t = 1; t < 8; ++t) mw[t] = C3L_PRMT(c.h[t - 1], c.h[t], 0x5432u);
+        // scores of the 16 columns
+        uint32_t sc[8];
+        if (act && nbase < 4) {
+            const uint4 s4 = *reinterpret_cast<const uint4 *>(W.qp + nbase * L.A.qp_stride + j0);
+            sc[0] = C3L_PRMT(s4.x, 0u, 0x9180u); sc[1] = C3L_PRMT(s4.x, 0u, 0xb3a2u);
+            sc[2] = C3L_PRMT(s4.y, 0u, 0x9180u); sc[3] = C3L_PRMT(s4.y, 0u, 0xb3a2u);
+            sc[4] = C3L_PRMT(s4.z, 0u, 0x9180u); sc[5] = C3L_PRMT(s4.z, 0u, 0xb3a2u);
+            sc[6] = C3L_PRMT(s4.w, 0u, 0x9180u); sc[7] = C3L_PRMT(s4.w, 0u, 0xb3a2u);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) sc[t] = 0u;
+        }
+        uint32_t hme[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) hme[t] = C3L_VMAX3_2(C3L_VADDMAX2(mw[t], sc[t], C3L_FLOOR2), c.x1[t], c.x2[t]);
+        const int lim = act ? end - j0 : -1;                       // last active column of this vector (>= 15: all)
+        if (lim < 15) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (2 * t > lim) hme[t] = C3L_FLOOR2;
+                else if (2 * t + 1 > lim) hme[t] = (hme[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
+            }
+        }
+        // horizontal gap, chain domain: g1 = F1 at the column, g2 = F2 at the column + (oe2 - oe1); both take
+        // a = hme - oe1 per column.  Local chain from "nothing enters the lane" first, then the 8-lane scan.
+        const int d21 = oe1 - oe2;
+        int g1 = C3L_FLOOR, g2 = C3L_FLOOR;
+        uint32_t fmp[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const uint32_t hs = C3L_VADDMAX2(hme[t], noe1, 0x80008000u);
+            const int a0 = (int)(int16_t)(hs & 0xffffu), a1 = (int)hs >> 16;
+            const int f0 = C3L_ADDMAX(g2, d21, g1);
+            g1 = C3L_ADDMAX(g1, -e1, a0); g2 = C3L_ADDMAX(g2, -e2, a0);
+            const int f1 = C3L_ADDMAX(g2, d21, g1);
+            g1 = C3L_ADDMAX(g1, -e1, a1); g2 = C3L_ADDMAX(g2, -e2, a1);
+            fmp[t] = C3L_PACK2(f0, f1);
+        }
+        // scan: value entering lane l = max(pass carry decayed, local outputs of the lanes before, decayed)
+        int t1 = g1 + 16 * e1 * l, t2 = g2 + 16 * e2 * l;
+#pragma unroll
+        for (int dd = 1; dd < C3G_GL; dd <<= 1) {
+            const int v1 = C3G_SHFL(gmask, t1, gbase + ((li - dd) & 7)), v2 = C3G_SHFL(gmask, t2, gbase + ((li - dd) & 7));
+            if (l >= dd) { t1 = max(t1, v1); t2 = max(t2, v2); }
+        }
+        int c1 = C3G_SHFL(gmask, t1, gbase + ((li - 1) & 7)), c2 = C3G_SHFL(gmask, t2, gbase + ((li - 1) & 7));
+        const int tot1 = C3G_SHFL(gmask, t1, gbase + ((sn0 + 7) & 7)), tot2 = C3G_SHFL(gmask, t2, gbase + ((sn0 + 7) & 7));
+        c1 = l == 0 ? pc1 : max(c1 - 16 * e1 * (l - 1), pc1 - 16 * e1 * l);
+        c2 = l == 0 ? pc2 : max(c2 - 16 * e2 * (l - 1), pc2 - 16 * e2 * l);
+        pc1 = max(tot1 - 16 * e1 * 7, pc1 - 16 * e1 * 8);
+        pc2 = max(tot2 - 16 * e2 * 7, pc2 - 16 * e2 * 8);
+        c1 = max(c1, C3L_FLOOR); c2 = max(c2 + d21, C3L_FLOOR);    // F1, F2 entering the vector
+        const uint32_t c1p = C3L_PACK2(c1, c1), c2p = C3L_PACK2(c2, c2);
+        uint32_t hh[8], n1[8], n2[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const uint32_t rp1 = C3L_PACK2(-e1 * 2 * t, -e1 * (2 * t + 1)), rp2 = C3L_PACK2(-e2 * 2 * t, -e2 * (2 * t + 1));
+            const uint32_t ff = C3L_VADDMAX2(c2p, rp2, C3L_VADDMAX2(c1p, rp1, fmp[t]));
+            hh[t] = C3L_VMAX2(hme[t], ff);
+            n1[t] = C3L_VADDMAX2(c.x1[t], ne1, C3L_VADDMAX2(hh[t], noe1, C3L_FLOOR2));
+            n2[t] = C3L_VADDMAX2(c.x2[t], ne2, C3L_VADDMAX2(hh[t], noe2, C3L_FLOOR2));
+        }
+        if (lim < 15) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (2 * t > lim) hh[t] = n1[t] = n2[t] = C3L_FLOOR2;
+                else if (2 * t + 1 > lim) {
+                    hh[t] = (hh[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
+                    n1[t] = (n1[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
+                    n2[t] = (n2[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
+                }
+            }
+        }
+        if (sn == beg_sn) h_first = (int)(int16_t)(hh[0] & 0xffffu);
+        // simd_abpoa_ada_max_i as one packed max: value in the high half, tie-break priority in the low half
+        // (lowest SIMD lane, then the last vector, then the earliest vector)
+        if (act) {
+            int lk = -0x7fffffff - 1;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int klo = (int)((hh[t] << 16) | (uint32_t)((15 - 2 * t) << 12));
+                const int khi = (int)((hh[t] & 0xffff0000u) | (uint32_t)((14 - 2 * t) << 12));
+                lk = C3L_MAX3(lk, klo, khi);
+            }
+            const int vp = (sn == end_sn) ? 0xfff : (0xffe - (sn - beg_sn));
+            bestkey = max(bestkey, lk | vp);
+        }
+        C3G_SYNC(gmask);
+        if (act) {
+            const uint4 oa0 = make_uint4(hh[0], hh[1], hh[2], hh[3]), oa1 = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+            if (to_ring) {
+                uint4 *s = ring + (((pos & (C3G_R - 1)) * 6) << L.rv_shift) + (sn & rvm);
+                const int st = rvm + 1;
+                s[0] = oa0; s[st] = oa1;
+                s[2 * st] = make_uint4(n1[0], n1[1], n1[2], n1[3]); s[3 * st] = make_uint4(n1[4], n1[5], n1[6], n1[7]);
+                s[4 * st] = make_uint4(n2[0], n2[1], n2[2], n2[3]); s[5 * st] = make_uint4(n2[4], n2[5], n2[6], n2[7]);
+            }
+            // E byte: n + ~H = -(H - n) - 1 per halfword, whose low bits are the complement of H - n; bits 0-2 from E1,
+            // bits 3-7 from E2 (what spills above bit 7 is dropped by the byte pack below)
+            uint32_t eb[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t nh = ~hh[t];
+                const uint32_t s1 = C3G_VADD2(n1[t], nh), s2 = C3G_VADD2(n2[t], nh) << 3;
+                eb[t] = (s1 & 0x00070007u) | (s2 & ~0x00070007u);
+            }
+            uint4 *dst = arena + (((int64_t)pos << L.vs_shift) + (sn & vsm)) * 3;
+            dst[0] = oa0; dst[1] = oa1;
+            dst[2] = make_uint4(C3L_PRMT(eb[0], eb[1], 0x6420u), C3L_PRMT(eb[2], eb[3], 0x6420u),
+                                C3L_PRMT(eb[4], eb[5], 0x6420u), C3L_PRMT(eb[6], eb[7], 0x6420u));
+        }
+    }
+    // exactness of the int16 form (see poa_lane.cuh): the first band cell comfortably above the floor means that
+    // every cell of the row is reachable and was never clamped
+    h_first = C3G_SHFL(gmask, h_first, gbase + (beg_sn & 7));
+    {
+        const int D = max(min(oe1, oe2), max(e1, e2));
+        if (h_first < C3L_FLOOR + C3L_LOW_GUARD + oe2 + D * (end - beg + 1)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return 0; }
+    }
+#pragma unroll
+    for (int dd = 1; dd < C3G_GL; dd <<= 1) bestkey = max(bestkey, C3G_SHFL(gmask, bestkey, gbase + (li ^ dd)));
+    int best_i = -1;
+    if ((bestkey >> 16) > C3L_FLOOR) {
+        const int sl = 15 - ((bestkey >> 12) & 15);
+        const int vp = bestkey & 0xfff;
+        const int snb = (vp == 0xfff) ? end_sn : beg_sn + (0xffe - vp);
+        best_i = (snb << 4) + sl;
+    }
+    const uint2 rec = make_uint2((uint32_t)beg_sn | ((uint32_t)end_sn << 16), (uint32_t)(best_i + 1));
+    if (li == 0) { W.rowrec[pos] = rec; srr[pos & (C3G_R - 1)] = rec; }
+    C3G_SYNC(gmask);
+    return end - beg + 1;
+}
+
+// ---------------------------------------------------------------------------
+// backtrack: abPOA's M -> E1 -> E2 -> F1 -> F2 order and op-mask state machine on the arena's (H, H-E1, H-E2)
+// cells.  Group-uniform; runs of match/mismatch moves along consecutive rows are verified 7 at a time.
+// Returns the number of cigar ops or a negative code.
+// ---------------------------------------------------------------------------
+C3_HD __forceinline__ int c3g_cell_h(const uint4 *arena, const int vs_shift, const int pos, const int j)
+{
+    const int16_t *p = reinterpret_cast<const int16_t *>(arena + (((int64_t)pos << vs_shift) + ((j >> 4) & ((1 << vs_shift) - 1))) * 3);
+    return c3l_map((int)p[j & 15]);
+}
+C3_HD __forceinline__ int c3g_cell_eb(const uint4 *arena, const int vs_shift, const int pos, const int j)
+{
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(arena + (((int64_t)pos << vs_shift) + ((j >> 4) & ((1 << vs_shift) - 1))) * 3 + 2);
+    return (int)(~p[j & 15] & 0xff);               // (H - E1) | (H - E2) << 3
+}
+C3_HD __forceinline__ int c3g_pred_pos(const c3g_ws &W, const uint4 d, const int k)
+{
+    return k == 0 ? C3G_D_P0(d) : k == 1 ? C3G_D_P1(d) : (int)W.xpred[C3G_D_XOFS(d) + k - 2];
+}
+
+C3G_FN int c3g_backtrack(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, const uint4 *arena,
+                         const int li, const int gbase, const unsigned gmask)
+{
+    const int e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
+    const int vs = L.vs_shift;
+    const uint8_t *q = G.q; const int qlen = G.qlen, n = G.n;
+    const int cap = L.A.cigar_cap;
+    unsigned long long *cg = W.cigar;
+    int nc = 0, j, pos, hij;
+    {
+        const uint4 ds = W.desc[n - 1];
+        int best = -0x7fffffff - 1, bj = -1, bk = -1;
+        const int skn = C3G_D_NPRE(ds);
+        for (int k = 0; k < skn; ++k) {
+            const int pk = c3g_pred_pos(W, ds, k);
+            const uint2 rp = W.rowrec[pk];
+            const int en = min(qlen, C3G_R_END(rp) * 16 + 15);
+            const int val = c3g_cell_h(arena, vs, pk, en);
+            if (val > best) { best = val; bj = en; bk = pk; }
+        }
+        if (bk < 0 || qlen - bj + 8 > cap) { C3G_DECLINE(); return C3G_E_RETRY; }
+        for (int t = qlen - li; t > bj; t -= C3G_GL)
+            cg[qlen - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
+        nc = qlen - bj; j = bj; pos = bk; hij = best;
+    }
+    int cur_op = C3_OP_ALL;
+    while (pos != 0 && j > 0) {
+        if (cur_op == C3_OP_ALL) {
+            // lane l looks at row pos - l, column j - l
+            const int pl = pos - li, jl = j - li;
+            uint4 dl = make_uint4(0u, 0u, 0u, 0u); uint2 rl = make_uint2(1u, 0u);
+            int hl = C3_NEG_INF;
+            if (pl >= 0) {
+                dl = W.desc[pl]; rl = W.rowrec[pl];
+                if (jl >= 0) hl = c3g_cell_h(arena, vs, pl, jl);
+            }
+            const int bl = C3G_R_BEG(rl) * 16, el = min(qlen, C3G_R_END(rl) * 16 + 15);
+            if (jl < bl || jl > el) hl = C3_NEG_INF;
+            const int src = gbase + ((li + 1) & 7);
+            const int hn = C3G_SHFL(gmask, hl, src), bn = C3G_SHFL(gmask, bl, src), en = C3G_SHFL(gmask, el, src);
+            bool ok = li < 7 && pl >= 1 && jl >= 1 && jl >= bl && jl <= el && C3G_D_P0(dl) == pl - 1;
+            if (ok) {
+                const int s = c3_score(P, C3G_D_BASE(dl), q[jl - 1]);
+                ok = jl - 1 >= max(bn, bl) && jl - 1 <= en && hn + s == hl;
+            }
+            const unsigned okm = (C3G_BALLOT(gmask, ok) >> gbase) & 0xffu;
+            int Lr = C3G_FFS(~okm) - 1;
+            Lr = min(Lr, cap - 8 - j - nc);
+            if (Lr > 0) {
+                if (li < Lr) cg[nc + li] = C3_CG_MATCH | ((unsigned long long)C3G_D_ID(dl) << 8) | ((unsigned long long)(jl - 1) << 32);
+                nc += Lr; j -= Lr; pos -= Lr;
+                hij = C3G_SHFL(gmask, hl, gbase + Lr);
+                continue;
+            }
+        }
+        // generic single step
+        const uint4 d = W.desc[pos];
+        const uint2 rt = W.rowrec[pos];
+        const int i = C3G_D_ID(d);
+        const int b = C3G_R_BEG(rt) * 16, en = min(qlen, C3G_R_END(rt) * 16 + 15);
+        if (j < b || j > en) { C3G_DECLINE(); return C3G_E_RETRY; }
+        const int s = c3_score(P, C3G_D_BASE(d), q[j - 1]);
+        const int npre = C3G_D_NPRE(d);
+        int hit = 0;
+        unsigned long long opw = 0;
+        if (cur_op & C3_OP_M) {
+            for (int k = 0; k < npre; ++k) {
+                const int pk = c3g_pred_pos(W, d, k);
+                const uint2 pr = W.rowrec[pk];
+                const int pbeg = C3G_R_BEG(pr) * 16, pend = min(qlen, C3G_R_END(pr) * 16 + 15);
+                if (j - 1 < max(pbeg, b) || j - 1 > pend) continue;
+                const int ph = c3g_cell_h(arena, vs, pk, j - 1);
+                if (ph + s == hij) {
+                    opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                    pos = pk; --j; hit = 1; cur_op = C3_OP_ALL; hij = ph;
+                    break;
+                }
+            }
+        }
+        if (!hit && (cur_op & C3_OP_E)) {
+            const int ceb = c3g_cell_eb(arena, vs, pos, j);
+            const int ce1 = hij - (ceb & 7), ce2 = hij - (ceb >> 3);
+            for (int k = 0; k < npre; ++k) {
+                const int pk = c3g_pred_pos(W, d, k);
+                const uint2 pr = W.rowrec[pk];
+                const int pbeg = C3G_R_BEG(pr) * 16, pend = min(qlen, C3G_R_END(pr) * 16 + 15);
+                if (j < pbeg || j > pend) continue;
+                const int ph = c3g_cell_h(arena, vs, pk, j);
+                int pe1, pe2;
+                if (pk == 0) { pe1 = j == 0 ? -oe1 : C3_NEG_INF; pe2 = j == 0 ? -oe2 : C3_NEG_INF; }
+                else { const int peb = c3g_cell_eb(arena, vs, pk, j); pe1 = ph - (peb & 7); pe2 = ph - (peb >> 3); }
+                if (cur_op & C3_OP_E1) {
+                    if (cur_op & C3_OP_M) {
+                        if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
+                    } else if (ce1 == pe1 - e1) {
+                        cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1;
+                    }
+                }
+                if (!hit && (cur_op & C3_OP_E2)) {
+                    if (cur_op & C3_OP_M) {
+                        if (hij == pe2) { cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1; }
+                    } else if (ce2 == pe2 - e2) {
+                        cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1;
+                    }
+                }
+                if (hit) {
+                    opw = C3_CG_DEL | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                    pos = pk; hij = ph;
+                    break;
+                }
+            }
+        }
+        if (!hit && (cur_op & C3_OP_F)) {
+            int hl = C3_NEG_INF;
+            if (j - 1 >= b) {
+                // F is not stored: rebuild F[j] and F[j-1] of this row from its H
+                int f1 = C3_NEG_INF, f2 = C3_NEG_INF, f1l = C3_NEG_INF, f2l = C3_NEG_INF;
+                for (int c = b; c < j; ++c) {
+                    hl = c3g_cell_h(arena, vs, pos, c);
+                    f1l = f1; f2l = f2;
+                    f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
+                }
+                if (cur_op & C3_OP_F1) {
+                    if (!(cur_op & C3_OP_M) || hij == f1) {
+                        if (hl - oe1 == f1) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                        else if (f1l - e1 == f1) { cur_op = C3_OP_F1; hit = 1; }
+                    }
+                }
+                if (!hit && (cur_op & C3_OP_F2)) {
+                    if (!(cur_op & C3_OP_M) || hij == f2) {
+                        if (hl - oe2 == f2) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                        else if (f2l - e2 == f2) { cur_op = C3_OP_F2; hit = 1; }
+                    }
+                }
+            }
+            if (hit) { opw = C3_CG_INS | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32); --j; hij = hl; }
+        }
+#ifdef C3G_DEBUG_BT
+        if (!hit && li == 0) {
+            printf("bt fail: pos %d j %d op %x hij %d npre %d b %d en %d id %d\n", pos, j, cur_op, hij, npre, b, en, i);
+            for (int k = 0; k < npre; ++k) {
+                const int pk = c3g_pred_pos(W, d, k); const uint2 pr = W.rowrec[pk];
+                printf("  pred %d pos %d band %d..%d H[j-1] %d H[j] %d eb %x\n", k, pk, C3G_R_BEG(pr) * 16, C3G_R_END(pr) * 16 + 15,
+                       c3g_cell_h(arena, vs, pk, j - 1), c3g_cell_h(arena, vs, pk, j), c3g_cell_eb(arena, vs, pk, j));
+            }
+            printf("  own eb %x H[j-1] %d\n", c3g_cell_eb(arena, vs, pos, j), c3g_cell_h(arena, vs, pos, j - 1));
+        }
+#endif
+        if (!hit) { C3G_DECLINE(); return C3G_E_RETRY; }
+        if (li == 0) cg[nc] = opw;
+        ++nc;
+        if (nc + j + 8 > cap) { C3G_DECLINE(); return C3G_E_RETRY; }
+    }
+    for (int t = j - li; t > 0; t -= C3G_GL)
+        cg[nc + j - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
+    nc += j;
+    C3G_SYNC(gmask);
+    return nc;
+}
+
+// ---------------------------------------------------------------------------
+// merge (abpoa_add_graph_alignment): the cigar is walked from its tail = forward order, 8 ops at a time; ops that
+// only bump the weight of an existing edge between two matched nodes are applied by all lanes at once, the rest
+// (new nodes / edges) goes through lane 0 in order.  A new node is not linked into a list: its place in the order
+// is the gap of the OLD order it falls into (W.gaps, non-decreasing in creation order), see c3g_reorder.
+// ---------------------------------------------------------------------------
+C3G_FN int c3g_tail_gap(const c3g_ws &W, const uint16_t *ord, const int n_old, const c3_pnode &na, const int p_start)
+{
+    int t = p_start;
+    for (;;) {
+        if (t + 1 >= n_old) break;
+        const int nx = ord[t + 1];
+        bool in_group = false;
+        for (int k = 0; k < na.aln_n; ++k) in_group |= (c3_aln_get(na, k) == nx);
+        if (!in_group) break;
+        ++t;
+    }
+    return t + 1;
+}
+
+C3G_FN int c3g_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const int nc, const int li, const int gbase, const unsigned gmask)
+{
+    const uint8_t *q = G.q;
+    const unsigned long long *cg = W.cigar;
+    const uint16_t *ord = W.order[G.ob];
+    const int n_old = G.n;
+    c3_graph g; g.nodes = W.nodes; g.pool = W.pool; g.node_n = G.node_n; g.pool_n = G.pool_n;
+    g.node_cap = L.A.node_cap; g.pool_cap = L.A.pool_cap; g.err = 0;
+    int last_id = C3_SRC, last_new = 0;                     // uniform
+    int last_gap = 0, last_p = 0;                           // lane 0: gap of the last new node / old position its group walk starts at
+    for (int tb = nc - 1; tb >= 0; tb -= C3G_GL) {
+        const int t = tb - li;
+        const bool have = t >= 0;
+        const unsigned long long op = have ? cg[t] : C3_CG_DEL;
+        const int kind = (int)(op & 0xff), node_id = (int)((op >> 8) & 0xffff), qpos = (int)(op >> 32);
+        const bool is_match = have && kind == (int)C3_CG_MATCH;
+        bool eq = false;
+        if (is_match) eq = W.nodes[node_id].base == q[qpos];
+        const unsigned m_nondel = (C3G_BALLOT(gmask, have && kind != (int)C3_CG_DEL) >> gbase) & 0xffu;
+        const unsigned m_eq = (C3G_BALLOT(gmask, eq) >> gbase) & 0xffu;
+        const unsigned lower = m_nondel & ((1u << li) - 1u);
+        const int pl = lower ? 31 - C3G_CLZ(lower) : -1;    // lane of the previous non-deletion op
+        const int pred_node = C3G_SHFL(gmask, node_id, gbase + (pl < 0 ? 0 : pl));
+        const int from = pl >= 0 ? pred_node : last_id;
+        const bool from_ok = pl >= 0 ? ((m_eq >> pl) & 1u) != 0 : last_new == 0;
+        bool done = false;
+        if (eq && from_ok) {                                 // bump the existing edge from -> node_id
+            c3_pnode *f = &W.nodes[from];
+            if (f->out_n > 0) {
+                if ((int)f->out0 == node_id) { f->w0 = (uint16_t)(f->w0 + 1); done = true; }
+                else {
+                    uint16_t e = f->out_more;
+                    while (e != C3_NONE) {
+                        if ((int)W.pool[e].id == node_id) { W.pool[e].w = (uint16_t)(W.pool[e].w + 1); done = true; break; }
+                        e = W.pool[e].next;
+                    }
+                }
+            }
+        }
+        const unsigned m_cx = m_nondel & ~((C3G_BALLOT(gmask, done) >> gbase) & 0xffu);
+        C3G_SYNC(gmask);
+        if (m_cx) {
+            if (li == 0) {
+                unsigned mc = m_cx;
+                while (mc && !g.err) {
+                    const int c = C3G_FFS(mc) - 1; mc &= mc - 1;
+                    const unsigned lowc = m_nondel & ((1u << c) - 1u);
+                    const int pc = lowc ? 31 - C3G_CLZ(lowc) : -1;
+                    if (pc >= 0 && ((m_eq >> pc) & 1u)) { last_id = (int)((cg[tb - pc] >> 8) & 0xffff); last_new = 0; }
+                    const unsigned long long opc = cg[tb - c];
+                    const int kc = (int)(opc & 0xff), nid = (int)((opc >> 8) & 0xffff), qp = (int)(opc >> 32);
+                    if (kc == (int)C3_CG_MATCH) {
+                        const uint8_t bq = q[qp];
+                        const c3_pnode nm = g.nodes[nid];
+                        if (nm.base != bq) {
+                            int al = -1;
+                            for (int k = 0; k < nm.aln_n; ++k) {
+                                const int a = c3_aln_get(nm, k);
+                                if (g.nodes[a].base == bq) { al = a; break; }
+                            }
+                            if (al != -1) {
+                                c3_g_add_edge(g, last_id, al, 1 - last_new);
+                                last_id = al; last_new = 0;
+                            } else {
+                                const int id = c3_g_add_node(g, bq);
+                                if (g.err) break;
+                                last_p = W.posof[nid]; last_gap = last_p;          // placed right before nid
+                                W.gaps[id - n_old] = (uint16_t)last_gap;
+                                c3_g_add_edge(g, last_id, id, 0);
+                                last_id = id; last_new = 1;
+                                for (int k = 0; k < nm.aln_n; ++k) {     // abpoa_add_graph_aligned_node
+                                    const int a = c3_aln_get(nm, k);
+                                    c3_aln_push(&g.nodes[a], (uint16_t)id);
+                                    c3_aln_push(&g.nodes[id], (uint16_t)a);
+                                }
+                                c3_aln_push(&g.nodes[nid], (uint16_t)id);
+                                c3_aln_push(&g.nodes[id], (uint16_t)nid);
+                            }
+                        } else {
+                            c3_g_add_edge(g, last_id, nid, 1 - last_new);
+                            last_id = nid; last_new = 0;
+                        }
+                    } else {                                     // insertion: right after the aligned block of last_id
+                        const int id = c3_g_add_node(g, q[qp]);
+                        if (g.err) break;
+                        const c3_pnode nl = g.nodes[last_id];
+                        int gap;
+                        if (last_id >= n_old) gap = nl.aln_n ? c3g_tail_gap(W, ord, n_old, nl, last_p) : last_gap;
+                        else gap = c3g_tail_gap(W, ord, n_old, nl, W.posof[last_id]);
+                        last_gap = gap;
+                        W.gaps[id - n_old] = (uint16_t)gap;
+                        c3_g_add_edge(g, last_id, id, 0);
+                        last_id = id; last_new = 1;
+                    }
+                }
+            }
+            g.err = C3G_SHFL(gmask, g.err, gbase);
+            g.node_n = C3G_SHFL(gmask, g.node_n, gbase);
+            g.pool_n = C3G_SHFL(gmask, g.pool_n, gbase);
+            last_id = C3G_SHFL(gmask, last_id, gbase);
+            last_new = C3G_SHFL(gmask, last_new, gbase);
+        }
+        if (m_nondel) {                                          // state after the chunk
+            const int ln = 31 - C3G_CLZ(m_nondel);
+            if ((m_eq >> ln) & 1u) { last_id = C3G_SHFL(gmask, node_id, gbase + ln); last_new = 0; }
+        }
+        C3G_SYNC(gmask);
+        if (g.err) break;
+    }
+    if (!g.err && li == 0) c3_g_add_edge(g, last_id, C3_SINK, 1 - last_new);
+    g.err = C3G_SHFL(gmask, g.err, gbase);
+    g.pool_n = C3G_SHFL(gmask, g.pool_n, gbase);
+    if (g.err) { C3G_DECLINE(); return C3G_E_RETRY; }
+    G.node_n = g.node_n; G.pool_n = g.pool_n;
+    C3G_SYNC(gmask);
+    return 0;
+}
+
+// new order = stable merge of the old order with the new nodes by gap: the t-th new node (id n_old + t, gap g)
+// lands at g + t, an old node at position p moves up by the number of new nodes with gap <= p
+C3G_FN void c3g_reorder(c3g_grp &G, const c3g_ws &W, const int li, const unsigned gmask)
+{
+    const int n_old = G.n, m = G.node_n - n_old;
+    const uint16_t *oo = W.order[G.ob];
+    uint16_t *on = W.order[G.ob ^ 1];
+    const int cs = (n_old + C3G_GL - 1) / C3G_GL;
+    const int ps = li * cs, pe = min(n_old, ps + cs);
+    int t = 0;
+    if (ps > 0) {                                                // first t with gaps[t] > ps - 1
+        int lo = 0, hi = m;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)W.gaps[mid] <= ps - 1) lo = mid + 1; else hi = mid; }
+        t = lo;
+    }
+    for (int p = ps; p < pe; ++p) {
+        while (t < m && (int)W.gaps[t] <= p) { on[p + t] = (uint16_t)(n_old + t); W.posof[n_old + t] = (uint16_t)(p + t); ++t; }
+        const int id = oo[p];
+        on[p + t] = (uint16_t)id; W.posof[id] = (uint16_t)(p + t);
+    }
+    C3G_SYNC(gmask);
+    G.ob ^= 1;
+}
+
+// heaviest bundling (abpoa_heaviest_bundling) + consensus walk; one lane.  Returns the length or a negative code.
+C3G_FN int c3g_consensus(const c3g_grp &G, const c3_poa_args &A, const c3g_ws &W, char *co)
+{
+    int32_t *score = reinterpret_cast<int32_t *>(W.desc);
+    const uint16_t *ord = W.order[G.ob];
+    for (int p = G.node_n - 1; p >= 0; --p) {
+        const int v = ord[p];
+        c3_pnode *nd = &W.nodes[v];
+        if (v == C3_SINK) { nd->max_out = C3_NONE; score[v] = 0; }
+        else if (v == C3_SRC) {
+            int max_id = -1, path_score = -1, path_w = -1;
+            uint16_t e = nd->out_more;
+            for (int k = 0; k < nd->out_n; ++k) {
+                int o, wv;
+                if (k == 0) { o = nd->out0; wv = nd->w0; } else { const c3_pedge pe = W.pool[e]; o = pe.id; wv = pe.w; e = pe.next; }
+                if (wv > path_w || (wv == path_w && score[o] > path_score)) { max_id = o; path_score = score[o]; path_w = wv; }
+            }
+            nd->max_out = (uint16_t)max_id;
+        } else {
+            int max_w = -0x7fffffff - 1, max_id = -1;
+            uint16_t e = nd->out_more;
+            for (int k = 0; k < nd->out_n; ++k) {
+                int o, wv;
+                if (k == 0) { o = nd->out0; wv = nd->w0; } else { const c3_pedge pe = W.pool[e]; o = pe.id; wv = pe.w; e = pe.next; }
+                if (max_w < wv) { max_w = wv; max_id = o; }
+                else if (max_w == wv && score[max_id] <= score[o]) max_id = o;
+            }
+            score[v] = max_w + score[max_id];
+            nd->max_out = (uint16_t)max_id;
+        }
+    }
+    int cons_len = 0;
+    int id = W.nodes[C3_SRC].max_out;
+    while (id != C3_SINK) {
+        if (id == C3_NONE || cons_len >= A.cons_cap) { C3G_DECLINE(); return C3G_E_RETRY; }
+        const c3_pnode nd = W.nodes[id];
+        co[cons_len++] = "ACGTN"[nd.base];
+        id = nd.max_out;
+    }
+    return cons_len;
+}
+
+// ---------------------------------------------------------------------------
+// the warp body: persistent, each group fetches its own items
+// ---------------------------------------------------------------------------
+C3G_FN void c3g_warp_body(const c3g_args &L, uint8_t *smem_warp, const int gwarp, const int lane)
+{
+    const c3_poa_args &A = L.A;
+    const c3_poa_para_dev P = A.P;
+    const int li = lane & 7, gbase = lane & 24, grp = lane >> 3;
+    const unsigned gmask = 0xffu << gbase;
+    const int64_t gid = (int64_t)gwarp * 4 + grp;
+    const c3g_ws W = c3g_ws_carve(L.ws + gid * L.ws_stride, A.node_cap, A.pool_cap, A.cigar_cap);
+    uint4 *arena = L.arena + gid * L.arena_stride4;
+    uint8_t *sg = smem_warp + (size_t)grp * c3g_smem_group_bytes(L.rv_shift);
+    uint4 *ring = reinterpret_cast<uint4 *>(sg);
+    uint2 *srr = reinterpret_cast<uint2 *>(sg + (C3G_R * 6 * 16 << L.rv_shift));
+    uint16_t *hw = reinterpret_cast<uint16_t *>(sg);           // prepare only (the ring is idle then)
+    c3g_grp G;
+    G.item = -1; G.err = 0; G.sq = 0; G.nseq = 0; G.node_n = 0; G.pool_n = 0; G.ob = 0; G.cells_total = 0;
+    bool exhausted = false;
+    for (;;) {
+        if (G.item < 0 && !exhausted) {
+            int it = 0;
+            if (li == 0) it = (int)C3G_ATOMIC_INC(A.counter);
+            it = C3G_SHFL(gmask, it, gbase);
+            if (it >= A.n_work) exhausted = true;
+            else {
+                c3g_item_begin(G, A, W, A.order ? A.order[it] : it, li);
+                C3G_SYNC(gmask);
+            }
+        }
+        if (!C3G_ANYG(C3_FULL, G.item >= 0)) break;
+        const bool act = G.item >= 0;
+        // ---- one alignment (or, for a single-sequence item, nothing) per trip ----
+        bool aligning = act && !G.err && G.sq < G.nseq;
+        if (aligning) {
+            c3g_prepare(G, A, P, W, hw, li, gbase, gmask);
+            if (G.err) aligning = false;
+        }
+        C3G_SYNC(C3_FULL);
+        if (aligning) {
+            c3g_source_row(G, L, P, W, ring, srr, arena, li, gmask);
+            C3G_SYNC(gmask);
+            if (!G.err) {
+                const int n = G.n;
+                uint4 dmine = make_uint4(0u, 0u, 0u, 0u);
+                for (int pos = 1; pos < n - 1; ++pos) {
+                    if (((pos - 1) & 7) == 0) { const int p = pos + li; if (p < n) dmine = W.desc[p]; }
+                    const int src = gbase + ((pos - 1) & 7);
+                    uint4 d;
+                    d.x = (uint32_t)C3G_SHFL(gmask, dmine.x, src); d.y = (uint32_t)C3G_SHFL(gmask, dmine.y, src);
+                    d.z = (uint32_t)C3G_SHFL(gmask, dmine.z, src); d.w = 0u;
+                    const int wd = c3g_row(G, L, P, W, ring, srr, arena, pos, d, li, gbase, gmask);
+                    if (wd <= 0) break;
+                    G.cells_total += wd;
+                }
+            }
+            if (G.err) aligning = false;
+        }
+        C3G_SYNC(C3_FULL);
+        int nc = 0;
+        if (aligning) {
+            nc = c3g_backtrack(G, L, P, W, arena, li, gbase, gmask);
+            if (nc < 0) { C3G_DECLINE(); G.err = C3G_E_RETRY; aligning = false; }
+        }
+        C3G_SYNC(C3_FULL);
+        if (aligning) {
+            if (c3g_merge(G, L, W, nc, li, gbase, gmask)) { C3G_DECLINE(); G.err = C3G_E_RETRY; aligning = false; }
+            else { c3g_reorder(G, W, li, gmask); ++G.sq; }
+        }
+        C3G_SYNC(C3_FULL);
+        // ---- item end ----
+        if (act && (G.err || G.sq >= G.nseq)) {
+            if (!G.err) {
+                char *co = A.cons + (int64_t)G.item * A.cons_cap;
+                int r = 0;
+                if (li == 0) r = c3g_consensus(G, A, W, co);
+                r = C3G_SHFL(gmask, r, gbase);
+                if (r >= 0 && li == 0) {
+                    const int64_t o = (int64_t)G.item * A.out_stride;
+                    A.status[o] = 0;
+                    A.cons_len[o] = r;
+                    A.nodes_out[o] = G.node_n;
+                    *(long long *)((int32_t *)A.cells_out + (int64_t)G.item * A.cells_stride) = G.cells_total;
+                    L.done[G.item] = 1;
+                }
+            }
+            G.item = -1; G.err = 0;
+        }
+        C3G_SYNC(C3_FULL);
+    }
+}
+
+#ifdef __CUDACC__
+#ifndef C3G_THREADS
+#define C3G_THREADS 128
+#endif
+#ifndef C3G_MINB
+#define C3G_MINB 4
+#endif
+__global__ void __launch_bounds__(C3G_THREADS, C3G_MINB) c3_poa_grp_kernel(c3g_args L)
+{
+    extern __shared__ uint4 c3g_smem[];
+    const int wib = threadIdx.x >> 5;
+    uint8_t *sw = reinterpret_cast<uint8_t *>(c3g_smem) + (size_t)wib * 4 * c3g_smem_group_bytes(L.rv_shift);
+    c3g_warp_body(L, sw, blockIdx.x * (blockDim.x >> 5) + wib, threadIdx.x & 31);
+}
+#endif
