@@ -49,8 +49,8 @@ def parse():
     ap.add_argument("--config", default="cfg2_1kb_x5", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--poa-mode", default="auto", choices=["auto", "warp", "lane"],
-                    help="POA kernel: auto = thread-per-read lane kernel for large batches, warp-per-read otherwise")
+    ap.add_argument("--poa-mode", default="auto", choices=["auto", "warp", "lane", "grp"],
+                    help="POA kernel: auto = group kernel (8 lanes per read) with the warp-per-read kernel as fallback")
     return ap.parse_args()
 
 
@@ -232,7 +232,7 @@ def main():
             pass
     poa_s = stage_ms["poa_ms"] * 1e-3 / a.steps
     conk_s = stage_ms["conk_ms"] * 1e-3 / a.steps
-    poa_kernel_name = "c3_poa_lane_kernel" if lane_done * 2 >= n else "c3_poa_kernel"
+    poa_kernel_name = ("c3_poa_lane_kernel" if a.poa_mode == "lane" else "c3_poa_grp_kernel") if lane_done * 2 >= n else "c3_poa_kernel"
     dominant = poa_kernel_name if poa_s >= conk_s else "c3_conk_kernel"
     sb = out["sub_bounds"]
     ns = res["n_sub"]

@@ -96,7 +96,7 @@ class GpuError(RuntimeError):
 class GpuConsensus:
     """One handle per device (not thread-safe; use one per host thread/GPU)."""
 
-    POA_MODES = {"auto": 0, "warp": 1, "lane": 2}
+    POA_MODES = {"auto": 0, "warp": 1, "lane": 2, "grp": 3}
 
     def __init__(self, device: int = 0, poa_mode: str = "auto"):
         self._L = _lib.load()

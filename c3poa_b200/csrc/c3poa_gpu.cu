@@ -6,6 +6,7 @@
 #include "peaks.cuh"
 #include "poa.cuh"
 #include "poa_lane.cuh"
+#include "poa_grp.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -47,9 +48,12 @@ struct c3_handle {
     DevBuf d_peaks, d_npk, d_sub, d_dang, d_res, d_stats, d_cons, d_ws;
     // B3 staging
     DevBuf d_item_base, d_bounds, d_nseq, d_status, d_clen, d_nodes, d_cells, d_order;
-    // POA kernel choice: 0 auto (lane kernel for large batches), 1 warp kernel only, 2 lane kernel whenever eligible
+    // POA kernel choice: 0 auto (group kernel for every eligible read), 1 warp kernel only, 2 lane kernel whenever
+    // eligible, 3 group kernel whenever eligible (= auto); the warp kernel always takes what the others leave
     int poa_mode = 0;
-    DevBuf d_order_lane, d_done;
+    DevBuf d_order_lane, d_done, d_order_grp, d_ws_grp;
+    int n_work_grp = 0, grp_max_nseq = 0, grp_max_q = 0; int64_t grp_max_total = 0;
+    std::vector<int32_t> grp_nseq;   // sequences per item of the group kernels' list (host copy: launches per wave)
     int n_work_lane = 0, lane_items = 0, lane_n_items = 0;
     int64_t lane_max_total = 0; int lane_max_nseq = 0, lane_max_q = 0;
     double lane_cost_spread = 1.0;       // estimated cost of the largest lane item / of the median one
@@ -110,7 +114,7 @@ extern "C" void c3_destroy(c3_handle *h)
                       &h->d_prof, &h->d_brow, &h->d_counter, &h->d_coef, &h->d_pk_scratch, &h->d_smoothed, &h->d_median,
                       &h->d_peaks, &h->d_npk, &h->d_sub, &h->d_dang, &h->d_res, &h->d_stats, &h->d_cons, &h->d_ws,
                       &h->d_item_base, &h->d_bounds, &h->d_nseq, &h->d_status, &h->d_clen, &h->d_nodes, &h->d_cells, &h->d_order,
-                      &h->d_order_lane, &h->d_done};
+                      &h->d_order_lane, &h->d_done, &h->d_order_grp, &h->d_ws_grp};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -131,7 +135,7 @@ extern "C" const char *c3_last_error(const c3_handle *h) { return h ? h->err : "
 extern "C" int c3_set_poa_mode(c3_handle *h, int32_t mode)
 {
     if (!h) return -1;
-    if (mode < 0 || mode > 2) return fail(h, -5, "poa mode must be 0 (auto), 1 (warp kernel) or 2 (lane kernel)");
+    if (mode < 0 || mode > 3) return fail(h, -5, "poa mode must be 0 (auto), 1 (warp kernel), 2 (lane kernel) or 3 (group kernel)");
     h->poa_mode = mode;
     return 0;
 }
@@ -289,6 +293,38 @@ static int upload_poa_order(c3_handle *h, c3_poa_args &A, const std::vector<int3
             h->lane_max_nseq = std::max(h->lane_max_nseq, nseq[i]);
         }
     }
+    // the group kernel's share (poa_grp.cuh): same order; items it is sure to cover (int16 score mode for every
+    // alignment of the item, default-sized gap costs); neighbours in this order become the 4 groups of a warp
+    {
+        std::vector<int32_t> grp((size_t)std::max(n_work, 1));
+        int ng = 0;
+        h->grp_nseq.clear();
+        h->grp_max_total = 0; h->grp_max_nseq = 0; h->grp_max_q = 0;
+        const bool para_ok = pp->simd_bits == 256 && pp->wb >= 0 && pp->gap_open1 + pp->gap_ext1 <= 7 &&
+                             pp->gap_open2 + pp->gap_ext2 <= 31 && pp->gap_ext1 >= 0 && pp->gap_ext2 >= 0 &&
+                             pp->gap_ext1 <= 16 && pp->gap_ext2 <= 16 && pp->match >= 0 && pp->mismatch >= 0 &&
+                             pp->match <= 100 && pp->mismatch <= 100 && pp->gap_open1 >= 0 && pp->gap_open2 >= 0;
+        if (para_ok) {
+            const int64_t lim = 32767 - pp->mismatch - pp->gap_open1 - pp->gap_ext1;
+            for (int k = 0; k < n_work; ++k) {
+                const int i = order[k];
+                if (A.msa2 && nseq[i] == 2) continue;
+                // int16 score mode of an alignment: max(qlen * 5, max(qlen, nodes) * e1 + o1) <= lim, with the usual
+                // graph growth (the kernel re-checks per alignment and declines what turns out larger)
+                const int64_t Lm = total[i] / nseq[i] * 5 / 4 + 1;
+                const int64_t nodes = 2 + Lm + (int64_t)(nseq[i] - 1) * (Lm * 35 / 100 + 16);
+                if (Lm * 5 > lim || std::max(Lm, nodes) * pp->gap_ext1 + pp->gap_open1 > lim || nodes > 65000) continue;
+                grp[ng++] = i;
+                h->grp_nseq.push_back(nseq[i]);
+                h->grp_max_total = std::max(h->grp_max_total, total[i]);
+                h->grp_max_nseq = std::max(h->grp_max_nseq, nseq[i]);
+            }
+        }
+        CK(h->d_order_grp.ensure((size_t)std::max(ng, 1) * 4));
+        CK(cudaMemcpyAsync(h->d_order_grp.p, grp.data(), (size_t)ng * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->n_work_grp = ng;
+    }
     h->lane_cost_spread = nl > 0 ? exp2((double)(cls[lane[0]] - cls[lane[nl / 2]]) / 16.0) : 1.0;
     CK(h->d_order_lane.ensure((size_t)std::max(nl, 1) * 4));
     CK(cudaMemcpyAsync(h->d_order_lane.p, lane.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, h->stream));
@@ -377,15 +413,105 @@ static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa
     return 0;
 }
 
+// Group kernels (poa_grp.cuh) ahead of the warp kernel: every read the host knows to be in their scope, in waves of as
+// many reads as fit the device memory (state + graph workspace + DP arena per read, all resident: a B200 holds a whole
+// 100k-read batch).  Per wave: graph kernel, then (DP kernel, graph kernel) per further sequence.  Whatever is declined
+// (capacity, exactness guard) stays not-done and is picked up by c3_poa_kernel afterwards.
+static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_params *pp)
+{
+    h->lane_items = 0;
+    A.done = nullptr;
+    const int ng = h->n_work_grp;
+    if ((h->poa_mode != 0 && h->poa_mode != 3) || ng <= 0) return 0;
+    const int max_nseq = h->grp_max_nseq;
+    const int64_t max_total = h->grp_max_total;
+    max_q = (int)std::min<int64_t>(max_q, max_total);
+    int64_t est = 2 + (int64_t)max_q + (int64_t)(max_nseq - 1) * ((int64_t)max_q * 35 / 100 + 16);
+    int64_t node_cap = std::min<int64_t>(std::min<int64_t>(est, max_total + 2), 65504);
+    node_cap = std::max<int64_t>((node_cap + 31) & ~31ll, 64);
+    const int pool_cap = (int)node_cap;
+    const int cigar_cap = (int)((max_q + node_cap + 64 + 1) & ~1ll);
+    const int qp_stride = (max_q + 48) & ~15;
+    // arena rows: a fixed stride of VS vectors (power of two) that the usual band fits with room for drift; ring slots
+    // of RV <= VS vectors.  A wider row only sends its read to the warp kernel.
+    const int w = pp->wb + (int)(pp->wf * max_q);
+    const int need = (2 * w + 1 + 48) / 16 + 2;
+    int vs_shift = 3;
+    while ((1 << vs_shift) < need && vs_shift < 8) ++vs_shift;
+    const int rv_shift = vs_shift == 3 ? 3 : 4;
+    const int64_t ws_bytes = c3g_ws_bytes((int)node_cap, pool_cap, cigar_cap, qp_stride);
+    const int64_t arena4 = (node_cap << vs_shift) * 3;
+    const int64_t read_bytes = ws_bytes + arena4 * 16 + (int64_t)sizeof(c3g_state);
+    const int wpb = C3G_THREADS / 32;
+    const size_t sm_dp = (size_t)wpb * 4 * c3g_smem_group_bytes(rv_shift), sm_gr = (size_t)wpb * (32 / C3G_GRAPH_GL) * C3G_GRAPH_SMEM(C3G_GRAPH_GL);
+    void (*kdp)(c3g_args) = vs_shift == 3 ? c3_poa_grp_dp_kernel<3, false> : c3_poa_grp_dp_kernel<4, true>;
+    CK(cudaFuncSetAttribute(kdp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dp));
+    CK(cudaFuncSetAttribute(c3_poa_grp_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gr));
+    int bps_dp = 1, bps_gr = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_dp, kdp, C3G_THREADS, sm_dp) != cudaSuccess || bps_dp < 1) bps_dp = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_gr, c3_poa_grp_graph_kernel, C3G_THREADS, sm_gr) != cudaSuccess || bps_gr < 1) bps_gr = 1;
+    if (const char *lim = getenv("C3POA_GRP_DP_CTAS")) bps_dp = std::max(1, std::min(bps_dp, atoi(lim)));     // tuning only
+    if (const char *lim = getenv("C3POA_GRP_GRAPH_CTAS")) bps_gr = std::max(1, std::min(bps_gr, atoi(lim)));
+    size_t free_b = 0, tot_b = 0;
+    CK(cudaMemGetInfo(&free_b, &tot_b));
+    const int64_t budget = (int64_t)((double)(free_b + h->d_ws_grp.cap) * 0.7);
+    int64_t wave = std::min<int64_t>(ng, budget / read_bytes);
+    if (wave < 64) return 0;                                       // does not fit: the warp kernel takes everything
+    const int n_counters = 2 * max_nseq + 2;
+    CK(h->d_ws_grp.ensure((size_t)(wave * read_bytes) + (size_t)n_counters * 4 + 256));
+    CK(h->d_done.ensure((size_t)A.n_items * 4));
+    CK(cudaMemsetAsync(h->d_done.p, 0, (size_t)A.n_items * 4, h->stream));
+    uint8_t *base = h->d_ws_grp.as<uint8_t>();
+    c3g_args L;
+    memset(&L, 0, sizeof(L));
+    L.A = A;
+    L.A.node_cap = (int)node_cap; L.A.pool_cap = pool_cap; L.A.cell_cap = 0; L.A.cigar_cap = cigar_cap; L.A.qp_stride = qp_stride;
+    L.ws = base; L.ws_stride = ws_bytes;
+    L.arena = reinterpret_cast<uint4 *>(base + wave * ws_bytes);
+    L.arena_stride4 = arena4; L.vs_shift = vs_shift; L.rv_shift = rv_shift;
+    L.state = reinterpret_cast<c3g_state *>(base + wave * (ws_bytes + arena4 * 16));
+    unsigned *counters = reinterpret_cast<unsigned *>(base + wave * read_bytes + 128);
+    L.done = h->d_done.as<int32_t>();
+    for (int64_t w0 = 0; w0 < ng; w0 += wave) {
+        const int nw = (int)std::min<int64_t>(wave, ng - w0);
+        int wave_nseq = 1;
+        for (int k = 0; k < nw; ++k) wave_nseq = std::max(wave_nseq, h->grp_nseq[(size_t)(w0 + k)]);
+        CK(cudaMemsetAsync(counters, 0, (size_t)n_counters * 4, h->stream));
+        L.A.order = h->d_order_grp.as<int32_t>() + w0; L.A.n_work = nw;
+        const int w_dp = (nw + 3) / 4, w_gr = (nw + 32 / C3G_GRAPH_GL - 1) / (32 / C3G_GRAPH_GL);      // warps that can be busy
+        const int grid_dp = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * bps_dp, (w_dp + wpb - 1) / wpb));
+        const int grid_gr = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * bps_gr, (w_gr + wpb - 1) / wpb));
+        int launch = 0;
+        L.first = 1; L.A.counter = counters + launch++;
+        c3_poa_grp_graph_kernel<<<grid_gr, C3G_THREADS, sm_gr, h->stream>>>(L);
+        h->tim.kernel_launches++;
+        L.first = 0;
+        for (int sq = 1; sq < wave_nseq; ++sq) {
+            L.A.counter = counters + launch++;
+            kdp<<<grid_dp, C3G_THREADS, sm_dp, h->stream>>>(L);
+            L.A.counter = counters + launch++;
+            c3_poa_grp_graph_kernel<<<grid_gr, C3G_THREADS, sm_gr, h->stream>>>(L);
+            h->tim.kernel_launches += 2;
+        }
+        CK(cudaGetLastError());
+    }
+    h->lane_items = ng; h->lane_n_items = A.n_items;
+    A.done = h->d_done.as<int32_t>();
+    return 0;
+}
+
 // workspace sizing from the batch maxima (longest sequence, most sequences, largest total)
 static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int64_t max_total, const c3_poa_params *pp)
 {
     to_dev_para(pp, &A.P);
     if (A.P.simd_bits != 128 && A.P.simd_bits != 256 && A.P.simd_bits != 512) return fail(h, -5, "simd_bits must be 128/256/512");
-    if (!A.order) h->n_work_lane = 0;
+    if (!A.order) { h->n_work_lane = 0; h->n_work_grp = 0; }
+    int fast_items = 0;                                            // reads handed to a fast kernel ahead of this one
     {
-        const int rc = launch_poa_lane(h, A, max_q, pp);
+        int rc = launch_poa_grp(h, A, max_q, pp);
         if (rc) return rc;
+        if (!A.done && h->poa_mode == 2 && (rc = launch_poa_lane(h, A, max_q, pp))) return rc;
+        if (A.done) fast_items = h->lane_items;
     }
     int64_t est = 2 + (int64_t)max_q + (int64_t)(max_nseq - 1) * ((int64_t)max_q * 35 / 100 + 16);
     int64_t node_cap = std::min<int64_t>(std::min<int64_t>(est, max_total + 2), 65534);
@@ -408,6 +534,9 @@ static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int
     int grid = h->sm_count * bps;
     if (!A.order) A.n_work = A.n_items;
     grid = std::max(1, std::min(grid, (A.n_work + rpb - 1) / rpb));
+    // what a fast kernel was given comes back only if it declined it: one CTA per SM is kept for those
+    if (fast_items > 0 && h->poa_mode != 2)
+        grid = std::max(1, std::min(grid, (A.n_work - fast_items + rpb - 1) / rpb + h->sm_count));
     size_t free_b = 0, tot_b = 0;
     CK(cudaMemGetInfo(&free_b, &tot_b));
     int64_t budget = (int64_t)((double)(free_b + h->d_ws.cap) * 0.8);

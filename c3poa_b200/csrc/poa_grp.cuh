@@ -36,15 +36,21 @@
 #define C3G_R 4                       // ring slots (rows) per group
 #define C3G_GL 8                      // lanes per group
 #define C3G_E_RETRY (-298)
-#define C3G_HWIN 1024                 // window of remaining-length words kept in shared memory during prepare
+// graph kernel: GL lanes per read (32: one warp per read, constant member masks; 8: four reads per warp)
+#define C3G_HWIN(GL) ((GL) == 32 ? 1024 : 512)   // window of remaining-length words kept in shared memory during prepare
+#define C3G_BTK(GL) ((GL) == 32 ? 48 : 16)       // rows per backtrack window
+#define C3G_BTV(GL) ((GL) == 32 ? 15 : 7)        // rows below the current one that a verification trip wants in the window
+#define C3G_GRAPH_SMEM(GL) ((GL) == 32 ? 5760 : 2048)   // shared memory per read of the graph kernel: max(HWIN * 2, BTK * 120)
+#define C3G_LMASK(GL) ((GL) == 32 ? 0xffffffffu : ((1u << ((GL) & 31)) - 1u))
+#define C3G_LOG2(GL) ((GL) == 32 ? 5 : 3)
 
 #if defined(C3G_EMUL) && !defined(__CUDA_ARCH__)
-extern "C" int c3emu_shfl(unsigned mask, int v, int src);
-extern "C" unsigned c3emu_ballot(unsigned mask, int pred);
-extern "C" void c3emu_sync(unsigned mask);
-#define C3G_SHFL(m, v, s) c3emu_shfl((m), (int)(v), (s))
-#define C3G_BALLOT(m, p) c3emu_ballot((m), (p))
-#define C3G_SYNC(m) c3emu_sync(m)
+extern "C" int c3emu_shfl(unsigned mask, int v, int src, int tag);
+extern "C" unsigned c3emu_ballot(unsigned mask, int pred, int tag);
+extern "C" void c3emu_sync(unsigned mask, int tag);
+#define C3G_SHFL(m, v, s) c3emu_shfl((m), (int)(v), (s), __LINE__)
+#define C3G_BALLOT(m, p) c3emu_ballot((m), (p), __LINE__)
+#define C3G_SYNC(m) c3emu_sync((m), __LINE__)
 #define C3G_ATOMIC_INC(p) ((*(p))++)
 #define C3G_FFS(x) __builtin_ffs((int)(x))
 #define C3G_CLZ(x) ((x) ? __builtin_clz((unsigned)(x)) : 32)
@@ -74,14 +80,17 @@ extern "C" void c3g_emul_note(int line);            // test hook: why an item wa
 #define C3G_DECLINE() do { } while (0)
 #endif
 
+struct c3g_state;
 struct c3g_args {
     c3_poa_args A;                    // inputs / outputs / parameters; order + n_work: items this kernel covers;
                                       // node_cap, pool_cap, cigar_cap, qp_stride: per-group capacities
-    uint8_t *ws; long long ws_stride; // per-group graph workspace
-    uint4 *arena; long long arena_stride4;   // per-group DP arena, in uint4: node_cap rows x VS vectors x 3
+    uint8_t *ws; long long ws_stride; // per-read graph workspace
+    uint4 *arena; long long arena_stride4;   // per-read DP arena, in uint4: node_cap rows x VS vectors x 3
     int vs_shift;                     // log2 VS: vectors per arena row
     int rv_shift;                     // log2 RV: vectors per shared-memory ring slot (RV <= VS)
     int32_t *done;                    // [n_items] 1 = finished here
+    struct c3g_state *state;          // per read of the wave
+    int first;                        // graph kernel: 1 = first launch of a wave (first sequence -> graph)
 };
 
 // per-group workspace
@@ -94,7 +103,7 @@ struct c3g_ws {
     uint16_t *xpred;                  // positions of the third and further predecessors (in-edge order)
     uint16_t *gaps;                   // new nodes of the running merge: old position they are inserted before
     unsigned long long *cigar;
-    int8_t *qp;                       // substitution scores: 4 rows (node base) x qp_stride, index = column
+    int8_t *qp;                       // substitution scores: 5 rows (node base; N: zeros) x qp_stride, index = column
 };
 
 __host__ __device__ inline int64_t c3g_ws_bytes(int node_cap, int pool_cap, int cigar_cap, int qp_stride)
@@ -102,7 +111,7 @@ __host__ __device__ inline int64_t c3g_ws_bytes(int node_cap, int pool_cap, int 
     int64_t b = 0;
     b += (int64_t)node_cap * 32 + (int64_t)pool_cap * 8 + (int64_t)node_cap * 16 + (int64_t)node_cap * 8;
     b += (int64_t)node_cap * 2 * 2 + (int64_t)node_cap * 2 + (int64_t)pool_cap * 2 + (int64_t)node_cap * 2;
-    b += (int64_t)cigar_cap * 8 + (int64_t)qp_stride * 4;
+    b += (int64_t)cigar_cap * 8 + (int64_t)qp_stride * 5 + 256;    // + 256: lanes past the band read scores beyond qlen
     return (b + 255) & ~(int64_t)255;
 }
 
@@ -147,6 +156,7 @@ struct c3g_grp {                       // group-uniform state (replicated in the
 // ---------------------------------------------------------------------------
 // item start: first sequence -> linear graph, order = SRC, 2, 3, ..., L+1, SINK
 // ---------------------------------------------------------------------------
+template <int GL>
 C3G_FN void c3g_item_begin(c3g_grp &G, const c3_poa_args &A, const c3g_ws &W, const int item, const int li)
 {
     G.item = item; G.sq = 1; G.err = 0; G.nseq = 0; G.node_n = 0; G.pool_n = 0; G.cells_total = 0; G.ob = 0;
@@ -159,7 +169,7 @@ C3G_FN void c3g_item_begin(c3g_grp &G, const c3_poa_args &A, const c3g_ws &W, co
     const int L = G.bnd[1] - G.bnd[0];
     if (L <= 0 || L > 65000 || L + 2 > A.node_cap) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
     uint16_t *ord = W.order[0];
-    for (int i = li; i < L + 2; i += C3G_GL) {
+    for (int i = li; i < L + 2; i += GL) {
         c3_pnode n;
         n.in_more = n.out_more = C3_NONE; n.rmask = 1; n.spare = 0;
         n.aln0 = n.aln1 = n.aln2 = n.aln3 = C3_NONE; n.max_out = C3_NONE; n.aln_n = 0;
@@ -185,6 +195,7 @@ C3G_FN void c3g_item_begin(c3g_grp &G, const c3_poa_args &A, const c3g_ws &W, co
 // prepare: score mode, band half-width, score profile, row descriptors by position (reverse sweep, 8 positions
 // per step) with the remaining path length along the heaviest out-edges.  hw: shared-memory window of hop counts.
 // ---------------------------------------------------------------------------
+template <int GL>
 C3G_FN void c3g_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_para_dev &P, const c3g_ws &W, uint16_t *hw,
                         const int li, const int gbase, const unsigned gmask)
 {
@@ -202,7 +213,7 @@ C3G_FN void c3g_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_para_dev 
     // profile: qp[b][j] = score of node base b against column j (= q[j-1]); j = 0 and the padding score 0
     {
         const int qs = A.qp_stride;
-        for (int j0 = 4 * li; j0 < qs; j0 += 4 * C3G_GL) {
+        for (int j0 = 4 * li; j0 < qs; j0 += 4 * GL) {
             uint32_t wv[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -215,13 +226,14 @@ C3G_FN void c3g_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_para_dev 
             }
 #pragma unroll
             for (int b = 0; b < 4; ++b) *reinterpret_cast<uint32_t *>(W.qp + b * qs + j0) = wv[b];
+            *reinterpret_cast<uint32_t *>(W.qp + 4 * qs + j0) = 0u;        // an N node scores 0 against everything
         }
     }
     const uint16_t *ord = W.order[G.ob];
     int xbase = 0;
-    const int nb = (n + C3G_GL - 1) / C3G_GL;
+    const int nb = (n + GL - 1) / GL;
     for (int bi = nb - 1; bi >= 0; --bi) {
-        const int pb = bi * C3G_GL, p = pb + li;
+        const int pb = bi * GL, p = pb + li;
         const bool valid = p < n;
         int id = C3_SINK, base = 4, in_n = 0, p0 = C3_NONE, p1 = C3_NONE, e_more = C3_NONE;
         int tgt = p, hops = 0, fin = 1;
@@ -251,12 +263,12 @@ C3G_FN void c3g_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_para_dev 
         const int nx = in_n > 2 ? in_n - 2 : 0;
         int incl = nx;
 #pragma unroll
-        for (int d = 1; d < C3G_GL; d <<= 1) {
-            const int v = C3G_SHFL(gmask, incl, gbase + ((li - d) & 7));
+        for (int d = 1; d < GL; d <<= 1) {
+            const int v = C3G_SHFL(gmask, incl, gbase + ((li - d) & (GL - 1)));
             if (li >= d) incl += v;
         }
         const int xo = xbase + incl - nx;
-        xbase += C3G_SHFL(gmask, incl, gbase + 7);
+        xbase += C3G_SHFL(gmask, incl, gbase + GL - 1);
         if (xbase > A.pool_cap) { C3G_DECLINE(); G.err = C3G_E_RETRY; }          // uniform
         if (nx > 0 && !G.err) {
             int e = e_more;
@@ -267,18 +279,18 @@ C3G_FN void c3g_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_para_dev 
         }
         // hops to the sink: pointer doubling inside the batch, then one look-up above it
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int src = gbase + ((tgt - pb) & 7);
+        for (int r = 0; r < C3G_LOG2(GL); ++r) {
+            const int src = gbase + ((tgt - pb) & (GL - 1));
             const int t2 = C3G_SHFL(gmask, tgt, src), h2 = C3G_SHFL(gmask, hops, src), f2 = C3G_SHFL(gmask, fin, src);
-            if (!fin && tgt >= pb && tgt < pb + C3G_GL) { hops += h2; if (f2) fin = 1; else tgt = t2; }
+            if (!fin && tgt >= pb && tgt < pb + GL) { hops += h2; if (f2) fin = 1; else tgt = t2; }
         }
         if (!fin) {
-            if (tgt - pb < C3G_HWIN - C3G_GL) hops += hw[tgt & (C3G_HWIN - 1)];
+            if (tgt - pb < C3G_HWIN(GL) - GL) hops += hw[tgt & (C3G_HWIN(GL) - 1)];
             else hops += C3G_D_HOPS(W.desc[tgt]);
         }
         C3G_SYNC(gmask);
         if (valid) {
-            hw[p & (C3G_HWIN - 1)] = (uint16_t)hops;
+            hw[p & (C3G_HWIN(GL) - 1)] = (uint16_t)hops;
             if (in_n > C3_MAXPRE || hops > 65535) { C3G_DECLINE(); G.err = C3G_E_RETRY; }
             W.desc[p] = make_uint4((uint32_t)id | ((uint32_t)p0 << 16), (uint32_t)p1 | ((uint32_t)hops << 16),
                                    (uint32_t)base | ((uint32_t)in_n << 8) | ((uint32_t)xo << 16), 0u);
@@ -292,60 +304,75 @@ C3G_FN void c3g_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_para_dev 
 // ---------------------------------------------------------------------------
 // DP
 // ---------------------------------------------------------------------------
-struct c3g_cells { uint32_t h[8], x1[8], x2[8]; };
+// Shared-memory ring of one group: C3G_R slots (row = position mod C3G_R) x 6 quarter-rows (H, E1, E2 x low / high
+// 8 columns) x RV vectors; vector sn sits at index sn mod RV, so the 8 lanes of a group read and write 128
+// consecutive bytes.  A row only writes the vectors of its band: readers check the row's record first.
+#define C3G_RING_PTR(ring, rvs, slot, sn) ((ring) + (((slot) * 6) << (rvs)) + ((sn) & ((1 << (rvs)) - 1)))
 
-// this lane's vector `sn` of the row at position pk (record rk): packed H, E1, E2.  Outside the row's band:
-// floor.  Rows not older than C3G_R positions whose band fits a ring slot come from shared memory, the others from
-// the arena (E1 = H - d1, E2 = H - d2; the source row keeps E only at column 0).
-C3G_FN void c3g_load_pred(c3g_cells &c, const uint4 *ring, const int rv_shift, const uint4 *arena, const int vs_shift,
-                          const int pos, const int pk, const uint2 rk, const int sn, const int ring_delta)
+C3G_FN uint2 c3g_get_rowrec(const uint2 *srr, const uint2 *rowrec, const int pos, const int pk)
 {
-    const int pb = C3G_R_BEG(rk), pe = C3G_R_END(rk);
-    if (sn < pb || sn > pe) {
-#pragma unroll
-        for (int t = 0; t < 8; ++t) c.h[t] = c.x1[t] = c.x2[t] = C3L_FLOOR2;
-        return;
-    }
-    if (pos - pk <= ring_delta && pe - pb < (1 << rv_shift)) {
-        const uint4 *s = ring + (((pk & (C3G_R - 1)) * 6) << rv_shift) + (sn & ((1 << rv_shift) - 1));
-        const int st = 1 << rv_shift;
-        const uint4 a0 = s[0], a1 = s[st], b0 = s[2 * st], b1 = s[3 * st], c0 = s[4 * st], c1 = s[5 * st];
-        c.h[0] = a0.x; c.h[1] = a0.y; c.h[2] = a0.z; c.h[3] = a0.w; c.h[4] = a1.x; c.h[5] = a1.y; c.h[6] = a1.z; c.h[7] = a1.w;
-        c.x1[0] = b0.x; c.x1[1] = b0.y; c.x1[2] = b0.z; c.x1[3] = b0.w; c.x1[4] = b1.x; c.x1[5] = b1.y; c.x1[6] = b1.z; c.x1[7] = b1.w;
-        c.x2[0] = c0.x; c.x2[1] = c0.y; c.x2[2] = c0.z; c.x2[3] = c0.w; c.x2[4] = c1.x; c.x2[5] = c1.y; c.x2[6] = c1.z; c.x2[7] = c1.w;
-        return;
-    }
+    uint2 r;
+    if (pos - pk <= C3G_R) r = srr[pk & (C3G_R - 1)]; else r = rowrec[pk];
+    return r;
+}
+
+// this lane's vector `sn` of the row at position pk (record rk) from the arena: E1 = H - d1, E2 = H - d2 with
+// byte = ~(d1 | d2 << 3); the source row keeps E only at column 0
+C3G_FN void c3g_arena_pred(uint32_t (&h)[8], uint32_t (&x1)[8], uint32_t (&x2)[8], const uint4 *arena, const int vs_shift,
+                           const int pk, const int sn)
+{
     const uint4 *s = arena + (((int64_t)pk << vs_shift) + (sn & ((1 << vs_shift) - 1))) * 3;
     const uint4 a0 = s[0], a1 = s[1], eb = s[2];
-    c.h[0] = a0.x; c.h[1] = a0.y; c.h[2] = a0.z; c.h[3] = a0.w; c.h[4] = a1.x; c.h[5] = a1.y; c.h[6] = a1.z; c.h[7] = a1.w;
+    h[0] = a0.x; h[1] = a0.y; h[2] = a0.z; h[3] = a0.w; h[4] = a1.x; h[5] = a1.y; h[6] = a1.z; h[7] = a1.w;
     if (pk == 0) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) c.x1[t] = c.x2[t] = C3L_FLOOR2;
+        for (int t = 0; t < 8; ++t) x1[t] = x2[t] = C3L_FLOOR2;
         if (sn == 0) {
             const uint32_t b0 = ~eb.x & 0xffu;
-            c.x1[0] = C3L_PACK2((int)(int16_t)(c.h[0] & 0xffffu) - (int)(b0 & 7u), C3L_FLOOR);
-            c.x2[0] = C3L_PACK2((int)(int16_t)(c.h[0] & 0xffffu) - (int)(b0 >> 3), C3L_FLOOR);
+            x1[0] = C3L_PACK2((int)(int16_t)(h[0] & 0xffffu) - (int)(b0 & 7u), C3L_FLOOR);
+            x2[0] = C3L_PACK2((int)(int16_t)(h[0] & 0xffffu) - (int)(b0 >> 3), C3L_FLOOR);
         }
         return;
     }
-    // byte = ~(d1 | d2 << 3): (byte & 7) - 7 = -d1, ((byte >> 3) & 31) - 31 = -d2, added per halfword
+    // (byte & 7) - 7 = -d1, ((byte >> 3) & 31) - 31 = -d2, added per halfword
     const uint32_t ew[4] = {eb.x, eb.y, eb.z, eb.w};
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         const uint32_t two = C3L_PRMT(ew[t >> 1], 0u, (t & 1) ? 0x4342u : 0x4140u);    // bytes -> halfwords
-        c.x1[t] = C3G_VADD2(c.h[t], C3G_VADD2(two & 0x00070007u, 0xfff9fff9u));
-        c.x2[t] = C3G_VADD2(c.h[t], C3G_VADD2((two >> 3) & 0x001f001fu, 0xffe1ffe1u));
+        x1[t] = C3G_VADD2(h[t], C3G_VADD2(two & 0x00070007u, 0xfff9fff9u));
+        x2[t] = C3G_VADD2(h[t], C3G_VADD2((two >> 3) & 0x001f001fu, 0xffe1ffe1u));
     }
 }
 
-C3G_FN uint2 c3g_get_rowrec(const uint2 *srr, const uint2 *rowrec, const int pos, const int pk)
+// this lane's vector `sn` of a predecessor row: from the ring when the row is at most ring_delta positions back and
+// fits a slot, else from the arena; floor outside the row's band.  `always`: lanes outside this row's band take
+// the plain path whatever they would read (their results are dropped).
+template <int RVS>
+C3G_FN void c3g_fetch_pred(uint32_t (&h)[8], uint32_t (&x1)[8], uint32_t (&x2)[8], const uint4 *ring, const uint4 *arena,
+                           const int vs_shift, const int pos, const int pk, const uint2 rk, const int sn, const int ring_delta,
+                           const bool always)
 {
-    return (pos - pk <= C3G_R) ? srr[pk & (C3G_R - 1)] : rowrec[pk];
+    const int pb = C3G_R_BEG(rk), pe = C3G_R_END(rk);
+    const bool in_ring = pos - pk <= ring_delta && pe - pb < (1 << RVS);
+    if (in_ring && (always || (sn >= pb && sn <= pe))) {
+        const uint4 *s = C3G_RING_PTR(ring, RVS, pk & (C3G_R - 1), sn);
+        constexpr int st = 1 << RVS;
+        const uint4 a0 = s[0], a1 = s[st], b0 = s[2 * st], b1 = s[3 * st], c0 = s[4 * st], c1 = s[5 * st];
+        h[0] = a0.x; h[1] = a0.y; h[2] = a0.z; h[3] = a0.w; h[4] = a1.x; h[5] = a1.y; h[6] = a1.z; h[7] = a1.w;
+        x1[0] = b0.x; x1[1] = b0.y; x1[2] = b0.z; x1[3] = b0.w; x1[4] = b1.x; x1[5] = b1.y; x1[6] = b1.z; x1[7] = b1.w;
+        x2[0] = c0.x; x2[1] = c0.y; x2[2] = c0.z; x2[3] = c0.w; x2[4] = c1.x; x2[5] = c1.y; x2[6] = c1.z; x2[7] = c1.w;
+    } else if (!always && sn >= pb && sn <= pe) {
+        c3g_arena_pred(h, x1, x2, arena, vs_shift, pk, sn);
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) h[t] = x1[t] = x2[t] = C3L_FLOOR2;
+    }
 }
 
 // source row: cells, ring slot 0, arena, record
+template <int RVS>
 C3G_FN void c3g_source_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, uint4 *ring, uint2 *srr,
-                           uint4 *arena, const int li, const unsigned gmask)
+                           uint4 *arena, uint2 &rec_out, const int li, const unsigned gmask)
 {
     const int oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const int qlen = G.qlen;
@@ -355,7 +382,7 @@ C3G_FN void c3g_source_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev 
     const int end_sn = end >> 4, e0 = min(qlen, end_sn * 16 + 15);
     const int nvec = end_sn + 1;
     if (nvec > (1 << L.vs_shift)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
-    const int rvm = (1 << L.rv_shift) - 1, vsm = (1 << L.vs_shift) - 1;
+    const int vsm = (1 << L.vs_shift) - 1;
     bool low = false;
     for (int sn = li; sn <= end_sn; sn += C3G_GL) {
         uint32_t h[8], x1[8], x2[8];
@@ -374,9 +401,9 @@ C3G_FN void c3g_source_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev 
             }
             h[t] = C3L_PACK2(hv[0], hv[1]); x1[t] = C3L_PACK2(a1[0], a1[1]); x2[t] = C3L_PACK2(a2[0], a2[1]);
         }
-        if (nvec <= rvm + 1) {
-            uint4 *s = ring + (sn & rvm);
-            const int st = rvm + 1;
+        if (nvec <= (1 << RVS)) {
+            uint4 *s = C3G_RING_PTR(ring, RVS, 0, sn);
+            constexpr int st = 1 << RVS;
             s[0] = make_uint4(h[0], h[1], h[2], h[3]); s[st] = make_uint4(h[4], h[5], h[6], h[7]);
             s[2 * st] = make_uint4(x1[0], x1[1], x1[2], x1[3]); s[3 * st] = make_uint4(x1[4], x1[5], x1[6], x1[7]);
             s[4 * st] = make_uint4(x2[0], x2[1], x2[2], x2[3]); s[5 * st] = make_uint4(x2[4], x2[5], x2[6], x2[7]);
@@ -388,21 +415,30 @@ C3G_FN void c3g_source_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev 
     if (C3G_ANYG(gmask, low)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
     const uint2 rec = make_uint2((uint32_t)end_sn << 16, 1u);      // successors of the source start at column 1
     if (li == 0) { W.rowrec[0] = rec; srr[0] = rec; }
+    rec_out = rec;
 }
 
-// one DP row (position pos, descriptor d).  Returns the band width in columns, 0 after an error.
+// One DP row (position pos, descriptor d; rprev: record of the row at pos - 1, replaced by this row's).  Returns the
+// band width in columns, 0 after an error.  Lanes whose vector lies outside the band run along with whatever they
+// load -- nothing they compute is stored or enters the row's arg-max.  Columns past qlen inside the last vector are
+// computed like any other (nothing at or left of qlen depends on them) and only kept out of the arg-max.
+// MULTI = false: the arena rows hold 8 vectors, so a row is one pass of the 8 lanes.
+template <int RVS, bool MULTI>
 C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, uint4 *ring, uint2 *srr,
-                   uint4 *arena, const int pos, const uint4 d, const int li, const int gbase, const unsigned gmask)
+                   uint4 *arena, const int pos, const uint4 d, uint2 &rprev, const bool live, const int li, const int gbase)
 {
+    // All 32 lanes of the warp run every row step together and every collective names the full warp (a member mask
+    // that differs between the groups costs a MATCH + vote per shuffle).  A group without a row (`live` false) runs
+    // along on harmless inputs and stores nothing.
     const int e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
-    const int qlen = G.qlen, w = G.w, n = G.n;
-    const int npre = C3G_D_NPRE(d), nbase = C3G_D_BASE(d);
-    const int p0 = C3G_D_P0(d), p1 = C3G_D_P1(d);
-    const uint2 r0 = c3g_get_rowrec(srr, W.rowrec, pos, p0);
+    const int qlen = G.qlen;
+    const int npre = live ? C3G_D_NPRE(d) : 1, nbase = live ? C3G_D_BASE(d) : 0;
+    const int p0 = live ? C3G_D_P0(d) : pos - 1, p1 = C3G_D_P1(d);
+    const uint2 r0 = (p0 == pos - 1) ? rprev : c3g_get_rowrec(srr, W.rowrec, pos, p0);
     uint2 r1 = make_uint2(1u, 0u);                                // empty band
-    int mpl = min(n, C3G_R_MP(r0)), mpr = C3G_R_MP(r0), minb = C3G_R_BEG(r0);
+    int mpl = min(G.n, C3G_R_MP(r0)), mpr = C3G_R_MP(r0), minb = C3G_R_BEG(r0);
     if (npre > 1) {
-        r1 = c3g_get_rowrec(srr, W.rowrec, pos, p1);
+        r1 = (p1 == pos - 1) ? rprev : c3g_get_rowrec(srr, W.rowrec, pos, p1);
         mpl = min(mpl, C3G_R_MP(r1)); mpr = max(mpr, C3G_R_MP(r1)); minb = min(minb, C3G_R_BEG(r1));
         for (int k = 2; k < npre; ++k) {
             const int pk = W.xpred[C3G_D_XOFS(d) + k - 2];
@@ -411,78 +447,55 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
         }
     }
     const int rr = qlen - (C3G_D_HOPS(d) - 1);
-    const int beg_sn = max(max(0, min(mpl, rr) - w) >> 4, minb);
-    const int end_sn = max(min(qlen, max(mpr, rr) + w) >> 4, beg_sn);
-    const int beg = beg_sn << 4, end = min(qlen, end_sn * 16 + 15);
+    int beg_sn = max(max(0, min(mpl, rr) - G.w) >> 4, minb);
+    int end_sn = max(min(qlen, max(mpr, rr) + G.w) >> 4, beg_sn);
+    if (!live) { beg_sn = 0; end_sn = 0; }
+    bool bad = false;
+    if (end_sn - beg_sn + 1 > (MULTI ? (1 << L.vs_shift) : C3G_GL)) { bad = true; end_sn = beg_sn; }   // wider than an arena row
     const int nvec = end_sn - beg_sn + 1;
-    if (nvec > (1 << L.vs_shift)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return 0; }
-    const bool to_ring = nvec <= (1 << L.rv_shift);
-    const int rvm = (1 << L.rv_shift) - 1, vsm = (1 << L.vs_shift) - 1;
+    const bool to_ring = MULTI ? nvec <= (1 << RVS) : true;
     const uint32_t ne1 = C3L_PACK2(-e1, -e1), ne2 = C3L_PACK2(-e2, -e2), noe1 = C3L_PACK2(-oe1, -oe1), noe2 = C3L_PACK2(-oe2, -oe2);
+    const int d21 = oe1 - oe2;
     int pc1 = C3L_FLOOR, pc2 = C3L_FLOOR;                          // F1, F2' entering the pass (chain domain, see below)
     uint32_t mcarry = C3L_FLOOR2;                                  // merged predecessor H of the vector before the pass
-    int bestkey = -0x7fffffff - 1, h_first = 0;
+    unsigned bestkey = 0u;
+    int h_first = 0x7fff;
     // everything read from the ring must be in registers before any lane overwrites the slot of row pos - C3G_R:
     // a row of several passes stores its first vectors before it has read the last ones, so it does not use that slot
-    const int ring_delta = nvec <= C3G_GL ? C3G_R : C3G_R - 1;
-    for (int sn0 = beg_sn; sn0 <= end_sn; sn0 += C3G_GL) {
+    const int ring_delta = (!MULTI || nvec <= C3G_GL) ? C3G_R : C3G_R - 1;
+    int sn0 = beg_sn;
+    do {
         const int l = (li - sn0) & 7, sn = sn0 + l;
         const bool act = sn <= end_sn;
         const int j0 = sn << 4;
-        c3g_cells c;
-        if (act) {
-            c3g_load_pred(c, ring, L.rv_shift, arena, L.vs_shift, pos, p0, r0, sn, ring_delta);
-            if (npre > 1) {
-                c3g_cells t;
-                c3g_load_pred(t, ring, L.rv_shift, arena, L.vs_shift, pos, p1, r1, sn, ring_delta);
+        // scores of the 16 columns against the node base (row 4 of the profile: zeros, an N node)
+        const uint4 s4 = *reinterpret_cast<const uint4 *>(W.qp + nbase * L.A.qp_stride + j0);
+        uint32_t h[8], x1[8], x2[8];
+        c3g_fetch_pred<RVS>(h, x1, x2, ring, arena, L.vs_shift, pos, p0, r0, sn, ring_delta, !act || !live);
+        for (int k = 1; k < npre; ++k) {
+            int pk = p1; uint2 rk = r1;
+            if (k > 1) { pk = W.xpred[C3G_D_XOFS(d) + k - 2]; rk = c3g_get_rowrec(srr, W.rowrec, pos, pk); }
+            uint32_t th[8], t1[8], t2[8];
+            c3g_fetch_pred<RVS>(th, t1, t2, ring, arena, L.vs_shift, pos, pk, rk, sn, ring_delta, !act || !live);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { c.h[u] = C3L_VMAX2(c.h[u], t.h[u]); c.x1[u] = C3L_VMAX2(c.x1[u], t.x1[u]); c.x2[u] = C3L_VMAX2(c.x2[u], t.x2[u]); }
-                for (int k = 2; k < npre; ++k) {
-                    const int pk = W.xpred[C3G_D_XOFS(d) + k - 2];
-                    const uint2 rk = c3g_get_rowrec(srr, W.rowrec, pos, pk);
-                    c3g_load_pred(t, ring, L.rv_shift, arena, L.vs_shift, pos, pk, rk, sn, ring_delta);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) { c.h[u] = C3L_VMAX2(c.h[u], t.h[u]); c.x1[u] = C3L_VMAX2(c.x1[u], t.x1[u]); c.x2[u] = C3L_VMAX2(c.x2[u], t.x2[u]); }
-                }
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) c.h[u] = c.x1[u] = c.x2[u] = C3L_FLOOR2;
+            for (int u = 0; u < 8; ++u) { h[u] = C3L_VMAX2(h[u], th[u]); x1[u] = C3L_VMAX2(x1[u], t1[u]); x2[u] = C3L_VMAX2(x2[u], t2[u]); }
         }
         // M: merged predecessor H one column to the left (the first cell of the band never takes M)
-        uint32_t top = (uint32_t)C3G_SHFL(gmask, c.h[7], gbase + ((li - 1) & 7));
+        uint32_t top = (uint32_t)C3G_SHFL(C3_FULL, h[7], gbase + ((li - 1) & 7));
         if (l == 0) top = mcarry;
-        mcarry = (uint32_t)C3G_SHFL(gmask, c.h[7], gbase + ((sn0 + 7) & 7));
-        uint32_t mw[8];
-        mw[0] = C3L_PRMT(top, c.h[0], 0x5432u);
-#pragma unroll
-        for (int t = 1; t < 8; ++t) mw[t] = C3L_PRMT(c.h[t - 1], c.h[t], 0x5432u);
-        // scores of the 16 columns
-        uint32_t sc[8];
-        if (act && nbase < 4) {
-            const uint4 s4 = *reinterpret_cast<const uint4 *>(W.qp + nbase * L.A.qp_stride + j0);
-            sc[0] = C3L_PRMT(s4.x, 0u, 0x9180u); sc[1] = C3L_PRMT(s4.x, 0u, 0xb3a2u);
-            sc[2] = C3L_PRMT(s4.y, 0u, 0x9180u); sc[3] = C3L_PRMT(s4.y, 0u, 0xb3a2u);
-            sc[4] = C3L_PRMT(s4.z, 0u, 0x9180u); sc[5] = C3L_PRMT(s4.z, 0u, 0xb3a2u);
-            sc[6] = C3L_PRMT(s4.w, 0u, 0x9180u); sc[7] = C3L_PRMT(s4.w, 0u, 0xb3a2u);
-        } else {
-#pragma unroll
-            for (int t = 0; t < 8; ++t) sc[t] = 0u;
-        }
+        if (MULTI) mcarry = (uint32_t)C3G_SHFL(C3_FULL, h[7], gbase + ((sn0 + 7) & 7));      // (every lane of the warp: no group-dependent condition around a collective)
         uint32_t hme[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) hme[t] = C3L_VMAX3_2(C3L_VADDMAX2(mw[t], sc[t], C3L_FLOOR2), c.x1[t], c.x2[t]);
-        const int lim = act ? end - j0 : -1;                       // last active column of this vector (>= 15: all)
-        if (lim < 15) {
+        {
+            const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                if (2 * t > lim) hme[t] = C3L_FLOOR2;
-                else if (2 * t + 1 > lim) hme[t] = (hme[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
+                const uint32_t sc = C3L_PRMT(sw[t >> 1], 0u, (t & 1) ? 0xb3a2u : 0x9180u);
+                const uint32_t mw = C3L_PRMT(t == 0 ? top : h[t - 1], h[t], 0x5432u);
+                hme[t] = C3L_VMAX3_2(C3L_VADDMAX2(mw, sc, C3L_FLOOR2), x1[t], x2[t]);
             }
         }
         // horizontal gap, chain domain: g1 = F1 at the column, g2 = F2 at the column + (oe2 - oe1); both take
         // a = hme - oe1 per column.  Local chain from "nothing enters the lane" first, then the 8-lane scan.
-        const int d21 = oe1 - oe2;
         int g1 = C3L_FLOOR, g2 = C3L_FLOOR;
         uint32_t fmp[8];
 #pragma unroll
@@ -495,19 +508,24 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
             g1 = C3L_ADDMAX(g1, -e1, a1); g2 = C3L_ADDMAX(g2, -e2, a1);
             fmp[t] = C3L_PACK2(f0, f1);
         }
-        // scan: value entering lane l = max(pass carry decayed, local outputs of the lanes before, decayed)
-        int t1 = g1 + 16 * e1 * l, t2 = g2 + 16 * e2 * l;
+        // scan over the lanes, both chains packed in one word (low half: chain 1): value entering lane l =
+        // max(pass carry decayed, local outputs of the lanes before, decayed).  All values are int16-sized.
+        const uint32_t dec = C3L_PACK2(16 * e1, 16 * e2);
+        uint32_t tt = C3G_VADD2(C3L_PACK2(g1, g2), dec * (uint32_t)l);
 #pragma unroll
         for (int dd = 1; dd < C3G_GL; dd <<= 1) {
-            const int v1 = C3G_SHFL(gmask, t1, gbase + ((li - dd) & 7)), v2 = C3G_SHFL(gmask, t2, gbase + ((li - dd) & 7));
-            if (l >= dd) { t1 = max(t1, v1); t2 = max(t2, v2); }
+            const uint32_t v = (uint32_t)C3G_SHFL(C3_FULL, tt, gbase + ((li - dd) & 7));
+            if (l >= dd) tt = C3L_VMAX2(tt, v);
         }
-        int c1 = C3G_SHFL(gmask, t1, gbase + ((li - 1) & 7)), c2 = C3G_SHFL(gmask, t2, gbase + ((li - 1) & 7));
-        const int tot1 = C3G_SHFL(gmask, t1, gbase + ((sn0 + 7) & 7)), tot2 = C3G_SHFL(gmask, t2, gbase + ((sn0 + 7) & 7));
-        c1 = l == 0 ? pc1 : max(c1 - 16 * e1 * (l - 1), pc1 - 16 * e1 * l);
-        c2 = l == 0 ? pc2 : max(c2 - 16 * e2 * (l - 1), pc2 - 16 * e2 * l);
-        pc1 = max(tot1 - 16 * e1 * 7, pc1 - 16 * e1 * 8);
-        pc2 = max(tot2 - 16 * e2 * 7, pc2 - 16 * e2 * 8);
+        const uint32_t ex = (uint32_t)C3G_SHFL(C3_FULL, tt, gbase + ((li - 1) & 7));
+        int c1 = (int)(int16_t)(ex & 0xffffu) - 16 * e1 * (l - 1), c2 = ((int)ex >> 16) - 16 * e2 * (l - 1);
+        if (MULTI) {
+            c1 = l == 0 ? pc1 : max(c1, pc1 - 16 * e1 * l);
+            c2 = l == 0 ? pc2 : max(c2, pc2 - 16 * e2 * l);
+            const uint32_t tot = (uint32_t)C3G_SHFL(C3_FULL, tt, gbase + ((sn0 + 7) & 7));
+            pc1 = max((int)(int16_t)(tot & 0xffffu) - 16 * e1 * 7, pc1 - 16 * e1 * 8);
+            pc2 = max(((int)tot >> 16) - 16 * e2 * 7, pc2 - 16 * e2 * 8);
+        } else if (l == 0) { c1 = C3L_FLOOR; c2 = C3L_FLOOR; }
         c1 = max(c1, C3L_FLOOR); c2 = max(c2 + d21, C3L_FLOOR);    // F1, F2 entering the vector
         const uint32_t c1p = C3L_PACK2(c1, c1), c2p = C3L_PACK2(c2, c2);
         uint32_t hh[8], n1[8], n2[8];
@@ -516,40 +534,31 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
             const uint32_t rp1 = C3L_PACK2(-e1 * 2 * t, -e1 * (2 * t + 1)), rp2 = C3L_PACK2(-e2 * 2 * t, -e2 * (2 * t + 1));
             const uint32_t ff = C3L_VADDMAX2(c2p, rp2, C3L_VADDMAX2(c1p, rp1, fmp[t]));
             hh[t] = C3L_VMAX2(hme[t], ff);
-            n1[t] = C3L_VADDMAX2(c.x1[t], ne1, C3L_VADDMAX2(hh[t], noe1, C3L_FLOOR2));
-            n2[t] = C3L_VADDMAX2(c.x2[t], ne2, C3L_VADDMAX2(hh[t], noe2, C3L_FLOOR2));
-        }
-        if (lim < 15) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                if (2 * t > lim) hh[t] = n1[t] = n2[t] = C3L_FLOOR2;
-                else if (2 * t + 1 > lim) {
-                    hh[t] = (hh[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
-                    n1[t] = (n1[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
-                    n2[t] = (n2[t] & 0xffffu) | (C3L_FLOOR2 & 0xffff0000u);
-                }
-            }
+            n1[t] = C3L_VADDMAX2(x1[t], ne1, C3L_VADDMAX2(hh[t], noe1, C3L_FLOOR2));
+            n2[t] = C3L_VADDMAX2(x2[t], ne2, C3L_VADDMAX2(hh[t], noe2, C3L_FLOOR2));
         }
         if (sn == beg_sn) h_first = (int)(int16_t)(hh[0] & 0xffffu);
-        // simd_abpoa_ada_max_i as one packed max: value in the high half, tie-break priority in the low half
-        // (lowest SIMD lane, then the last vector, then the earliest vector)
+        // simd_abpoa_ada_max_i as one packed max: value (biased to unsigned) in the high half, tie-break priority in
+        // the low half (lowest SIMD lane, then the last vector, then the earliest vector)
         if (act) {
-            int lk = -0x7fffffff - 1;
+            unsigned lk = 0u;
+            const int lim = min(qlen, end_sn * 16 + 15) - j0;        // last column of this vector that exists (>= 15: all)
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                const int klo = (int)((hh[t] << 16) | (uint32_t)((15 - 2 * t) << 12));
-                const int khi = (int)((hh[t] & 0xffff0000u) | (uint32_t)((14 - 2 * t) << 12));
-                lk = C3L_MAX3(lk, klo, khi);
+                unsigned klo = C3L_PRMT(hh[t], (uint32_t)((15 - 2 * t) << 12), 0x1054u) ^ 0x80000000u;   // lo half -> high half, priority below
+                unsigned khi = C3L_PRMT(hh[t], (uint32_t)((14 - 2 * t) << 12), 0x3254u) ^ 0x80000000u;
+                if (lim < 15) { if (2 * t > lim) klo = 0u; if (2 * t + 1 > lim) khi = 0u; }
+                lk = max(lk, max(klo, khi));
             }
-            const int vp = (sn == end_sn) ? 0xfff : (0xffe - (sn - beg_sn));
+            const unsigned vp = (sn == end_sn) ? 0xfffu : (unsigned)(0xffe - (sn - beg_sn));
             bestkey = max(bestkey, lk | vp);
         }
-        C3G_SYNC(gmask);
-        if (act) {
+        C3G_SYNC(C3_FULL);
+        if (act && live) {
             const uint4 oa0 = make_uint4(hh[0], hh[1], hh[2], hh[3]), oa1 = make_uint4(hh[4], hh[5], hh[6], hh[7]);
             if (to_ring) {
-                uint4 *s = ring + (((pos & (C3G_R - 1)) * 6) << L.rv_shift) + (sn & rvm);
-                const int st = rvm + 1;
+                uint4 *s = C3G_RING_PTR(ring, RVS, pos & (C3G_R - 1), sn);
+                constexpr int st = 1 << RVS;
                 s[0] = oa0; s[st] = oa1;
                 s[2 * st] = make_uint4(n1[0], n1[1], n1[2], n1[3]); s[3 * st] = make_uint4(n1[4], n1[5], n1[6], n1[7]);
                 s[4 * st] = make_uint4(n2[0], n2[1], n2[2], n2[3]); s[5 * st] = make_uint4(n2[4], n2[5], n2[6], n2[7]);
@@ -563,32 +572,35 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
                 const uint32_t s1 = C3G_VADD2(n1[t], nh), s2 = C3G_VADD2(n2[t], nh) << 3;
                 eb[t] = (s1 & 0x00070007u) | (s2 & ~0x00070007u);
             }
-            uint4 *dst = arena + (((int64_t)pos << L.vs_shift) + (sn & vsm)) * 3;
+            uint4 *dst = arena + (((int64_t)pos << L.vs_shift) + (sn & ((1 << L.vs_shift) - 1))) * 3;
             dst[0] = oa0; dst[1] = oa1;
             dst[2] = make_uint4(C3L_PRMT(eb[0], eb[1], 0x6420u), C3L_PRMT(eb[2], eb[3], 0x6420u),
                                 C3L_PRMT(eb[4], eb[5], 0x6420u), C3L_PRMT(eb[6], eb[7], 0x6420u));
         }
-    }
+        sn0 += C3G_GL;
+    } while (MULTI && C3G_ANYG(C3_FULL, sn0 <= end_sn));
     // exactness of the int16 form (see poa_lane.cuh): the first band cell comfortably above the floor means that
-    // every cell of the row is reachable and was never clamped
-    h_first = C3G_SHFL(gmask, h_first, gbase + (beg_sn & 7));
+    // every cell of the row is reachable and was never clamped.  The verdict rides on the arg-max reduction.
     {
+        const int end = min(qlen, end_sn * 16 + 15);
         const int D = max(min(oe1, oe2), max(e1, e2));
-        if (h_first < C3L_FLOOR + C3L_LOW_GUARD + oe2 + D * (end - beg + 1)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return 0; }
+        if (bad || h_first < C3L_FLOOR + C3L_LOW_GUARD + oe2 + D * (end - (beg_sn << 4) + 1)) bestkey = 0xffffffffu;
     }
 #pragma unroll
-    for (int dd = 1; dd < C3G_GL; dd <<= 1) bestkey = max(bestkey, C3G_SHFL(gmask, bestkey, gbase + (li ^ dd)));
+    for (int dd = 1; dd < C3G_GL; dd <<= 1) bestkey = max(bestkey, (unsigned)C3G_SHFL(C3_FULL, bestkey, gbase + (li ^ dd)));
+    if (bestkey == 0xffffffffu && live) { C3G_DECLINE(); G.err = C3G_E_RETRY; }
     int best_i = -1;
-    if ((bestkey >> 16) > C3L_FLOOR) {
-        const int sl = 15 - ((bestkey >> 12) & 15);
-        const int vp = bestkey & 0xfff;
+    if ((int)(bestkey >> 16) - 32768 > C3L_FLOOR) {
+        const int sl = 15 - (int)((bestkey >> 12) & 15u);
+        const int vp = (int)(bestkey & 0xfffu);
         const int snb = (vp == 0xfff) ? end_sn : beg_sn + (0xffe - vp);
         best_i = (snb << 4) + sl;
     }
     const uint2 rec = make_uint2((uint32_t)beg_sn | ((uint32_t)end_sn << 16), (uint32_t)(best_i + 1));
-    if (li == 0) { W.rowrec[pos] = rec; srr[pos & (C3G_R - 1)] = rec; }
-    C3G_SYNC(gmask);
-    return end - beg + 1;
+    if (li == 0 && live) { W.rowrec[pos] = rec; srr[pos & (C3G_R - 1)] = rec; }
+    if (live) rprev = rec;
+    C3G_SYNC(C3_FULL);
+    return min(qlen, end_sn * 16 + 15) - (beg_sn << 4) + 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -611,8 +623,64 @@ C3_HD __forceinline__ int c3g_pred_pos(const c3g_ws &W, const uint4 d, const int
     return k == 0 ? C3G_D_P0(d) : k == 1 ? C3G_D_P1(d) : (int)W.xpred[C3G_D_XOFS(d) + k - 2];
 }
 
+// Backtrack window: the rows top .. top - C3G_BTK + 1 staged in shared memory (the idle ring) with ONE round of
+// independent loads: per row the two 16-column vectors (H and E bytes) around the column the path is expected
+// to cross it at (j0 - r: one column per row along the diagonal, +- 8 columns of drift), its descriptor and its
+// record.  Whatever falls outside is read from global memory.
+struct c3g_btw { const uint4 *wH, *wE, *wD; const uint2 *wR; int top, bot, j0; };
+
+template <int GL>
+C3G_FN void c3g_bt_fill(c3g_btw &B, uint8_t *sg, const c3g_ws &W, const uint4 *arena, const int vs, const int top, const int j0,
+                        const int li, const unsigned gmask)
+{
+    constexpr int K = C3G_BTK(GL);
+    uint4 *wH = reinterpret_cast<uint4 *>(sg), *wE = wH + K * 4, *wD = wE + K * 2;
+    uint2 *wR = reinterpret_cast<uint2 *>(wD + K);
+    const int vsm = (1 << vs) - 1;
+    C3G_SYNC(gmask);                                          // nobody still reads the previous window
+#pragma unroll
+    for (int u = 0; u < (K + GL - 1) / GL; ++u) {
+        const int r = li + u * GL, p = top - r;
+        if (r < K && p >= 0) {
+            const int vlo = max(0, (j0 - r - 8) >> 4);
+            const uint4 *s0 = arena + (((int64_t)p << vs) + (vlo & vsm)) * 3, *s1 = arena + (((int64_t)p << vs) + ((vlo + 1) & vsm)) * 3;
+            const uint4 a0 = s0[0], a1 = s0[1], a2 = s0[2], b0 = s1[0], b1 = s1[1], b2 = s1[2];
+            const uint4 dd = W.desc[p]; const uint2 rr = W.rowrec[p];
+            wH[r * 4] = a0; wH[r * 4 + 1] = a1; wH[r * 4 + 2] = b0; wH[r * 4 + 3] = b1;
+            wE[r * 2] = a2; wE[r * 2 + 1] = b2; wD[r] = dd; wR[r] = rr;
+        }
+    }
+    C3G_SYNC(gmask);
+    B.wH = wH; B.wE = wE; B.wD = wD; B.wR = wR; B.top = top; B.bot = max(0, top - K + 1); B.j0 = j0;
+}
+C3G_FN uint4 c3g_bt_desc(const c3g_btw &B, const c3g_ws &W, const int p)
+{
+    return (p <= B.top && p >= B.bot) ? B.wD[B.top - p] : W.desc[p];
+}
+C3G_FN uint2 c3g_bt_rec(const c3g_btw &B, const c3g_ws &W, const int p)
+{
+    return (p <= B.top && p >= B.bot) ? B.wR[B.top - p] : W.rowrec[p];
+}
+C3G_FN int c3g_bt_h(const c3g_btw &B, const uint4 *arena, const int vs, const int p, const int j)
+{
+    if (p <= B.top && p >= B.bot) {
+        const int r = B.top - p, v = (j >> 4) - max(0, (B.j0 - r - 8) >> 4);
+        if ((unsigned)v < 2u) return c3l_map((int)reinterpret_cast<const int16_t *>(B.wH + r * 4 + v * 2)[j & 15]);
+    }
+    return c3g_cell_h(arena, vs, p, j);
+}
+C3G_FN int c3g_bt_eb(const c3g_btw &B, const uint4 *arena, const int vs, const int p, const int j)
+{
+    if (p <= B.top && p >= B.bot) {
+        const int r = B.top - p, v = (j >> 4) - max(0, (B.j0 - r - 8) >> 4);
+        if ((unsigned)v < 2u) return (int)(~reinterpret_cast<const uint8_t *>(B.wE + r * 2 + v)[j & 15] & 0xff);
+    }
+    return c3g_cell_eb(arena, vs, p, j);
+}
+
+template <int GL>
 C3G_FN int c3g_backtrack(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, const uint4 *arena,
-                         const int li, const int gbase, const unsigned gmask)
+                         uint8_t *sg, const int li, const int gbase, const unsigned gmask)
 {
     const int e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
     const int vs = L.vs_shift;
@@ -632,31 +700,34 @@ C3G_FN int c3g_backtrack(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P
             if (val > best) { best = val; bj = en; bk = pk; }
         }
         if (bk < 0 || qlen - bj + 8 > cap) { C3G_DECLINE(); return C3G_E_RETRY; }
-        for (int t = qlen - li; t > bj; t -= C3G_GL)
+        for (int t = qlen - li; t > bj; t -= GL)
             cg[qlen - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
         nc = qlen - bj; j = bj; pos = bk; hij = best;
     }
+    c3g_btw B;
+    B.top = -1; B.bot = 0; B.j0 = 0; B.wH = B.wE = B.wD = nullptr; B.wR = nullptr;
     int cur_op = C3_OP_ALL;
     while (pos != 0 && j > 0) {
+        if (pos > B.top || (pos - C3G_BTV(GL) < B.bot && B.bot > 0)) c3g_bt_fill<GL>(B, sg, W, arena, vs, pos, j, li, gmask);
         if (cur_op == C3_OP_ALL) {
             // lane l looks at row pos - l, column j - l
             const int pl = pos - li, jl = j - li;
             uint4 dl = make_uint4(0u, 0u, 0u, 0u); uint2 rl = make_uint2(1u, 0u);
             int hl = C3_NEG_INF;
             if (pl >= 0) {
-                dl = W.desc[pl]; rl = W.rowrec[pl];
-                if (jl >= 0) hl = c3g_cell_h(arena, vs, pl, jl);
+                dl = c3g_bt_desc(B, W, pl); rl = c3g_bt_rec(B, W, pl);
+                if (jl >= 0) hl = c3g_bt_h(B, arena, vs, pl, jl);
             }
             const int bl = C3G_R_BEG(rl) * 16, el = min(qlen, C3G_R_END(rl) * 16 + 15);
             if (jl < bl || jl > el) hl = C3_NEG_INF;
-            const int src = gbase + ((li + 1) & 7);
+            const int src = gbase + ((li + 1) & (GL - 1));
             const int hn = C3G_SHFL(gmask, hl, src), bn = C3G_SHFL(gmask, bl, src), en = C3G_SHFL(gmask, el, src);
-            bool ok = li < 7 && pl >= 1 && jl >= 1 && jl >= bl && jl <= el && C3G_D_P0(dl) == pl - 1;
+            bool ok = li < GL - 1 && pl >= 1 && jl >= 1 && jl >= bl && jl <= el && C3G_D_P0(dl) == pl - 1;
             if (ok) {
                 const int s = c3_score(P, C3G_D_BASE(dl), q[jl - 1]);
                 ok = jl - 1 >= max(bn, bl) && jl - 1 <= en && hn + s == hl;
             }
-            const unsigned okm = (C3G_BALLOT(gmask, ok) >> gbase) & 0xffu;
+            const unsigned okm = (C3G_BALLOT(gmask, ok) >> gbase) & C3G_LMASK(GL);
             int Lr = C3G_FFS(~okm) - 1;
             Lr = min(Lr, cap - 8 - j - nc);
             if (Lr > 0) {
@@ -667,8 +738,8 @@ C3G_FN int c3g_backtrack(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P
             }
         }
         // generic single step
-        const uint4 d = W.desc[pos];
-        const uint2 rt = W.rowrec[pos];
+        const uint4 d = c3g_bt_desc(B, W, pos);
+        const uint2 rt = c3g_bt_rec(B, W, pos);
         const int i = C3G_D_ID(d);
         const int b = C3G_R_BEG(rt) * 16, en = min(qlen, C3G_R_END(rt) * 16 + 15);
         if (j < b || j > en) { C3G_DECLINE(); return C3G_E_RETRY; }
@@ -679,10 +750,10 @@ C3G_FN int c3g_backtrack(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P
         if (cur_op & C3_OP_M) {
             for (int k = 0; k < npre; ++k) {
                 const int pk = c3g_pred_pos(W, d, k);
-                const uint2 pr = W.rowrec[pk];
+                const uint2 pr = c3g_bt_rec(B, W, pk);
                 const int pbeg = C3G_R_BEG(pr) * 16, pend = min(qlen, C3G_R_END(pr) * 16 + 15);
                 if (j - 1 < max(pbeg, b) || j - 1 > pend) continue;
-                const int ph = c3g_cell_h(arena, vs, pk, j - 1);
+                const int ph = c3g_bt_h(B, arena, vs, pk, j - 1);
                 if (ph + s == hij) {
                     opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
                     pos = pk; --j; hit = 1; cur_op = C3_OP_ALL; hij = ph;
@@ -691,17 +762,17 @@ C3G_FN int c3g_backtrack(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P
             }
         }
         if (!hit && (cur_op & C3_OP_E)) {
-            const int ceb = c3g_cell_eb(arena, vs, pos, j);
+            const int ceb = c3g_bt_eb(B, arena, vs, pos, j);
             const int ce1 = hij - (ceb & 7), ce2 = hij - (ceb >> 3);
             for (int k = 0; k < npre; ++k) {
                 const int pk = c3g_pred_pos(W, d, k);
-                const uint2 pr = W.rowrec[pk];
+                const uint2 pr = c3g_bt_rec(B, W, pk);
                 const int pbeg = C3G_R_BEG(pr) * 16, pend = min(qlen, C3G_R_END(pr) * 16 + 15);
                 if (j < pbeg || j > pend) continue;
-                const int ph = c3g_cell_h(arena, vs, pk, j);
+                const int ph = c3g_bt_h(B, arena, vs, pk, j);
                 int pe1, pe2;
                 if (pk == 0) { pe1 = j == 0 ? -oe1 : C3_NEG_INF; pe2 = j == 0 ? -oe2 : C3_NEG_INF; }
-                else { const int peb = c3g_cell_eb(arena, vs, pk, j); pe1 = ph - (peb & 7); pe2 = ph - (peb >> 3); }
+                else { const int peb = c3g_bt_eb(B, arena, vs, pk, j); pe1 = ph - (peb & 7); pe2 = ph - (peb >> 3); }
                 if (cur_op & C3_OP_E1) {
                     if (cur_op & C3_OP_M) {
                         if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
@@ -726,13 +797,57 @@ C3G_FN int c3g_backtrack(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P
         if (!hit && (cur_op & C3_OP_F)) {
             int hl = C3_NEG_INF;
             if (j - 1 >= b) {
-                // F is not stored: rebuild F[j] and F[j-1] of this row from its H
+                // F is not stored: rebuild F[j] and F[j-1] of this row from its H, 8 lanes x 16 columns with the same
+                // (max,+) scan as the DP; only the lane that holds column j - 1 decides
+                const int jm = j - 1, sb = b >> 4;
                 int f1 = C3_NEG_INF, f2 = C3_NEG_INF, f1l = C3_NEG_INF, f2l = C3_NEG_INF;
-                for (int c = b; c < j; ++c) {
-                    hl = c3g_cell_h(arena, vs, pos, c);
-                    f1l = f1; f2l = f2;
-                    f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
+                int pc1 = C3_NEG_INF, pc2 = C3_NEG_INF;            // F entering the pass
+                for (int sn0 = sb; sn0 <= (jm >> 4); sn0 += GL) {
+                    const int sn = sn0 + li;
+                    const int16_t *hp = reinterpret_cast<const int16_t *>(arena + (((int64_t)pos << vs) + (sn & ((1 << vs) - 1))) * 3);
+                    int hv[16];
+                    if (sn <= (jm >> 4)) {
+                        const uint4 a0 = reinterpret_cast<const uint4 *>(hp)[0], a1 = reinterpret_cast<const uint4 *>(hp)[1];
+                        int t8[8];
+                        c3l_unpack8(a0, t8);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) hv[k] = c3l_map(t8[k]);
+                        c3l_unpack8(a1, t8);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) hv[8 + k] = c3l_map(t8[k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) hv[k] = C3_NEG_INF;
+                    }
+                    // local outputs with nothing entering: value leaving the vector
+                    int o1 = C3_NEG_INF, o2 = C3_NEG_INF;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) { o1 = max(o1 - e1, hv[k] - oe1); o2 = max(o2 - e2, hv[k] - oe2); }
+                    int t1 = o1 + 16 * e1 * li, t2 = o2 + 16 * e2 * li;
+#pragma unroll
+                    for (int dd = 1; dd < GL; dd <<= 1) {
+                        const int v1 = C3G_SHFL(gmask, t1, gbase + ((li - dd) & (GL - 1))), v2 = C3G_SHFL(gmask, t2, gbase + ((li - dd) & (GL - 1)));
+                        if (li >= dd) { t1 = max(t1, v1); t2 = max(t2, v2); }
+                    }
+                    int c1 = C3G_SHFL(gmask, t1, gbase + ((li - 1) & (GL - 1))), c2 = C3G_SHFL(gmask, t2, gbase + ((li - 1) & (GL - 1)));
+                    const int tot1 = C3G_SHFL(gmask, t1, gbase + GL - 1), tot2 = C3G_SHFL(gmask, t2, gbase + GL - 1);
+                    c1 = li == 0 ? pc1 : max(c1 - 16 * e1 * (li - 1), pc1 - 16 * e1 * li);
+                    c2 = li == 0 ? pc2 : max(c2 - 16 * e2 * (li - 1), pc2 - 16 * e2 * li);
+                    pc1 = max(tot1 - 16 * e1 * (GL - 1), pc1 - 16 * e1 * GL);
+                    pc2 = max(tot2 - 16 * e2 * (GL - 1), pc2 - 16 * e2 * GL);
+                    if (sn == (jm >> 4)) {                         // this lane holds column j - 1: F[j-1] and F[j]
+                        int a1 = c1, a2 = c2, hlast = C3_NEG_INF, p1 = C3_NEG_INF, p2 = C3_NEG_INF;
+                        const int tm = jm & 15;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            if (k <= tm) { hlast = hv[k]; p1 = a1; p2 = a2; a1 = max(a1 - e1, hlast - oe1); a2 = max(a2 - e2, hlast - oe2); }
+                        }
+                        f1 = a1; f2 = a2; f1l = p1; f2l = p2; hl = hlast;
+                    }
                 }
+                const int own = gbase + (((jm >> 4) - sb) & (GL - 1));
+                f1 = C3G_SHFL(gmask, f1, own); f2 = C3G_SHFL(gmask, f2, own); f1l = C3G_SHFL(gmask, f1l, own);
+                f2l = C3G_SHFL(gmask, f2l, own); hl = C3G_SHFL(gmask, hl, own);
                 if (cur_op & C3_OP_F1) {
                     if (!(cur_op & C3_OP_M) || hij == f1) {
                         if (hl - oe1 == f1) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
@@ -748,23 +863,12 @@ C3G_FN int c3g_backtrack(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P
             }
             if (hit) { opw = C3_CG_INS | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32); --j; hij = hl; }
         }
-#ifdef C3G_DEBUG_BT
-        if (!hit && li == 0) {
-            printf("bt fail: pos %d j %d op %x hij %d npre %d b %d en %d id %d\n", pos, j, cur_op, hij, npre, b, en, i);
-            for (int k = 0; k < npre; ++k) {
-                const int pk = c3g_pred_pos(W, d, k); const uint2 pr = W.rowrec[pk];
-                printf("  pred %d pos %d band %d..%d H[j-1] %d H[j] %d eb %x\n", k, pk, C3G_R_BEG(pr) * 16, C3G_R_END(pr) * 16 + 15,
-                       c3g_cell_h(arena, vs, pk, j - 1), c3g_cell_h(arena, vs, pk, j), c3g_cell_eb(arena, vs, pk, j));
-            }
-            printf("  own eb %x H[j-1] %d\n", c3g_cell_eb(arena, vs, pos, j), c3g_cell_h(arena, vs, pos, j - 1));
-        }
-#endif
         if (!hit) { C3G_DECLINE(); return C3G_E_RETRY; }
         if (li == 0) cg[nc] = opw;
         ++nc;
         if (nc + j + 8 > cap) { C3G_DECLINE(); return C3G_E_RETRY; }
     }
-    for (int t = j - li; t > 0; t -= C3G_GL)
+    for (int t = j - li; t > 0; t -= GL)
         cg[nc + j - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
     nc += j;
     C3G_SYNC(gmask);
@@ -791,6 +895,7 @@ C3G_FN int c3g_tail_gap(const c3g_ws &W, const uint16_t *ord, const int n_old, c
     return t + 1;
 }
 
+template <int GL>
 C3G_FN int c3g_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const int nc, const int li, const int gbase, const unsigned gmask)
 {
     const uint8_t *q = G.q;
@@ -801,7 +906,7 @@ C3G_FN int c3g_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const int n
     g.node_cap = L.A.node_cap; g.pool_cap = L.A.pool_cap; g.err = 0;
     int last_id = C3_SRC, last_new = 0;                     // uniform
     int last_gap = 0, last_p = 0;                           // lane 0: gap of the last new node / old position its group walk starts at
-    for (int tb = nc - 1; tb >= 0; tb -= C3G_GL) {
+    for (int tb = nc - 1; tb >= 0; tb -= GL) {
         const int t = tb - li;
         const bool have = t >= 0;
         const unsigned long long op = have ? cg[t] : C3_CG_DEL;
@@ -809,8 +914,8 @@ C3G_FN int c3g_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const int n
         const bool is_match = have && kind == (int)C3_CG_MATCH;
         bool eq = false;
         if (is_match) eq = W.nodes[node_id].base == q[qpos];
-        const unsigned m_nondel = (C3G_BALLOT(gmask, have && kind != (int)C3_CG_DEL) >> gbase) & 0xffu;
-        const unsigned m_eq = (C3G_BALLOT(gmask, eq) >> gbase) & 0xffu;
+        const unsigned m_nondel = (C3G_BALLOT(gmask, have && kind != (int)C3_CG_DEL) >> gbase) & C3G_LMASK(GL);
+        const unsigned m_eq = (C3G_BALLOT(gmask, eq) >> gbase) & C3G_LMASK(GL);
         const unsigned lower = m_nondel & ((1u << li) - 1u);
         const int pl = lower ? 31 - C3G_CLZ(lower) : -1;    // lane of the previous non-deletion op
         const int pred_node = C3G_SHFL(gmask, node_id, gbase + (pl < 0 ? 0 : pl));
@@ -830,7 +935,7 @@ C3G_FN int c3g_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const int n
                 }
             }
         }
-        const unsigned m_cx = m_nondel & ~((C3G_BALLOT(gmask, done) >> gbase) & 0xffu);
+        const unsigned m_cx = m_nondel & ~((C3G_BALLOT(gmask, done) >> gbase) & C3G_LMASK(GL));
         C3G_SYNC(gmask);
         if (m_cx) {
             if (li == 0) {
@@ -911,12 +1016,13 @@ C3G_FN int c3g_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const int n
 
 // new order = stable merge of the old order with the new nodes by gap: the t-th new node (id n_old + t, gap g)
 // lands at g + t, an old node at position p moves up by the number of new nodes with gap <= p
+template <int GL>
 C3G_FN void c3g_reorder(c3g_grp &G, const c3g_ws &W, const int li, const unsigned gmask)
 {
     const int n_old = G.n, m = G.node_n - n_old;
     const uint16_t *oo = W.order[G.ob];
     uint16_t *on = W.order[G.ob ^ 1];
-    const int cs = (n_old + C3G_GL - 1) / C3G_GL;
+    const int cs = (n_old + GL - 1) / GL;
     const int ps = li * cs, pe = min(n_old, ps + cs);
     int t = 0;
     if (ps > 0) {                                                // first t with gaps[t] > ps - 1
@@ -976,94 +1082,140 @@ C3G_FN int c3g_consensus(const c3g_grp &G, const c3_poa_args &A, const c3g_ws &W
 }
 
 // ---------------------------------------------------------------------------
-// the warp body: persistent, each group fetches its own items
+// Two kernels per alignment, all reads of a wave resident in HBM (state, graph workspace and arena per read):
+//   graph kernel  per read: [first launch: first sequence -> graph] or [backtrack + merge + reorder of the alignment
+//                 the DP kernel just finished]; then `prepare` for the next sequence, or -- after the last one --
+//                 heaviest bundling + outputs.  Pointer chasing: few registers, many resident warps.
+//   DP kernel     per read: source row + all rows of the prepared alignment.  One flat loop: a group that finishes
+//                 its read fetches the next one while the other groups of the warp keep computing rows.
+// Host: graph, (DP, graph) x (most sequences of a read - 1); every launch has its own work counter.
 // ---------------------------------------------------------------------------
-C3G_FN void c3g_warp_body(const c3g_args &L, uint8_t *smem_warp, const int gwarp, const int lane)
+struct c3g_state {                    // per read (work index), 48 bytes
+    int32_t item, sq, nseq, node_n, pool_n, err, ob, qlen, n, w;
+    long long cells_total;
+};
+
+C3G_FN void c3g_state_load(c3g_grp &G, const c3g_state *S, const c3_poa_args &A)
+{
+    G.item = S->item; G.sq = S->sq; G.nseq = S->nseq; G.node_n = S->node_n; G.pool_n = S->pool_n; G.err = S->err;
+    G.ob = S->ob; G.qlen = S->qlen; G.n = S->n; G.w = S->w; G.cells_total = S->cells_total;
+    G.ibase = A.codes + A.item_base[G.item];
+    G.bnd = A.bounds + (int64_t)G.item * A.max_seqs * 2;
+    G.q = G.ibase + G.bnd[2 * (G.sq < G.nseq ? G.sq : 0)];
+}
+C3G_FN void c3g_state_store(const c3g_grp &G, c3g_state *S)
+{
+    S->item = G.item; S->sq = G.sq; S->nseq = G.nseq; S->node_n = G.node_n; S->pool_n = G.pool_n; S->err = G.err;
+    S->ob = G.ob; S->qlen = G.qlen; S->n = G.n; S->w = G.w; S->cells_total = G.cells_total;
+}
+
+template <int GL>
+C3G_FN void c3g_graph_body(const c3g_args &L, uint8_t *smem_warp, const int lane)
+{
+    const c3_poa_args &A = L.A;
+    const c3_poa_para_dev P = A.P;
+    const int li = lane & (GL - 1), gbase = lane & ~(GL - 1) & 31, grp = lane / GL;
+    const unsigned gmask = C3G_LMASK(GL) << gbase;
+    uint8_t *sg = smem_warp + (size_t)grp * C3G_GRAPH_SMEM(GL);
+    for (;;) {
+        int it = 0;
+        if (li == 0) it = (int)C3G_ATOMIC_INC(A.counter);
+        it = C3G_SHFL(gmask, it, gbase);
+        if (it >= A.n_work) break;
+        c3g_state *S = L.state + it;
+        const c3g_ws W = c3g_ws_carve(L.ws + (int64_t)it * L.ws_stride, A.node_cap, A.pool_cap, A.cigar_cap);
+        uint4 *arena = L.arena + (int64_t)it * L.arena_stride4;
+        c3g_grp G;
+        if (L.first) {
+            c3g_item_begin<GL>(G, A, W, A.order ? A.order[it] : it, li);
+            C3G_SYNC(gmask);
+        } else {
+            c3g_state_load(G, S, A);
+            if (G.err || G.sq >= G.nseq) continue;                 // declined earlier / finished earlier
+            const int nc = c3g_backtrack<GL>(G, L, P, W, arena, sg, li, gbase, gmask);
+            if (nc < 0) { C3G_DECLINE(); G.err = C3G_E_RETRY; }
+            else if (c3g_merge<GL>(G, L, W, nc, li, gbase, gmask)) { C3G_DECLINE(); G.err = C3G_E_RETRY; }
+            else { c3g_reorder<GL>(G, W, li, gmask); ++G.sq; }
+        }
+        if (!G.err && G.sq < G.nseq) c3g_prepare<GL>(G, A, P, W, reinterpret_cast<uint16_t *>(sg), li, gbase, gmask);
+        else if (!G.err) {
+            char *co = A.cons + (int64_t)G.item * A.cons_cap;
+            int r = 0;
+            if (li == 0) r = c3g_consensus(G, A, W, co);
+            r = C3G_SHFL(gmask, r, gbase);
+            if (r >= 0 && li == 0) {
+                const int64_t o = (int64_t)G.item * A.out_stride;
+                A.status[o] = 0;
+                A.cons_len[o] = r;
+                A.nodes_out[o] = G.node_n;
+                *(long long *)((int32_t *)A.cells_out + (int64_t)G.item * A.cells_stride) = G.cells_total;
+                L.done[G.item] = 1;
+            }
+            if (r < 0) G.err = C3G_E_RETRY;
+        }
+        if (li == 0) c3g_state_store(G, S);
+        C3G_SYNC(gmask);
+    }
+}
+
+template <int RVS, bool MULTI>
+C3G_FN void c3g_dp_body(const c3g_args &L, uint8_t *smem_warp, const int lane)
 {
     const c3_poa_args &A = L.A;
     const c3_poa_para_dev P = A.P;
     const int li = lane & 7, gbase = lane & 24, grp = lane >> 3;
     const unsigned gmask = 0xffu << gbase;
-    const int64_t gid = (int64_t)gwarp * 4 + grp;
-    const c3g_ws W = c3g_ws_carve(L.ws + gid * L.ws_stride, A.node_cap, A.pool_cap, A.cigar_cap);
-    uint4 *arena = L.arena + gid * L.arena_stride4;
-    uint8_t *sg = smem_warp + (size_t)grp * c3g_smem_group_bytes(L.rv_shift);
+    uint8_t *sg = smem_warp + (size_t)grp * c3g_smem_group_bytes(RVS);
     uint4 *ring = reinterpret_cast<uint4 *>(sg);
-    uint2 *srr = reinterpret_cast<uint2 *>(sg + (C3G_R * 6 * 16 << L.rv_shift));
-    uint16_t *hw = reinterpret_cast<uint16_t *>(sg);           // prepare only (the ring is idle then)
+    uint2 *srr = reinterpret_cast<uint2 *>(sg + (C3G_R * 6 * 16 << RVS));
+#if defined(__CUDA_ARCH__)
+    __builtin_assume(__isShared(ring)); __builtin_assume(__isShared(srr));
+#endif
     c3g_grp G;
-    G.item = -1; G.err = 0; G.sq = 0; G.nseq = 0; G.node_n = 0; G.pool_n = 0; G.ob = 0; G.cells_total = 0;
-    bool exhausted = false;
+    G.item = -1; G.err = 0; G.n = 0; G.qlen = 0; G.w = 0; G.cells_total = 0;
+    c3g_ws W = c3g_ws_carve(L.ws, A.node_cap, A.pool_cap, A.cigar_cap);
+    uint4 *arena = L.arena;
+    c3g_state *S = L.state;
+    bool have = false, exhausted = false;
+    int pos = 0;
+    uint2 rprev = make_uint2(0u, 0u);
+    uint4 dn = make_uint4(0u, 0u, 0u, 0u);
     for (;;) {
-        if (G.item < 0 && !exhausted) {
+        if (!have && !exhausted) {
             int it = 0;
             if (li == 0) it = (int)C3G_ATOMIC_INC(A.counter);
             it = C3G_SHFL(gmask, it, gbase);
             if (it >= A.n_work) exhausted = true;
             else {
-                c3g_item_begin(G, A, W, A.order ? A.order[it] : it, li);
-                C3G_SYNC(gmask);
-            }
-        }
-        if (!C3G_ANYG(C3_FULL, G.item >= 0)) break;
-        const bool act = G.item >= 0;
-        // ---- one alignment (or, for a single-sequence item, nothing) per trip ----
-        bool aligning = act && !G.err && G.sq < G.nseq;
-        if (aligning) {
-            c3g_prepare(G, A, P, W, hw, li, gbase, gmask);
-            if (G.err) aligning = false;
-        }
-        C3G_SYNC(C3_FULL);
-        if (aligning) {
-            c3g_source_row(G, L, P, W, ring, srr, arena, li, gmask);
-            C3G_SYNC(gmask);
-            if (!G.err) {
-                const int n = G.n;
-                uint4 dmine = make_uint4(0u, 0u, 0u, 0u);
-                for (int pos = 1; pos < n - 1; ++pos) {
-                    if (((pos - 1) & 7) == 0) { const int p = pos + li; if (p < n) dmine = W.desc[p]; }
-                    const int src = gbase + ((pos - 1) & 7);
-                    uint4 d;
-                    d.x = (uint32_t)C3G_SHFL(gmask, dmine.x, src); d.y = (uint32_t)C3G_SHFL(gmask, dmine.y, src);
-                    d.z = (uint32_t)C3G_SHFL(gmask, dmine.z, src); d.w = 0u;
-                    const int wd = c3g_row(G, L, P, W, ring, srr, arena, pos, d, li, gbase, gmask);
-                    if (wd <= 0) break;
-                    G.cells_total += wd;
+                S = L.state + it;
+                c3g_state_load(G, S, A);
+                if (!G.err && G.sq < G.nseq) {
+                    W = c3g_ws_carve(L.ws + (int64_t)it * L.ws_stride, A.node_cap, A.pool_cap, A.cigar_cap);
+                    arena = L.arena + (int64_t)it * L.arena_stride4;
+                    c3g_source_row<RVS>(G, L, P, W, ring, srr, arena, rprev, li, gmask);
+                    C3G_SYNC(gmask);
+                    if (G.err) { if (li == 0) S->err = G.err; }
+                    else { have = true; pos = 1; dn = W.desc[1]; }
                 }
             }
-            if (G.err) aligning = false;
         }
-        C3G_SYNC(C3_FULL);
-        int nc = 0;
-        if (aligning) {
-            nc = c3g_backtrack(G, L, P, W, arena, li, gbase, gmask);
-            if (nc < 0) { C3G_DECLINE(); G.err = C3G_E_RETRY; aligning = false; }
+        if (!C3G_ANYG(C3_FULL, have)) {
+            if (!C3G_ANYG(C3_FULL, !exhausted)) break;
+            continue;
         }
-        C3G_SYNC(C3_FULL);
-        if (aligning) {
-            if (c3g_merge(G, L, W, nc, li, gbase, gmask)) { C3G_DECLINE(); G.err = C3G_E_RETRY; aligning = false; }
-            else { c3g_reorder(G, W, li, gmask); ++G.sq; }
-        }
-        C3G_SYNC(C3_FULL);
-        // ---- item end ----
-        if (act && (G.err || G.sq >= G.nseq)) {
-            if (!G.err) {
-                char *co = A.cons + (int64_t)G.item * A.cons_cap;
-                int r = 0;
-                if (li == 0) r = c3g_consensus(G, A, W, co);
-                r = C3G_SHFL(gmask, r, gbase);
-                if (r >= 0 && li == 0) {
-                    const int64_t o = (int64_t)G.item * A.out_stride;
-                    A.status[o] = 0;
-                    A.cons_len[o] = r;
-                    A.nodes_out[o] = G.node_n;
-                    *(long long *)((int32_t *)A.cells_out + (int64_t)G.item * A.cells_stride) = G.cells_total;
-                    L.done[G.item] = 1;
+        {
+            const uint4 d = dn;
+            if (have) dn = W.desc[pos + 1];
+            const int wd = c3g_row<RVS, MULTI>(G, L, P, W, ring, srr, arena, pos, d, rprev, have, li, gbase);
+            if (have) {
+                G.cells_total += wd;
+                ++pos;
+                if (G.err || pos >= G.n - 1) {
+                    if (li == 0) { S->err = G.err; S->cells_total = G.cells_total; }
+                    have = false;
                 }
             }
-            G.item = -1; G.err = 0;
         }
-        C3G_SYNC(C3_FULL);
     }
 }
 
@@ -1074,11 +1226,23 @@ C3G_FN void c3g_warp_body(const c3g_args &L, uint8_t *smem_warp, const int gwarp
 #ifndef C3G_MINB
 #define C3G_MINB 4
 #endif
-__global__ void __launch_bounds__(C3G_THREADS, C3G_MINB) c3_poa_grp_kernel(c3g_args L)
+#ifndef C3G_GRAPH_MINB
+#define C3G_GRAPH_MINB 6
+#endif
+template <int RVS, bool MULTI>
+__global__ void __launch_bounds__(C3G_THREADS, C3G_MINB) c3_poa_grp_dp_kernel(c3g_args L)
 {
     extern __shared__ uint4 c3g_smem[];
     const int wib = threadIdx.x >> 5;
-    uint8_t *sw = reinterpret_cast<uint8_t *>(c3g_smem) + (size_t)wib * 4 * c3g_smem_group_bytes(L.rv_shift);
-    c3g_warp_body(L, sw, blockIdx.x * (blockDim.x >> 5) + wib, threadIdx.x & 31);
+    uint8_t *sw = reinterpret_cast<uint8_t *>(c3g_smem) + (size_t)wib * 4 * c3g_smem_group_bytes(RVS);
+    c3g_dp_body<RVS, MULTI>(L, sw, threadIdx.x & 31);
+}
+#define C3G_GRAPH_GL 32
+__global__ void __launch_bounds__(C3G_THREADS, C3G_GRAPH_MINB) c3_poa_grp_graph_kernel(c3g_args L)
+{
+    extern __shared__ uint4 c3g_smem[];
+    const int wib = threadIdx.x >> 5;
+    uint8_t *sw = reinterpret_cast<uint8_t *>(c3g_smem) + (size_t)wib * (32 / C3G_GRAPH_GL) * C3G_GRAPH_SMEM(C3G_GRAPH_GL);
+    c3g_graph_body<C3G_GRAPH_GL>(L, sw, threadIdx.x & 31);
 }
 #endif

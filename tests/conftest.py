@@ -15,8 +15,8 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", params=["auto", "lane"])
 def gpu(request):
     """The CUDA handle.  No skip: on a GPU box a missing library/device must FAIL the test.
-    Every GPU test runs twice: POA through the warp-per-read kernel ("auto" picks it for small batches) and
-    through the thread-per-read lane kernel (with the warp kernel as its fallback)."""
+    Every GPU test runs twice: POA through the group kernel ("auto": 8 lanes per read, the warp-per-read kernel takes
+    what it declines) and through the thread-per-read lane kernel (same fallback)."""
     from c3poa_b200.api import GpuConsensus
     h = GpuConsensus(0, poa_mode=request.param)
     h.poa_mode = request.param

@@ -16,18 +16,21 @@ extern "C" void c3g_emul_note(int line)
 }
 
 namespace {
-struct WarpArg { const c3g_args *L; uint8_t *smem; int gwarp; };
+struct WarpArg { const c3g_args *L; uint8_t *smem; int kind, gl; };
 void warp_lane(void *p, int lane)
 {
     const WarpArg *a = (const WarpArg *)p;
-    c3g_warp_body(*a->L, a->smem, a->gwarp, lane);
+    if (a->kind == 0) { if (a->gl == 32) c3g_graph_body<32>(*a->L, a->smem, lane); else c3g_graph_body<8>(*a->L, a->smem, lane); }
+    else if (a->L->vs_shift == 3) c3g_dp_body<3, false>(*a->L, a->smem, lane);
+    else if (a->L->rv_shift == 3) c3g_dp_body<3, true>(*a->L, a->smem, lane);
+    else c3g_dp_body<4, true>(*a->L, a->smem, lane);
 }
 }
 
 extern "C" int c3g_emul_batch(int n_items, const uint8_t *codes, const int64_t *item_base, const int32_t *bounds,
                               const int32_t *n_seqs, int max_seqs, int min_seqs, int msa2,
                               int match, int mismatch, int o1, int e1, int o2, int e2, int wb, double wf, int simd_bits,
-                              int node_cap, int cigar_cap, int qp_stride, int vs_shift, int rv_shift, int n_warps,
+                              int node_cap, int cigar_cap, int qp_stride, int vs_shift, int rv_shift, int n_warps, int graph_gl,
                               char *cons, int cons_cap, int32_t *status, int32_t *cons_len, int32_t *nodes_out,
                               long long *cells_out, int32_t *done)
 {
@@ -42,27 +45,37 @@ extern "C" int c3g_emul_batch(int n_items, const uint8_t *codes, const int64_t *
     A.cons = cons; A.cons_cap = cons_cap; A.status = status; A.cons_len = cons_len; A.nodes_out = nodes_out;
     A.cells_out = cells_out; A.out_stride = 1; A.cells_stride = 2;
     A.n_work = n_items;
-    unsigned counter = 0;
-    A.counter = &counter;
-    const int n_groups = n_warps * 4;
+    int max_nseq = 1;
+    for (int i = 0; i < n_items; ++i) if (n_seqs[i] > max_nseq) max_nseq = n_seqs[i];
+    std::vector<unsigned> counters((size_t)2 * max_nseq + 2, 0u);
     const int64_t ws_bytes = c3g_ws_bytes(node_cap, node_cap, cigar_cap, qp_stride);
     const int64_t arena4 = ((int64_t)node_cap << vs_shift) * 3;
-    uint8_t *ws = (uint8_t *)aligned_alloc(256, (size_t)ws_bytes * n_groups);
-    uint4 *arena = (uint4 *)aligned_alloc(256, (size_t)arena4 * 16 * n_groups);
-    const size_t smw = (size_t)4 * c3g_smem_group_bytes(rv_shift);
+    uint8_t *ws = (uint8_t *)aligned_alloc(256, (size_t)ws_bytes * n_items);
+    uint4 *arena = (uint4 *)aligned_alloc(256, (size_t)arena4 * 16 * n_items);
+    size_t smw = (size_t)4 * c3g_smem_group_bytes(rv_shift);
+    if (smw < (size_t)4 * C3G_GRAPH_SMEM(8)) smw = (size_t)4 * C3G_GRAPH_SMEM(8);
+    if (smw < (size_t)C3G_GRAPH_SMEM(32)) smw = (size_t)C3G_GRAPH_SMEM(32);
     uint8_t *smem = (uint8_t *)aligned_alloc(256, (smw * n_warps + 255) & ~(size_t)255);
+    std::vector<c3g_state> state((size_t)n_items);
     if (!ws || !arena || !smem) return -1;
-    memset(ws, 0xA5, (size_t)ws_bytes * n_groups);              // poison: nothing may depend on zeroed memory
-    memset(arena, 0xA5, (size_t)arena4 * 16 * n_groups);
+    memset(ws, 0xA5, (size_t)ws_bytes * n_items);               // poison: nothing may depend on zeroed memory
+    memset(arena, 0xA5, (size_t)arena4 * 16 * n_items);
     memset(smem, 0xA5, smw * n_warps);
+    memset(state.data(), 0xA5, state.size() * sizeof(c3g_state));
     L.ws = ws; L.ws_stride = ws_bytes; L.arena = arena; L.arena_stride4 = arena4;
-    L.vs_shift = vs_shift; L.rv_shift = rv_shift; L.done = done;
-    int rc = 0;
-    // warps run one after the other; they only share the work counter
-    for (int w = 0; w < n_warps && !rc; ++w) {
-        WarpArg a{&L, smem + smw * w, w};
-        rc = c3emu_run_warp(warp_lane, &a);
-    }
+    L.vs_shift = vs_shift; L.rv_shift = rv_shift; L.done = done; L.state = state.data();
+    int rc = 0, launch = 0;
+    // the host's launch sequence: graph (first), then (DP, graph) per further sequence; the warps of a launch run one
+    // after the other (they only share the launch's work counter)
+    auto run = [&](int kind, int first) {
+        L.first = first; L.A.counter = &counters[launch++];
+        for (int w = 0; w < n_warps && !rc; ++w) {
+            WarpArg a{&L, smem + smw * w, kind, graph_gl};
+            rc = c3emu_run_warp(warp_lane, &a);
+        }
+    };
+    run(0, 1);
+    for (int sq = 1; sq < max_nseq && !rc; ++sq) { run(1, 0); run(0, 0); }
     free(ws); free(arena); free(smem);
     return rc;
 }

@@ -12,6 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <csignal>
+#include <execinfo.h>
+#include <unistd.h>
 
 extern "C" void c3emu_switch(void **save_sp, void *load_sp);
 asm(R"(
@@ -42,7 +45,7 @@ constexpr int kLanes = 32;
 constexpr size_t kStack = 1 << 20;
 
 struct Fiber { void *sp; char *stack; bool done; unsigned wait_mask; };
-struct Coll { unsigned mask; int arrived; unsigned gen; long long val[2][kLanes]; };
+struct Coll { unsigned mask; int arrived; unsigned gen; long long val[2][kLanes]; int tag[2]; };
 
 Fiber g_f[kLanes];
 void *g_sched_sp;
@@ -74,12 +77,19 @@ Coll *find(unsigned mask)
     return c;
 }
 
-long long collective(unsigned mask, long long v, int src, bool want_ballot)
+long long collective(unsigned mask, long long v, int src, bool want_ballot, int tag)
 {
     const int lane = g_cur;
     if (!((mask >> lane) & 1u)) { fprintf(stderr, "warp_emu: lane %d not in its own mask %08x\n", lane, mask); abort(); }
     Coll *c = find(mask);
     const unsigned my = c->gen;
+    // every lane of a rendezvous must come from the same call site: lanes meeting at DIFFERENT collectives is a
+    // deadlock (or undefined behaviour) on the GPU
+    if (c->arrived == 0) c->tag[my & 1] = tag;
+    else if (c->tag[my & 1] != tag) {
+        fprintf(stderr, "warp_emu: lanes of mask %08x meet at different collectives (source lines %d and %d, lane %d)\n", mask, c->tag[my & 1], tag, lane);
+        abort();
+    }
     c->val[my & 1][lane] = v;
     if (++c->arrived == __builtin_popcount(mask)) { c->arrived = 0; c->gen++; ++g_progress; }
     else {
@@ -99,16 +109,25 @@ long long collective(unsigned mask, long long v, int src, bool want_ballot)
 }
 }  // namespace
 
+static void segv_handler(int sig)
+{
+    void *bt[32];
+    const int n = backtrace(bt, 32);
+    fprintf(stderr, "warp_emu: signal %d in lane %d\n", sig, g_cur);
+    backtrace_symbols_fd(bt, n, 2);
+    _exit(139);
+}
 extern "C" {
 int c3emu_lane(void) { return g_cur; }
-int c3emu_shfl(unsigned mask, int v, int src) { return (int)collective(mask, v, src, false); }
-unsigned c3emu_ballot(unsigned mask, int pred) { return (unsigned)collective(mask, pred ? 1 : 0, -1, true); }
-void c3emu_sync(unsigned mask) { (void)collective(mask, 0, -1, false); }
+int c3emu_shfl(unsigned mask, int v, int src, int tag) { return (int)collective(mask, v, src, false, tag); }
+unsigned c3emu_ballot(unsigned mask, int pred, int tag) { return (unsigned)collective(mask, pred ? 1 : 0, -1, true, tag); }
+void c3emu_sync(unsigned mask, int tag) { (void)collective(mask, 0, -1, false, tag); }
 
 // runs body(arg, lane) for the 32 lanes of one warp to completion; returns 0, or -1 on a deadlock
 int c3emu_run_warp(void (*body)(void *, int), void *arg)
 {
     g_body = body; g_arg = arg; g_ncoll = 0; g_progress = 0;
+    if (getenv("C3EMU_BACKTRACE")) { signal(SIGSEGV, segv_handler); signal(SIGBUS, segv_handler); }
     for (int l = 0; l < kLanes; ++l) {
         Fiber &f = g_f[l];
         if (!f.stack) f.stack = (char *)aligned_alloc(64, kStack);

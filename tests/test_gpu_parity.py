@@ -121,7 +121,8 @@ def test_poa_parity(gpu, oracle):
 
 
 def test_lane_kernel_serves_what_it_covers(gpu, oracle):
-    """In lane mode the thread-per-read kernel finishes every plain consensus group itself (no silent fallback)."""
+    """The fast kernel of the mode (auto: group kernel, lane: thread-per-read kernel) finishes every plain consensus
+    group itself (no silent fallback to the warp kernel)."""
     rng = np.random.default_rng(12)
     groups = []
     for L in rng.integers(40, 1500, size=100):
@@ -129,10 +130,7 @@ def test_lane_kernel_serves_what_it_covers(gpu, oracle):
         groups.append([synth.mutate(rng, a).tobytes().decode() for _ in range(int(rng.integers(3, 8)))])
     r = gpu.poa_batch(groups)
     given, done = gpu.lane_counts()
-    if gpu.poa_mode == "lane":
-        assert (given, done) == (len(groups), len(groups))
-    else:
-        assert given == 0
+    assert (given, done) == (len(groups), len(groups))          # auto: the group kernel; lane: the lane kernel
     for i in range(0, len(groups), 7):
         o = oracle.poa_msa(groups[i])
         assert r["status"][i] == 0 and r["cons"][i] == o["cons"] and r["cells"][i] == o["cells"] and r["nodes"][i] == o["node_n"], i
@@ -425,8 +423,8 @@ def test_cfg5_like_mixed_batch_properties(gpu, oracle):
 
 
 def test_lane_and_warp_kernels_agree_at_scale(gpu):
-    """45 000 cfg2 reads: `auto` hands a batch of this size to the thread-per-read lane kernel; the warp-per-read kernel
-    must return the same bytes for every read (status, peaks, bounds, consensus, DP cell counts, graph sizes)."""
+    """45 000 cfg2 reads: `auto` hands the batch to the group kernel; the warp-per-read kernel must return the same
+    bytes for every read (status, peaks, bounds, consensus, DP cell counts, graph sizes)."""
     if gpu.poa_mode != "auto":
         pytest.skip("runs once, switching modes itself")
     blob, off, strand = synth.make_batch(45000, insert_len=1000, repeats=5, seed=77)
@@ -436,7 +434,7 @@ def test_lane_and_warp_kernels_agree_at_scale(gpu):
     try:
         a = gpu.consensus_batch(b, max_peaks=16, cons_cap=2048)
         given, done = gpu.lane_counts()
-        assert given >= 44000 and done == given, (given, done)          # the lane kernel ran, and finished all it took
+        assert given >= 44000 and done == given, (given, done)          # the group kernel ran, and finished all it took
         a = {k: np.array(v, copy=True) for k, v in a.items()}
         gpu.set_poa_mode("warp")
         w = gpu.consensus_batch(b, max_peaks=16, cons_cap=2048)

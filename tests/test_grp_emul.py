@@ -43,7 +43,7 @@ def emul():
     return build_emul()
 
 
-def run_emul(lib, groups, para=None, msa2=0, min_seqs=1, node_cap=None, vs_shift=None, rv_shift=3, n_warps=1):
+def run_emul(lib, groups, para=None, msa2=0, min_seqs=1, node_cap=None, vs_shift=None, rv_shift=3, n_warps=1, graph_gl=32):
     n = len(groups)
     max_seqs = max(len(g) for g in groups)
     blob = []
@@ -88,11 +88,11 @@ def run_emul(lib, groups, para=None, msa2=0, min_seqs=1, node_cap=None, vs_shift
     lib.c3g_emul_batch.restype = C.c_int
     lib.c3g_emul_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
-                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     rc = lib.c3g_emul_batch(n, codes.ctypes.data, item_base.ctypes.data, bounds.ctypes.data, nseq.ctypes.data, max_seqs,
                             min_seqs, msa2, p["match"], p["mismatch"], p["o1"], p["e1"], p["o2"], p["e2"], p["wb"],
-                            p["wf"], p["simd_bits"], node_cap, cigar_cap, qp_stride, vs_shift, rv_shift, n_warps,
+                            p["wf"], p["simd_bits"], node_cap, cigar_cap, qp_stride, vs_shift, rv_shift, n_warps, graph_gl,
                             cons.ctypes.data, cons_cap, status.ctypes.data, clen.ctypes.data, nodes.ctypes.data,
                             cells.ctypes.data, done.ctypes.data)
     assert rc == 0, "warp emulator reported a deadlock"
