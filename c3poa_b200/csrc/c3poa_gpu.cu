@@ -457,7 +457,7 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     const int64_t budget = (int64_t)((double)(free_b + h->d_ws_grp.cap) * 0.7);
     int64_t wave = std::min<int64_t>(ng, budget / read_bytes);
     if (wave < 64) return 0;                                       // does not fit: the warp kernel takes everything
-    const int n_counters = 2 * max_nseq + 2;
+    const int n_counters = 2 * max_nseq + 3;
     CK(h->d_ws_grp.ensure((size_t)(wave * read_bytes) + (size_t)n_counters * 4 + 256));
     CK(h->d_done.ensure((size_t)A.n_items * 4));
     CK(cudaMemsetAsync(h->d_done.p, 0, (size_t)A.n_items * 4, h->stream));
@@ -493,6 +493,9 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
             c3_poa_grp_graph_kernel<<<grid_gr, C3G_THREADS, sm_gr, h->stream>>>(L);
             h->tim.kernel_launches += 2;
         }
+        L.A.counter = counters + launch++;
+        c3_poa_grp_finish_kernel<<<grid_dp, C3G_THREADS, (size_t)wpb * 4 * C3G_FIN_SMEM, h->stream>>>(L);
+        h->tim.kernel_launches++;
         CK(cudaGetLastError());
     }
     h->lane_items = ng; h->lane_n_items = A.n_items;

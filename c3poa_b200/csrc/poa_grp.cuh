@@ -38,9 +38,9 @@
 #define C3G_E_RETRY (-298)
 // graph kernel: GL lanes per read (32: one warp per read, constant member masks; 8: four reads per warp)
 #define C3G_HWIN(GL) ((GL) == 32 ? 1024 : 512)   // window of remaining-length words kept in shared memory during prepare
-#define C3G_BTK(GL) ((GL) == 32 ? 48 : 16)       // rows per backtrack window
-#define C3G_BTV(GL) ((GL) == 32 ? 15 : 7)        // rows below the current one that a verification trip wants in the window
-#define C3G_GRAPH_SMEM(GL) ((GL) == 32 ? 5760 : 2048)   // shared memory per read of the graph kernel: max(HWIN * 2, BTK * 120)
+#define C3G_BTK(GL) ((GL) == 32 ? 64 : 16)       // rows per backtrack window
+#define C3G_BTV(GL) ((GL) == 32 ? 31 : 7)        // rows below the current one that a verification trip wants in the window
+#define C3G_GRAPH_SMEM(GL) ((GL) == 32 ? 7680 : 2048)   // shared memory per read of the graph kernel: max(HWIN * 2, BTK * 120)
 #define C3G_LMASK(GL) ((GL) == 32 ? 0xffffffffu : ((1u << ((GL) & 31)) - 1u))
 #define C3G_LOG2(GL) ((GL) == 32 ? 5 : 3)
 
@@ -710,30 +710,53 @@ C3G_FN int c3g_backtrack(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P
     while (pos != 0 && j > 0) {
         if (pos > B.top || (pos - C3G_BTV(GL) < B.bot && B.bot > 0)) c3g_bt_fill<GL>(B, sg, W, arena, vs, pos, j, li, gmask);
         if (cur_op == C3_OP_ALL) {
-            // lane l looks at row pos - l, column j - l
-            const int pl = pos - li, jl = j - li;
+            // Window slot w = lane <-> position pos - w.  The chain of FIRST predecessors inside the slots is resolved
+            // by pointer doubling over shuffles (it runs on through the bubbles of the graph); lane t then looks at the
+            // t-th row of the chain at column j - t, and the leading run of verified match/mismatch moves is taken at once.
+            const int pw = pos - li;
             uint4 dl = make_uint4(0u, 0u, 0u, 0u); uint2 rl = make_uint2(1u, 0u);
-            int hl = C3_NEG_INF;
-            if (pl >= 0) {
-                dl = c3g_bt_desc(B, W, pl); rl = c3g_bt_rec(B, W, pl);
-                if (jl >= 0) hl = c3g_bt_h(B, arena, vs, pl, jl);
+            if (pw >= 0) { dl = c3g_bt_desc(B, W, pw); rl = c3g_bt_rec(B, W, pw); }
+            int f = GL;                                        // slot of this row's first predecessor; GL = outside / none
+            if (pw >= 1) { const int dlt = pos - C3G_D_P0(dl); if (dlt < GL) f = dlt; }
+            int tbl[C3G_LOG2(GL)];
+            tbl[0] = f;
+#pragma unroll
+            for (int b2 = 1; b2 < C3G_LOG2(GL); ++b2) {
+                const int prev = tbl[b2 - 1];
+                const int nx = C3G_SHFL(gmask, prev, gbase + (prev & (GL - 1)));
+                tbl[b2] = prev < GL ? nx : GL;
             }
-            const int bl = C3G_R_BEG(rl) * 16, el = min(qlen, C3G_R_END(rl) * 16 + 15);
-            if (jl < bl || jl > el) hl = C3_NEG_INF;
-            const int src = gbase + ((li + 1) & (GL - 1));
-            const int hn = C3G_SHFL(gmask, hl, src), bn = C3G_SHFL(gmask, bl, src), en = C3G_SHFL(gmask, el, src);
-            bool ok = li < GL - 1 && pl >= 1 && jl >= 1 && jl >= bl && jl <= el && C3G_D_P0(dl) == pl - 1;
+            int sl = 0;                                        // slot of the t-th row of the chain (t = lane)
+#pragma unroll
+            for (int b2 = 0; b2 < C3G_LOG2(GL); ++b2) {
+                const int nx = C3G_SHFL(gmask, tbl[b2], gbase + (sl & (GL - 1)));
+                if ((li >> b2) & 1) sl = sl < GL ? nx : GL;
+            }
+            const bool have = sl < GL;
+            const int srcl = gbase + (sl & (GL - 1));
+            const uint32_t cdx = (uint32_t)C3G_SHFL(gmask, dl.x, srcl), cdz = (uint32_t)C3G_SHFL(gmask, dl.z, srcl);
+            const uint32_t crx = (uint32_t)C3G_SHFL(gmask, rl.x, srcl);
+            const int pc = pos - sl, jt = j - li;              // chain row t: position, column
+            const int bl = (int)(crx & 0xffffu) * 16, el = min(qlen, (int)(crx >> 16) * 16 + 15);
+            const bool inb = have && jt >= 1 && jt >= bl && jt <= el;
+            int ht = C3_NEG_INF;
+            if (inb) ht = c3g_bt_h(B, arena, vs, pc, jt);
+            const int nxl = gbase + ((li + 1) & (GL - 1));
+            const int hn = C3G_SHFL(gmask, ht, nxl), bn = C3G_SHFL(gmask, bl, nxl), en = C3G_SHFL(gmask, el, nxl);
+            const int haven = C3G_SHFL(gmask, (int)have, nxl);
+            bool ok = li < GL - 1 && inb && haven && pc >= 1;
             if (ok) {
-                const int s = c3_score(P, C3G_D_BASE(dl), q[jl - 1]);
-                ok = jl - 1 >= max(bn, bl) && jl - 1 <= en && hn + s == hl;
+                const int st = c3_score(P, (int)(cdz & 0xffu), q[jt - 1]);
+                ok = jt - 1 >= max(bn, bl) && jt - 1 <= en && ht == hn + st;
             }
             const unsigned okm = (C3G_BALLOT(gmask, ok) >> gbase) & C3G_LMASK(GL);
             int Lr = C3G_FFS(~okm) - 1;
             Lr = min(Lr, cap - 8 - j - nc);
             if (Lr > 0) {
-                if (li < Lr) cg[nc + li] = C3_CG_MATCH | ((unsigned long long)C3G_D_ID(dl) << 8) | ((unsigned long long)(jl - 1) << 32);
-                nc += Lr; j -= Lr; pos -= Lr;
-                hij = C3G_SHFL(gmask, hl, gbase + Lr);
+                if (li < Lr) cg[nc + li] = C3_CG_MATCH | ((unsigned long long)(cdx & 0xffffu) << 8) | ((unsigned long long)(jt - 1) << 32);
+                nc += Lr; j -= Lr;
+                pos -= C3G_SHFL(gmask, sl, gbase + Lr);
+                hij = C3G_SHFL(gmask, ht, gbase + Lr);
                 continue;
             }
         }
@@ -1084,11 +1107,12 @@ C3G_FN int c3g_consensus(const c3g_grp &G, const c3_poa_args &A, const c3g_ws &W
 // ---------------------------------------------------------------------------
 // Two kernels per alignment, all reads of a wave resident in HBM (state, graph workspace and arena per read):
 //   graph kernel  per read: [first launch: first sequence -> graph] or [backtrack + merge + reorder of the alignment
-//                 the DP kernel just finished]; then `prepare` for the next sequence, or -- after the last one --
-//                 heaviest bundling + outputs.  Pointer chasing: few registers, many resident warps.
+//                 the DP kernel just finished]; then `prepare` for the next sequence.  One warp per read (constant
+//                 member masks), few registers, many resident warps.
+//   finish kernel once per wave: heaviest bundling + consensus walk + outputs (c3g_finish_body).
 //   DP kernel     per read: source row + all rows of the prepared alignment.  One flat loop: a group that finishes
 //                 its read fetches the next one while the other groups of the warp keep computing rows.
-// Host: graph, (DP, graph) x (most sequences of a read - 1); every launch has its own work counter.
+// Host: graph, (DP, graph) x (most sequences of a read - 1), finish; every launch has its own work counter.
 // ---------------------------------------------------------------------------
 struct c3g_state {                    // per read (work index), 48 bytes
     int32_t item, sq, nseq, node_n, pool_n, err, ob, qlen, n, w;
@@ -1138,23 +1162,145 @@ C3G_FN void c3g_graph_body(const c3g_args &L, uint8_t *smem_warp, const int lane
             else { c3g_reorder<GL>(G, W, li, gmask); ++G.sq; }
         }
         if (!G.err && G.sq < G.nseq) c3g_prepare<GL>(G, A, P, W, reinterpret_cast<uint16_t *>(sg), li, gbase, gmask);
-        else if (!G.err) {
-            char *co = A.cons + (int64_t)G.item * A.cons_cap;
-            int r = 0;
-            if (li == 0) r = c3g_consensus(G, A, W, co);
-            r = C3G_SHFL(gmask, r, gbase);
-            if (r >= 0 && li == 0) {
-                const int64_t o = (int64_t)G.item * A.out_stride;
-                A.status[o] = 0;
-                A.cons_len[o] = r;
-                A.nodes_out[o] = G.node_n;
-                *(long long *)((int32_t *)A.cells_out + (int64_t)G.item * A.cells_stride) = G.cells_total;
-                L.done[G.item] = 1;
-            }
-            if (r < 0) G.err = C3G_E_RETRY;
-        }
         if (li == 0) c3g_state_store(G, S);
         C3G_SYNC(gmask);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// finish kernel: heaviest bundling (abpoa_heaviest_bundling) + consensus walk + outputs, once per wave.  8 lanes per
+// read, 4 reads per warp in one flat loop with full-warp collectives (like the DP kernel).  Scores are resolved by
+// position in reverse order, 8 positions per step: every lane evaluates its node's out-edges each of the 8 turns, the
+// turn's lane is final (all its successors sit at higher positions) and its score is handed to the lanes before it.
+// ---------------------------------------------------------------------------
+#define C3G_FIN_WIN 512               // window of scores by position kept in shared memory (int32)
+#define C3G_FIN_SMEM (C3G_FIN_WIN * 4)
+#define C3G_FIN_EDGES 8               // out-edges of a node held in registers (more: the read goes to the warp kernel)
+
+C3G_FN void c3g_finish_body(const c3g_args &L, uint8_t *smem_warp, const int lane)
+{
+    const c3_poa_args &A = L.A;
+    const int li = lane & 7, gbase = lane & 24, grp = lane >> 3;
+    const unsigned gmask = 0xffu << gbase;
+    int32_t *sw = reinterpret_cast<int32_t *>(smem_warp + (size_t)grp * C3G_FIN_SMEM);
+    c3g_grp G;
+    G.item = -1; G.err = 0; G.node_n = 2; G.ob = 0; G.cells_total = 0;
+    c3g_ws W = c3g_ws_carve(L.ws, A.node_cap, A.pool_cap, A.cigar_cap);
+    c3g_state *S = L.state;
+    bool have = false, exhausted = false;
+    int pb = 0;
+    for (;;) {
+        if (!have && !exhausted) {
+            int it = 0;
+            if (li == 0) it = (int)C3G_ATOMIC_INC(A.counter);
+            it = C3G_SHFL(gmask, it, gbase);
+            if (it >= A.n_work) exhausted = true;
+            else {
+                S = L.state + it;
+                c3g_state_load(G, S, A);
+                if (!G.err && G.sq >= G.nseq) {
+                    W = c3g_ws_carve(L.ws + (int64_t)it * L.ws_stride, A.node_cap, A.pool_cap, A.cigar_cap);
+                    have = true;
+                    pb = ((G.node_n - 1) / C3G_GL) * C3G_GL;
+                }
+            }
+        }
+        if (!C3G_ANYG(C3_FULL, have)) {
+            if (!C3G_ANYG(C3_FULL, !exhausted)) break;
+            continue;
+        }
+        // ---- one step of 8 positions (a group without a read runs along on its last inputs and stores nothing) ----
+        const bool live = have;
+        const int n = G.node_n;
+        const uint16_t *ord = W.order[G.ob];
+        int32_t *gscore = reinterpret_cast<int32_t *>(W.desc);        // by node id
+        uint32_t *nxt = reinterpret_cast<uint32_t *>(W.rowrec);       // by position: position of the chosen successor | base << 16
+        const int p = pb + li;
+        const bool valid = live && p < n;
+        int v = C3_SINK, nout = 0, base = 4;
+        int o[C3G_FIN_EDGES], wt[C3G_FIN_EDGES], tp[C3G_FIN_EDGES], sc[C3G_FIN_EDGES];
+#pragma unroll
+        for (int k = 0; k < C3G_FIN_EDGES; ++k) { o[k] = C3_SINK; wt[k] = -1; tp[k] = -1; sc[k] = 0; }
+        if (valid) {
+            v = ord[p];
+            const c3_nrec nd = c3_ld_node(&W.nodes[v]);
+            nout = C3_N_OUTN(nd); base = C3_N_BASE(nd);
+            if (nout > C3G_FIN_EDGES) { G.err = C3G_E_RETRY; nout = C3G_FIN_EDGES; }
+            if (nout > 0) { o[0] = C3_N_OUT0(nd); wt[0] = C3_N_W0(nd); }
+            if (nout > 1) {
+                int e = W.nodes[v].out_more;
+#pragma unroll
+                for (int k = 1; k < C3G_FIN_EDGES; ++k) {
+                    if (k < nout && e != (int)C3_NONE) { const c3_pedge pe = W.pool[e]; o[k] = pe.id; wt[k] = pe.w; e = pe.next; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < C3G_FIN_EDGES; ++k) {
+                if (k < nout) {
+                    tp[k] = W.posof[o[k]];
+                    if (tp[k] >= pb + C3G_GL) sc[k] = (tp[k] - pb < C3G_FIN_WIN - C3G_GL) ? sw[tp[k] & (C3G_FIN_WIN - 1)] : gscore[o[k]];
+                }
+            }
+        }
+        int myscore = 0, mybest = 0;
+#pragma unroll
+        for (int r = C3G_GL - 1; r >= 0; --r) {
+            // abpoa_heaviest_bundling: the heaviest out-edge, ties to the later edge whose target scores at least as
+            // much; the source takes the heaviest with strictly larger score on ties
+            int bk = 0, bw = wt[0], bs = sc[0];
+            if (v == C3_SRC) {
+#pragma unroll
+                for (int k = 1; k < C3G_FIN_EDGES; ++k)
+                    if (k < nout && (wt[k] > bw || (wt[k] == bw && sc[k] > bs))) { bk = k; bw = wt[k]; bs = sc[k]; }
+            } else {
+#pragma unroll
+                for (int k = 1; k < C3G_FIN_EDGES; ++k)
+                    if (k < nout && (bw < wt[k] || (bw == wt[k] && bs <= sc[k]))) { bk = k; bw = wt[k]; bs = sc[k]; }
+            }
+            const int mine = (v == C3_SINK || nout == 0) ? 0 : bw + bs;
+            if (li == r) { myscore = mine; mybest = bk; }
+            const int sr = C3G_SHFL(C3_FULL, mine, gbase + r);
+#pragma unroll
+            for (int k = 0; k < C3G_FIN_EDGES; ++k) if (tp[k] == pb + r) sc[k] = sr;
+        }
+        if (valid) {
+            int bo = o[0], bt = tp[0];
+#pragma unroll
+            for (int k = 1; k < C3G_FIN_EDGES; ++k) if (mybest == k) { bo = o[k]; bt = tp[k]; }
+            if (v == C3_SINK || nout == 0) { bo = C3_NONE; bt = 0xffff; }
+            sw[p & (C3G_FIN_WIN - 1)] = myscore;
+            gscore[v] = myscore;
+            W.nodes[v].max_out = (uint16_t)bo;
+            nxt[p] = (uint32_t)(bt & 0xffff) | ((uint32_t)base << 16);
+        }
+        G.err = (C3G_BALLOT(C3_FULL, G.err != 0) & gmask) ? C3G_E_RETRY : 0;
+        C3G_SYNC(C3_FULL);
+        if (have) {
+            pb -= C3G_GL;
+            if (pb < 0 || G.err) {
+                // ---- consensus walk along the chosen successors + outputs (this group alone) ----
+                int cons_len = 0;
+                if (!G.err && li == 0) {
+                    char *co = A.cons + (int64_t)G.item * A.cons_cap;
+                    int cur = (int)(nxt[0] & 0xffffu);
+                    while (cur != n - 1) {
+                        if (cur >= n || cons_len >= A.cons_cap) { cons_len = -1; break; }
+                        const uint32_t x = nxt[cur];
+                        co[cons_len++] = "ACGTN"[(x >> 16) & 7u];
+                        cur = (int)(x & 0xffffu);
+                    }
+                    if (cons_len >= 0) {
+                        const int64_t oo = (int64_t)G.item * A.out_stride;
+                        A.status[oo] = 0;
+                        A.cons_len[oo] = cons_len;
+                        A.nodes_out[oo] = G.node_n;
+                        *(long long *)((int32_t *)A.cells_out + (int64_t)G.item * A.cells_stride) = G.cells_total;
+                        L.done[G.item] = 1;
+                    }
+                }
+                have = false;
+            }
+        }
     }
 }
 
@@ -1236,6 +1382,12 @@ __global__ void __launch_bounds__(C3G_THREADS, C3G_MINB) c3_poa_grp_dp_kernel(c3
     const int wib = threadIdx.x >> 5;
     uint8_t *sw = reinterpret_cast<uint8_t *>(c3g_smem) + (size_t)wib * 4 * c3g_smem_group_bytes(RVS);
     c3g_dp_body<RVS, MULTI>(L, sw, threadIdx.x & 31);
+}
+__global__ void __launch_bounds__(C3G_THREADS, 4) c3_poa_grp_finish_kernel(c3g_args L)
+{
+    extern __shared__ uint4 c3g_smem[];
+    const int wib = threadIdx.x >> 5;
+    c3g_finish_body(L, reinterpret_cast<uint8_t *>(c3g_smem) + (size_t)wib * 4 * C3G_FIN_SMEM, threadIdx.x & 31);
 }
 #define C3G_GRAPH_GL 32
 __global__ void __launch_bounds__(C3G_THREADS, C3G_GRAPH_MINB) c3_poa_grp_graph_kernel(c3g_args L)

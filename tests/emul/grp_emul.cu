@@ -21,6 +21,7 @@ void warp_lane(void *p, int lane)
 {
     const WarpArg *a = (const WarpArg *)p;
     if (a->kind == 0) { if (a->gl == 32) c3g_graph_body<32>(*a->L, a->smem, lane); else c3g_graph_body<8>(*a->L, a->smem, lane); }
+    else if (a->kind == 2) c3g_finish_body(*a->L, a->smem, lane);
     else if (a->L->vs_shift == 3) c3g_dp_body<3, false>(*a->L, a->smem, lane);
     else if (a->L->rv_shift == 3) c3g_dp_body<3, true>(*a->L, a->smem, lane);
     else c3g_dp_body<4, true>(*a->L, a->smem, lane);
@@ -47,7 +48,7 @@ extern "C" int c3g_emul_batch(int n_items, const uint8_t *codes, const int64_t *
     A.n_work = n_items;
     int max_nseq = 1;
     for (int i = 0; i < n_items; ++i) if (n_seqs[i] > max_nseq) max_nseq = n_seqs[i];
-    std::vector<unsigned> counters((size_t)2 * max_nseq + 2, 0u);
+    std::vector<unsigned> counters((size_t)2 * max_nseq + 3, 0u);
     const int64_t ws_bytes = c3g_ws_bytes(node_cap, node_cap, cigar_cap, qp_stride);
     const int64_t arena4 = ((int64_t)node_cap << vs_shift) * 3;
     uint8_t *ws = (uint8_t *)aligned_alloc(256, (size_t)ws_bytes * n_items);
@@ -55,6 +56,7 @@ extern "C" int c3g_emul_batch(int n_items, const uint8_t *codes, const int64_t *
     size_t smw = (size_t)4 * c3g_smem_group_bytes(rv_shift);
     if (smw < (size_t)4 * C3G_GRAPH_SMEM(8)) smw = (size_t)4 * C3G_GRAPH_SMEM(8);
     if (smw < (size_t)C3G_GRAPH_SMEM(32)) smw = (size_t)C3G_GRAPH_SMEM(32);
+    if (smw < (size_t)4 * C3G_FIN_SMEM) smw = (size_t)4 * C3G_FIN_SMEM;
     uint8_t *smem = (uint8_t *)aligned_alloc(256, (smw * n_warps + 255) & ~(size_t)255);
     std::vector<c3g_state> state((size_t)n_items);
     if (!ws || !arena || !smem) return -1;
@@ -76,6 +78,7 @@ extern "C" int c3g_emul_batch(int n_items, const uint8_t *codes, const int64_t *
     };
     run(0, 1);
     for (int sq = 1; sq < max_nseq && !rc; ++sq) { run(1, 0); run(0, 0); }
+    if (!rc) run(2, 0);
     free(ws); free(arena); free(smem);
     return rc;
 }
