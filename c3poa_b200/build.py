@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "c3poa_gpu.cu")
 SRC_HOST = os.path.join(HERE, "csrc", "ingest.cpp")
 OUT = os.path.join(HERE, "libc3poa_gpu.so")
-DEPS = [SRC, SRC_HOST] + [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "conk.cuh", "peaks.cuh", "poa.cuh", "poa_lane.cuh", "poa_grp.cuh")] + [
+DEPS = [SRC, SRC_HOST] + [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "conk.cuh", "peaks.cuh", "poa.cuh", "poa_lane.cuh", "poa_grp.cuh", "poa_graph.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "c3poa_gpu.h")]
 
 

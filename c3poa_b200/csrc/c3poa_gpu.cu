@@ -7,6 +7,7 @@
 #include "poa.cuh"
 #include "poa_lane.cuh"
 #include "poa_grp.cuh"
+#include "poa_graph.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -443,15 +444,12 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     const int64_t arena4 = (node_cap << vs_shift) * 3;
     const int64_t read_bytes = ws_bytes + arena4 * 16 + (int64_t)sizeof(c3g_state);
     const int wpb = C3G_THREADS / 32;
-    const size_t sm_dp = (size_t)wpb * 4 * c3g_smem_group_bytes(rv_shift), sm_gr = (size_t)wpb * (32 / C3G_GRAPH_GL) * C3G_GRAPH_SMEM(C3G_GRAPH_GL);
+    const size_t sm_dp = (size_t)wpb * 4 * c3g_smem_group_bytes(rv_shift);
     void (*kdp)(c3g_args) = vs_shift == 3 ? c3_poa_grp_dp_kernel<3, false> : c3_poa_grp_dp_kernel<4, true>;
     CK(cudaFuncSetAttribute(kdp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dp));
-    CK(cudaFuncSetAttribute(c3_poa_grp_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gr));
-    int bps_dp = 1, bps_gr = 1;
+    int bps_dp = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_dp, kdp, C3G_THREADS, sm_dp) != cudaSuccess || bps_dp < 1) bps_dp = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_gr, c3_poa_grp_graph_kernel, C3G_THREADS, sm_gr) != cudaSuccess || bps_gr < 1) bps_gr = 1;
     if (const char *lim = getenv("C3POA_GRP_DP_CTAS")) bps_dp = std::max(1, std::min(bps_dp, atoi(lim)));     // tuning only
-    if (const char *lim = getenv("C3POA_GRP_GRAPH_CTAS")) bps_gr = std::max(1, std::min(bps_gr, atoi(lim)));
     size_t free_b = 0, tot_b = 0;
     CK(cudaMemGetInfo(&free_b, &tot_b));
     const int64_t budget = (int64_t)((double)(free_b + h->d_ws_grp.cap) * 0.7);
@@ -478,24 +476,18 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
         for (int k = 0; k < nw; ++k) wave_nseq = std::max(wave_nseq, h->grp_nseq[(size_t)(w0 + k)]);
         CK(cudaMemsetAsync(counters, 0, (size_t)n_counters * 4, h->stream));
         L.A.order = h->d_order_grp.as<int32_t>() + w0; L.A.n_work = nw;
-        const int w_dp = (nw + 3) / 4, w_gr = (nw + 32 / C3G_GRAPH_GL - 1) / (32 / C3G_GRAPH_GL);      // warps that can be busy
+        const int w_dp = (nw + 3) / 4;                              // warps that can be busy
         const int grid_dp = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * bps_dp, (w_dp + wpb - 1) / wpb));
-        const int grid_gr = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * bps_gr, (w_gr + wpb - 1) / wpb));
+        const int grid_gr = (nw + C3S_THREADS - 1) / C3S_THREADS;  // one thread per read
         int launch = 0;
-        L.first = 1; L.A.counter = counters + launch++;
-        c3_poa_grp_graph_kernel<<<grid_gr, C3G_THREADS, sm_gr, h->stream>>>(L);
+        c3_poa_graph_init_kernel<<<nw, 128, 0, h->stream>>>(L);
         h->tim.kernel_launches++;
-        L.first = 0;
         for (int sq = 1; sq < wave_nseq; ++sq) {
             L.A.counter = counters + launch++;
             kdp<<<grid_dp, C3G_THREADS, sm_dp, h->stream>>>(L);
-            L.A.counter = counters + launch++;
-            c3_poa_grp_graph_kernel<<<grid_gr, C3G_THREADS, sm_gr, h->stream>>>(L);
+            c3_poa_graph_kernel<<<grid_gr, C3S_THREADS, 0, h->stream>>>(L);
             h->tim.kernel_launches += 2;
         }
-        L.A.counter = counters + launch++;
-        c3_poa_grp_finish_kernel<<<grid_dp, C3G_THREADS, (size_t)wpb * 4 * C3G_FIN_SMEM, h->stream>>>(L);
-        h->tim.kernel_launches++;
         CK(cudaGetLastError());
     }
     h->lane_items = ng; h->lane_n_items = A.n_items;

@@ -1,0 +1,501 @@
+// poa_graph.cuh -- stage 3b, the serial phases of the group POA: one THREAD per read.
+//
+// Between two DP launches (poa_grp.cuh) a read needs: backtrack of the alignment just computed, merge of the
+// path into the graph, the new topological order, and the row descriptors of the next alignment; before the first
+// one: the first sequence as a linear graph; after the last one: heaviest bundling and the consensus walk.
+// All of that is pointer chasing with a few thousand dependent steps per read and no parallelism inside a read
+// worth the name -- measured: with 8 or 32 lanes per read those phases ran ONE read per warp instruction and cost
+// more than the DP.  So here every thread runs the plain scalar algorithm on its own read, all reads of the wave
+// at once (a B200 holds >300 000 threads): the latency of each dependent load is hidden by the other reads, and
+// the instruction stream is shared by the 32 reads of a warp.  The data is the same position-ordered layout the
+// DP kernel reads and writes (poa_grp.cuh); the next row record / descriptor / cell of the usual path are
+// requested one step ahead.
+//
+// Same results as poa.cuh (abPOA 1.0.5 semantics; /root/reference/bin/determine_consensus.py:30-47).
+// Everything here is plain host+device code: tests/emul/grp_emul.cu calls it directly.
+#pragma once
+#include "poa_grp.cuh"
+
+// First sequence -> linear graph, order = SRC, 2, 3, ..., L+1, SINK, and the row descriptors of the first alignment
+// (a chain: predecessor = position - 1, hops to the sink = n - 1 - position).  `tid` of `nthr` workers share the
+// node loop: the init kernel gives a read a whole CTA (coalesced stores), the emulation one worker.
+C3_HD inline void c3s_item_begin(c3g_grp &G, const c3_poa_args &A, const c3_poa_para_dev &P, const c3g_ws &W, const int item,
+                                 const int tid, const int nthr)
+{
+    G.item = item; G.sq = 1; G.err = 0; G.nseq = 0; G.node_n = 0; G.pool_n = 0; G.cells_total = 0; G.ob = 0;
+    G.qlen = 0; G.n = 0; G.w = 0;
+    const int nseq = A.n_seqs[(int64_t)item * A.n_seqs_stride];
+    if (nseq < A.min_seqs || nseq > A.max_seqs || nseq < 1 || (A.msa2 && nseq == 2)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+    G.ibase = A.codes + A.item_base[item];
+    G.bnd = A.bounds + (int64_t)item * A.max_seqs * 2;
+    G.nseq = nseq;
+    const uint8_t *q = G.ibase + G.bnd[0];
+    const int L = G.bnd[1] - G.bnd[0];
+    if (L <= 0 || L > 65000 || L + 2 > A.node_cap) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+    G.node_n = L + 2;
+    if (nseq > 1) {                                // what c3s_prepare checks and sets, for the second sequence
+        const int qlen = G.bnd[3] - G.bnd[2], n = L + 2;
+        const int len = qlen > n ? qlen : n;
+        const int max_score = max(qlen * 5, len * P.e1 + P.o1);
+        const int pn = (max_score <= 32767 - P.mismatch - P.o1 - P.e1) ? P.simd_bits / 16 : P.simd_bits / 32;
+        if (qlen <= 0 || qlen > 65000 || qlen + 32 > A.qp_stride || pn != 16 || P.wb < 0) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+        G.q = G.ibase + G.bnd[2]; G.qlen = qlen; G.n = n; G.w = P.wb + (int)(P.wf * (double)qlen);
+    }
+    uint16_t *ord = W.order[0];
+    for (int i = tid; i < L + 2; i += nthr) {
+        c3_pnode n;
+        n.in_more = n.out_more = C3_NONE; n.rmask = 1; n.spare = 0;
+        n.aln0 = n.aln1 = n.aln2 = n.aln3 = C3_NONE; n.max_out = C3_NONE; n.aln_n = 0;
+        n.prev = n.next = C3_NONE;
+        int pos;
+        if (i == C3_SRC) {
+            n.base = 4; n.in_n = 0; n.out_n = 1; n.in0 = C3_NONE; n.out0 = 2; n.w0 = 1; pos = 0;
+        } else if (i == C3_SINK) {
+            n.base = 4; n.in_n = 1; n.out_n = 0; n.in0 = (uint16_t)(L + 1); n.out0 = C3_NONE; n.w0 = 0; pos = L + 1;
+        } else {
+            n.base = q[i - 2]; n.in_n = 1; n.out_n = 1; n.w0 = 1;
+            n.in0 = (uint16_t)(i == 2 ? C3_SRC : i - 1);
+            n.out0 = (uint16_t)(i == L + 1 ? C3_SINK : i + 1);
+            pos = i - 1;
+        }
+        W.nodes[i] = n;
+        ord[pos] = (uint16_t)i; W.posof[i] = (uint16_t)pos;
+        const int hops = L + 1 - pos;
+        W.desc[pos] = make_uint4((uint32_t)i | ((uint32_t)(pos == 0 ? C3_NONE : pos - 1) << 16), (uint32_t)C3_NONE | ((uint32_t)hops << 16),
+                                 (uint32_t)n.base | ((uint32_t)n.in_n << 8), 0u);
+    }
+}
+
+// score mode, band half-width, score profile, row descriptors by position (reverse sweep) with the remaining path
+// length along the heaviest out-edges (hops to the sink; a successor sits at a higher position: already written)
+C3_HD inline void c3s_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_para_dev &P, const c3g_ws &W)
+{
+    const int sq = G.sq;
+    const uint8_t *q = G.ibase + G.bnd[2 * sq];
+    const int qlen = G.bnd[2 * sq + 1] - G.bnd[2 * sq];
+    const int n = G.node_n;
+    {
+        const int len = qlen > n ? qlen : n;
+        const int max_score = max(qlen * 5, len * P.e1 + P.o1);
+        const int pn = (max_score <= 32767 - P.mismatch - P.o1 - P.e1) ? P.simd_bits / 16 : P.simd_bits / 32;
+        if (qlen <= 0 || qlen > 65000 || qlen + 32 > A.qp_stride || pn != 16 || P.wb < 0) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+    }
+    G.q = q; G.qlen = qlen; G.n = n; G.w = P.wb + (int)(P.wf * (double)qlen);
+    const uint16_t *ord = W.order[G.ob];
+    int xbase = 0;
+    int idn = ord[n - 1];
+    c3_nrec ndn = c3_ld_node(&W.nodes[idn]);
+    int prev_id = -1, prev_hops = 0;              // the node handled one step earlier (position p + 1)
+    for (int p = n - 1; p >= 0; --p) {
+        const int id = idn;
+        const c3_nrec nd = ndn;
+        if (p > 0) { idn = ord[p - 1]; ndn = c3_ld_node(&W.nodes[idn]); }      // the next node's record is requested now
+        const int base = C3_N_BASE(nd), in_n = C3_N_INN(nd);
+        int p0 = C3_NONE, p1 = C3_NONE;
+        const int xo = xbase;
+        // (the usual first predecessor is the node before this one in the order, the usual heaviest successor the
+        // node after it: no look-up then)
+        if (in_n > 0) p0 = (p > 0 && C3_N_IN0(nd) == idn) ? p - 1 : (int)W.posof[C3_N_IN0(nd)];
+        if (in_n > 1) {
+            c3_pedge pe = W.pool[C3_N_INMORE(nd)];
+            p1 = W.posof[pe.id];
+            int e = pe.next;
+            for (int k = 2; k < in_n && e != (int)C3_NONE; ++k) {
+                pe = W.pool[e];
+                if (xbase >= A.pool_cap) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+                W.xpred[xbase++] = W.posof[pe.id]; e = pe.next;
+            }
+        }
+        int hops = 0;
+        if (id != C3_SINK) {
+            int best_w = C3_N_W0(nd), best = C3_N_OUT0(nd);
+            if (C3_N_OUTN(nd) > 1) {
+                int e = W.nodes[id].out_more;
+                while (e != (int)C3_NONE) {
+                    const c3_pedge pe = W.pool[e];
+                    if ((int)pe.w > best_w) { best_w = pe.w; best = pe.id; }
+                    e = pe.next;
+                }
+            }
+            hops = (best == prev_id ? prev_hops : C3G_D_HOPS(W.desc[W.posof[best]])) + 1;
+        }
+        prev_id = id; prev_hops = hops;
+        if (in_n > C3_MAXPRE || hops > 65535) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+        W.desc[p] = make_uint4((uint32_t)id | ((uint32_t)p0 << 16), (uint32_t)p1 | ((uint32_t)hops << 16),
+                               (uint32_t)base | ((uint32_t)in_n << 8) | ((uint32_t)xo << 16), 0u);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backtrack: abPOA's M -> E1 -> E2 -> F1 -> F2 order and op-mask state machine on the arena's (H, H-E1, H-E2) cells.
+// The record, descriptor and cell of the first predecessor -- where the path goes next nine times out of ten -- are
+// requested together, so a match/mismatch move costs one memory round trip.  Returns the number of cigar ops or <0.
+// ---------------------------------------------------------------------------
+C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, const uint4 *arena)
+{
+    const int e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
+    const int vs = L.vs_shift;
+    const uint8_t *q = G.q; const int qlen = G.qlen, n = G.n;
+    const int cap = L.A.cigar_cap;
+    unsigned long long *cg = W.cigar;
+    int nc = 0, j, pos, hij;
+    {
+        const uint4 ds = W.desc[n - 1];
+        int best = -0x7fffffff - 1, bj = -1, bk = -1;
+        const int skn = C3G_D_NPRE(ds);
+        for (int k = 0; k < skn; ++k) {
+            const int pk = c3g_pred_pos(W, ds, k);
+            const uint2 rp = W.rowrec[pk];
+            const int en = min(qlen, C3G_R_END(rp) * 16 + 15);
+            const int val = c3g_cell_h(arena, vs, pk, en);
+            if (val > best) { best = val; bj = en; bk = pk; }
+        }
+        if (bk < 0 || qlen - bj + 8 > cap) { C3G_DECLINE(); return C3G_E_RETRY; }
+        for (int t = qlen; t > bj; --t)
+            cg[qlen - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
+        nc = qlen - bj; j = bj; pos = bk; hij = best;
+    }
+    int cur_op = C3_OP_ALL;
+    uint4 d = W.desc[pos];
+    uint2 rt = W.rowrec[pos];
+    while (pos != 0 && j > 0) {
+        const int i = C3G_D_ID(d);
+        const int b = C3G_R_BEG(rt) * 16, en = min(qlen, C3G_R_END(rt) * 16 + 15);
+        if (j < b || j > en) { C3G_DECLINE(); return C3G_E_RETRY; }
+        const int s = c3_score(P, C3G_D_BASE(d), q[j - 1]);
+        const int npre = C3G_D_NPRE(d);
+        int hit = 0;
+        unsigned long long opw = 0;
+        // first predecessor: record, descriptor and both cells the tests can ask for, all requested at once
+        const int p0 = C3G_D_P0(d);
+        const uint2 r0 = W.rowrec[p0];
+        const uint4 d0 = W.desc[p0];
+        const int ph0 = c3g_cell_h(arena, vs, p0, j - 1);           // (inside the read's arena whatever the band is)
+        if (cur_op & C3_OP_M) {
+            for (int k = 0; k < npre; ++k) {
+                const int pk = k == 0 ? p0 : c3g_pred_pos(W, d, k);
+                const uint2 pr = k == 0 ? r0 : W.rowrec[pk];
+                const int pbeg = C3G_R_BEG(pr) * 16, pend = min(qlen, C3G_R_END(pr) * 16 + 15);
+                if (j - 1 < max(pbeg, b) || j - 1 > pend) continue;
+                const int ph = k == 0 ? ph0 : c3g_cell_h(arena, vs, pk, j - 1);
+                if (ph + s == hij) {
+                    opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                    pos = pk; --j; hit = 1; cur_op = C3_OP_ALL; hij = ph;
+                    rt = pr; d = k == 0 ? d0 : W.desc[pk];
+                    break;
+                }
+            }
+        }
+        if (!hit && (cur_op & C3_OP_E)) {
+            const int ceb = c3g_cell_eb(arena, vs, pos, j);
+            const int ce1 = hij - (ceb & 7), ce2 = hij - (ceb >> 3);
+            for (int k = 0; k < npre; ++k) {
+                const int pk = k == 0 ? p0 : c3g_pred_pos(W, d, k);
+                const uint2 pr = k == 0 ? r0 : W.rowrec[pk];
+                const int pbeg = C3G_R_BEG(pr) * 16, pend = min(qlen, C3G_R_END(pr) * 16 + 15);
+                if (j < pbeg || j > pend) continue;
+                const int ph = c3g_cell_h(arena, vs, pk, j);
+                int pe1, pe2;
+                if (pk == 0) { pe1 = j == 0 ? -oe1 : C3_NEG_INF; pe2 = j == 0 ? -oe2 : C3_NEG_INF; }
+                else { const int peb = c3g_cell_eb(arena, vs, pk, j); pe1 = ph - (peb & 7); pe2 = ph - (peb >> 3); }
+                if (cur_op & C3_OP_E1) {
+                    if (cur_op & C3_OP_M) {
+                        if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
+                    } else if (ce1 == pe1 - e1) {
+                        cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1;
+                    }
+                }
+                if (!hit && (cur_op & C3_OP_E2)) {
+                    if (cur_op & C3_OP_M) {
+                        if (hij == pe2) { cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1; }
+                    } else if (ce2 == pe2 - e2) {
+                        cur_op = (ph - oe2 == pe2) ? (C3_OP_M | C3_OP_F) : C3_OP_E2; hit = 1;
+                    }
+                }
+                if (hit) {
+                    opw = C3_CG_DEL | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
+                    pos = pk; hij = ph;
+                    rt = pr; d = k == 0 ? d0 : W.desc[pk];
+                    break;
+                }
+            }
+        }
+        if (!hit && (cur_op & C3_OP_F)) {
+            int hl = C3_NEG_INF;
+            if (j - 1 >= b) {
+                // F is not stored: rebuild F[j] and F[j-1] of this row from its H, 16 columns per load
+                // (F[c+1] = max(F[c]-e, H[c]-o-e); equal to the DP's F wherever F decides)
+                int f1 = C3_NEG_INF, f2 = C3_NEG_INF, f1l = C3_NEG_INF, f2l = C3_NEG_INF;
+                for (int c0 = b; c0 < j; c0 += 16) {
+                    const uint4 *hp = arena + (((int64_t)pos << vs) + ((c0 >> 4) & ((1 << vs) - 1))) * 3;
+                    int t16[16];
+                    { int t8[8]; c3l_unpack8(hp[0], t8);
+#pragma unroll
+                      for (int k = 0; k < 8; ++k) t16[k] = t8[k];
+                      c3l_unpack8(hp[1], t8);
+#pragma unroll
+                      for (int k = 0; k < 8; ++k) t16[8 + k] = t8[k]; }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        if (c0 + k < j) {
+                            hl = c3l_map(t16[k]);
+                            f1l = f1; f2l = f2;
+                            f1 = max(f1 - e1, hl - oe1); f2 = max(f2 - e2, hl - oe2);
+                        }
+                    }
+                }
+                if (cur_op & C3_OP_F1) {
+                    if (!(cur_op & C3_OP_M) || hij == f1) {
+                        if (hl - oe1 == f1) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                        else if (f1l - e1 == f1) { cur_op = C3_OP_F1; hit = 1; }
+                    }
+                }
+                if (!hit && (cur_op & C3_OP_F2)) {
+                    if (!(cur_op & C3_OP_M) || hij == f2) {
+                        if (hl - oe2 == f2) { cur_op = C3_OP_M | C3_OP_E; hit = 1; }
+                        else if (f2l - e2 == f2) { cur_op = C3_OP_F2; hit = 1; }
+                    }
+                }
+            }
+            if (hit) { opw = C3_CG_INS | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32); --j; hij = hl; }
+        }
+        if (!hit) { C3G_DECLINE(); return C3G_E_RETRY; }
+        cg[nc] = opw;
+        ++nc;
+        if (nc + j + 8 > cap) { C3G_DECLINE(); return C3G_E_RETRY; }
+    }
+    for (int t = j; t > 0; --t)
+        cg[nc + j - t] = C3_CG_INS | ((unsigned long long)C3_NONE << 8) | ((unsigned long long)(t - 1) << 32);
+    nc += j;
+    return nc;
+}
+
+// ---------------------------------------------------------------------------
+// merge (abpoa_add_graph_alignment): the cigar is walked from its tail = forward order.  A new node is not linked
+// into a list: its place in the order is the gap of the OLD order it falls into (W.gaps, non-decreasing in creation
+// order), see c3s_reorder.
+// ---------------------------------------------------------------------------
+C3_HD inline int c3s_tail_gap(const uint16_t *ord, const int n_old, const c3_pnode &na, const int p_start)
+{
+    int t = p_start;
+    for (;;) {
+        if (t + 1 >= n_old) break;
+        const int nx = ord[t + 1];
+        bool in_group = false;
+        for (int k = 0; k < na.aln_n; ++k) in_group |= (c3_aln_get(na, k) == nx);
+        if (!in_group) break;
+        ++t;
+    }
+    return t + 1;
+}
+
+C3_HD inline int c3s_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const int nc)
+{
+    const uint8_t *q = G.q;
+    const unsigned long long *cg = W.cigar;
+    const uint16_t *ord = W.order[G.ob];
+    const int n_old = G.n;
+    c3_graph g; g.nodes = W.nodes; g.pool = W.pool; g.node_n = G.node_n; g.pool_n = G.pool_n;
+    g.node_cap = L.A.node_cap; g.pool_cap = L.A.pool_cap; g.err = 0;
+    int last_id = C3_SRC, last_new = 0;
+    int last_gap = 0, last_p = 0;                // gap of the last new node / old position its group walk starts at
+    unsigned long long opn = nc > 0 ? cg[nc - 1] : 0ull;
+    for (int t = nc - 1; t >= 0 && !g.err; --t) {
+        const unsigned long long opc = opn;
+        if (t > 0) {                             // next op now, and its node record on the way
+            opn = cg[t - 1];
+            const int nn = (int)((opn >> 8) & 0xffff);
+            if (nn != (int)C3_NONE) C3L_PREFETCH(&g.nodes[nn]);
+        }
+        const int kc = (int)(opc & 0xff), nid = (int)((opc >> 8) & 0xffff), qp = (int)(opc >> 32);
+        if (kc == (int)C3_CG_DEL) continue;
+        if (kc == (int)C3_CG_MATCH) {
+            const uint8_t bq = q[qp];
+            const c3_pnode nm = g.nodes[nid];
+            if (nm.base != bq) {
+                int al = -1;
+                for (int k = 0; k < nm.aln_n; ++k) {
+                    const int a = c3_aln_get(nm, k);
+                    if (g.nodes[a].base == bq) { al = a; break; }
+                }
+                if (al != -1) {
+                    c3_g_add_edge(g, last_id, al, 1 - last_new);
+                    last_id = al; last_new = 0;
+                } else {
+                    const int id = c3_g_add_node(g, bq);
+                    if (g.err) break;
+                    last_p = W.posof[nid]; last_gap = last_p;          // placed right before nid
+                    W.gaps[id - n_old] = (uint16_t)last_gap;
+                    c3_g_add_edge(g, last_id, id, 0);
+                    last_id = id; last_new = 1;
+                    for (int k = 0; k < nm.aln_n; ++k) {               // abpoa_add_graph_aligned_node
+                        const int a = c3_aln_get(nm, k);
+                        c3_aln_push(&g.nodes[a], (uint16_t)id);
+                        c3_aln_push(&g.nodes[id], (uint16_t)a);
+                    }
+                    c3_aln_push(&g.nodes[nid], (uint16_t)id);
+                    c3_aln_push(&g.nodes[id], (uint16_t)nid);
+                }
+            } else {
+                c3_g_add_edge(g, last_id, nid, 1 - last_new);
+                last_id = nid; last_new = 0;
+            }
+        } else {                                                     // insertion: right after the aligned block of last_id
+            const int id = c3_g_add_node(g, q[qp]);
+            if (g.err) break;
+            const c3_pnode nl = g.nodes[last_id];
+            int gap;
+            if (last_id >= n_old) gap = nl.aln_n ? c3s_tail_gap(ord, n_old, nl, last_p) : last_gap;
+            else gap = c3s_tail_gap(ord, n_old, nl, W.posof[last_id]);
+            last_gap = gap;
+            W.gaps[id - n_old] = (uint16_t)gap;
+            c3_g_add_edge(g, last_id, id, 0);
+            last_id = id; last_new = 1;
+        }
+    }
+    if (!g.err) c3_g_add_edge(g, last_id, C3_SINK, 1 - last_new);
+    if (g.err) { C3G_DECLINE(); return C3G_E_RETRY; }
+    G.node_n = g.node_n; G.pool_n = g.pool_n;
+    return 0;
+}
+
+// new order = stable merge of the old order with the new nodes by gap: the t-th new node (id n_old + t, gap g)
+// lands at g + t, an old node at position p moves up by the number of new nodes with gap <= p
+C3_HD inline void c3s_reorder(c3g_grp &G, const c3g_ws &W)
+{
+    const int n_old = G.n, m = G.node_n - n_old;
+    const uint16_t *oo = W.order[G.ob];
+    uint16_t *on = W.order[G.ob ^ 1];
+    int t = 0;
+    int gt = m > 0 ? (int)W.gaps[0] : 0x7fffffff;
+    for (int p = 0; p < n_old; ++p) {
+        while (gt <= p) {
+            on[p + t] = (uint16_t)(n_old + t); W.posof[n_old + t] = (uint16_t)(p + t); ++t;
+            gt = t < m ? (int)W.gaps[t] : 0x7fffffff;
+        }
+        const int id = oo[p];
+        on[p + t] = (uint16_t)id; W.posof[id] = (uint16_t)(p + t);
+    }
+    G.ob ^= 1;
+}
+
+// heaviest bundling (abpoa_heaviest_bundling) + consensus walk.  Returns the length or a negative code.
+C3_HD inline int c3s_consensus(const c3g_grp &G, const c3_poa_args &A, const c3g_ws &W, char *co)
+{
+    int32_t *score = reinterpret_cast<int32_t *>(W.desc);
+    const uint16_t *ord = W.order[G.ob];
+    for (int p = G.node_n - 1; p >= 0; --p) {
+        const int v = ord[p];
+        c3_pnode *nd = &W.nodes[v];
+        if (v == C3_SINK) { nd->max_out = C3_NONE; score[v] = 0; }
+        else if (v == C3_SRC) {
+            int max_id = -1, path_score = -1, path_w = -1;
+            uint16_t e = nd->out_more;
+            for (int k = 0; k < nd->out_n; ++k) {
+                int o, wv;
+                if (k == 0) { o = nd->out0; wv = nd->w0; } else { const c3_pedge pe = W.pool[e]; o = pe.id; wv = pe.w; e = pe.next; }
+                if (wv > path_w || (wv == path_w && score[o] > path_score)) { max_id = o; path_score = score[o]; path_w = wv; }
+            }
+            nd->max_out = (uint16_t)max_id;
+        } else {
+            int max_w = -0x7fffffff - 1, max_id = -1;
+            uint16_t e = nd->out_more;
+            for (int k = 0; k < nd->out_n; ++k) {
+                int o, wv;
+                if (k == 0) { o = nd->out0; wv = nd->w0; } else { const c3_pedge pe = W.pool[e]; o = pe.id; wv = pe.w; e = pe.next; }
+                if (max_w < wv) { max_w = wv; max_id = o; }
+                else if (max_w == wv && score[max_id] <= score[o]) max_id = o;
+            }
+            score[v] = max_w + score[max_id];
+            nd->max_out = (uint16_t)max_id;
+        }
+    }
+    int cons_len = 0;
+    int id = W.nodes[C3_SRC].max_out;
+    while (id != C3_SINK) {
+        if (id == C3_NONE || cons_len >= A.cons_cap) { C3G_DECLINE(); return C3G_E_RETRY; }
+        const c3_pnode nd = W.nodes[id];
+        co[cons_len++] = "ACGTN"[nd.base];
+        id = nd.max_out;
+    }
+    return cons_len;
+}
+
+// last sequence merged: heaviest bundling, consensus and the per-read outputs
+C3_HD inline void c3s_finish(c3g_grp &G, const c3g_args &L, const c3g_ws &W)
+{
+    const c3_poa_args &A = L.A;
+    char *co = A.cons + (int64_t)G.item * A.cons_cap;
+    const int r = c3s_consensus(G, A, W, co);
+    if (r >= 0) {
+        const int64_t o = (int64_t)G.item * A.out_stride;
+        A.status[o] = 0;
+        A.cons_len[o] = r;
+        A.nodes_out[o] = G.node_n;
+        *(long long *)((int32_t *)A.cells_out + (int64_t)G.item * A.cells_stride) = G.cells_total;
+        L.done[G.item] = 1;
+    } else G.err = C3G_E_RETRY;
+}
+
+// ---------------------------------------------------------------------------
+// one read's turn between two DP launches.  The 32 threads of a warp are brought
+// back together after every phase (C3S_SYNC): the phases are loops of data-dependent length with early exits, and
+// without it a thread that leaves one loop early runs all later phases alone.
+// ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define C3S_SYNC() __syncwarp()
+#else
+#define C3S_SYNC() do { } while (0)
+#endif
+C3_HD inline void c3s_graph_step(const c3g_args &L, const int it, const bool valid)
+{
+    const c3_poa_args &A = L.A;
+    const c3_poa_para_dev P = A.P;
+    c3g_state *S = L.state + (valid ? it : 0);
+    const c3g_ws W = c3g_ws_carve(L.ws + (int64_t)(valid ? it : 0) * L.ws_stride, A.node_cap, A.pool_cap, A.cigar_cap);
+    const uint4 *arena = L.arena + (int64_t)(valid ? it : 0) * L.arena_stride4;
+    c3g_grp G;
+    G.err = 0; G.sq = 0; G.nseq = 0;
+    bool run = valid;
+    {
+        if (run) { c3g_state_load(G, S, A); if (G.err || G.sq >= G.nseq) run = false; }   // declined earlier / finished earlier
+        int nc = 0;
+        C3S_SYNC();
+        if (run) { nc = c3s_backtrack(G, L, P, W, arena); if (nc < 0) G.err = C3G_E_RETRY; }
+        C3S_SYNC();
+        if (run && !G.err && c3s_merge(G, L, W, nc)) G.err = C3G_E_RETRY;
+        C3S_SYNC();
+        if (run && !G.err) { c3s_reorder(G, W); ++G.sq; }
+    }
+    C3S_SYNC();
+    if (run && !G.err && G.sq < G.nseq) c3s_prepare(G, A, P, W);
+    C3S_SYNC();
+    if (run && !G.err && G.sq >= G.nseq) c3s_finish(G, L, W);
+    if (run) c3g_state_store(G, S);
+}
+
+#ifdef __CUDACC__
+#ifndef C3S_THREADS
+#define C3S_THREADS 64
+#endif
+__global__ void __launch_bounds__(C3S_THREADS) c3_poa_graph_kernel(c3g_args L)
+{
+    const int it = blockIdx.x * C3S_THREADS + threadIdx.x;
+    c3s_graph_step(L, it, it < L.A.n_work);
+}
+// first launch of a wave: one CTA per read writes the first sequence's linear graph (coalesced stores); a read of a
+// single sequence has nothing to align and is finished here
+__global__ void __launch_bounds__(128) c3_poa_graph_init_kernel(c3g_args L)
+{
+    const int it = blockIdx.x;
+    const c3_poa_args &A = L.A;
+    const c3g_ws W = c3g_ws_carve(L.ws + (int64_t)it * L.ws_stride, A.node_cap, A.pool_cap, A.cigar_cap);
+    c3g_grp G;
+    c3s_item_begin(G, A, A.P, W, A.order ? A.order[it] : it, threadIdx.x, 128);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!G.err && G.sq >= G.nseq) c3s_finish(G, L, W);
+        c3g_state_store(G, L.state + it);
+    }
+}
+#endif

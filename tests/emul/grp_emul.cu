@@ -2,7 +2,7 @@
 // runs, compiled as host code with -DC3G_EMUL) on the fiber warp emulator (warp_emu.cpp), one warp after the
 // other, so the group kernel's logic can be checked against the oracle without a GPU.
 #define C3G_EMUL 1
-#include "../../c3poa_b200/csrc/poa_grp.cuh"
+#include "../../c3poa_b200/csrc/poa_graph.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -16,13 +16,11 @@ extern "C" void c3g_emul_note(int line)
 }
 
 namespace {
-struct WarpArg { const c3g_args *L; uint8_t *smem; int kind, gl; };
+struct WarpArg { const c3g_args *L; uint8_t *smem; };
 void warp_lane(void *p, int lane)
 {
     const WarpArg *a = (const WarpArg *)p;
-    if (a->kind == 0) { if (a->gl == 32) c3g_graph_body<32>(*a->L, a->smem, lane); else c3g_graph_body<8>(*a->L, a->smem, lane); }
-    else if (a->kind == 2) c3g_finish_body(*a->L, a->smem, lane);
-    else if (a->L->vs_shift == 3) c3g_dp_body<3, false>(*a->L, a->smem, lane);
+    if (a->L->vs_shift == 3) c3g_dp_body<3, false>(*a->L, a->smem, lane);
     else if (a->L->rv_shift == 3) c3g_dp_body<3, true>(*a->L, a->smem, lane);
     else c3g_dp_body<4, true>(*a->L, a->smem, lane);
 }
@@ -54,9 +52,6 @@ extern "C" int c3g_emul_batch(int n_items, const uint8_t *codes, const int64_t *
     uint8_t *ws = (uint8_t *)aligned_alloc(256, (size_t)ws_bytes * n_items);
     uint4 *arena = (uint4 *)aligned_alloc(256, (size_t)arena4 * 16 * n_items);
     size_t smw = (size_t)4 * c3g_smem_group_bytes(rv_shift);
-    if (smw < (size_t)4 * C3G_GRAPH_SMEM(8)) smw = (size_t)4 * C3G_GRAPH_SMEM(8);
-    if (smw < (size_t)C3G_GRAPH_SMEM(32)) smw = (size_t)C3G_GRAPH_SMEM(32);
-    if (smw < (size_t)4 * C3G_FIN_SMEM) smw = (size_t)4 * C3G_FIN_SMEM;
     uint8_t *smem = (uint8_t *)aligned_alloc(256, (smw * n_warps + 255) & ~(size_t)255);
     std::vector<c3g_state> state((size_t)n_items);
     if (!ws || !arena || !smem) return -1;
@@ -67,18 +62,28 @@ extern "C" int c3g_emul_batch(int n_items, const uint8_t *codes, const int64_t *
     L.ws = ws; L.ws_stride = ws_bytes; L.arena = arena; L.arena_stride4 = arena4;
     L.vs_shift = vs_shift; L.rv_shift = rv_shift; L.done = done; L.state = state.data();
     int rc = 0, launch = 0;
-    // the host's launch sequence: graph (first), then (DP, graph) per further sequence; the warps of a launch run one
-    // after the other (they only share the launch's work counter)
-    auto run = [&](int kind, int first) {
-        L.first = first; L.A.counter = &counters[launch++];
+    // the host's launch sequence: init kernel, then (DP kernel, graph kernel) per further sequence.  Init and graph
+    // kernel are scalar code, one worker per read: called directly.  The DP kernel's warps run on the fiber emulator
+    // one after the other (they only share the launch's work counter).
+    auto init = [&]() {
+        for (int it = 0; it < n_items; ++it) {
+            const c3g_ws W = c3g_ws_carve(L.ws + (int64_t)it * L.ws_stride, A.node_cap, A.pool_cap, A.cigar_cap);
+            c3g_grp G;
+            c3s_item_begin(G, A, A.P, W, it, 0, 1);
+            if (!G.err && G.sq >= G.nseq) c3s_finish(G, L, W);
+            c3g_state_store(G, L.state + it);
+        }
+    };
+    auto graph = [&]() { for (int it = 0; it < n_items; ++it) c3s_graph_step(L, it, true); };
+    auto dp = [&]() {
+        L.A.counter = &counters[launch++];
         for (int w = 0; w < n_warps && !rc; ++w) {
-            WarpArg a{&L, smem + smw * w, kind, graph_gl};
+            WarpArg a{&L, smem + smw * w};
             rc = c3emu_run_warp(warp_lane, &a);
         }
     };
-    run(0, 1);
-    for (int sq = 1; sq < max_nseq && !rc; ++sq) { run(1, 0); run(0, 0); }
-    if (!rc) run(2, 0);
+    init();
+    for (int sq = 1; sq < max_nseq && !rc; ++sq) { dp(); graph(); }
     free(ws); free(arena); free(smem);
     return rc;
 }

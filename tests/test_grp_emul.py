@@ -26,7 +26,7 @@ def build_emul():
     out = os.path.join(ROOT, "build", "grp_emul.so")
     src = os.path.join(ROOT, "tests", "emul", "grp_emul.cu")
     rt = os.path.join(ROOT, "tests", "emul", "warp_emu.cpp")
-    deps = [src, rt] + [os.path.join(ROOT, "c3poa_b200", "csrc", f) for f in ("poa_grp.cuh", "poa_lane.cuh", "poa.cuh", "common.cuh")]
+    deps = [src, rt] + [os.path.join(ROOT, "c3poa_b200", "csrc", f) for f in ("poa_grp.cuh", "poa_graph.cuh", "poa_lane.cuh", "poa.cuh", "common.cuh")]
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         obj = os.path.join(ROOT, "build", "warp_emu.o")

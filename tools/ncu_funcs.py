@@ -7,16 +7,17 @@ from collections import defaultdict
 
 rep, sym = sys.argv[1], sys.argv[2]
 so = os.path.abspath(sys.argv[3] if len(sys.argv) > 3 else "c3poa_b200/libc3poa_gpu.so")
-src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "c3poa_b200", "csrc", "poa_grp.cuh")
+SRCFILE = os.environ.get("NCU_SRC", "poa_grp.cuh")
+src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "c3poa_b200", "csrc", SRCFILE)
 starts = []
 for i, ln in enumerate(open(src), 1):
-    m = re.match(r"^(?:C3G_FN|C3_HD __forceinline__|__global__)\s+.*?\b(c3g?_\w+)\s*\(", ln)
+    m = re.match(r"^(?:C3G_FN|C3_HD __forceinline__|C3_HD inline|__global__)\s+.*?\b(c3[gs]?_\w+)\s*\(", ln)
     if m:
         starts.append((i, m.group(1)))
 def func_of(f, l):
-    if f != "poa_grp.cuh":
+    if f != SRCFILE:
         return f
-    name = "poa_grp.cuh(top)"
+    name = SRCFILE + "(top)"
     for s, n in starts:
         if s <= l: name = n
     return name
@@ -50,9 +51,9 @@ for ln in dis.splitlines():
         continue
     if re.search(r"/\*[0-9a-f]{4,}\*/", ln) and not ln.strip().startswith("//"):
         key = cur_line
-        if key and key[0] != "poa_grp.cuh" and stack:
+        if key and key[0] != SRCFILE and stack:
             for s in stack:
-                if s[0] == "poa_grp.cuh": key = s; break
+                if s[0] == SRCFILE: key = s; break
         lines.append(key)
 agg = defaultdict(lambda: [0, 0, 0])
 for k in range(min(len(data), len(lines))):
