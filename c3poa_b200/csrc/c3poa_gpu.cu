@@ -427,22 +427,37 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     const int max_nseq = h->grp_max_nseq;
     const int64_t max_total = h->grp_max_total;
     max_q = (int)std::min<int64_t>(max_q, max_total);
-    int64_t est = 2 + (int64_t)max_q + (int64_t)(max_nseq - 1) * ((int64_t)max_q * 35 / 100 + 16);
-    int64_t node_cap = std::min<int64_t>(std::min<int64_t>(est, max_total + 2), 65504);
-    node_cap = std::max<int64_t>((node_cap + 31) & ~31ll, 64);
-    const int pool_cap = (int)node_cap;
-    const int cigar_cap = (int)((max_q + node_cap + 64 + 1) & ~1ll);
-    const int qp_stride = (max_q + 48) & ~15;
-    // arena rows: a fixed stride of VS vectors (power of two) that the usual band fits with room for drift; ring slots
-    // of RV <= VS vectors.  A wider row only sends its read to the warp kernel.
+    // Per-read capacity: nodes = first sequence + a share of every further one.  The serial phases run one thread per
+    // read and are bound by the length of their dependent chains, not by the number of reads, so one wave for the whole
+    // batch is worth a tighter node estimate (what outgrows it is declined and goes to the warp kernel with its own,
+    // roomier workspace): the largest growth share of {35, 25, 20} % that lets the batch fit in one wave, else 20 %.
+    int budget_pct = 70, grow_env = 0;
+    if (const char *e = getenv("C3POA_GRP_GROW_PCT")) grow_env = std::max(1, atoi(e));           // tuning only
+    if (const char *e = getenv("C3POA_GRP_BUDGET_PCT")) budget_pct = std::max(1, std::min(95, atoi(e)));
+    size_t free_b = 0, tot_b = 0;
+    CK(cudaMemGetInfo(&free_b, &tot_b));
+    const int64_t budget = (int64_t)((double)(free_b + h->d_ws_grp.cap) * (budget_pct / 100.0));
     const int w = pp->wb + (int)(pp->wf * max_q);
     const int need = (2 * w + 1 + 48) / 16 + 2;
     int vs_shift = 3;
     while ((1 << vs_shift) < need && vs_shift < 8) ++vs_shift;
     const int rv_shift = vs_shift == 3 ? 3 : 4;
-    const int64_t ws_bytes = c3g_ws_bytes((int)node_cap, pool_cap, cigar_cap, qp_stride);
-    const int64_t arena4 = (node_cap << vs_shift) * 3;
-    const int64_t read_bytes = ws_bytes + arena4 * 16 + (int64_t)sizeof(c3g_state);
+    const int qp_stride = (max_q + 48) & ~15;
+    int64_t node_cap = 0, ws_bytes = 0, arena4 = 0, read_bytes = 0;
+    int cigar_cap = 0;
+    static const int grow_try[3] = {35, 25, 20};
+    for (int t = 0; t < 3; ++t) {
+        const int grow_pct = grow_env ? grow_env : grow_try[t];
+        const int64_t est = 2 + (int64_t)max_q + (int64_t)(max_nseq - 1) * ((int64_t)max_q * grow_pct / 100 + 16);
+        node_cap = std::min<int64_t>(std::min<int64_t>(est, max_total + 2), 65504);
+        node_cap = std::max<int64_t>((node_cap + 31) & ~31ll, 64);
+        cigar_cap = (int)((max_q + node_cap + 64 + 1) & ~1ll);
+        ws_bytes = c3g_ws_bytes((int)node_cap, (int)node_cap, cigar_cap, qp_stride);
+        arena4 = (node_cap << vs_shift) * 3;
+        read_bytes = ws_bytes + arena4 * 16 + (int64_t)sizeof(c3g_state);
+        if (grow_env || budget / read_bytes >= ng) break;
+    }
+    const int pool_cap = (int)node_cap;
     const int wpb = C3G_THREADS / 32;
     const size_t sm_dp = (size_t)wpb * 4 * c3g_smem_group_bytes(rv_shift);
     void (*kdp)(c3g_args) = vs_shift == 3 ? c3_poa_grp_dp_kernel<3, false> : c3_poa_grp_dp_kernel<4, true>;
@@ -450,11 +465,9 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     int bps_dp = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_dp, kdp, C3G_THREADS, sm_dp) != cudaSuccess || bps_dp < 1) bps_dp = 1;
     if (const char *lim = getenv("C3POA_GRP_DP_CTAS")) bps_dp = std::max(1, std::min(bps_dp, atoi(lim)));     // tuning only
-    size_t free_b = 0, tot_b = 0;
-    CK(cudaMemGetInfo(&free_b, &tot_b));
-    const int64_t budget = (int64_t)((double)(free_b + h->d_ws_grp.cap) * 0.7);
     int64_t wave = std::min<int64_t>(ng, budget / read_bytes);
     if (wave < 64) return 0;                                       // does not fit: the warp kernel takes everything
+    wave = (ng + (ng + wave - 1) / wave - 1) / ((ng + wave - 1) / wave);    // several waves: equal sizes
     const int n_counters = 2 * max_nseq + 3;
     CK(h->d_ws_grp.ensure((size_t)(wave * read_bytes) + (size_t)n_counters * 4 + 256));
     CK(h->d_done.ensure((size_t)A.n_items * 4));
@@ -470,6 +483,8 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     L.state = reinterpret_cast<c3g_state *>(base + wave * (ws_bytes + arena4 * 16));
     unsigned *counters = reinterpret_cast<unsigned *>(base + wave * read_bytes + 128);
     L.done = h->d_done.as<int32_t>();
+    const bool timing = getenv("C3POA_GRP_TIMING") != nullptr;
+    if (const char *e = getenv("C3POA_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));   // tuning only
     for (int64_t w0 = 0; w0 < ng; w0 += wave) {
         const int nw = (int)std::min<int64_t>(wave, ng - w0);
         int wave_nseq = 1;
@@ -480,15 +495,33 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
         const int grid_dp = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * bps_dp, (w_dp + wpb - 1) / wpb));
         const int grid_gr = (nw + C3S_THREADS - 1) / C3S_THREADS;  // one thread per read
         int launch = 0;
+        std::vector<cudaEvent_t> ev;                               // C3POA_GRP_TIMING=1 (tuning only): per-launch times on stderr
+        auto mark = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); ev.push_back(e); } };
+        mark();
         c3_poa_graph_init_kernel<<<nw, 128, 0, h->stream>>>(L);
+        mark();
         h->tim.kernel_launches++;
         for (int sq = 1; sq < wave_nseq; ++sq) {
             L.A.counter = counters + launch++;
             kdp<<<grid_dp, C3G_THREADS, sm_dp, h->stream>>>(L);
+            mark();
             c3_poa_graph_kernel<<<grid_gr, C3S_THREADS, 0, h->stream>>>(L);
+            mark();
             h->tim.kernel_launches += 2;
         }
         CK(cudaGetLastError());
+        if (timing) {
+            CK(cudaStreamSynchronize(h->stream));
+            float dp = 0.f, gr = 0.f, t = 0.f;
+            fprintf(stderr, "grp wave %d reads (node_cap %lld, %lld B/read):", nw, (long long)node_cap, (long long)read_bytes);
+            for (size_t k = 1; k < ev.size(); ++k) {
+                cudaEventElapsedTime(&t, ev[k - 1], ev[k]);
+                fprintf(stderr, " %.2f", t);
+                if (k >= 2) { if (k & 1) gr += t; else dp += t; }
+            }
+            fprintf(stderr, "  | dp %.2f graph %.2f ms\n", dp, gr);
+            for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        }
     }
     h->lane_items = ng; h->lane_n_items = A.n_items;
     A.done = h->d_done.as<int32_t>();

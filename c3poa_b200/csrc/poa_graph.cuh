@@ -16,6 +16,56 @@
 #pragma once
 #include "poa_grp.cuh"
 
+#ifndef C3S_PFK
+#define C3S_PFK 0                     // kind of the sweeps' software prefetch: 0 none, 1 towards L1, 2 towards L2
+#endif
+#if C3S_PFK == 2
+#define C3S_PREFETCH(p) C3L_PREFETCH2(p)
+#elif C3S_PFK == 1
+#define C3S_PREFETCH(p) C3L_PREFETCH(p)
+#else
+#define C3S_PREFETCH(p) do { (void)(p); } while (0)
+#endif
+#ifndef C3S_PF
+#define C3S_PF 6                      // look-ahead (loop steps) of the software prefetches in the sweeps
+#endif
+
+// Sequential streams of small elements are read and written in 16-byte pieces kept in registers: with several hundred
+// threads per SM, each on its own read, a line does not survive in L1 (nor reliably in L2) from one element to the next,
+// so an element-wise sweep would fetch the same sector up to 16 times.
+struct c3s_q4 { const uint8_t *q; uintptr_t wa; uint32_t w; };       // byte reader over the query codes, one word cached
+C3_HD __forceinline__ void c3s_q4_init(c3s_q4 &c, const uint8_t *q) { c.q = q; c.wa = ~(uintptr_t)0; c.w = 0u; }
+C3_HD __forceinline__ int c3s_q4_get(c3s_q4 &c, const int idx)
+{
+    const uintptr_t a = (uintptr_t)(c.q + idx), wa = a & ~(uintptr_t)3;
+    if (wa != c.wa) { c.wa = wa; c.w = *reinterpret_cast<const uint32_t *>(wa); }
+    return (int)((c.w >> (8 * (int)(a & 3))) & 0xffu);
+}
+C3_HD __forceinline__ int c3s_u16_of(const uint4 v, const int k)      // halfword k (0..7) of a 16-byte piece
+{
+    const uint32_t w = (k & 4) ? ((k & 2) ? v.w : v.z) : ((k & 2) ? v.y : v.x);
+    return (int)((w >> ((k & 1) * 16)) & 0xffffu);
+}
+struct c3s_out8 { uint16_t *dst; unsigned long long lo, hi; int n; };  // sequential uint16 writer, 8 per store
+C3_HD __forceinline__ void c3s_out8_push(c3s_out8 &o, const int v)
+{
+    o.lo = (o.lo >> 16) | (o.hi << 48);
+    o.hi = (o.hi >> 16) | ((unsigned long long)(unsigned)v << 48);
+    if ((++o.n & 7) == 0)
+        *reinterpret_cast<uint4 *>(o.dst + o.n - 8) = make_uint4((uint32_t)o.lo, (uint32_t)(o.lo >> 32), (uint32_t)o.hi, (uint32_t)(o.hi >> 32));
+}
+C3_HD __forceinline__ void c3s_out8_flush(c3s_out8 &o)                // the last, partial piece: element-wise
+{
+    const int r = o.n & 7;
+    if (!r) return;
+    // the r newest values sit in the top r halfwords of (hi:lo)
+    for (int k = 0; k < r; ++k) {
+        const int sh = (8 - r + k) * 16;
+        const unsigned long long w = sh >= 64 ? (o.hi >> (sh - 64)) : (o.lo >> sh);
+        o.dst[o.n - r + k] = (uint16_t)(w & 0xffffu);
+    }
+}
+
 // First sequence -> linear graph, order = SRC, 2, 3, ..., L+1, SINK, and the row descriptors of the first alignment
 // (a chain: predecessor = position - 1, hops to the sink = n - 1 - position).  `tid` of `nthr` workers share the
 // node loop: the init kernel gives a read a whole CTA (coalesced stores), the emulation one worker.
@@ -83,13 +133,17 @@ C3_HD inline void c3s_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_par
     G.q = q; G.qlen = qlen; G.n = n; G.w = P.wb + (int)(P.wf * (double)qlen);
     const uint16_t *ord = W.order[G.ob];
     int xbase = 0;
-    int idn = ord[n - 1];
+    uint4 oc = *reinterpret_cast<const uint4 *>(ord + ((n - 1) & ~7));       // the 8 order entries around the current position
+    int idn = c3s_u16_of(oc, (n - 1) & 7);
     c3_nrec ndn = c3_ld_node(&W.nodes[idn]);
     int prev_id = -1, prev_hops = 0;              // the node handled one step earlier (position p + 1)
     for (int p = n - 1; p >= 0; --p) {
         const int id = idn;
         const c3_nrec nd = ndn;
-        if (p > 0) { idn = ord[p - 1]; ndn = c3_ld_node(&W.nodes[idn]); }      // the next node's record is requested now
+        if (p > 0) {                              // the next node's record is requested now
+            if (((p - 1) & 7) == 7) oc = *reinterpret_cast<const uint4 *>(ord + ((p - 1) & ~7));
+            idn = c3s_u16_of(oc, (p - 1) & 7); ndn = c3_ld_node(&W.nodes[idn]);
+        }
         const int base = C3_N_BASE(nd), in_n = C3_N_INN(nd);
         int p0 = C3_NONE, p1 = C3_NONE;
         const int xo = xbase;
@@ -131,6 +185,9 @@ C3_HD inline void c3s_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_par
 // The record, descriptor and cell of the first predecessor -- where the path goes next nine times out of ten -- are
 // requested together, so a match/mismatch move costs one memory round trip.  Returns the number of cigar ops or <0.
 // ---------------------------------------------------------------------------
+#ifndef C3S_BK
+#define C3S_BK 2
+#endif
 C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, const uint4 *arena)
 {
     const int e1 = P.e1, e2 = P.e2, oe1 = P.o1 + P.e1, oe2 = P.o2 + P.e2;
@@ -156,13 +213,45 @@ C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa
         nc = qlen - bj; j = bj; pos = bk; hij = best;
     }
     int cur_op = C3_OP_ALL;
+    c3s_q4 qc; c3s_q4_init(qc, q);
     uint4 d = W.desc[pos];
     uint2 rt = W.rowrec[pos];
     while (pos != 0 && j > 0) {
+        // Fast block: the path mostly runs (pos, j) -> (pos - 1, j - 1) by match/mismatch moves through first
+        // predecessors that sit one position back.  The addresses of the next C3S_BK such steps do not depend on any
+        // value, so everything they need is requested at once (one memory round trip instead of C3S_BK); each step is
+        // then accepted only if the generic step below would have made exactly this move (M is tested first, the
+        // first predecessor first), and the block stops at the first step that is anything else.
+        int fast = 0;
+        if (cur_op & C3_OP_M) {
+            uint4 dk[C3S_BK]; uint2 rk[C3S_BK]; int hk[C3S_BK], qk[C3S_BK];
+#pragma unroll
+            for (int k = 0; k < C3S_BK; ++k) {
+                const int pp = max(pos - 1 - k, 0), jj = max(j - 1 - k, 0);
+                dk[k] = W.desc[pp]; rk[k] = W.rowrec[pp];
+                hk[k] = c3g_cell_h(arena, vs, pp, jj); qk[k] = c3s_q4_get(qc, jj);
+            }
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < C3S_BK; ++k) {
+                if (ok) {
+                    const int b = C3G_R_BEG(rt) * 16, en = min(qlen, C3G_R_END(rt) * 16 + 15);
+                    const int pbeg = C3G_R_BEG(rk[k]) * 16, pend = min(qlen, C3G_R_END(rk[k]) * 16 + 15);
+                    ok = pos != 0 && j > 0 && C3G_D_NPRE(d) > 0 && C3G_D_P0(d) == pos - 1 && j >= b && j <= en &&
+                         j - 1 >= max(pbeg, b) && j - 1 <= pend &&
+                         hk[k] + c3_score(P, C3G_D_BASE(d), qk[k]) == hij && nc + j + 8 <= cap;
+                    if (ok) {
+                        cg[nc++] = C3_CG_MATCH | ((unsigned long long)C3G_D_ID(d) << 8) | ((unsigned long long)(j - 1) << 32);
+                        --pos; --j; hij = hk[k]; rt = rk[k]; d = dk[k]; cur_op = C3_OP_ALL; ++fast;
+                    }
+                }
+            }
+        }
+        if (fast == C3S_BK || pos == 0 || j <= 0) continue;
         const int i = C3G_D_ID(d);
         const int b = C3G_R_BEG(rt) * 16, en = min(qlen, C3G_R_END(rt) * 16 + 15);
         if (j < b || j > en) { C3G_DECLINE(); return C3G_E_RETRY; }
-        const int s = c3_score(P, C3G_D_BASE(d), q[j - 1]);
+        const int s = c3_score(P, C3G_D_BASE(d), c3s_q4_get(qc, j - 1));
         const int npre = C3G_D_NPRE(d);
         int hit = 0;
         unsigned long long opw = 0;
@@ -299,18 +388,20 @@ C3_HD inline int c3s_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const
     g.node_cap = L.A.node_cap; g.pool_cap = L.A.pool_cap; g.err = 0;
     int last_id = C3_SRC, last_new = 0;
     int last_gap = 0, last_p = 0;                // gap of the last new node / old position its group walk starts at
-    unsigned long long opn = nc > 0 ? cg[nc - 1] : 0ull;
+    c3s_q4 qc; c3s_q4_init(qc, q);
+    // two ops per load (the cigar is 16-byte aligned); the op after the current one is always in registers
+    ulonglong2 cp = nc > 0 ? *reinterpret_cast<const ulonglong2 *>(cg + ((nc - 1) & ~1)) : make_ulonglong2(0ull, 0ull);
+    unsigned long long opn = ((nc - 1) & 1) ? cp.y : cp.x;
     for (int t = nc - 1; t >= 0 && !g.err; --t) {
         const unsigned long long opc = opn;
-        if (t > 0) {                             // next op now, and its node record on the way
-            opn = cg[t - 1];
-            const int nn = (int)((opn >> 8) & 0xffff);
-            if (nn != (int)C3_NONE) C3L_PREFETCH(&g.nodes[nn]);
+        if (t > 0) {
+            if ((t - 1) & 1) cp = *reinterpret_cast<const ulonglong2 *>(cg + ((t - 1) & ~1));
+            opn = ((t - 1) & 1) ? cp.y : cp.x;
         }
         const int kc = (int)(opc & 0xff), nid = (int)((opc >> 8) & 0xffff), qp = (int)(opc >> 32);
         if (kc == (int)C3_CG_DEL) continue;
         if (kc == (int)C3_CG_MATCH) {
-            const uint8_t bq = q[qp];
+            const uint8_t bq = (uint8_t)c3s_q4_get(qc, qp);
             const c3_pnode nm = g.nodes[nid];
             if (nm.base != bq) {
                 int al = -1;
@@ -341,7 +432,7 @@ C3_HD inline int c3s_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const
                 last_id = nid; last_new = 0;
             }
         } else {                                                     // insertion: right after the aligned block of last_id
-            const int id = c3_g_add_node(g, q[qp]);
+            const int id = c3_g_add_node(g, (uint8_t)c3s_q4_get(qc, qp));
             if (g.err) break;
             const c3_pnode nl = g.nodes[last_id];
             int gap;
@@ -365,17 +456,25 @@ C3_HD inline void c3s_reorder(c3g_grp &G, const c3g_ws &W)
 {
     const int n_old = G.n, m = G.node_n - n_old;
     const uint16_t *oo = W.order[G.ob];
-    uint16_t *on = W.order[G.ob ^ 1];
+    c3s_out8 on; on.dst = W.order[G.ob ^ 1]; on.lo = on.hi = 0ull; on.n = 0;
     int t = 0;
     int gt = m > 0 ? (int)W.gaps[0] : 0x7fffffff;
-    for (int p = 0; p < n_old; ++p) {
-        while (gt <= p) {
-            on[p + t] = (uint16_t)(n_old + t); W.posof[n_old + t] = (uint16_t)(p + t); ++t;
-            gt = t < m ? (int)W.gaps[t] : 0x7fffffff;
+    for (int p0 = 0; p0 < n_old; p0 += 8) {
+        const uint4 oc = *reinterpret_cast<const uint4 *>(oo + p0);          // (the arrays are padded to 32 entries)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int p = p0 + k;
+            if (p < n_old) {
+                while (gt <= p) {
+                    W.posof[n_old + t] = (uint16_t)on.n; c3s_out8_push(on, n_old + t); ++t;
+                    gt = t < m ? (int)W.gaps[t] : 0x7fffffff;
+                }
+                const int id = c3s_u16_of(oc, k);
+                W.posof[id] = (uint16_t)on.n; c3s_out8_push(on, id);
+            }
         }
-        const int id = oo[p];
-        on[p + t] = (uint16_t)id; W.posof[id] = (uint16_t)(p + t);
     }
+    c3s_out8_flush(on);
     G.ob ^= 1;
 }
 
@@ -387,6 +486,8 @@ C3_HD inline int c3s_consensus(const c3g_grp &G, const c3_poa_args &A, const c3g
     for (int p = G.node_n - 1; p >= 0; --p) {
         const int v = ord[p];
         c3_pnode *nd = &W.nodes[v];
+        if (p >= C3S_PF) C3S_PREFETCH(&W.nodes[ord[p - C3S_PF]]);
+        if ((p & 15) == 0 && p >= C3S_PF + 80) C3S_PREFETCH(&ord[p - C3S_PF - 80]);
         if (v == C3_SINK) { nd->max_out = C3_NONE; score[v] = 0; }
         else if (v == C3_SRC) {
             int max_id = -1, path_score = -1, path_w = -1;
@@ -457,20 +558,31 @@ C3_HD inline void c3s_graph_step(const c3g_args &L, const int it, const bool val
     c3g_grp G;
     G.err = 0; G.sq = 0; G.nseq = 0;
     bool run = valid;
+#if defined(C3L_PROF) && defined(__CUDA_ARCH__)
+    const int lane = threadIdx.x & 31;
+#endif
+    C3L_TICK_INIT;
     {
         if (run) { c3g_state_load(G, S, A); if (G.err || G.sq >= G.nseq) run = false; }   // declined earlier / finished earlier
         int nc = 0;
         C3S_SYNC();
+        C3L_TICK(6);
         if (run) { nc = c3s_backtrack(G, L, P, W, arena); if (nc < 0) G.err = C3G_E_RETRY; }
         C3S_SYNC();
+        C3L_TICK(7);
         if (run && !G.err && c3s_merge(G, L, W, nc)) G.err = C3G_E_RETRY;
         C3S_SYNC();
+        C3L_TICK(8);
         if (run && !G.err) { c3s_reorder(G, W); ++G.sq; }
     }
     C3S_SYNC();
+    C3L_TICK(9);
     if (run && !G.err && G.sq < G.nseq) c3s_prepare(G, A, P, W);
     C3S_SYNC();
+    C3L_TICK(10);
     if (run && !G.err && G.sq >= G.nseq) c3s_finish(G, L, W);
+    C3S_SYNC();
+    C3L_TICK(11);
     if (run) c3g_state_store(G, S);
 }
 
@@ -478,7 +590,10 @@ C3_HD inline void c3s_graph_step(const c3g_args &L, const int it, const bool val
 #ifndef C3S_THREADS
 #define C3S_THREADS 64
 #endif
-__global__ void __launch_bounds__(C3S_THREADS) c3_poa_graph_kernel(c3g_args L)
+#ifndef C3S_MINB
+#define C3S_MINB 12                    // 768 threads per SM: a 100k-read wave is resident at once
+#endif
+__global__ void __launch_bounds__(C3S_THREADS, C3S_MINB) c3_poa_graph_kernel(c3g_args L)
 {
     const int it = blockIdx.x * C3S_THREADS + threadIdx.x;
     c3s_graph_step(L, it, it < L.A.n_work);

@@ -1,4 +1,4 @@
-"""Per-phase cycle shares of c3_poa_grp_kernel (library built with -DC3L_PROF into build/variants/lib_gprof.so).
+"""Per-phase cycle shares of c3_poa_graph_kernel (warp-cycles per phase, lane 0 of every warp) (library built with -DC3L_PROF into build/variants/lib_gprof.so).
 usage: python tools/grp_prof_run.py [reads]"""
 import ctypes as C
 import os
@@ -23,8 +23,8 @@ L.c3_debug_lane_prof(z, 1)
 out = g.consensus_batch(b, max_peaks=16, cons_cap=2048)
 L.c3_debug_lane_prof(z, 0)
 v = list(z)
-names = ['fetch+item_begin', 'prepare', 'source+DP rows', 'backtrack', 'merge+reorder', 'consensus+end']
-tot = max(sum(v[:6]), 1)
+names = ['load state', 'backtrack', 'merge', 'reorder', 'prepare', 'consensus+end']
+tot = max(sum(v[6:12]), 1)
 for i, nm in enumerate(names):
-    print(f'{nm:18s} {v[i]/1e9:10.3f} Gcycles {100*v[i]/tot:6.2f} %')
+    print(f'{nm:18s} {v[6+i]/1e9:10.3f} Gcycles {100*v[6+i]/tot:6.2f} %')
 print('timings', g.timings(), 'grp', g.lane_counts(), 'ok', int((out['results']['status'] == 0).sum()))

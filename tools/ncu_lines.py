@@ -51,7 +51,8 @@ def main():
         if re.search(r"/\*[0-9a-f]{4,}\*/", ln) and not ln.strip().startswith("//"):
             lines.append(cur_line)
     print(f"# {blk['name']}: {len(data)} SASS rows in report, {len(lines)} in cubin")
-    agg = defaultdict(lambda: [0, 0, 0])
+    agg = defaultdict(lambda: [0, 0, 0, 0])
+    sort_col = 3 if os.environ.get('NCU_SORT') == 'sectors' else 0
     n = min(len(data), len(lines))
     for k in range(n):
         r = data[k]
@@ -59,13 +60,15 @@ def main():
         te = int(r[ci["Thread Instructions Executed"]] or 0)
         ss = int(r[ci["Warp Stall Sampling (All Samples)"]] or 0)
         a = agg[lines[k]]
-        a[0] += ie; a[1] += te; a[2] += ss
+        a[0] += ie; a[1] += te; a[2] += ss; a[3] += int(r[ci["L2 Theoretical Sectors Global"]] or 0)
     tot_i = sum(a[0] for a in agg.values()); tot_s = sum(a[2] for a in agg.values())
     print(f"# total warp-instructions {tot_i:,}  stall samples {tot_s:,}")
-    print("# file:line  warp_inst  %inst  avg_threads  stall_samples  %stall")
-    for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
+    tot_x = sum(a[3] for a in agg.values())
+    print(f"# L2 theoretical sectors (global) {tot_x:,}")
+    print("# file:line  warp_inst  %inst  avg_threads  stall_samples  %stall  l2_sectors  %sectors")
+    for key, a in sorted(agg.items(), key=lambda kv: -kv[1][sort_col])[:topn]:
         print(f"{key[0] if key else '?'}:{key[1] if key else 0:<5d} {a[0]:>14,} {100*a[0]/max(tot_i,1):6.2f}% "
-              f"{a[1]/max(a[0],1):6.1f} {a[2]:>9,} {100*a[2]/max(tot_s,1):6.2f}%")
+              f"{a[1]/max(a[0],1):6.1f} {a[2]:>9,} {100*a[2]/max(tot_s,1):6.2f}% {a[3]:>13,} {100*a[3]/max(tot_x,1):6.2f}%")
 
 
 if __name__ == "__main__":
