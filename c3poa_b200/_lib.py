@@ -31,7 +31,9 @@ class PoaParams(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("encode_ms", C.c_float), ("conk_ms", C.c_float), ("peaks_ms", C.c_float), ("split_ms", C.c_float),
                 ("poa_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_int32),
-                ("poa_items", C.c_int32)]
+                ("poa_items", C.c_int32), ("poa_dp_ms", C.c_float), ("poa_graph_ms", C.c_float),
+                ("poa_warp_ms", C.c_float), ("poa_lane_ms", C.c_float), ("poa_dp_launches", C.c_int32),
+                ("poa_graph_launches", C.c_int32)]
 
 
 RESULT_DTYPE = np.dtype([("status", "<i4"), ("n_peaks", "<i4"), ("n_sub", "<i4"), ("n_dang", "<i4"),

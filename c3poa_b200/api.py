@@ -247,10 +247,26 @@ class GpuConsensus:
                                   out["results"].ctypes.data), "c3_fetch")
         return out
 
-    def consensus_batch(self, batch: ReadBatch, out=None, **kw):
-        self.stage(batch)
-        self.run(**kw)
-        return self.fetch(out)
+    def consensus_batch(self, batch: ReadBatch, out=None, penalty=20, min_dist=500, iters=3, window=41, order=2,
+                        coef=None, params=None, max_peaks=64, cons_cap=4096):
+        """B4 as one call of the fused C-ABI entry point `c3_consensus_batch` (host buffers in, host buffers out): what
+        the reference's `for read in reads:` loop (C3POa.py:112-165) is replaced by.  stage / run / fetch are the same
+        three steps for callers that keep a batch resident."""
+        coef = sg_coeffs(window, order) if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
+        params = params or default_poa_params()
+        n = batch.n
+        if out is None:
+            out = dict(peaks=np.zeros((n, max_peaks), dtype=np.int32), sub_bounds=np.zeros((n, max_peaks, 2), dtype=np.int32),
+                       dang_bounds=np.zeros((n, 2, 2), dtype=np.int32), cons=np.zeros((n, cons_cap), dtype=np.uint8),
+                       results=np.zeros(n, dtype=RESULT_DTYPE))
+        self._ck(self._L.c3_consensus_batch(self._h, n, batch.blob.ctypes.data, batch.off.ctypes.data,
+                                            batch.sp_off.size - 1, batch.sp_blob.ctypes.data, batch.sp_off.ctypes.data,
+                                            batch.sp_idx.ctypes.data, penalty, coef.ctypes.data, coef.size, iters, min_dist,
+                                            C.byref(params), max_peaks, cons_cap, out["peaks"].ctypes.data,
+                                            out["sub_bounds"].ctypes.data, out["dang_bounds"].ctypes.data,
+                                            out["cons"].ctypes.data, out["results"].ctypes.data), "c3_consensus_batch")
+        self._n, self._max_peaks, self._cons_cap = n, max_peaks, cons_cap
+        return out
 
 
 def pairwise_rows(out, i):

@@ -40,6 +40,30 @@ struct c3_handle {
     char err[512] = {0};
     cudaEvent_t ev[8] = {nullptr};
     c3_timings tim{};
+    // per-launch timing of the POA kernels: event pairs recorded around every launch, summed by kind after the call's
+    // final synchronisation (kt_collect)
+    std::vector<cudaEvent_t> kt_ev; std::vector<int> kt_kind; size_t kt_used = 0;
+    void kt_begin() { kt_mark(-1); }
+    void kt_end(int kind) { kt_mark(kind); }
+    void kt_mark(int kind)
+    {
+        if (kt_used == kt_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); kt_ev.push_back(e); kt_kind.push_back(0); }
+        cudaEventRecord(kt_ev[kt_used], stream); kt_kind[kt_used] = kind; ++kt_used;
+    }
+    void kt_collect()
+    {
+        for (size_t k = 1; k < kt_used; ++k) {
+            if (kt_kind[k] < 0) continue;
+            float t = 0.f; cudaEventElapsedTime(&t, kt_ev[k - 1], kt_ev[k]);
+            switch (kt_kind[k]) {
+            case 0: tim.poa_dp_ms += t; tim.poa_dp_launches++; break;
+            case 1: tim.poa_graph_ms += t; tim.poa_graph_launches++; break;
+            case 2: tim.poa_warp_ms += t; break;
+            default: tim.poa_lane_ms += t; break;
+            }
+        }
+        kt_used = 0;
+    }
     // staged batch
     int n_reads = 0, n_splints = 0, max_lr = 0, max_ls = 0, max_peaks = 0, cons_cap = 0;
     int64_t total_bases = 0, total_sp = 0;
@@ -118,6 +142,7 @@ extern "C" void c3_destroy(c3_handle *h)
                       &h->d_order_lane, &h->d_done, &h->d_order_grp, &h->d_ws_grp};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->kt_ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -252,6 +277,10 @@ static void to_dev_para(const c3_poa_params *p, c3_poa_para_dev *d)
     d->o2 = p->gap_open2; d->e2 = p->gap_ext2; d->wb = p->wb; d->simd_bits = p->simd_bits; d->wf = p->wf;
 }
 
+// auto mode: what goes to the group kernel (poa_grp.cuh + poa_graph.cuh); measured on B200, see profiles/README.md
+#define C3_GRP_AUTO_MAX_LEN 2600       // mean subread length of a read
+#define C3_GRP_AUTO_MAX_NSEQ 32
+#define C3_GRP_AUTO_MIN_READS 24000
 // Work order for the persistent POA grid: items with >= min_seqs sequences, largest estimated DP cost first
 // (LPT scheduling: the longest reads start first, so a batch ends with short ones).  cost ~ alignments x
 // mean length x band width.  O(n) bucket sort on 1/16-octave cost classes.
@@ -315,12 +344,18 @@ static int upload_poa_order(c3_handle *h, c3_poa_args &A, const std::vector<int3
                 const int64_t Lm = total[i] / nseq[i] * 5 / 4 + 1;
                 const int64_t nodes = 2 + Lm + (int64_t)(nseq[i] - 1) * (Lm * 35 / 100 + 16);
                 if (Lm * 5 > lim || std::max(Lm, nodes) * pp->gap_ext1 + pp->gap_open1 > lim || nodes > 65000) continue;
+                // auto: the bulk of short subreads only.  The serial phases of the group path run one thread per read
+                // with a latency floor per launch that grows with the sequence length, and a read's workspace grows
+                // with length x depth: long or very deep reads are better off in the warp kernel (profiles/README.md)
+                if (h->poa_mode == 0 && (total[i] / nseq[i] > C3_GRP_AUTO_MAX_LEN || nseq[i] > C3_GRP_AUTO_MAX_NSEQ)) continue;
                 grp[ng++] = i;
                 h->grp_nseq.push_back(nseq[i]);
                 h->grp_max_total = std::max(h->grp_max_total, total[i]);
                 h->grp_max_nseq = std::max(h->grp_max_nseq, nseq[i]);
+                h->grp_max_q = std::max<int>(h->grp_max_q, h->poa_mode == 0 ? (int)std::min<int64_t>(Lm, 65000) : 65000);
             }
         }
+        if (h->poa_mode == 0 && ng < C3_GRP_AUTO_MIN_READS) { ng = 0; h->grp_nseq.clear(); }    // too few to amortise the launches
         CK(h->d_order_grp.ensure((size_t)std::max(ng, 1) * 4));
         CK(cudaMemcpyAsync(h->d_order_grp.p, grp.data(), (size_t)ng * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -406,7 +441,9 @@ static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa
     L.arena = reinterpret_cast<int4 *>(h->d_ws.as<uint8_t>() + warps * 32 * ws_bytes);
     L.arena_stride4 = arena4; L.arena_cap4 = (int)arena4; L.sm_vec = sm_vec;
     L.done = h->d_done.as<int32_t>();
+    h->kt_begin();
     c3_poa_lane_kernel<<<(int)(warps / wpb), C3L_THREADS, sm_bytes, h->stream>>>(L);
+    h->kt_end(3);
     CK(cudaGetLastError());
     h->tim.kernel_launches++;
     h->lane_items = nl; h->lane_n_items = A.n_items;
@@ -426,7 +463,7 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     if ((h->poa_mode != 0 && h->poa_mode != 3) || ng <= 0) return 0;
     const int max_nseq = h->grp_max_nseq;
     const int64_t max_total = h->grp_max_total;
-    max_q = (int)std::min<int64_t>(max_q, max_total);
+    max_q = (int)std::min<int64_t>(std::min<int64_t>(max_q, max_total), std::max(h->grp_max_q, 64));
     // Per-read capacity: nodes = first sequence + a share of every further one.  The serial phases run one thread per
     // read and are bound by the length of their dependent chains, not by the number of reads, so one wave for the whole
     // batch is worth a tighter node estimate (what outgrows it is declined and goes to the warp kernel with its own,
@@ -495,33 +532,20 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
         const int grid_dp = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * bps_dp, (w_dp + wpb - 1) / wpb));
         const int grid_gr = (nw + C3S_THREADS - 1) / C3S_THREADS;  // one thread per read
         int launch = 0;
-        std::vector<cudaEvent_t> ev;                               // C3POA_GRP_TIMING=1 (tuning only): per-launch times on stderr
-        auto mark = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); ev.push_back(e); } };
-        mark();
+        h->kt_begin();
         c3_poa_graph_init_kernel<<<nw, 128, 0, h->stream>>>(L);
-        mark();
+        h->kt_end(1);
         h->tim.kernel_launches++;
         for (int sq = 1; sq < wave_nseq; ++sq) {
             L.A.counter = counters + launch++;
             kdp<<<grid_dp, C3G_THREADS, sm_dp, h->stream>>>(L);
-            mark();
+            h->kt_end(0);
             c3_poa_graph_kernel<<<grid_gr, C3S_THREADS, 0, h->stream>>>(L);
-            mark();
+            h->kt_end(1);
             h->tim.kernel_launches += 2;
         }
         CK(cudaGetLastError());
-        if (timing) {
-            CK(cudaStreamSynchronize(h->stream));
-            float dp = 0.f, gr = 0.f, t = 0.f;
-            fprintf(stderr, "grp wave %d reads (node_cap %lld, %lld B/read):", nw, (long long)node_cap, (long long)read_bytes);
-            for (size_t k = 1; k < ev.size(); ++k) {
-                cudaEventElapsedTime(&t, ev[k - 1], ev[k]);
-                fprintf(stderr, " %.2f", t);
-                if (k >= 2) { if (k & 1) gr += t; else dp += t; }
-            }
-            fprintf(stderr, "  | dp %.2f graph %.2f ms\n", dp, gr);
-            for (cudaEvent_t e : ev) cudaEventDestroy(e);
-        }
+        if (timing) fprintf(stderr, "grp wave %d reads (node_cap %lld, %lld B/read, %d alignments)\n", nw, (long long)node_cap, (long long)read_bytes, wave_nseq - 1);
     }
     h->lane_items = ng; h->lane_n_items = A.n_items;
     A.done = h->d_done.as<int32_t>();
@@ -577,7 +601,9 @@ static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int
     A.ws = h->d_ws.as<uint8_t>(); A.ws_stride = ws_bytes;
     A.node_cap = (int)node_cap; A.pool_cap = pool_cap; A.cell_cap = (int)cell_cap; A.cigar_cap = cigar_cap; A.qp_stride = qp_stride;
     A.counter = h->d_counter.as<unsigned>();
+    h->kt_begin();
     c3_poa_kernel<<<grid, threads, 0, h->stream>>>(A);
+    h->kt_end(2);
     CK(cudaGetLastError());
     h->tim.kernel_launches++;
     return 0;
@@ -645,7 +671,7 @@ extern "C" int c3_conk_batch(c3_handle *h, int32_t n_reads, const char *reads, c
     int rc = stage_reads(h, n_reads, reads, read_off, n_splints, splints, splint_off, splint_idx);
     if (rc) return rc;
     if (!out_profile) return fail(h, -5, "out_profile is null");
-    h->tim = c3_timings{};
+    h->tim = c3_timings{}; h->kt_used = 0;
     CK(cudaEventRecord(h->ev[0], h->stream));
     if ((rc = encode_staged(h))) return rc;
     CK(cudaEventRecord(h->ev[1], h->stream));
@@ -689,7 +715,7 @@ extern "C" int c3_assign_splints(c3_handle *h, int32_t n_reads, const char *read
     std::vector<int32_t> zero((size_t)std::max(n_reads, 1), 0);
     int rc = stage_reads(h, n_reads, reads, read_off, n_cands, cands, cand_off, zero.data());
     if (rc) return rc;
-    h->tim = c3_timings{};
+    h->tim = c3_timings{}; h->kt_used = 0;
     CK(h->d_status.ensure((size_t)n_cands * n_reads * 4));          // scores [n_cands][n_reads]
     CK(cudaEventRecord(h->ev[0], h->stream));
     if ((rc = encode_staged(h))) return rc;
@@ -737,7 +763,7 @@ extern "C" int c3_peaks_batch(c3_handle *h, int32_t n, const int32_t *profile, c
     CK(h->d_off.ensure((size_t)(n + 1) * 8));
     CK(cudaMemcpyAsync(h->d_prof.p, profile, (size_t)total * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_off.p, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    h->tim = c3_timings{};
+    h->tim = c3_timings{}; h->kt_used = 0;
     CK(cudaEventRecord(h->ev[0], h->stream));
     int rc = launch_peaks(h, h->d_prof.as<int32_t>(), h->d_off.as<int64_t>(), n, max_len, coef, window, iters, min_dist,
                           height_mult, gate_mult, out_smoothed != nullptr, out_median != nullptr, max_peaks, total);
@@ -813,7 +839,7 @@ extern "C" int c3_poa_batch(c3_handle *h, int32_t n_groups, const char *seqs, co
     CK(cudaMemsetAsync(h->d_nodes.p, 0, (size_t)n_groups * 4, h->stream));
     CK(cudaMemsetAsync(h->d_cells.p, 0, (size_t)n_groups * 8, h->stream));
     CK(cudaMemsetAsync(h->d_cons.p, 0, (size_t)n_groups * cons_cap, h->stream));
-    h->tim = c3_timings{};
+    h->tim = c3_timings{}; h->kt_used = 0;
     CK(cudaEventRecord(h->ev[0], h->stream));
     int rc = launch_encode(h, h->d_ascii.p, h->d_codes.p, total);
     if (rc) return rc;
@@ -851,6 +877,7 @@ extern "C" int c3_poa_batch(c3_handle *h, int32_t n_groups, const char *seqs, co
             out_msa_len[g] = L; out_cons_len[g] = 0;
         }
     }
+    h->kt_collect();
     cudaEventElapsedTime(&h->tim.encode_ms, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->tim.poa_ms, h->ev[1], h->ev[2]);
     h->tim.total_ms = h->tim.encode_ms + h->tim.poa_ms;
@@ -894,7 +921,7 @@ extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t
     CK(cudaSetDevice(h->device));
     const int n = h->n_reads;
     h->max_peaks = max_peaks; h->cons_cap = cons_cap;
-    h->tim = c3_timings{};
+    h->tim = c3_timings{}; h->kt_used = 0;
     CK(h->d_sub.ensure((size_t)n * max_peaks * 2 * 4 + 16));
     CK(h->d_dang.ensure((size_t)n * 4 * 4 + 16));
     CK(h->d_res.ensure((size_t)n * sizeof(c3_read_result)));
@@ -958,6 +985,7 @@ extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t
     cudaEventElapsedTime(&h->tim.conk_ms, h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&h->tim.peaks_ms, h->ev[2], h->ev[3]);
     cudaEventElapsedTime(&h->tim.split_ms, h->ev[3], h->ev[4]);
+    h->kt_collect();
     cudaEventElapsedTime(&h->tim.poa_ms, h->ev[4], h->ev[5]);
     cudaEventElapsedTime(&h->tim.total_ms, h->ev[0], h->ev[5]);
     h->ran = true;

@@ -133,17 +133,23 @@ C3_HD inline void c3s_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_par
     G.q = q; G.qlen = qlen; G.n = n; G.w = P.wb + (int)(P.wf * (double)qlen);
     const uint16_t *ord = W.order[G.ob];
     int xbase = 0;
-    uint4 oc = *reinterpret_cast<const uint4 *>(ord + ((n - 1) & ~7));       // the 8 order entries around the current position
-    int idn = c3s_u16_of(oc, (n - 1) & 7);
-    c3_nrec ndn = c3_ld_node(&W.nodes[idn]);
     int prev_id = -1, prev_hops = 0;              // the node handled one step earlier (position p + 1)
-    for (int p = n - 1; p >= 0; --p) {
-        const int id = idn;
-        const c3_nrec nd = ndn;
-        if (p > 0) {                              // the next node's record is requested now
-            if (((p - 1) & 7) == 7) oc = *reinterpret_cast<const uint4 *>(ord + ((p - 1) & ~7));
-            idn = c3s_u16_of(oc, (p - 1) & 7); ndn = c3_ld_node(&W.nodes[idn]);
-        }
+    // 8 positions per block: their order entries are one 16-byte piece, their node records are requested together
+    // (one memory round trip for the block); the entry before the block comes from the next block's piece
+    uint4 ocn = *reinterpret_cast<const uint4 *>(ord + ((n - 1) & ~7));
+    for (int pc = (n - 1) & ~7; pc >= 0; pc -= 8) {
+        const uint4 oc = ocn;
+        if (pc > 0) ocn = *reinterpret_cast<const uint4 *>(ord + pc - 8);
+        c3_nrec rk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (pc + k < n) rk[k] = c3_ld_node(&W.nodes[c3s_u16_of(oc, k)]);
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+        const int p = pc + k;
+        if (p >= n) continue;
+        const int id = c3s_u16_of(oc, k);
+        const c3_nrec nd = rk[k];
+        const int idn = k > 0 ? c3s_u16_of(oc, k - 1) : c3s_u16_of(ocn, 7);     // id at position p - 1 (unused when p = 0)
         const int base = C3_N_BASE(nd), in_n = C3_N_INN(nd);
         int p0 = C3_NONE, p1 = C3_NONE;
         const int xo = xbase;
@@ -177,6 +183,7 @@ C3_HD inline void c3s_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_par
         if (in_n > C3_MAXPRE || hops > 65535) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
         W.desc[p] = make_uint4((uint32_t)id | ((uint32_t)p0 << 16), (uint32_t)p1 | ((uint32_t)hops << 16),
                                (uint32_t)base | ((uint32_t)in_n << 8) | ((uint32_t)xo << 16), 0u);
+        }
     }
 }
 
@@ -186,7 +193,10 @@ C3_HD inline void c3s_prepare(c3g_grp &G, const c3_poa_args &A, const c3_poa_par
 // requested together, so a match/mismatch move costs one memory round trip.  Returns the number of cigar ops or <0.
 // ---------------------------------------------------------------------------
 #ifndef C3S_BK
-#define C3S_BK 2
+#define C3S_BK 4
+#endif
+#ifndef C3S_MK
+#define C3S_MK 4                      // ops per fast block of the merge
 #endif
 C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, const uint4 *arena)
 {
@@ -389,15 +399,42 @@ C3_HD inline int c3s_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const
     int last_id = C3_SRC, last_new = 0;
     int last_gap = 0, last_p = 0;                // gap of the last new node / old position its group walk starts at
     c3s_q4 qc; c3s_q4_init(qc, q);
-    // two ops per load (the cigar is 16-byte aligned); the op after the current one is always in registers
-    ulonglong2 cp = nc > 0 ? *reinterpret_cast<const ulonglong2 *>(cg + ((nc - 1) & ~1)) : make_ulonglong2(0ull, 0ull);
-    unsigned long long opn = ((nc - 1) & 1) ? cp.y : cp.x;
-    for (int t = nc - 1; t >= 0 && !g.err; --t) {
-        const unsigned long long opc = opn;
-        if (t > 0) {
-            if ((t - 1) & 1) cp = *reinterpret_cast<const ulonglong2 *>(cg + ((t - 1) & ~1));
-            opn = ((t - 1) & 1) ? cp.y : cp.x;
+    int t = nc - 1;
+    while (t >= 0 && !g.err) {
+        // Fast block: most ops are deletions (nothing to do) or matches onto a node with the read's base whose edge from
+        // the previous node already exists as that node's first out-edge (one weight to bump).  The next C3S_MK ops and
+        // the hot halves of their node records are requested together -- two memory round trips for the block instead
+        // of two per op -- and consumed while they are of that kind; the first op that is anything else is left to the
+        // generic code below, which reads everything afresh.
+        {
+            unsigned long long ok_[C3S_MK]; c3_nrec rk[C3S_MK];
+#pragma unroll
+            for (int k = 0; k < C3S_MK; ++k) ok_[k] = t - k >= 0 ? cg[t - k] : C3_CG_DEL;
+            c3_nrec prev = c3_ld_node(&g.nodes[last_id]);
+#pragma unroll
+            for (int k = 0; k < C3S_MK; ++k) {
+                const int nn = (int)((ok_[k] >> 8) & 0xffff);
+                rk[k] = c3_ld_node(&g.nodes[(ok_[k] & 0xff) == C3_CG_MATCH ? nn : 0]);
+            }
+            bool ok = true;
+            int used = 0;
+#pragma unroll
+            for (int k = 0; k < C3S_MK; ++k) {
+                if (ok && t - k >= 0) {
+                    const int kc = (int)(ok_[k] & 0xff), nid = (int)((ok_[k] >> 8) & 0xffff), qp = (int)(ok_[k] >> 32);
+                    if (kc == (int)C3_CG_DEL) ++used;
+                    else if (kc == (int)C3_CG_MATCH && !last_new && C3_N_BASE(rk[k]) == c3s_q4_get(qc, qp) &&
+                             C3_N_OUTN(prev) > 0 && C3_N_OUT0(prev) == nid) {
+                        g.nodes[last_id].w0 = (uint16_t)(C3_N_W0(prev) + 1);
+                        last_id = nid; prev = rk[k]; ++used;
+                    } else ok = false;
+                }
+            }
+            t -= used;
+            if (ok) continue;
         }
+        const unsigned long long opc = cg[t];
+        --t;
         const int kc = (int)(opc & 0xff), nid = (int)((opc >> 8) & 0xffff), qp = (int)(opc >> 32);
         if (kc == (int)C3_CG_DEL) continue;
         if (kc == (int)C3_CG_MATCH) {

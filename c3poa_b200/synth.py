@@ -171,3 +171,52 @@ def make_batch(n_reads: int, insert_len=1000, repeats=5, seed=20251018, splint: 
     off = np.zeros(n_reads + 1, dtype=np.int64)
     off[1:] = np.cumsum(np.concatenate([p[1] for p in parts]))
     return blob, off, np.concatenate([p[2] for p in parts])
+
+
+def make_mixed_batch(n_reads: int, inserts, repeat_range, splints=None, seed=20251018, err=(0.04, 0.03, 0.03),
+                     flank=(100, 400), both_strands=True, workers=None):
+    """Vectorised generator for mixed configs: every read draws its insert length from `inserts` (a list of lengths),
+    its repeat count from repeat_range (inclusive) and its splint from `splints` (list of str; default Splint1), all
+    uniformly.  Reads of one (insert, repeats, splint) class are generated together (_make_chunk) and then put back at
+    their drawn places, so the batch is mixed read by read.  Returns (blob uint8 ASCII, off int64[n+1],
+    sp_idx int32[n] = 2 * splint + (strand == '-'), splint list in both orientations)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    splints = list(splints) if splints else [SPLINT1]
+    sp_arr = [np.frombuffer(s.encode(), dtype=np.uint8) for s in splints]
+    rng = np.random.default_rng([seed, 7])
+    inserts = [int(x) for x in inserts]
+    ci = rng.integers(0, len(inserts), size=n_reads)
+    ck = rng.integers(repeat_range[0], repeat_range[1] + 1, size=n_reads)
+    cs = rng.integers(0, len(splints), size=n_reads)
+    key = (ci * 64 + ck) * 16 + cs
+    order = np.argsort(key, kind="stable")
+    ks, starts = np.unique(key[order], return_index=True)
+    ends = list(starts[1:]) + [n_reads]
+    jobs, where = [], []
+    for kk, a, b in zip(ks, starts, ends):
+        il, k, sp = inserts[int(kk) // 16 // 64], int(kk) // 16 % 64, int(kk) % 16
+        m_max = max(64, min(4096, (192 << 20) // ((k + 2) * (il + sp_arr[sp].size))))      # <= ~192 MB of clean bases per chunk
+        for c0 in range(int(a), int(b), m_max):
+            c1 = min(int(b), c0 + m_max)
+            jobs.append((c1 - c0, il, k, sp_arr[sp], seed, c0, err, flank, both_strands))
+            where.append((order[c0:c1], sp))
+    workers = workers or min(16, os.cpu_count() or 1)
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        parts = list(ex.map(lambda a: _make_chunk(*a), jobs))
+    lens = np.zeros(n_reads, dtype=np.int64)
+    sp_idx = np.zeros(n_reads, dtype=np.int32)
+    for (idx, sp), (_, ln, st) in zip(where, parts):
+        lens[idx] = ln
+        sp_idx[idx] = 2 * sp + st.astype(np.int32)
+    off = np.zeros(n_reads + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    blob = np.empty(int(off[-1]), dtype=np.uint8)
+    for (idx, _), (nz, ln, _) in zip(where, parts):
+        src = np.concatenate(([0], np.cumsum(ln)))
+        for t, i in enumerate(idx):
+            blob[off[i]:off[i + 1]] = nz[src[t]:src[t + 1]]
+    both = []
+    for s_ in splints:
+        both += [s_, revcomp(s_)]
+    return blob, off, sp_idx, both

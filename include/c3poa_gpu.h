@@ -62,6 +62,11 @@ typedef struct {
     float encode_ms, conk_ms, peaks_ms, split_ms, poa_ms, total_ms;
     int32_t kernel_launches;   /* kernels launched by that call */
     int32_t poa_items;         /* reads that went through the POA kernel */
+    /* POA stage by kernel (sums of per-launch event pairs on the launch stream; they add up to poa_ms less the host's
+     * work-order preparation): group DP kernel, group graph kernels (init + per-alignment), warp-per-read kernel,
+     * lane kernel */
+    float poa_dp_ms, poa_graph_ms, poa_warp_ms, poa_lane_ms;
+    int32_t poa_dp_launches, poa_graph_launches;
 } c3_timings;
 
 const char *c3_version(void);

@@ -12,11 +12,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-@pytest.fixture(scope="session", params=["auto", "lane"])
+@pytest.fixture(scope="session", params=["auto", "grp", "lane"])
 def gpu(request):
     """The CUDA handle.  No skip: on a GPU box a missing library/device must FAIL the test.
-    Every GPU test runs twice: POA through the group kernel ("auto": 8 lanes per read, the warp-per-read kernel takes
-    what it declines) and through the thread-per-read lane kernel (same fallback)."""
+    Every GPU test runs three times: "auto" (the group kernel for the bulk of short subreads in batches of >= 24 000
+    reads, else the warp-per-read kernel), "grp" (the group kernel -- 8 lanes per read for the DP, one thread per read
+    for the graph phases -- for everything it covers, the warp kernel takes what it declines) and "lane" (the
+    thread-per-read lane kernel of round 1, same fallback)."""
     from c3poa_b200.api import GpuConsensus
     h = GpuConsensus(0, poa_mode=request.param)
     h.poa_mode = request.param

@@ -30,7 +30,8 @@ def main():
         elif cur is not None:
             cur["rows"].append(r)
     plain = re.sub(r"^_Z\d+", "", sym)
-    blk = next(b for b in blocks if plain in b["name"])
+    kname = os.environ.get("NCU_KERNEL", plain)          # name as the report prints it (templates are demangled there)
+    blk = next(b for b in blocks if kname in b["name"])
     hdr, data = blk["rows"][0], blk["rows"][1:]
     ci = {h: i for i, h in enumerate(hdr)}
     with tempfile.TemporaryDirectory() as td:
