@@ -503,7 +503,7 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_dp, kdp, C3G_THREADS, sm_dp) != cudaSuccess || bps_dp < 1) bps_dp = 1;
     if (const char *lim = getenv("C3POA_GRP_DP_CTAS")) bps_dp = std::max(1, std::min(bps_dp, atoi(lim)));     // tuning only
     int64_t wave = std::min<int64_t>(ng, budget / read_bytes);
-    if (wave < 64) return 0;                                       // does not fit: the warp kernel takes everything
+    if (wave < std::min<int64_t>(ng, 64)) return 0;                // does not fit: the warp kernel takes everything
     wave = (ng + (ng + wave - 1) / wave - 1) / ((ng + wave - 1) / wave);    // several waves: equal sizes
     const int n_counters = 2 * max_nseq + 3;
     CK(h->d_ws_grp.ensure((size_t)(wave * read_bytes) + (size_t)n_counters * 4 + 256));

@@ -962,7 +962,7 @@ static void batch_one(batch_job_t *J, int r, poa_ctx_t *ctx, int32_t **prof, int
         c3o_poa_stats_t st; int cl = 0;
         int rc = poa_run(ctx, J->para, nsub, sp, sl, co, J->cons_cap, &cl, NULL, 0, NULL, &st, NULL);
         if (rc) { res->status = rc; J->err = 1; return; }
-        res->cons_len = cl; res->poa_cells = st.cells;
+        res->cons_len = cl; res->poa_cells = st.cells; res->poa_nodes = st.node_n;
     } else if (nsub == 1) {                               /* determine_consensus.py:31-32 */
         int L = sb[1] - sb[0];
         if (L > J->cons_cap) { res->status = -3; J->err = 1; return; }
@@ -976,7 +976,7 @@ static void batch_one(batch_job_t *J, int r, poa_ctx_t *ctx, int32_t **prof, int
         int rc = poa_run(ctx, J->para, 2, sp, sl, NULL, 0, NULL, co, half, &ml, &st, NULL);
         if (rc) { res->status = rc == -21 ? -209 : rc; if (rc != -21) J->err = 1; return; }
         memmove(co + ml, co + half, (size_t)ml);
-        res->status = 2; res->cons_len = ml; res->poa_cells = st.cells;
+        res->status = 2; res->cons_len = ml; res->poa_cells = st.cells; res->poa_nodes = st.node_n;
     } else {
         res->status = 2;                                  /* 0-repeat path (needs mappy): bounds only */
     }

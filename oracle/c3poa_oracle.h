@@ -86,7 +86,7 @@ typedef struct {
     int32_t n_sub;
     int32_t n_dang;
     int32_t cons_len;
-    int32_t pad;
+    int32_t poa_nodes;   /* final graph size (0 when no POA ran) */
     int64_t poa_cells;
     int64_t conk_cells;
 } c3o_read_result_t;

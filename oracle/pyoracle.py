@@ -45,7 +45,7 @@ class ReadResult(C.Structure):
 
 
 RESULT_DTYPE = np.dtype([("status", "<i4"), ("n_peaks", "<i4"), ("n_sub", "<i4"), ("n_dang", "<i4"),
-                         ("cons_len", "<i4"), ("pad", "<i4"), ("poa_cells", "<i8"), ("conk_cells", "<i8")])
+                         ("cons_len", "<i4"), ("poa_nodes", "<i4"), ("poa_cells", "<i8"), ("conk_cells", "<i8")])
 
 
 def lib():

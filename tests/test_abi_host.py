@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import ctypes as C
     from c3poa_b200 import _lib
-    assert C.sizeof(_lib.PoaParams) == 40 and _lib.RESULT_DTYPE.itemsize == 32 and C.sizeof(_lib.Timings) == 32
+    assert C.sizeof(_lib.PoaParams) == 40 and _lib.RESULT_DTYPE.itemsize == 32 and C.sizeof(_lib.Timings) == 56   # 6 + 4 floats, 4 int32
 
 
 def test_no_cpu_fallback_without_device():

@@ -121,7 +121,7 @@ def test_poa_parity(gpu, oracle):
 
 
 def test_lane_kernel_serves_what_it_covers(gpu, oracle):
-    """The fast kernel of the mode (auto: group kernel, lane: thread-per-read kernel) finishes every plain consensus
+    """The fast kernel of the mode (grp: group kernel, lane: thread-per-read kernel) finishes every plain consensus
     group itself (no silent fallback to the warp kernel)."""
     rng = np.random.default_rng(12)
     groups = []
@@ -130,7 +130,10 @@ def test_lane_kernel_serves_what_it_covers(gpu, oracle):
         groups.append([synth.mutate(rng, a).tobytes().decode() for _ in range(int(rng.integers(3, 8)))])
     r = gpu.poa_batch(groups)
     given, done = gpu.lane_counts()
-    assert (given, done) == (len(groups), len(groups))          # auto: the group kernel; lane: the lane kernel
+    if gpu.poa_mode == "auto":
+        assert (given, done) == (0, 0)                            # a batch this small goes to the warp kernel
+    else:
+        assert (given, done) == (len(groups), len(groups))        # grp: the group kernel; lane: the lane kernel
     for i in range(0, len(groups), 7):
         o = oracle.poa_msa(groups[i])
         assert r["status"][i] == 0 and r["cons"][i] == o["cons"] and r["cells"][i] == o["cells"] and r["nodes"][i] == o["node_n"], i
@@ -555,3 +558,52 @@ def test_drop_in_shims(gpu, oracle):
     assert res.cons_seq[0] == oracle.poa_msa(subs)["cons"] and res.n_seq == len(subs)
     res2 = poa.msa_aligner(match=5).msa(subs[:2], out_cons=False, out_msa=True)
     assert res2.msa_seq == oracle.poa_msa(subs[:2], out_cons=False, out_msa=True)["msa"] and not res2.cons_seq
+
+
+@pytest.mark.gpu
+def test_auto_group_kernel_vs_oracle_24k(gpu, oracle):
+    """24 000 reads of the bench workload's shape: the smallest batch `auto` hands to the group kernel.  Every output of the
+    fused C-ABI call (c3_consensus_batch) against the oracle on the same reads."""
+    if gpu.poa_mode != "auto":
+        pytest.skip("runs once")
+    import bench
+    n = 24000
+    blob, off, sp_idx, splints = bench.make_workload("cfg2_1kb_x5", n, 4242)
+    b = ReadBatch(blob, off, np.frombuffer("".join(splints).encode(), dtype=np.uint8).copy(),
+                  np.array([0, 284, 568], dtype=np.int32), np.ascontiguousarray(sp_idx, dtype=np.int32))
+    out = gpu.consensus_batch(b, max_peaks=16, cons_cap=2048)
+    given, done = gpu.lane_counts()
+    assert given >= 23000 and done >= given - 20, (given, done)
+    t = gpu.timings()
+    assert t["poa_dp_launches"] >= 4 and t["poa_graph_launches"] >= 5 and t["poa_dp_ms"] > 0
+    seqs = [blob[off[i]:off[i + 1]].tobytes().decode() for i in range(n)]
+    r = oracle.consensus_batch(seqs, splints, sp_idx, n_threads=os.cpu_count() or 1, max_peaks=16, cons_cap=2048)
+    assert bench.compare_with_oracle(out, r, n) == 0
+    assert np.array_equal(out["dang_bounds"], r["dang_bounds"])
+    assert (out["results"]["status"] == 0).mean() > 0.95
+
+
+@pytest.mark.gpu
+def test_mixed_batch_bulk_to_group_kernel_tail_to_warp(gpu, oracle):
+    """cfg5-like mix (inserts 500-4000, 2-10 repeats, 4 splints) padded with short reads so that `auto` sends the bulk of
+    short subreads to the group kernel and the long / 2-repeat ones to the warp kernel in the same call; a sample of both
+    kinds against the oracle."""
+    if gpu.poa_mode != "auto":
+        pytest.skip("runs once")
+    import bench
+    n = 44000
+    blob, off, sp_idx, splints = bench.make_workload("cfg5", n, 99)
+    sp_off = np.zeros(len(splints) + 1, dtype=np.int32)
+    sp_off[1:] = np.cumsum([len(x) for x in splints])
+    b = ReadBatch(blob, off, np.frombuffer("".join(splints).encode(), dtype=np.uint8).copy(), sp_off,
+                  np.ascontiguousarray(sp_idx, dtype=np.int32))
+    out = gpu.consensus_batch(b, max_peaks=16, cons_cap=10240)
+    given, done = gpu.lane_counts()
+    res = out["results"]
+    in_poa = int((res["n_sub"] >= 2).sum())
+    assert given >= 24000 and done >= given - 50 and in_poa - done > 1000, (given, done, in_poa)
+    assert (res["status"] < 0).sum() == 0
+    m = 600
+    seqs = [blob[off[i]:off[i + 1]].tobytes().decode() for i in range(m)]
+    r = oracle.consensus_batch(seqs, splints, sp_idx[:m], n_threads=os.cpu_count() or 1, max_peaks=16, cons_cap=10240)
+    assert bench.compare_with_oracle(out, r, m) == 0

@@ -116,3 +116,30 @@ def test_oracle_batch_threads_agree(oracle):
     b = oracle.consensus_batch(d["seqs"], sp, idx, n_threads=4)
     assert np.array_equal(a["results"], b["results"]) and np.array_equal(a["cons"], b["cons"])
     assert a["rc"] == 0 and (a["results"]["status"] == 0).sum() > 10
+
+
+def test_mixed_batch_generator_and_bench_compare(oracle):
+    """synth.make_mixed_batch (bench cfg3-cfg5 workloads): classes drawn per read, splint/strand indices consistent with
+    the bases; the oracle finds the repeats; bench.compare_with_oracle counts exactly the reads that differ."""
+    import bench
+    from c3poa_b200 import synth
+    blob, off, sp_idx, splints = bench.make_workload("cfg5", 48, 11)
+    assert off.size == 49 and off[-1] == blob.size and len(splints) == 8 and sp_idx.min() >= 0 and sp_idx.max() < 8
+    b2, o2, i2, _ = bench.make_workload("cfg5", 48, 11)
+    assert np.array_equal(blob, b2) and np.array_equal(off, o2) and np.array_equal(sp_idx, i2)      # deterministic
+    seqs = [blob[off[i]:off[i + 1]].tobytes().decode() for i in range(48)]
+    r = oracle.consensus_batch(seqs, splints, sp_idx, n_threads=4, max_peaks=16, cons_cap=10240)
+    st = r["results"]["status"]
+    assert (st >= 0).all() and ((st == 0) | (st == 2)).sum() >= 40         # the right splint in the right orientation
+    assert len(set(np.diff(off) // 1500)) > 4                              # mixed lengths
+    assert bench.compare_with_oracle(r, r, 48) == 0
+    r2 = {k: np.array(v, copy=True) for k, v in r.items() if k != "rc"}
+    i = int(np.flatnonzero(st == 0)[0])
+    r2["cons"][i, 3] ^= 1
+    j = int(np.flatnonzero(st == 0)[1])
+    r2["results"]["poa_cells"][j] += 1
+    assert bench.compare_with_oracle(r2, r, 48) == 2
+    blob3, off3, idx3, sp3 = bench.make_workload("cfg3", 6, 5)
+    r3 = oracle.consensus_batch([blob3[off3[i]:off3[i + 1]].tobytes().decode() for i in range(6)], sp3, idx3, n_threads=4,
+                                max_peaks=64, cons_cap=1536)
+    assert (r3["results"]["n_sub"] >= 12).all() and (r3["results"]["status"] == 0).all()
