@@ -18,7 +18,7 @@ EXPORTS = [
     "c3_get_timings", "c3_conk_batch", "c3_peaks_batch", "c3_poa_batch", "c3_stage", "c3_run", "c3_fetch",
     "c3_consensus_batch", "c3_measure_int_peak", "c3_host_alloc", "c3_host_free",
     "c3_fastq_open", "c3_fastq_next", "c3_fastq_close", "c3_assign_splints", "c3_set_poa_mode", "c3_lane_counts",
-    "c3_format_batch",
+    "c3_format_batch", "c3_set_abpoa_switches",
 ]
 
 
@@ -68,6 +68,7 @@ def load():
     L.c3_default_poa_params.restype = None
     L.c3_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.c3_set_poa_mode.argtypes = [vp, i32]
+    L.c3_set_abpoa_switches.argtypes = [vp, i32, i32]
     L.c3_lane_counts.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.c3_conk_batch.argtypes = [vp, i32, vp, i64p, i32, vp, vp, vp, i32, vp]
     L.c3_peaks_batch.argtypes = [vp, i32, vp, i64p, vp, i32, i32, i32, C.c_double, C.c_double, vp, vp, vp, i32, vp]

@@ -116,6 +116,10 @@ class GpuConsensus:
         (thread-per-read kernel whenever eligible).  Same results."""
         self._ck(self._L.c3_set_poa_mode(self._h, self.POA_MODES[mode]), "c3_set_poa_mode")
 
+    def set_abpoa_switches(self, int8_lanes: bool = False, end_clamp: bool = False):
+        """Named switches of the abPOA restatement; both off by default."""
+        self._ck(self._L.c3_set_abpoa_switches(self._h, int(int8_lanes), int(end_clamp)), "c3_set_abpoa_switches")
+
     def lane_counts(self):
         """(reads given to the lane kernel, reads it finished) of the last poa_batch / run."""
         a, b = C.c_int32(), C.c_int32()

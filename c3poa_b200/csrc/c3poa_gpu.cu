@@ -76,6 +76,7 @@ struct c3_handle {
     // POA kernel choice: 0 auto (group kernel for every eligible read), 1 warp kernel only, 2 lane kernel whenever
     // eligible, 3 group kernel whenever eligible (= auto); the warp kernel always takes what the others leave
     int poa_mode = 0;
+    int sw_int8_lanes = 0, sw_end_clamp = 0;   // c3_set_abpoa_switches: only the warp kernel implements them
     DevBuf d_order_lane, d_done, d_order_grp, d_ws_grp;
     int n_work_grp = 0, grp_max_nseq = 0, grp_max_q = 0; int64_t grp_max_total = 0;
     std::vector<int32_t> grp_nseq;   // sequences per item of the group kernels' list (host copy: launches per wave)
@@ -167,6 +168,13 @@ extern "C" int c3_set_poa_mode(c3_handle *h, int32_t mode)
 }
 
 // reads of the last B3/B4 call that the lane kernel was given / finished (the rest went to the warp kernel)
+extern "C" int c3_set_abpoa_switches(c3_handle *h, int32_t int8_lanes, int32_t end_clamp)
+{
+    if (!h) return -1;
+    h->sw_int8_lanes = int8_lanes ? 1 : 0; h->sw_end_clamp = end_clamp ? 1 : 0;
+    return 0;
+}
+
 extern "C" int c3_lane_counts(c3_handle *h, int32_t *out_given, int32_t *out_done)
 {
     if (!h || !out_given || !out_done) return -1;
@@ -271,10 +279,11 @@ static int launch_peaks(c3_handle *h, const int32_t *d_prof, const int64_t *d_of
     return 0;
 }
 
-static void to_dev_para(const c3_poa_params *p, c3_poa_para_dev *d)
+static void to_dev_para(const c3_handle *h, const c3_poa_params *p, c3_poa_para_dev *d)
 {
     d->match = p->match; d->mismatch = p->mismatch; d->o1 = p->gap_open1; d->e1 = p->gap_ext1;
     d->o2 = p->gap_open2; d->e2 = p->gap_ext2; d->wb = p->wb; d->simd_bits = p->simd_bits; d->wf = p->wf;
+    d->int8_lanes = h->sw_int8_lanes; d->end_clamp = h->sw_end_clamp;
 }
 
 // auto mode: what goes to the group kernel (poa_grp.cuh + poa_graph.cuh); measured on B200, see profiles/README.md
@@ -377,7 +386,7 @@ static int launch_poa_lane(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa
     h->lane_items = 0;
     A.done = nullptr;
     const int nl = h->n_work_lane;
-    if (h->poa_mode == 1 || nl <= 0) return 0;
+    if (h->poa_mode == 1 || nl <= 0 || h->sw_int8_lanes || h->sw_end_clamp) return 0;
     const int max_nseq = h->lane_max_nseq;
     const int64_t max_total = h->lane_max_total;
     max_q = (int)std::min<int64_t>(max_q, max_total);
@@ -460,7 +469,7 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     h->lane_items = 0;
     A.done = nullptr;
     const int ng = h->n_work_grp;
-    if ((h->poa_mode != 0 && h->poa_mode != 3) || ng <= 0) return 0;
+    if ((h->poa_mode != 0 && h->poa_mode != 3) || ng <= 0 || h->sw_int8_lanes || h->sw_end_clamp) return 0;
     const int max_nseq = h->grp_max_nseq;
     const int64_t max_total = h->grp_max_total;
     max_q = (int)std::min<int64_t>(std::min<int64_t>(max_q, max_total), std::max(h->grp_max_q, 64));
@@ -555,7 +564,7 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
 // workspace sizing from the batch maxima (longest sequence, most sequences, largest total)
 static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int64_t max_total, const c3_poa_params *pp)
 {
-    to_dev_para(pp, &A.P);
+    to_dev_para(h, pp, &A.P);
     if (A.P.simd_bits != 128 && A.P.simd_bits != 256 && A.P.simd_bits != 512) return fail(h, -5, "simd_bits must be 128/256/512");
     if (!A.order) { h->n_work_lane = 0; h->n_work_grp = 0; }
     int fast_items = 0;                                            // reads handed to a fast kernel ahead of this one

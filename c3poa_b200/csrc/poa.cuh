@@ -115,6 +115,7 @@ C3_HD __forceinline__ c3_nrec c3_ld_node(const c3_pnode *p)
 struct c3_poa_para_dev {
     int match, mismatch, o1, e1, o2, e2, wb, simd_bits;
     double wf;
+    int int8_lanes, end_clamp;     // named switches of the abPOA restatement, c3_set_abpoa_switches; default 0
 };
 
 #ifdef C3_POA_STATS
@@ -746,7 +747,8 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
             // score width -> SIMD lanes of the reference build -> band granule
             const int len = qlen > n ? qlen : n;
             const int max_score = max(qlen * 5, len * e1 + o1);
-            const int pn = (max_score <= 32767 - P.mismatch - o1 - e1) ? P.simd_bits / 16 : P.simd_bits / 32;
+            int pn = (max_score <= 32767 - P.mismatch - o1 - e1) ? P.simd_bits / 16 : P.simd_bits / 32;
+            if (P.int8_lanes && max_score <= 127 - P.mismatch - o1 - e1) pn = P.simd_bits / 8;
             int w = P.wb < 0 ? qlen : P.wb + (int)(P.wf * (double)qlen);
             asm volatile("" : "+r"(w));      // keep the band half-width in a register (ptxas re-derived the fp64 product per row)
 
@@ -857,7 +859,7 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                     if (sl >= 0) { r0 = rrec[sl]; p0ptr = &ring[sl][0]; p0str = 32; }
                     else { r0 = W.rows[p]; p0ptr = reinterpret_cast<const int4 *>(W.cells + r0.off); p0str = c3_row_ng(r0); }
                 }
-                int mpl = min(n, (int)r0.mp), mpr = r0.mp, min_pre_beg = r0.beg;
+                int mpl = min(n, (int)r0.mp), mpr = r0.mp, min_pre_beg = r0.beg, max_pre_end = r0.end;
                 if (npre > 1) {
                     int e = C3_N_INMORE(nd);
                     for (int k = 1; k < npre; ++k) {
@@ -869,12 +871,15 @@ __global__ void __launch_bounds__(C3_POA_THREADS, C3_POA_MINB) c3_poa_kernel(c3_
                         else { ri = W.rows[p]; pp = reinterpret_cast<const int4 *>(W.cells + ri.off); ps = c3_row_ng(ri); }
                         if (lane == 0) { pptr[k] = pp; pstr[k] = ps; pbe[k] = (int)ri.beg | ((int)ri.end << 16); }
                         mpl = min(mpl, (int)ri.mp); mpr = max(mpr, (int)ri.mp); min_pre_beg = min(min_pre_beg, (int)ri.beg);
+                        max_pre_end = max(max_pre_end, (int)ri.end);
                     }
                 }
                 int beg = max(0, min(mpl, rr) - w);
                 int end = min(qlen, max(mpr, rr) + w);
                 const int beg_sn = max(beg >> pn_shift, min_pre_beg >> pn_shift);
-                const int end_sn = max(end >> pn_shift, beg_sn);
+                int end_sn = end >> pn_shift;
+                if (P.end_clamp) end_sn = min(end_sn, (max_pre_end >> pn_shift) + 1);
+                end_sn = max(end_sn, beg_sn);
                 beg = beg_sn << pn_shift; end = min(qlen, ((end_sn + 1) << pn_shift) - 1);
                 const int wd = end - beg + 1;
                 if (wd <= 0) { err = C3_E_BAND; break; }

@@ -81,6 +81,13 @@ int  c3_get_timings(const c3_handle *h, c3_timings *out);
  * for everything the lane kernel declines), 1 = warp kernel only, 2 = lane kernel whenever a read is eligible.
  * Results are identical in every mode.                                                                        */
 int  c3_set_poa_mode(c3_handle *h, int32_t mode);
+/* Named switches of the abPOA restatement, both 0 by default: two upstream branches that are
+ * recalled from abPOA 1.0.5 but could not be checked offline.  int8_lanes: the band granule becomes simd_bits/8 when the
+ * score bound fits int8 (only sequences under ~25 nt); end_clamp: a row's band end is clamped to one SIMD vector past
+ * the largest predecessor band end.  With either set every read runs through the warp-per-read kernel.  The oracle has
+ * the same two switches (c3o_poa_para_t).  Replaces nothing in the reference: pins pyabpoa 1.0.5's behaviour
+ * (/root/reference/setup.sh:8, bin/determine_consensus.py:30) once it can be compared.                          */
+int  c3_set_abpoa_switches(c3_handle *h, int32_t int8_lanes, int32_t end_clamp);
 /* Reads of the last B3/B4 call handed to the lane kernel, and how many of them it finished.                */
 int  c3_lane_counts(c3_handle *h, int32_t *out_given, int32_t *out_done);
 

@@ -263,6 +263,7 @@ void c3o_poa_default_para(c3o_poa_para_t *p)
     p->match = 5; p->mismatch = 4;
     p->gap_open1 = 4; p->gap_ext1 = 2; p->gap_open2 = 24; p->gap_ext2 = 1;
     p->wb = 10; p->wf = 0.01; p->simd_bits = 256;
+    p->int8_lanes = 0; p->end_clamp = 0;
 }
 
 typedef struct {
@@ -472,6 +473,7 @@ static int poa_align(pgraph_t *g, const c3o_poa_para_t *P, const uint8_t *query,
     int len = qlen > n ? qlen : n;
     int max_score = imax(qlen * ALPHA_M, len * e1 + o1);
     int pn = (max_score <= 32767 - P->mismatch - o1 - e1) ? P->simd_bits / 16 : P->simd_bits / 32;
+    if (P->int8_lanes && max_score <= 127 - P->mismatch - o1 - e1) pn = P->simd_bits / 8;
     int w = P->wb < 0 ? qlen : P->wb + (int)(P->wf * qlen);
 
     if (ws->rows_m < n) {
@@ -541,12 +543,14 @@ static int poa_align(pgraph_t *g, const c3o_poa_para_t *P, const uint8_t *query,
         int beg = imax(0, imin(g->max_pos_left[node_id], r) - w);
         int end = imin(qlen, imax(g->max_pos_right[node_id], r) + w);
         int beg_sn = beg / pn, end_sn = end / pn;
-        int min_pre_beg_sn = 0x7fffffff;
+        int min_pre_beg_sn = 0x7fffffff, max_pre_end_sn = -1;
         for (int k = 0; k < nd->in_n; ++k) {
             int pi = g->node_to_index[nd->in_id[k]];
             if (ws->dp_beg_sn[pi] < min_pre_beg_sn) min_pre_beg_sn = ws->dp_beg_sn[pi];
+            if (ws->dp_end_sn[pi] > max_pre_end_sn) max_pre_end_sn = ws->dp_end_sn[pi];
         }
         if (beg_sn < min_pre_beg_sn) beg_sn = min_pre_beg_sn;
+        if (P->end_clamp && end_sn > max_pre_end_sn + 1) end_sn = max_pre_end_sn + 1;
         if (end_sn < beg_sn) end_sn = beg_sn;             /* robustness guard (never seen) */
         ws->dp_beg_sn[idx] = beg_sn; ws->dp_end_sn[idx] = end_sn;
         beg = ws->dp_beg[idx] = beg_sn * pn;

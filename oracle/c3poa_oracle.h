@@ -58,6 +58,10 @@ typedef struct {
     int wb;                       /* extra_b = 10 */
     double wf;                    /* extra_f = 0.01 */
     int simd_bits;                /* 256 (AVX2 build): band rounded to 16 int16 / 8 int32 lanes */
+    /* Named switches for two upstream branches that are recalled, not restated; both default 0:
+     * int8_lanes: abPOA picks int8 SIMD lanes (granule simd_bits/8) when the score bound fits int8;
+     * end_clamp:  a row's band end is clamped to (largest predecessor band end vector + 1).               */
+    int int8_lanes, end_clamp;
 } c3o_poa_para_t;
 void c3o_poa_default_para(c3o_poa_para_t *p);
 

@@ -31,7 +31,7 @@ def build(force: bool = False) -> str:
 class PoaPara(C.Structure):
     _fields_ = [("match", C.c_int), ("mismatch", C.c_int), ("gap_open1", C.c_int), ("gap_ext1", C.c_int),
                 ("gap_open2", C.c_int), ("gap_ext2", C.c_int), ("wb", C.c_int), ("wf", C.c_double),
-                ("simd_bits", C.c_int)]
+                ("simd_bits", C.c_int), ("int8_lanes", C.c_int), ("end_clamp", C.c_int)]
 
 
 class PoaStats(C.Structure):

@@ -6,6 +6,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+_REF = os.path.join(ROOT, "oracle", "_ref")        # the real pyabpoa / conk when `make -C oracle ref` could build them
+if os.path.isdir(_REF) and _REF not in sys.path:
+    sys.path.insert(1, _REF)
 
 
 def pytest_configure(config):

@@ -607,3 +607,50 @@ def test_mixed_batch_bulk_to_group_kernel_tail_to_warp(gpu, oracle):
     seqs = [blob[off[i]:off[i + 1]].tobytes().decode() for i in range(m)]
     r = oracle.consensus_batch(seqs, splints, sp_idx[:m], n_threads=os.cpu_count() or 1, max_peaks=16, cons_cap=10240)
     assert bench.compare_with_oracle(out, r, m) == 0
+
+
+@pytest.mark.gpu
+def test_abpoa_named_switches_on_gpu(gpu, oracle):
+    """c3_set_abpoa_switches: with either switch set every read runs through the warp kernel, which implements both; same
+    bytes, cell counts and graph sizes as the oracle with the same switches."""
+    rng = np.random.default_rng(8)
+    groups = [["ACGTACGTACGTAC", "ACGTACGAACGTAC", "ACGTACGTACGTAC"], ["ACGTTGCAAC"] * 3]
+    for L in (18, 60, 300, 900, 1500):
+        a = synth.random_seq(rng, L)
+        groups.append([synth.mutate(rng, a, 0.06, 0.05, 0.05).tobytes().decode() for _ in range(4)])
+    try:
+        for i8, ec in ((1, 0), (0, 1), (1, 1)):
+            gpu.set_abpoa_switches(bool(i8), bool(ec))
+            r = gpu.poa_batch(groups)
+            assert gpu.lane_counts() == (0, 0)
+            for k, g in enumerate(groups):
+                o = oracle.poa_msa(g, para=oracle.default_para(int8_lanes=i8, end_clamp=ec))
+                assert r["status"][k] == 0 and r["cons"][k] == o["cons"] and r["cells"][k] == o["cells"] \
+                    and r["nodes"][k] == o["node_n"], (i8, ec, k)
+    finally:
+        gpu.set_abpoa_switches(False, False)
+
+
+@pytest.mark.gpu
+def test_against_real_pyabpoa_and_conk_when_importable(gpu, oracle):
+    """wherever the real natives are importable (pyabpoa 1.0.5, conk) the GPU path and the oracle are
+    compared with them and the suite reports `oracle = real`; offline (this image) the test is skipped and parity with
+    upstream stays unpinned."""
+    pa = pytest.importorskip("pyabpoa")
+    rng = np.random.default_rng(21)
+    groups = []
+    for L in (300, 800, 1284, 1284, 2200):
+        a = synth.random_seq(rng, L)
+        groups.append([synth.mutate(rng, a).tobytes().decode() for _ in range(5)])
+    r = gpu.poa_batch(groups)
+    aligner = pa.msa_aligner(match=5)
+    for k, g in enumerate(groups):
+        real = aligner.msa(g, True, False).cons_seq[0]
+        assert oracle.poa_msa(g)["cons"] == real, ("oracle vs pyabpoa", k)
+        assert r["cons"][k] == real, ("GPU vs pyabpoa", k)
+    conk = pytest.importorskip("conk")
+    seq = synth.make_reads(1, insert_len=600, repeats=4, seed=3)["seqs"][0]
+    real_prof = np.asarray(conk.conk(synth.SPLINT1, seq, 20), dtype=np.int64)
+    b = ReadBatch.from_strings([seq], [synth.SPLINT1], np.zeros(1, dtype=np.int32))
+    assert np.array_equal(gpu.conk_batch(b, 20).astype(np.int64), real_prof)
+    print("oracle = real")

@@ -143,3 +143,35 @@ def test_mixed_batch_generator_and_bench_compare(oracle):
     r3 = oracle.consensus_batch([blob3[off3[i]:off3[i + 1]].tobytes().decode() for i in range(6)], sp3, idx3, n_threads=4,
                                 max_peaks=64, cons_cap=1536)
     assert (r3["results"]["n_sub"] >= 12).all() and (r3["results"]["status"] == 0).all()
+
+
+def test_abpoa_named_switches_in_oracle(oracle):
+    """the two recalled-but-unverified upstream branches are switches (default off).  int8 lanes only
+    matter below ~25 nt; both leave the consensus of clean repeats alone and keep the run valid."""
+    from c3poa_b200 import synth
+    rng = np.random.default_rng(3)
+    a = synth.random_seq(rng, 600)
+    g = [synth.mutate(rng, a).tobytes().decode() for _ in range(5)]
+    base = oracle.poa_msa(g)
+    i8 = oracle.poa_msa(g, para=oracle.default_para(int8_lanes=1))
+    assert i8["cons"] == base["cons"] and i8["cells"] == base["cells"] and i8["node_n"] == base["node_n"]
+    ec = oracle.poa_msa(g, para=oracle.default_para(end_clamp=1))
+    assert ec["cells"] <= base["cells"] and len(ec["cons"]) > 500
+    tiny = ["ACGTACGTACGTAC", "ACGTACGAACGTAC", "ACGTACGTACGTAC"]
+    t0, t1 = oracle.poa_msa(tiny), oracle.poa_msa(tiny, para=oracle.default_para(int8_lanes=1))
+    assert t0["cons"] == t1["cons"] == tiny[0] and t1["cells"] >= t0["cells"]          # granule 32 instead of 16
+
+
+def test_oracle_against_real_pyabpoa_and_conk_when_importable(oracle):
+    """The oracle pinned to the real natives wherever they are importable (skipped offline: parity unpinned)."""
+    pa = pytest.importorskip("pyabpoa")
+    from c3poa_b200 import synth
+    rng = np.random.default_rng(22)
+    aligner = pa.msa_aligner(match=5)
+    for L in (200, 700, 1284, 2600):
+        a = synth.random_seq(rng, L)
+        g = [synth.mutate(rng, a).tobytes().decode() for _ in range(5)]
+        assert oracle.poa_msa(g)["cons"] == aligner.msa(g, True, False).cons_seq[0], L
+    conk = pytest.importorskip("conk")
+    seq = synth.make_reads(1, insert_len=600, repeats=4, seed=3)["seqs"][0]
+    assert np.array_equal(np.asarray(oracle.conk(synth.SPLINT1, seq, 20)), np.asarray(conk.conk(synth.SPLINT1, seq, 20)))
