@@ -255,9 +255,12 @@ static int launch_peaks(c3_handle *h, const int32_t *d_prof, const int64_t *d_of
                         bool want_smoothed, bool want_median, int max_peaks, int64_t total)
 {
     if (window < 1 || window > C3_PK_MAXWIN || !(window & 1)) return fail(h, -5, "window must be odd and <= %d", C3_PK_MAXWIN);
-    CK(h->d_coef.ensure((size_t)window * 8));
-    CK(cudaMemcpyAsync(h->d_coef.p, coef, (size_t)window * 8, cudaMemcpyHostToDevice, h->stream));
-    int grid = std::max(1, std::min(h->sm_count * 4, n));
+    // (Smoothing a read in place in shared memory -- the whole read resident, no scratch round trip -- was measured: 33.9
+    // vs 29.2 ms per 100k reads.  60 KB per CTA leave two CTAs per SM, and the kernel's time is barriers and latency in
+    // the select / maxima phases, not the FIR: the scratch stays, it is L2-resident.)
+    int bps = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_peaks_kernel, C3_PK_THREADS, 0) != cudaSuccess || bps < 1) bps = 4;
+    int grid = std::max(1, std::min(h->sm_count * bps, n));
     int64_t stride = ((int64_t)max_len + 63) & ~63ll;
     CK(h->d_pk_scratch.ensure((size_t)grid * 2 * stride * 8));
     CK(h->d_peaks.ensure((size_t)n * max_peaks * 4 + 16));
@@ -268,7 +271,8 @@ static int launch_peaks(c3_handle *h, const int32_t *d_prof, const int64_t *d_of
     CK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
     CK(cudaMemsetAsync(h->d_peaks.p, 0, (size_t)n * max_peaks * 4, h->stream));
     c3_peaks_args A;
-    A.prof = d_prof; A.off = d_off; A.n = n; A.coef = h->d_coef.as<double>(); A.window = window; A.iters = iters;
+    A.prof = d_prof; A.off = d_off; A.n = n; A.window = window; A.iters = iters;
+    for (int k = 0; k < C3_PK_MAXWIN; ++k) A.coefv[k] = k < window ? coef[k] : 0.0;
     A.min_dist = min_dist; A.height_mult = hm; A.gate_mult = gm; A.scratch = h->d_pk_scratch.as<double>();
     A.scratch_stride = stride; A.out_smoothed = want_smoothed ? h->d_smoothed.as<double>() : nullptr;
     A.out_median = want_median ? h->d_median.as<double>() : nullptr; A.out_peaks = h->d_peaks.as<int32_t>();
@@ -289,7 +293,7 @@ static void to_dev_para(const c3_handle *h, const c3_poa_params *p, c3_poa_para_
 // auto mode: what goes to the group kernel (poa_grp.cuh + poa_graph.cuh); measured on B200, see profiles/README.md
 #define C3_GRP_AUTO_MAX_LEN 2600       // mean subread length of a read
 #define C3_GRP_AUTO_MAX_NSEQ 32
-#define C3_GRP_AUTO_MIN_READS 24000
+#define C3_GRP_AUTO_MIN_READS 12000
 // Work order for the persistent POA grid: items with >= min_seqs sequences, largest estimated DP cost first
 // (LPT scheduling: the longest reads start first, so a batch ends with short ones).  cost ~ alignments x
 // mean length x band width.  O(n) bucket sort on 1/16-octave cost classes.

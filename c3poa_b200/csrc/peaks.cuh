@@ -21,7 +21,7 @@ struct c3_peaks_args {
     const int32_t *prof;      // int32 CSR
     const int64_t *off;       // [n+1]
     int n;
-    const double *coef;       // [window]
+    double coefv[C3_PK_MAXWIN];   // [window] by value: the taps are read from the kernel-parameter constant bank
     int window, iters, min_dist;
     double height_mult, gate_mult;
     double *scratch;          // per-CTA 2 * scratch_stride doubles
@@ -103,10 +103,61 @@ __device__ double c3_radix_select(const double *buf, int n, int k, unsigned *his
     return c3_dunkey(prefix);
 }
 
-__global__ void __launch_bounds__(C3_PK_THREADS) c3_peaks_kernel(c3_peaks_args A)
+
+// 4 consecutive outputs of the FIR from a staged tile: out[j] = sum_k coef[k] * tile[u + j + k], k ascending, separate
+// IEEE multiply and add (the oracle's order).  The window is read once as 16-byte words; the taps come from the constant
+// bank (kernel parameters).  WT > 0: compile-time window (41, the reference's), fully unrolled; WT = 0: any odd window.
+template <int WT>
+__device__ __forceinline__ void c3_pk_fir4(const c3_peaks_args &A, const double *tile_u, const int W, double (&a)[4])
 {
-    __shared__ double s_coef[C3_PK_MAXWIN];
-    __shared__ __align__(16) double s_tile[C3_PK_TILE + C3_PK_MAXWIN + 3];
+    a[0] = a[1] = a[2] = a[3] = 0.0;
+    const double2 *tp = reinterpret_cast<const double2 *>(tile_u);
+    double2 p0 = tp[0], p1 = tp[1];
+    if (WT > 0) {
+#pragma unroll
+        for (int k = 0; k < WT; k += 2) {
+            const double2 p2 = tp[(k >> 1) + 2];
+            const double c0 = A.coefv[k];
+            a[0] = __dadd_rn(a[0], __dmul_rn(c0, p0.x)); a[1] = __dadd_rn(a[1], __dmul_rn(c0, p0.y));
+            a[2] = __dadd_rn(a[2], __dmul_rn(c0, p1.x)); a[3] = __dadd_rn(a[3], __dmul_rn(c0, p1.y));
+            if (k + 1 < WT) {
+                const double c1 = A.coefv[k + 1];
+                a[0] = __dadd_rn(a[0], __dmul_rn(c1, p0.y)); a[1] = __dadd_rn(a[1], __dmul_rn(c1, p1.x));
+                a[2] = __dadd_rn(a[2], __dmul_rn(c1, p1.y)); a[3] = __dadd_rn(a[3], __dmul_rn(c1, p2.x));
+            }
+            p0 = p1; p1 = p2;
+        }
+    } else {
+        for (int k = 0; k < W; k += 2) {
+            const double2 p2 = tp[(k >> 1) + 2];
+            const double c0 = A.coefv[k];
+            a[0] = __dadd_rn(a[0], __dmul_rn(c0, p0.x)); a[1] = __dadd_rn(a[1], __dmul_rn(c0, p0.y));
+            a[2] = __dadd_rn(a[2], __dmul_rn(c0, p1.x)); a[3] = __dadd_rn(a[3], __dmul_rn(c0, p1.y));
+            if (k + 1 < W) {
+                const double c1 = A.coefv[k + 1];
+                a[0] = __dadd_rn(a[0], __dmul_rn(c1, p0.y)); a[1] = __dadd_rn(a[1], __dmul_rn(c1, p1.x));
+                a[2] = __dadd_rn(a[2], __dmul_rn(c1, p1.y)); a[3] = __dadd_rn(a[3], __dmul_rn(c1, p2.x));
+            }
+            p0 = p1; p1 = p2;
+        }
+    }
+}
+
+// padded signal (bin/savitzky_golay.py:33-35) at padded index t: left mirror about y0, the signal, right mirror about yl
+template <typename F>
+__device__ __forceinline__ double c3_pk_padded(const int t, const int n, const int half, const double y0, const double yl, F at)
+{
+    if (t < half) return y0 - fabs(at(half - t) - y0);
+    if (t < half + n) return at(t - half);
+    return yl + fabs(at(n - 2 - (t - half - n)) - yl);
+}
+
+#ifndef C3_PK_MINB
+#define C3_PK_MINB 6
+#endif
+__global__ void __launch_bounds__(C3_PK_THREADS, C3_PK_MINB) c3_peaks_kernel(c3_peaks_args A)
+{
+    __shared__ __align__(16) double s_tile[C3_PK_TILE + C3_PK_MAXWIN + 9];
     __shared__ double s_pr[C3_PK_MAXC];
     __shared__ int s_pos[C3_PK_MAXC];
     __shared__ int s_order[C3_PK_MAXC];
@@ -119,10 +170,8 @@ __global__ void __launch_bounds__(C3_PK_THREADS) c3_peaks_kernel(c3_peaks_args A
 
     const int tid = threadIdx.x;
     const int W = A.window, half = (A.window - 1) / 2;
-    for (int i = tid; i < W; i += blockDim.x) s_coef[i] = A.coef[i];
     double *bufA = A.scratch + (int64_t)blockIdx.x * 2 * A.scratch_stride;
     double *bufB = bufA + A.scratch_stride;
-    __syncthreads();
 
     for (;;) {
         if (tid == 0) s_r = (int)atomicAdd(A.counter, 1u);
@@ -146,48 +195,20 @@ __global__ void __launch_bounds__(C3_PK_THREADS) c3_peaks_kernel(c3_peaks_args A
             // edge anchors (bin/savitzky_golay.py:33-34)
             const double y0 = from_int ? (double)prof[0] : src[0];
             const double yl = from_int ? (double)prof[n - 1] : src[n - 1];
+            auto at = [&](const int idx) { return from_int ? (double)prof[idx] : src[idx]; };
             for (int t0 = 0; t0 < n; t0 += C3_PK_TILE) {
                 const int tn = min(C3_PK_TILE, n - t0);
-                const int need = tn + W - 1;
-                for (int u = tid; u < need; u += blockDim.x) {
-                    const int t = t0 + u;        // index into the padded signal
-                    double v;
-                    if (t < half) {
-                        const int idx = half - t;
-                        const double yy = from_int ? (double)prof[idx] : src[idx];
-                        v = y0 - fabs(yy - y0);
-                    } else if (t < half + n) {
-                        const int idx = t - half;
-                        v = from_int ? (double)prof[idx] : src[idx];
-                    } else {
-                        const int idx = n - 2 - (t - half - n);
-                        const double yy = from_int ? (double)prof[idx] : src[idx];
-                        v = yl + fabs(yy - yl);
-                    }
-                    s_tile[u] = v;
+                for (int u = tid; u < tn + W - 1 + 8; u += blockDim.x) {
+                    const int t = t0 + u;
+                    s_tile[u] = t < n + W - 1 ? c3_pk_padded(t, n, half, y0, yl, at) : 0.0;
                 }
-                if (tid < 2) s_tile[need + tid] = 0.0;       // read (never used) by the second output of an odd-length tile
                 __syncthreads();
-                // two consecutive outputs per thread: the window is read once as 16-byte words (the kernel is bound by
-                // shared-memory wavefronts, not by the fp64 pipe); summation order per output unchanged (k = 0..W-1)
-                for (int u = 2 * tid; u < tn; u += 2 * blockDim.x) {
-                    double a0 = 0.0, a1 = 0.0;
-                    const double2 *tp = reinterpret_cast<const double2 *>(s_tile + u);
-                    double2 w2 = tp[0];
-                    int k = 0;
-                    for (; k + 1 < W; k += 2) {
-                        const double2 nx = tp[(k >> 1) + 1];
-                        const double c0 = s_coef[k], c1 = s_coef[k + 1];
-                        a0 = __dadd_rn(a0, __dmul_rn(c0, w2.x)); a1 = __dadd_rn(a1, __dmul_rn(c0, w2.y));
-                        a0 = __dadd_rn(a0, __dmul_rn(c1, w2.y)); a1 = __dadd_rn(a1, __dmul_rn(c1, nx.x));
-                        w2 = nx;
-                    }
-                    if (k < W) {                         // odd window: last tap
-                        const double c0 = s_coef[k];
-                        a0 = __dadd_rn(a0, __dmul_rn(c0, w2.x)); a1 = __dadd_rn(a1, __dmul_rn(c0, w2.y));
-                    }
-                    dst[t0 + u] = a0;
-                    if (u + 1 < tn) dst[t0 + u + 1] = a1;
+                const int u4 = 4 * tid;
+                if (u4 < tn) {
+                    double a[4];
+                    if (W == 41) c3_pk_fir4<41>(A, s_tile + u4, W, a); else c3_pk_fir4<0>(A, s_tile + u4, W, a);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (u4 + k < tn) dst[t0 + u4 + k] = a[k];
                 }
                 __syncthreads();
             }
