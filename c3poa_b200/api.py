@@ -111,9 +111,10 @@ class GpuConsensus:
             self.set_poa_mode(poa_mode)
 
     def set_poa_mode(self, mode: str):
-        """POA kernel choice: 'auto' (thread-per-read kernel for batches whose eligible reads fill >= 3/4 of its grid
-        -- 42 624 reads on a B200 -- and are of similar size), 'warp' (warp-per-read kernel only), 'lane'
-        (thread-per-read kernel whenever eligible).  Same results."""
+        """POA kernel choice: 'auto' (the group path -- 8 lanes per read for the DP, one thread per read for the graph phases
+        -- for the reads with a mean subread length <= 2 600 and <= 32 subreads when a batch holds >= 12 000 of them, the
+        warp-per-read kernel for the rest), 'warp' (warp-per-read kernel only), 'lane' (round 1's thread-per-read kernel
+        whenever eligible), 'grp' (the group path whenever eligible).  Same results."""
         self._ck(self._L.c3_set_poa_mode(self._h, self.POA_MODES[mode]), "c3_set_poa_mode")
 
     def set_abpoa_switches(self, int8_lanes: bool = False, end_clamp: bool = False):

@@ -76,10 +76,12 @@ void c3_destroy(c3_handle *h);
 const char *c3_last_error(const c3_handle *h);
 void c3_default_poa_params(c3_poa_params *p);
 int  c3_get_timings(const c3_handle *h, c3_timings *out);
-/* Which POA kernel serves B3/B4: 0 = auto (thread-per-read "lane" kernel when the eligible reads fill at least
- * three quarters of its grid -- 56 832 reads on a B200 -- and are of similar size; warp-per-read kernel otherwise and
- * for everything the lane kernel declines), 1 = warp kernel only, 2 = lane kernel whenever a read is eligible.
- * Results are identical in every mode.                                                                        */
+/* Which POA kernel serves B3/B4.  0 = auto: the group path (c3_poa_grp_dp_kernel + c3_poa_graph_kernel: 8 lanes per
+ * read for the DP, one thread per read for the graph phases) takes the reads with a mean subread length <= 2 600,
+ * <= 32 subreads and int16 score mode when a batch holds at least 12 000 of them; everything else, and whatever the
+ * group path declines, runs through the warp-per-read kernel in the same call.  1 = warp kernel only.  2 = the
+ * thread-per-read "lane" kernel of round 1 whenever a read is eligible.  3 = the group path whenever a read is eligible
+ * (no minimum batch, no length limit).  Results are identical in every mode.                                     */
 int  c3_set_poa_mode(c3_handle *h, int32_t mode);
 /* Named switches of the abPOA restatement, both 0 by default: two upstream branches that are
  * recalled from abPOA 1.0.5 but could not be checked offline.  int8_lanes: the band granule becomes simd_bits/8 when the
@@ -88,7 +90,8 @@ int  c3_set_poa_mode(c3_handle *h, int32_t mode);
  * the same two switches (c3o_poa_para_t).  Replaces nothing in the reference: pins pyabpoa 1.0.5's behaviour
  * (/root/reference/setup.sh:8, bin/determine_consensus.py:30) once it can be compared.                          */
 int  c3_set_abpoa_switches(c3_handle *h, int32_t int8_lanes, int32_t end_clamp);
-/* Reads of the last B3/B4 call handed to the lane kernel, and how many of them it finished.                */
+/* Reads of the last B3/B4 call handed to the fast kernel of the mode (group path / lane kernel), and how many of them
+ * it finished (the rest went to the warp kernel).                                                              */
 int  c3_lane_counts(c3_handle *h, int32_t *out_given, int32_t *out_done);
 
 /* B1.  reads: concatenated ASCII, read_off[n_reads+1]; splints likewise
