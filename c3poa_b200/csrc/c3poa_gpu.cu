@@ -9,6 +9,7 @@
 #include "poa_grp.cuh"
 #include "poa_graph.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
@@ -39,6 +40,15 @@ struct c3_handle {
     cudaStream_t stream = nullptr;
     char err[512] = {0};
     cudaEvent_t ev[8] = {nullptr};
+    // Host waits go through an event created with cudaEventBlockingSync: the waiting thread sleeps instead of spinning, so
+    // a handle does not burn a core per batch in flight (the driver's reader / writer threads want them).
+    cudaEvent_t ev_wait = nullptr;
+    cudaError_t sync()
+    {
+        if (!ev_wait) return cudaStreamSynchronize(stream);
+        cudaError_t e = cudaEventRecord(ev_wait, stream);
+        return e != cudaSuccess ? e : cudaEventSynchronize(ev_wait);
+    }
     c3_timings tim{};
     // per-launch timing of the POA kernels: event pairs recorded around every launch, summed by kind after the call's
     // final synchronisation (kt_collect)
@@ -76,8 +86,10 @@ struct c3_handle {
     // POA kernel choice: 0 auto (group kernel for every eligible read), 1 warp kernel only, 2 lane kernel whenever
     // eligible, 3 group kernel whenever eligible (= auto); the warp kernel always takes what the others leave
     int poa_mode = 0;
+    double dbg_sync_ms = 0; std::chrono::steady_clock::time_point dbg_t1;     // C3POA_GRP_TIMING only
+    int grp_bps[2] = {0, 0}, warp_bps = 0, grp_grow_idx = 0, grp_ask_wait = 0;
     int sw_int8_lanes = 0, sw_end_clamp = 0;   // c3_set_abpoa_switches: only the warp kernel implements them
-    DevBuf d_order_lane, d_done, d_order_grp, d_ws_grp;
+    DevBuf d_order_lane, d_done, d_order_grp, d_ws_grp, d_order_scratch;
     int n_work_grp = 0, grp_max_nseq = 0, grp_max_q = 0; int64_t grp_max_total = 0;
     std::vector<int32_t> grp_nseq;   // sequences per item of the group kernels' list (host copy: launches per wave)
     int n_work_lane = 0, lane_items = 0, lane_n_items = 0;
@@ -127,6 +139,7 @@ extern "C" int c3_init(int device, c3_handle **out)
     h->total_mem = prop.totalGlobalMem;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -4; }
     for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
+    if (cudaEventCreateWithFlags(&h->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) { h->ev_wait = nullptr; (void)cudaGetLastError(); }
     *out = h;
     return 0;
 }
@@ -135,15 +148,16 @@ extern "C" void c3_destroy(c3_handle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    h->sync();
     DevBuf *bufs[] = {&h->d_ascii, &h->d_codes, &h->d_off, &h->d_sp_ascii, &h->d_sp_codes, &h->d_sp_off, &h->d_sp_idx,
                       &h->d_prof, &h->d_brow, &h->d_counter, &h->d_coef, &h->d_pk_scratch, &h->d_smoothed, &h->d_median,
                       &h->d_peaks, &h->d_npk, &h->d_sub, &h->d_dang, &h->d_res, &h->d_stats, &h->d_cons, &h->d_ws,
                       &h->d_item_base, &h->d_bounds, &h->d_nseq, &h->d_status, &h->d_clen, &h->d_nodes, &h->d_cells, &h->d_order,
-                      &h->d_order_lane, &h->d_done, &h->d_order_grp, &h->d_ws_grp};
+                      &h->d_order_lane, &h->d_done, &h->d_order_grp, &h->d_ws_grp, &h->d_order_scratch};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->kt_ev) cudaEventDestroy(e);
+    if (h->ev_wait) cudaEventDestroy(h->ev_wait);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -294,92 +308,210 @@ static void to_dev_para(const c3_handle *h, const c3_poa_params *p, c3_poa_para_
 #define C3_GRP_AUTO_MAX_LEN 2600       // mean subread length of a read
 #define C3_GRP_AUTO_MAX_NSEQ 32
 #define C3_GRP_AUTO_MIN_READS 12000
+// ---------------------------------------------------------------------------
+// POA work order.  Shared by the host builder (B3: the inputs are host arrays) and the device builder (B4: the per-read
+// repeat counts and subread bases are on the device, nothing is copied back but 64 bytes of totals).
+// ---------------------------------------------------------------------------
+#define C3_ORD_NB (64 * 16)            // 1/16-octave cost classes
+struct c3_order_rule {                 // what decides list membership, by value into the kernels
+    double wb, wf;
+    int min_seqs, msa2, mode;
+    int lane_ok, grp_ok;               // parameter sets the fast kernels cover
+    long long lim16;                   // int16 score bound
+    int e1, o1;
+};
+// cost class of an item: cost ~ alignments x mean length x band width
+__host__ __device__ inline int c3_order_class(const int nseq, const long long total, const c3_order_rule &R)
+{
+    const double L = (double)total / nseq;
+    const double cost = (double)(nseq - 1 > 1 ? nseq - 1 : 1) * L * (2.0 * (R.wb + R.wf * L) + 48.0) + 1.0;
+    int e; const double m = frexp(cost, &e);                      // cost = m * 2^e, m in [0.5, 1)
+    int b = e * 16 + (int)((m - 0.5) * 32.0);
+    return b < 0 ? 0 : (b > C3_ORD_NB - 1 ? C3_ORD_NB - 1 : b);
+}
+// bit 0: lane kernel's list, bit 1: group path's list
+__host__ __device__ inline int c3_order_flags(const int nseq, const long long total, const c3_order_rule &R, int *grp_q)
+{
+    int f = 0;
+    if (R.msa2 && nseq == 2) return 0;
+    const long long L = total / nseq;
+    if (R.lane_ok && L <= 5000 && nseq <= 40) f |= 1;             // long / deep reads: per-thread arenas would not fit
+    if (R.grp_ok) {
+        // int16 score mode of an alignment: max(qlen * 5, max(qlen, nodes) * e1 + o1) <= lim, with the usual graph
+        // growth (the kernel re-checks per alignment and declines what turns out larger)
+        const long long Lm = L * 5 / 4 + 1;
+        const long long nodes = 2 + Lm + (long long)(nseq - 1) * (Lm * 35 / 100 + 16);
+        const bool fits = !(Lm * 5 > R.lim16 || (Lm > nodes ? Lm : nodes) * R.e1 + R.o1 > R.lim16 || nodes > 65000);
+        // auto: the bulk of short subreads only.  The serial phases of the group path run one thread per read with a
+        // latency floor per launch that grows with the sequence length, and a read's workspace grows with length x
+        // depth: long or very deep reads are better off in the warp kernel (profiles/README.md)
+        const bool bulk = R.mode != 0 || (L <= C3_GRP_AUTO_MAX_LEN && nseq <= C3_GRP_AUTO_MAX_NSEQ);
+        if (fits && bulk) { f |= 2; *grp_q = R.mode == 0 ? (int)(Lm < 65000 ? Lm : 65000) : 65000; }
+    }
+    return f;
+}
+static c3_order_rule make_order_rule(const c3_handle *h, const c3_poa_args &A, int min_seqs, const c3_poa_params *pp)
+{
+    c3_order_rule R;
+    R.wb = pp->wb; R.wf = pp->wf; R.min_seqs = min_seqs; R.msa2 = A.msa2; R.mode = h->poa_mode;
+    R.lane_ok = pp->simd_bits == 256 && pp->wb >= 0;
+    R.grp_ok = pp->simd_bits == 256 && pp->wb >= 0 && pp->gap_open1 + pp->gap_ext1 <= 7 &&
+               pp->gap_open2 + pp->gap_ext2 <= 31 && pp->gap_ext1 >= 0 && pp->gap_ext2 >= 0 &&
+               pp->gap_ext1 <= 16 && pp->gap_ext2 <= 16 && pp->match >= 0 && pp->mismatch >= 0 &&
+               pp->match <= 100 && pp->mismatch <= 100 && pp->gap_open1 >= 0 && pp->gap_open2 >= 0;
+    R.lim16 = 32767 - pp->mismatch - pp->gap_open1 - pp->gap_ext1; R.e1 = pp->gap_ext1; R.o1 = pp->gap_open1;
+    return R;
+}
+
+// device builder: histogram by class for the three lists, descending scan, scatter.  Inside a class the order is the
+// order of arrival (it only decides which reads share a warp; every read's result is its own).
+struct c3_order_tot {                  // 64 bytes copied back
+    int n_work, n_lane, n_grp, grp_max_nseq, grp_max_q, lane_max_nseq, lane_cls_first, lane_cls_median;
+    long long grp_max_total, lane_max_total;
+    int pad[4];
+};
+__global__ void c3_order_classify_kernel(int n, const c3_read_result_dev *res, c3_order_rule R, int32_t *cls, unsigned *hist,
+                                         c3_order_tot *tot)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ns = res[i].status >= 0 ? res[i].n_sub : 0;
+    const long long total = ns >= 2 ? res[i].poa_cells : 0;        // the split kernel leaves the subread bases there
+    if (ns < R.min_seqs || ns < 1) { cls[i] = -1; return; }
+    const int b = c3_order_class(ns, total, R);
+    int gq = 0;
+    const int f = c3_order_flags(ns, total, R, &gq);
+    cls[i] = b | (f << 16);
+    atomicAdd(&hist[b], 1u);
+    if (f & 1) {
+        atomicAdd(&hist[C3_ORD_NB + b], 1u);
+        atomicMax((unsigned long long *)&tot->lane_max_total, (unsigned long long)total); atomicMax(&tot->lane_max_nseq, ns);
+    }
+    if (f & 2) {
+        atomicAdd(&hist[2 * C3_ORD_NB + b], 1u);
+        atomicMax((unsigned long long *)&tot->grp_max_total, (unsigned long long)total); atomicMax(&tot->grp_max_nseq, ns);
+        atomicMax(&tot->grp_max_q, gq);
+    }
+}
+__global__ void __launch_bounds__(32) c3_order_scan_kernel(const unsigned *hist, unsigned *start, c3_order_tot *tot)
+{
+    const int l = threadIdx.x;                                      // lanes 0..2: one list each, classes from the top
+    if (l >= 3) return;
+    unsigned acc = 0;
+    for (int b = C3_ORD_NB - 1; b >= 0; --b) { start[l * C3_ORD_NB + b] = acc; acc += hist[l * C3_ORD_NB + b]; }
+    if (l == 0) tot->n_work = (int)acc;
+    if (l == 2) tot->n_grp = (int)acc;
+    if (l == 1) {
+        tot->n_lane = (int)acc;
+        int first = -1, med = -1; unsigned seen = 0;
+        for (int b = C3_ORD_NB - 1; b >= 0 && med < 0; --b) {
+            const unsigned c = hist[C3_ORD_NB + b];
+            if (c && first < 0) first = b;
+            seen += c;
+            if (c && seen > acc / 2) med = b;
+        }
+        tot->lane_cls_first = first; tot->lane_cls_median = med;
+    }
+}
+__global__ void c3_order_scatter_kernel(int n, const int32_t *cls, const unsigned *start, unsigned *fill, int32_t *order,
+                                        int32_t *lane, int32_t *grp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cls[i];
+    if (c < 0) return;
+    const int b = c & 0xffff, f = c >> 16;
+    order[start[b] + atomicAdd(&fill[b], 1u)] = i;
+    if (f & 1) lane[start[C3_ORD_NB + b] + atomicAdd(&fill[C3_ORD_NB + b], 1u)] = i;
+    if (f & 2) grp[start[2 * C3_ORD_NB + b] + atomicAdd(&fill[2 * C3_ORD_NB + b], 1u)] = i;
+}
+
+static int build_poa_order_device(c3_handle *h, c3_poa_args &A, int n, const c3_read_result_dev *res, int min_seqs,
+                                  const c3_poa_params *pp)
+{
+    const c3_order_rule R = make_order_rule(h, A, min_seqs, pp);
+    CK(h->d_order.ensure((size_t)std::max(n, 1) * 4));
+    CK(h->d_order_lane.ensure((size_t)std::max(n, 1) * 4));
+    CK(h->d_order_grp.ensure((size_t)std::max(n, 1) * 4));
+    const size_t hb = (size_t)3 * C3_ORD_NB * 4;
+    CK(h->d_order_scratch.ensure((size_t)n * 4 + 3 * hb + sizeof(c3_order_tot) + 256));
+    uint8_t *sc = h->d_order_scratch.as<uint8_t>();
+    unsigned *hist = reinterpret_cast<unsigned *>(sc), *start = hist + 3 * C3_ORD_NB, *fill = start + 3 * C3_ORD_NB;
+    c3_order_tot *tot = reinterpret_cast<c3_order_tot *>(sc + 3 * hb);
+    int32_t *cls = reinterpret_cast<int32_t *>(sc + 3 * hb + 64 + 64);
+    CK(cudaMemsetAsync(sc, 0, 3 * hb + sizeof(c3_order_tot), h->stream));
+    c3_order_classify_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, res, R, cls, hist, tot);
+    c3_order_scan_kernel<<<1, 32, 0, h->stream>>>(hist, start, tot);
+    c3_order_scatter_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, cls, start, fill, h->d_order.as<int32_t>(),
+                                                                    h->d_order_lane.as<int32_t>(), h->d_order_grp.as<int32_t>());
+    CK(cudaGetLastError());
+    h->tim.kernel_launches += 3;
+    c3_order_tot T;
+    const auto dbg0 = std::chrono::steady_clock::now();
+    CK(cudaMemcpyAsync(&T, tot, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    CK(h->sync());
+    h->dbg_sync_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - dbg0).count();
+    h->dbg_t1 = std::chrono::steady_clock::now();                          // 64 bytes: list sizes and maxima size the workspaces
+    A.order = h->d_order.as<int32_t>(); A.n_work = T.n_work;
+    h->n_work_lane = T.n_lane; h->lane_max_total = T.lane_max_total; h->lane_max_nseq = T.lane_max_nseq; h->lane_max_q = 0;
+    h->lane_cost_spread = T.n_lane > 0 ? exp2((double)(T.lane_cls_first - T.lane_cls_median) / 16.0) : 1.0;
+    h->n_work_grp = T.n_grp; h->grp_max_total = T.grp_max_total; h->grp_max_nseq = T.grp_max_nseq; h->grp_max_q = T.grp_max_q;
+    h->grp_nseq.clear();                                           // waves of the group path use the list's maximum
+    if (h->poa_mode == 0 && h->n_work_grp < C3_GRP_AUTO_MIN_READS) h->n_work_grp = 0;     // too few to amortise the launches
+    return 0;
+}
+
 // Work order for the persistent POA grid: items with >= min_seqs sequences, largest estimated DP cost first
 // (LPT scheduling: the longest reads start first, so a batch ends with short ones).  cost ~ alignments x
 // mean length x band width.  O(n) bucket sort on 1/16-octave cost classes.
 static int upload_poa_order(c3_handle *h, c3_poa_args &A, const std::vector<int32_t> &nseq, const std::vector<int64_t> &total,
                             int min_seqs, const c3_poa_params *pp)
 {
+    const c3_order_rule R = make_order_rule(h, A, min_seqs, pp);
     const int n = (int)nseq.size();
     std::vector<int32_t> cls((size_t)n, -1);
-    const int NB = 64 * 16;
-    std::vector<int32_t> cnt(NB + 1, 0);
+    std::vector<int32_t> cnt(C3_ORD_NB + 1, 0);
     int n_work = 0;
     for (int i = 0; i < n; ++i) {
-        if (nseq[i] < min_seqs) continue;
-        const double L = (double)total[i] / nseq[i];
-        const double cost = (double)std::max(nseq[i] - 1, 1) * L * (2.0 * (pp->wb + pp->wf * L) + 48.0) + 1.0;
-        int e; const double m = frexp(cost, &e);                  // cost = m * 2^e, m in [0.5, 1)
-        int b = e * 16 + (int)((m - 0.5) * 32.0);
-        b = std::max(0, std::min(NB - 1, b));
-        cls[i] = b; ++cnt[b]; ++n_work;
+        if (nseq[i] < min_seqs || nseq[i] < 1) continue;
+        cls[i] = c3_order_class(nseq[i], total[i], R); ++cnt[cls[i]]; ++n_work;
     }
-    std::vector<int32_t> start(NB + 1, 0);
-    for (int b = NB - 1, acc = 0; b >= 0; --b) { start[b] = acc; acc += cnt[b]; }   // descending classes
+    std::vector<int32_t> start(C3_ORD_NB + 1, 0);
+    for (int b = C3_ORD_NB - 1, acc = 0; b >= 0; --b) { start[b] = acc; acc += cnt[b]; }   // descending classes
     std::vector<int32_t> order((size_t)std::max(n_work, 1));
     for (int i = 0; i < n; ++i) if (cls[i] >= 0) order[start[cls[i]]++] = i;
-    CK(h->d_order.ensure((size_t)std::max(n_work, 1) * 4));
-    CK(cudaMemcpyAsync(h->d_order.p, order.data(), (size_t)n_work * 4, cudaMemcpyHostToDevice, h->stream));
-    // the lane kernel's share (poa_lane.cuh): same order, items it covers; neighbours in this order become the
-    // 32 threads of a warp, so they are of similar size.  Its workspace is sized from these items alone.
-    std::vector<int32_t> lane((size_t)std::max(n_work, 1));
-    int nl = 0;
+    // the fast kernels' shares: same order (neighbours become the threads / groups of a warp, so they are of similar
+    // size); their workspaces are sized from these items alone
+    std::vector<int32_t> lane((size_t)std::max(n_work, 1)), grp((size_t)std::max(n_work, 1));
+    int nl = 0, ng = 0;
     h->lane_max_total = 0; h->lane_max_nseq = 0; h->lane_max_q = 0;
-    if (pp->simd_bits == 256 && pp->wb >= 0) {
-        for (int k = 0; k < n_work; ++k) {
-            const int i = order[k];
-            if (A.msa2 && nseq[i] == 2) continue;
-            const int64_t L = total[i] / nseq[i];
-            if (L > 5000 || nseq[i] > 40) continue;                // long / deep reads: per-thread arenas would not fit
+    h->grp_nseq.clear(); h->grp_max_total = 0; h->grp_max_nseq = 0; h->grp_max_q = 0;
+    for (int k = 0; k < n_work; ++k) {
+        const int i = order[k];
+        int gq = 0;
+        const int f = c3_order_flags(nseq[i], total[i], R, &gq);
+        if (f & 1) {
             lane[nl++] = i;
-            h->lane_max_total = std::max(h->lane_max_total, total[i]);
-            h->lane_max_nseq = std::max(h->lane_max_nseq, nseq[i]);
+            h->lane_max_total = std::max(h->lane_max_total, total[i]); h->lane_max_nseq = std::max(h->lane_max_nseq, nseq[i]);
+        }
+        if (f & 2) {
+            grp[ng++] = i;
+            h->grp_nseq.push_back(nseq[i]);
+            h->grp_max_total = std::max(h->grp_max_total, total[i]); h->grp_max_nseq = std::max(h->grp_max_nseq, nseq[i]);
+            h->grp_max_q = std::max(h->grp_max_q, gq);
         }
     }
-    // the group kernel's share (poa_grp.cuh): same order; items it is sure to cover (int16 score mode for every
-    // alignment of the item, default-sized gap costs); neighbours in this order become the 4 groups of a warp
-    {
-        std::vector<int32_t> grp((size_t)std::max(n_work, 1));
-        int ng = 0;
-        h->grp_nseq.clear();
-        h->grp_max_total = 0; h->grp_max_nseq = 0; h->grp_max_q = 0;
-        const bool para_ok = pp->simd_bits == 256 && pp->wb >= 0 && pp->gap_open1 + pp->gap_ext1 <= 7 &&
-                             pp->gap_open2 + pp->gap_ext2 <= 31 && pp->gap_ext1 >= 0 && pp->gap_ext2 >= 0 &&
-                             pp->gap_ext1 <= 16 && pp->gap_ext2 <= 16 && pp->match >= 0 && pp->mismatch >= 0 &&
-                             pp->match <= 100 && pp->mismatch <= 100 && pp->gap_open1 >= 0 && pp->gap_open2 >= 0;
-        if (para_ok) {
-            const int64_t lim = 32767 - pp->mismatch - pp->gap_open1 - pp->gap_ext1;
-            for (int k = 0; k < n_work; ++k) {
-                const int i = order[k];
-                if (A.msa2 && nseq[i] == 2) continue;
-                // int16 score mode of an alignment: max(qlen * 5, max(qlen, nodes) * e1 + o1) <= lim, with the usual
-                // graph growth (the kernel re-checks per alignment and declines what turns out larger)
-                const int64_t Lm = total[i] / nseq[i] * 5 / 4 + 1;
-                const int64_t nodes = 2 + Lm + (int64_t)(nseq[i] - 1) * (Lm * 35 / 100 + 16);
-                if (Lm * 5 > lim || std::max(Lm, nodes) * pp->gap_ext1 + pp->gap_open1 > lim || nodes > 65000) continue;
-                // auto: the bulk of short subreads only.  The serial phases of the group path run one thread per read
-                // with a latency floor per launch that grows with the sequence length, and a read's workspace grows
-                // with length x depth: long or very deep reads are better off in the warp kernel (profiles/README.md)
-                if (h->poa_mode == 0 && (total[i] / nseq[i] > C3_GRP_AUTO_MAX_LEN || nseq[i] > C3_GRP_AUTO_MAX_NSEQ)) continue;
-                grp[ng++] = i;
-                h->grp_nseq.push_back(nseq[i]);
-                h->grp_max_total = std::max(h->grp_max_total, total[i]);
-                h->grp_max_nseq = std::max(h->grp_max_nseq, nseq[i]);
-                h->grp_max_q = std::max<int>(h->grp_max_q, h->poa_mode == 0 ? (int)std::min<int64_t>(Lm, 65000) : 65000);
-            }
-        }
-        if (h->poa_mode == 0 && ng < C3_GRP_AUTO_MIN_READS) { ng = 0; h->grp_nseq.clear(); }    // too few to amortise the launches
-        CK(h->d_order_grp.ensure((size_t)std::max(ng, 1) * 4));
-        CK(cudaMemcpyAsync(h->d_order_grp.p, grp.data(), (size_t)ng * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        h->n_work_grp = ng;
-    }
+    if (h->poa_mode == 0 && ng < C3_GRP_AUTO_MIN_READS) { ng = 0; h->grp_nseq.clear(); }    // too few to amortise the launches
     h->lane_cost_spread = nl > 0 ? exp2((double)(cls[lane[0]] - cls[lane[nl / 2]]) / 16.0) : 1.0;
+    CK(h->d_order.ensure((size_t)std::max(n_work, 1) * 4));
+    CK(h->d_order_grp.ensure((size_t)std::max(ng, 1) * 4));
     CK(h->d_order_lane.ensure((size_t)std::max(nl, 1) * 4));
+    CK(cudaMemcpyAsync(h->d_order.p, order.data(), (size_t)n_work * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_order_grp.p, grp.data(), (size_t)ng * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_order_lane.p, lane.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));                          // `order` and `lane` are locals
+    CK(h->sync());                          // the lists are locals
     A.order = h->d_order.as<int32_t>(); A.n_work = n_work;
-    h->n_work_lane = nl;
+    h->n_work_lane = nl; h->n_work_grp = ng;
     return 0;
 }
 
@@ -484,9 +616,19 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     int budget_pct = 70, grow_env = 0;
     if (const char *e = getenv("C3POA_GRP_GROW_PCT")) grow_env = std::max(1, atoi(e));           // tuning only
     if (const char *e = getenv("C3POA_GRP_BUDGET_PCT")) budget_pct = std::max(1, std::min(95, atoi(e)));
-    size_t free_b = 0, tot_b = 0;
-    CK(cudaMemGetInfo(&free_b, &tot_b));
-    const int64_t budget = (int64_t)((double)(free_b + h->d_ws_grp.cap) * (budget_pct / 100.0));
+    // cudaMemGetInfo is a driver round trip that takes anything from 0.1 to 100 ms once >100 GB are allocated (measured: it
+    // was the whole gap between the mid-pipeline readback and the first POA kernel, 5-60 ms in one step out of three, and
+    // the run-to-run spread of round 1's numbers): asked only when the workspace this handle owns does not do
+    int64_t budget = (int64_t)h->d_ws_grp.cap;
+    bool asked = false;
+    auto ask = [&]() -> int {
+        if (asked) return 0;
+        size_t free_b = 0, tot_b = 0;
+        CK(cudaMemGetInfo(&free_b, &tot_b));
+        budget = (int64_t)((double)(free_b + h->d_ws_grp.cap) * (budget_pct / 100.0));
+        asked = true;
+        return 0;
+    };
     const int w = pp->wb + (int)(pp->wf * max_q);
     const int need = (2 * w + 1 + 48) / 16 + 2;
     int vs_shift = 3;
@@ -496,8 +638,7 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     int64_t node_cap = 0, ws_bytes = 0, arena4 = 0, read_bytes = 0;
     int cigar_cap = 0;
     static const int grow_try[3] = {35, 25, 20};
-    for (int t = 0; t < 3; ++t) {
-        const int grow_pct = grow_env ? grow_env : grow_try[t];
+    auto size_for = [&](const int grow_pct) {
         const int64_t est = 2 + (int64_t)max_q + (int64_t)(max_nseq - 1) * ((int64_t)max_q * grow_pct / 100 + 16);
         node_cap = std::min<int64_t>(std::min<int64_t>(est, max_total + 2), 65504);
         node_cap = std::max<int64_t>((node_cap + 31) & ~31ll, 64);
@@ -505,21 +646,46 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
         ws_bytes = c3g_ws_bytes((int)node_cap, (int)node_cap, cigar_cap, qp_stride);
         arena4 = (node_cap << vs_shift) * 3;
         read_bytes = ws_bytes + arena4 * 16 + (int64_t)sizeof(c3g_state);
-        if (grow_env || budget / read_bytes >= ng) break;
-    }
+    };
+    // steady state (batch after batch of the same shape): the growth share chosen last time, inside the workspace the
+    // handle already owns -- no driver query.  Otherwise ask once and choose again.
+    size_for(grow_env ? grow_env : grow_try[h->grp_grow_idx]);
+    const bool may_ask = h->d_ws_grp.cap == 0 || h->grp_ask_wait <= 0;      // a batch that needs several waves: not every call
+    if (h->grp_ask_wait > 0) --h->grp_ask_wait;
+    if (!grow_env && budget / read_bytes < ng && may_ask) {
+        h->grp_ask_wait = 64;
+        if (int rc = ask()) return rc;
+        for (int t = 0; t < 3; ++t) {
+            size_for(grow_try[t]);
+            h->grp_grow_idx = t;
+            if (budget / read_bytes >= ng) break;
+        }
+    } else if (grow_env && budget / read_bytes < ng && may_ask) { h->grp_ask_wait = 64; if (int rc = ask()) return rc; }
     const int pool_cap = (int)node_cap;
     const int wpb = C3G_THREADS / 32;
     const size_t sm_dp = (size_t)wpb * 4 * c3g_smem_group_bytes(rv_shift);
     void (*kdp)(c3g_args) = vs_shift == 3 ? c3_poa_grp_dp_kernel<3, false> : c3_poa_grp_dp_kernel<4, true>;
-    CK(cudaFuncSetAttribute(kdp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dp));
-    int bps_dp = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_dp, kdp, C3G_THREADS, sm_dp) != cudaSuccess || bps_dp < 1) bps_dp = 1;
+    // function attributes and occupancy once per handle and instantiation: driver calls on the path between the batch's
+    // only mid-pipeline synchronisation and the first POA launch were seen to stall for milliseconds now and then
+    const int kv = vs_shift == 3 ? 0 : 1;
+    if (!h->grp_bps[kv]) {
+        CK(cudaFuncSetAttribute(kdp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dp));
+        int b = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kdp, C3G_THREADS, sm_dp) != cudaSuccess || b < 1) b = 1;
+        h->grp_bps[kv] = b;
+    }
+    int bps_dp = h->grp_bps[kv];
     if (const char *lim = getenv("C3POA_GRP_DP_CTAS")) bps_dp = std::max(1, std::min(bps_dp, atoi(lim)));     // tuning only
     int64_t wave = std::min<int64_t>(ng, budget / read_bytes);
     if (wave < std::min<int64_t>(ng, 64)) return 0;                // does not fit: the warp kernel takes everything
     wave = (ng + (ng + wave - 1) / wave - 1) / ((ng + wave - 1) / wave);    // several waves: equal sizes
     const int n_counters = 2 * max_nseq + 3;
-    CK(h->d_ws_grp.ensure((size_t)(wave * read_bytes) + (size_t)n_counters * 4 + 256));
+    // several handles of one device (the driver keeps batches in flight) size themselves from the same free figure: an
+    // allocation that fails is not an error of the batch -- the warp kernel, with its small workspace, takes the reads
+    if (h->d_ws_grp.ensure((size_t)(wave * read_bytes) + (size_t)n_counters * 4 + 256) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
     CK(h->d_done.ensure((size_t)A.n_items * 4));
     CK(cudaMemsetAsync(h->d_done.p, 0, (size_t)A.n_items * 4, h->stream));
     uint8_t *base = h->d_ws_grp.as<uint8_t>();
@@ -538,13 +704,16 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     for (int64_t w0 = 0; w0 < ng; w0 += wave) {
         const int nw = (int)std::min<int64_t>(wave, ng - w0);
         int wave_nseq = 1;
-        for (int k = 0; k < nw; ++k) wave_nseq = std::max(wave_nseq, h->grp_nseq[(size_t)(w0 + k)]);
+        if (h->grp_nseq.empty()) wave_nseq = std::max(1, max_nseq);      // order built on the device: the list's maximum
+        else for (int k = 0; k < nw; ++k) wave_nseq = std::max(wave_nseq, h->grp_nseq[(size_t)(w0 + k)]);
         CK(cudaMemsetAsync(counters, 0, (size_t)n_counters * 4, h->stream));
         L.A.order = h->d_order_grp.as<int32_t>() + w0; L.A.n_work = nw;
         const int w_dp = (nw + 3) / 4;                              // warps that can be busy
         const int grid_dp = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * bps_dp, (w_dp + wpb - 1) / wpb));
         const int grid_gr = (nw + C3S_THREADS - 1) / C3S_THREADS;  // one thread per read
         int launch = 0;
+        if (timing) fprintf(stderr, "host: order sync %.2f ms, sync->first POA launch %.2f ms\n", h->dbg_sync_ms,
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h->dbg_t1).count());
         h->kt_begin();
         c3_poa_graph_init_kernel<<<nw, 128, 0, h->stream>>>(L);
         h->kt_end(1);
@@ -594,17 +763,24 @@ static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int
     // the kernel is bound by per-row dependency latency, not by the lanes left idle -- and was dropped.)
     const int threads = C3_POA_THREADS;
     const int rpb = threads / 32;                                     // reads per block
-    int bps = 4;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, c3_poa_kernel, threads, 0) != cudaSuccess || bps < 1) bps = 4;
+    if (!h->warp_bps) {
+        int b = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, c3_poa_kernel, threads, 0) != cudaSuccess || b < 1) b = 4;
+        h->warp_bps = b;
+    }
+    const int bps = h->warp_bps;
     int grid = h->sm_count * bps;
     if (!A.order) A.n_work = A.n_items;
     grid = std::max(1, std::min(grid, (A.n_work + rpb - 1) / rpb));
     // what a fast kernel was given comes back only if it declined it: one CTA per SM is kept for those
     if (fast_items > 0 && h->poa_mode != 2)
         grid = std::max(1, std::min(grid, (A.n_work - fast_items + rpb - 1) / rpb + h->sm_count));
-    size_t free_b = 0, tot_b = 0;
-    CK(cudaMemGetInfo(&free_b, &tot_b));
-    int64_t budget = (int64_t)((double)(free_b + h->d_ws.cap) * 0.8);
+    int64_t budget = (int64_t)h->d_ws.cap;
+    if ((int64_t)grid * rpb * ws_bytes > budget) {                 // (see launch_poa_grp: asked only when the buffer must grow)
+        size_t free_b = 0, tot_b = 0;
+        CK(cudaMemGetInfo(&free_b, &tot_b));
+        budget = (int64_t)((double)(free_b + h->d_ws.cap) * 0.8);
+    }
     int64_t max_slots = budget / ws_bytes;
     if (max_slots < rpb) return fail(h, -6, "POA workspace of %lld bytes per read does not fit", (long long)ws_bytes);
     if ((int64_t)grid * rpb > max_slots) grid = (int)std::max<int64_t>(1, max_slots / rpb);
@@ -662,7 +838,7 @@ static int stage_reads(c3_handle *h, int32_t n_reads, const char *reads, const i
     CK(cudaMemcpyAsync(h->d_sp_ascii.p, splints, (size_t)total_sp, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_sp_off.p, splint_off, (size_t)(n_splints + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_sp_idx.p, splint_idx, (size_t)n_reads * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(h->sync());
     h->staged = true; h->ran = false;
     return 0;
 }
@@ -691,7 +867,7 @@ extern "C" int c3_conk_batch(c3_handle *h, int32_t n_reads, const char *reads, c
     if ((rc = launch_conk(h, penalty))) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));
     CK(cudaMemcpyAsync(out_profile, h->d_prof.p, (size_t)h->total_bases * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(h->sync());
     cudaEventElapsedTime(&h->tim.encode_ms, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->tim.conk_ms, h->ev[1], h->ev[2]);
     h->tim.total_ms = h->tim.encode_ms + h->tim.conk_ms;
@@ -744,7 +920,7 @@ extern "C" int c3_assign_splints(c3_handle *h, int32_t n_reads, const char *read
     CK(cudaEventRecord(h->ev[1], h->stream));
     std::vector<int32_t> sc((size_t)n_cands * n_reads);
     CK(cudaMemcpyAsync(sc.data(), h->d_status.p, sc.size() * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(h->sync());
     cudaEventElapsedTime(&h->tim.conk_ms, h->ev[0], h->ev[1]);
     h->tim.total_ms = h->tim.conk_ms;
     for (int r = 0; r < n_reads; ++r) {
@@ -786,7 +962,7 @@ extern "C" int c3_peaks_batch(c3_handle *h, int32_t n, const int32_t *profile, c
     CK(cudaMemcpyAsync(out_n_peaks, h->d_npk.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     if (out_smoothed) CK(cudaMemcpyAsync(out_smoothed, h->d_smoothed.p, (size_t)total * 8, cudaMemcpyDeviceToHost, h->stream));
     if (out_median) CK(cudaMemcpyAsync(out_median, h->d_median.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(h->sync());
     cudaEventElapsedTime(&h->tim.peaks_ms, h->ev[0], h->ev[1]);
     h->tim.total_ms = h->tim.peaks_ms;
     h->staged = false;
@@ -876,7 +1052,7 @@ extern "C" int c3_poa_batch(c3_handle *h, int32_t n_groups, const char *seqs, co
     CK(cudaMemcpyAsync(out_status, h->d_status.p, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, h->stream));
     if (out_cells) CK(cudaMemcpyAsync(out_cells, h->d_cells.p, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, h->stream));
     if (out_nodes) CK(cudaMemcpyAsync(out_nodes, h->d_nodes.p, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(h->sync());
     if (want_msa) {      // 2-sequence groups: the consensus slot holds [row0 | row1], cons_len = columns
         memset(out_msa, '-', (size_t)n_seqs * msa_cap);
         for (int g = 0; g < n_groups; ++g) {
@@ -965,39 +1141,47 @@ extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t
     CK(cudaGetLastError());
     h->tim.kernel_launches++;
     CK(cudaEventRecord(h->ev[4], h->stream));
+    // The host's only look at the batch between the kernels: 16 bytes of batch maxima from the split kernel and 64 bytes
+    // of list sizes from the work-order kernels, one synchronisation (inside build_poa_order_device); they size the POA
+    // workspaces.  The per-read repeat counts and subread bases (left in poa_cells by the split kernel) stay on the
+    // device: the work order is a histogram by cost class + scan + scatter there.
     int32_t stats[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(stats, h->d_stats.p, 16, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));        // 16-byte readback: sizes the POA workspace
-    h->tim.poa_items = stats[3];
-    if (stats[3] > 0) {
+    {
         c3_poa_args A;
         memset(&A, 0, sizeof(A));
         c3_read_result *res = h->d_res.as<c3_read_result>();
         A.codes = h->d_codes.as<uint8_t>(); A.item_base = h->d_off.as<int64_t>(); A.bounds = h->d_sub.as<int32_t>();
         A.n_seqs = &res->n_sub; A.n_seqs_stride = sizeof(c3_read_result) / 4; A.n_items = n; A.max_seqs = max_peaks; A.min_seqs = 2;
         A.msa2 = 1; A.ok_status = 2;    // 2-repeat reads: [row0 | row1] of the pairwise MSA in the consensus slot
-        {   // per-read repeat count and subread bases (left in poa_cells by the split kernel) -> work order
+        if (getenv("C3POA_HOST_ORDER")) {                          // tuning only: round 1's host-side order
             std::vector<c3_read_result> hr((size_t)n);
             CK(cudaMemcpyAsync(hr.data(), h->d_res.p, (size_t)n * sizeof(c3_read_result), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
+            CK(h->sync());
             std::vector<int32_t> ns((size_t)n); std::vector<int64_t> tot((size_t)n);
-            for (int i = 0; i < n; ++i) {
-                ns[i] = hr[i].status >= 0 ? hr[i].n_sub : 0;
-                tot[i] = ns[i] >= 2 ? hr[i].poa_cells : 0;
-            }
+            for (int i = 0; i < n; ++i) { ns[i] = hr[i].status >= 0 ? hr[i].n_sub : 0; tot[i] = ns[i] >= 2 ? hr[i].poa_cells : 0; }
             if ((rc = upload_poa_order(h, A, ns, tot, 2, params))) return rc;
-        }
+        } else
+        if ((rc = build_poa_order_device(h, A, n, h->d_res.as<c3_read_result_dev>(), 2, params))) return rc;
+        h->tim.poa_items = stats[3];
         A.cons = h->d_cons.as<char>(); A.cons_cap = cons_cap; A.status = &res->status; A.cons_len = &res->cons_len;
         A.nodes_out = &res->poa_nodes; A.cells_out = (long long *)&res->poa_cells;
         A.out_stride = sizeof(c3_read_result) / 4; A.cells_stride = sizeof(c3_read_result) / 4;
-        if ((rc = launch_poa(h, A, stats[0], stats[1], stats[2], params))) return rc;
+        if (stats[3] > 0 && (rc = launch_poa(h, A, stats[0], stats[1], stats[2], params))) return rc;
     }
     CK(cudaEventRecord(h->ev[5], h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(h->sync());
     cudaEventElapsedTime(&h->tim.encode_ms, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->tim.conk_ms, h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&h->tim.peaks_ms, h->ev[2], h->ev[3]);
     cudaEventElapsedTime(&h->tim.split_ms, h->ev[3], h->ev[4]);
+    if (getenv("C3POA_GRP_TIMING") && h->kt_used > 1) {          // tuning only: where the POA stage's non-kernel time sits
+        float head = 0.f, tail = 0.f, span = 0.f;
+        cudaEventElapsedTime(&head, h->ev[4], h->kt_ev[0]);
+        cudaEventElapsedTime(&tail, h->kt_ev[h->kt_used - 1], h->ev[5]);
+        cudaEventElapsedTime(&span, h->kt_ev[0], h->kt_ev[h->kt_used - 1]);
+        fprintf(stderr, "poa stage: %.2f ms before the first POA kernel, %.2f ms first..last kernel, %.2f ms after\n", head, span, tail);
+    }
     h->kt_collect();
     cudaEventElapsedTime(&h->tim.poa_ms, h->ev[4], h->ev[5]);
     cudaEventElapsedTime(&h->tim.total_ms, h->ev[0], h->ev[5]);
@@ -1018,7 +1202,7 @@ extern "C" int c3_fetch(c3_handle *h, int32_t *out_peaks, int32_t *out_sub_bound
     if (out_dang_bounds) CK(cudaMemcpyAsync(out_dang_bounds, h->d_dang.p, n * 16, cudaMemcpyDeviceToHost, h->stream));
     if (out_cons) CK(cudaMemcpyAsync(out_cons, h->d_cons.p, n * h->cons_cap, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(out_results, h->d_res.p, n * sizeof(c3_read_result), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(h->sync());
     return 0;
 }
 
@@ -1083,7 +1267,7 @@ extern "C" int c3_measure_int_peak(c3_handle *h, double *out_ops_per_s)
         CK(cudaEventRecord(h->ev[6], h->stream));
         c3_intpeak_kernel<<<grid, 256, 0, h->stream>>>(iters, h->d_stats.as<int>());
         CK(cudaEventRecord(h->ev[7], h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        CK(h->sync());
         float ms = 0;
         cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]);
         // one VIADDMNMX = 2 integer ops (add + max)

@@ -102,7 +102,8 @@ def run_blat(blat, reads_fastq, splint_file, tmp_dir, lencutoff):
                 f.write(f">{name}\n{seq}\n")
     psl = os.path.join(tmp_dir, "splint_to_read_alignments.psl")
     with open(os.path.join(tmp_dir, "blat_messages.log"), "w") as log:
-        subprocess.run([blat, "-noHead", "-stepSize=1", "-tileSize=6", "-t=DNA", "-q=DNA", "-minScore=15",
+        # the reference's flags, bin/preprocess.py:71-75
+        subprocess.run([blat, "-noHead", "-stepSize=1", "-t=DNA", "-q=DNA", "-minScore=15",
                         "-minIdentity=10", splint_file, fa, psl], stdout=log, stderr=log, check=True)
     os.remove(fa)
     return psl
@@ -131,7 +132,7 @@ def compute_batch(gpu, names, blob, off, splint_dict, adapter_dict, mdist):
     return gpu.consensus_batch(batch, min_dist=mdist, max_peaks=128, cons_cap=min(2 * max_len, 131072))
 
 
-def write_batch(out, names, blob, off, qual, qual_sum, adapter_dict, handles, polish=None):
+def write_batch(out, names, blob, off, qual, qual_sum, adapter_dict, handles, polish=None, zero=True):
     """The host part: consensus FASTA + subread FASTQ exactly as analyze_reads / determine_consensus write them.
     Reads with a plain consensus (status 0) are formatted by the library in one pass per splint directory
     (c3_format_batch); only the 2-repeat reads, whose quality-aware pairwise consensus is host-side Python
@@ -159,10 +160,20 @@ def write_batch(out, names, blob, off, qual, qual_sum, adapter_dict, handles, po
         name = names[i]
         cons_fh, sub_fh = handles[adapter_dict[name][0]]
         ns, nd = int(R["n_sub"][i]), int(R["n_dang"][i])
-        if not (ns == 2 and R["cons_len"][i] > 0):
-            stats["zero"] = stats.get("zero", 0) + 1     # 0-repeat path (mappy overlap of the dangling halves): not produced
-            continue
         a0, a1 = int(off[i]), int(off[i + 1])
+        if not (ns == 2 and R["cons_len"][i] > 0):
+            # 0-repeat read (one peak, or every subread an outlier).  The reference's zero_repeats
+            # (bin/determine_consensus.py:14-18,107-139; --zero, default on) first writes the two dangling halves as
+            # @name_0 / @name_1 and then overlaps them with mappy, which is absent here: the records are written, the
+            # consensus is not produced, and the count goes to c3poa.log -- never silent.
+            stats["zero"] = stats.get("zero", 0) + 1
+            if zero and ns == 0 and nd == 2:
+                seq = blob[a0:a1].tobytes().decode()
+                q = qual[a0:a1].tobytes().decode()
+                db = out["dang_bounds"][i, :2]
+                sub_fh.write("".join(f"@{name}_{k}\n{seq[a:b]}\n+\n{q[a:b]}\n" for k, (a, b) in enumerate(db)).encode())
+                stats["zero_records"] = stats.get("zero_records", 0) + 1
+            continue
         seq = blob[a0:a1].tobytes().decode()
         q = qual[a0:a1].tobytes().decode()
         sb, db = out["sub_bounds"][i, :ns], out["dang_bounds"][i, :nd]
@@ -215,6 +226,9 @@ def main(args):
         print("Total thrown away reads:", short_reads + no_splint,
               "({:.2f}%)".format((short_reads + no_splint) / max(all_reads, 1) * 100), file=log)
         print("Reads after preprocessing:", all_reads - (short_reads + no_splint), file=log)
+        # not in the reference's log: what this driver does not produce must not disappear silently
+        print("Zero-repeat reads without consensus (zero_repeats needs mappy; dangling subreads written:",
+              str(totals.get("zero_records", 0)) + "):", totals.get("zero", 0), file=log)
     print("GPU consensus:", totals, file=sys.stderr)
     return totals
 
@@ -246,13 +260,13 @@ def _run_all(args, adapter_dict, splint_dict, adapter_set):
     return totals
 
 
-def _drain_one(pending, handles, totals, polish=None):
+def _drain_one(pending, handles, totals, polish=None, zero=True):
     fut, names, blob, off, qual, qsum, ad = pending.pop(0)
     out = fut.result()
     if polish is not None:
         polish = dict(polish, serial=totals.get("batches", 0))
     totals["batches"] = totals.get("batches", 0) + 1
-    for key, v in write_batch(out, names, blob, off, qual, qsum, ad, handles, polish).items():
+    for key, v in write_batch(out, names, blob, off, qual, qsum, ad, handles, polish, zero=zero).items():
         totals[key] = totals.get(key, 0) + v
 
 
@@ -310,6 +324,25 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
         sp_names = sorted(splint_dict)
         cands = [s for n in sp_names for s in splint_dict[n]]
         perfect = np.array([5 * len(s) * (len(s) + 1) // 2 for s in cands], dtype=np.float64)
+    held = []                                   # reads held back for a batch of their own (see below)
+
+    def submit(names, blob, off, qual, qsum, ad):
+        fut = pool.submit(run_on_free_handle, names, blob, off, splint_dict, ad, args.mdistcutoff)
+        pending.append((fut, names, blob, off, qual, qsum, ad))
+        while len(pending) >= len(gpus) + 1 or (pending and pending[0][0].done()):
+            _drain_one(pending, handles, totals, polish, zero=bool(args.zero))
+
+    def flush_held():
+        if not held:
+            return
+        held.sort(key=lambda t: len(t[1]))
+        h_off = np.zeros(len(held) + 1, dtype=np.int64)
+        h_off[1:] = np.cumsum([len(t[1]) for t in held])
+        submit([t[0] for t in held], np.concatenate([t[1] for t in held]), h_off, np.concatenate([t[2] for t in held]),
+               np.array([t[3] for t in held]), {t[0]: t[4] for t in held})
+        totals["held_back_long_reads"] = totals.get("held_back_long_reads", 0) + len(held)
+        held.clear()
+
     for b in reader:
         # keep the reads that have a splint and belong to this rank (round-robin over the kept reads)
         sel = []
@@ -349,15 +382,32 @@ def _consume(args, device, rank, world, adapter_dict, splint_dict, adapter_set, 
             names = [names[i] for i in sel]
             off = np.zeros(len(sel) + 1, dtype=np.int64)
             off[1:] = np.cumsum(lens)
+        ad = dict(adapter_dict) if gpu_assign else adapter_dict
+        # The consensus buffers of a batch are dense ([reads][cons_cap], cons_cap from the longest read): one 100-kb read
+        # in a 50 000-read batch would cost gigabytes on host and device.  Reads far longer than the rest of their batch
+        # are held back and run as batches of their own.
+        lens = np.diff(off)
+        long_cut = max(32768, 4 * int(np.median(lens)))
+        is_long = lens > long_cut
+        if is_long.any() and not is_long.all():
+            for i in np.flatnonzero(is_long):
+                a0, a1 = int(off[i]), int(off[i + 1])
+                held.append((names[i], blob[a0:a1].copy(), qual[a0:a1].copy(), qsum[i], ad[names[i]]))
+            keep = np.flatnonzero(~is_long)
+            blob = np.concatenate([blob[off[i]:off[i + 1]] for i in keep])
+            qual = np.concatenate([qual[off[i]:off[i + 1]] for i in keep])
+            qsum = qsum[keep]
+            names = [names[i] for i in keep]
+            off = np.zeros(len(keep) + 1, dtype=np.int64)
+            off[1:] = np.cumsum(lens[keep])
         # two batches in flight per GPU (one handle + host thread each): the next batch's copies and kernels
         # overlap the tail of the previous persistent POA grid and the Python-side output writing
-        ad = dict(adapter_dict) if gpu_assign else adapter_dict
-        fut = pool.submit(run_on_free_handle, names, blob, off, splint_dict, ad, args.mdistcutoff)
-        pending.append((fut, names, blob, off, qual, qsum, ad))
-        while len(pending) >= len(gpus) + 1 or (pending and pending[0][0].done()):
-            _drain_one(pending, handles, totals, polish)
+        submit(names, blob, off, qual, qsum, ad)
+        if len(held) >= 2048:
+            flush_held()
+    flush_held()
     while pending:
-        _drain_one(pending, handles, totals, polish)
+        _drain_one(pending, handles, totals, polish, zero=bool(args.zero))
     pool.shutdown()
     for g2 in gpus[1:]:
         g2.close()

@@ -13,7 +13,9 @@ def revcomp(seq: str) -> str:
 
 def fastx_read(path: str):
     """Yields (name, seq, qual) like mappy.fastx_read(path, read_comment=False); qual is None for FASTA."""
-    op = gzip.open if path.endswith(".gz") else open
+    with open(path, "rb") as probe:                       # gzip by magic bytes, like the C++ ingest (not by suffix)
+        is_gz = probe.read(2) == b"\x1f\x8b"
+    op = gzip.open if is_gz else open
     with op(path, "rt") as f:
         line = f.readline()
         while line:

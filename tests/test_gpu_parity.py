@@ -291,7 +291,8 @@ def test_driver_end_to_end(gpu, oracle, tmp_path):
         seen += 1
     assert seen == len(cons)
     assert {s[0].rsplit("_", 1)[0] for s in subs} <= set(d["names"])
-    assert sum(1 for s in subs if s[0].endswith("_1")) == len(cons)
+    have_cons = {h.rsplit("_", 4)[0] for h in cons}
+    assert sum(1 for s in subs if s[0].endswith("_1") and s[0][:-2] in have_cons) == len(cons)
 
 
 def test_driver_polish_flag_runs_one_process_per_batch(gpu, tmp_path):
@@ -654,3 +655,48 @@ def test_against_real_pyabpoa_and_conk_when_importable(gpu, oracle):
     b = ReadBatch.from_strings([seq], [synth.SPLINT1], np.zeros(1, dtype=np.int32))
     assert np.array_equal(gpu.conk_batch(b, 20).astype(np.int64), real_prof)
     print("oracle = real")
+
+
+@pytest.mark.gpu
+def test_driver_zero_repeat_records_and_long_read_batches(gpu, oracle, tmp_path):
+    """Two things the advisor found in round 1.  (1) Zero-repeat reads (one splint): the reference's zero_repeats writes the
+    two dangling halves as @name_0 / @name_1 before it overlaps them with mappy; the driver writes those records and
+    counts the reads in c3poa.log instead of dropping them silently (-z switches the records off).  (2) A read far longer
+    than the rest of its batch is held back and run in a batch of its own (the consensus buffers are dense), with the
+    same result."""
+    if gpu.poa_mode != "auto":
+        pytest.skip("driver creates its own handles")
+    from c3poa_b200 import driver
+    from c3poa_b200.fastx import fastx_read
+    d = synth.make_reads(30, insert_len=700, repeat_range=(3, 5), seed=71)
+    z = synth.make_reads(4, insert_len=1500, repeats=0, seed=72, flank=(600, 1200))
+    lg = synth.make_reads(1, insert_len=1000, repeats=40, seed=73)
+    names = d["names"] + [f"z{i}" for i in range(4)] + ["long0"]
+    seqs, quals = d["seqs"] + z["seqs"] + lg["seqs"], d["quals"] + z["quals"] + lg["quals"]
+    assert len(lg["seqs"][0]) > 40000
+    for sub, extra in (("a", []), ("b", ["-z"])):
+        out = tmp_path / sub
+        (out / "tmp").mkdir(parents=True)
+        synth.write_fastq(tmp_path / "reads.fastq", names, seqs, quals)
+        (tmp_path / "splint.fasta").write_text(f">Splint1\n{synth.SPLINT1}\n")
+        synth.write_psl(out / "tmp" / "splint_to_read_alignments.psl", names, ["Splint1"] * len(names),
+                        d["strand"] + z["strand"] + lg["strand"])
+        totals = driver.main(driver.parse_args(["-r", str(tmp_path / "reads.fastq"), "-s", str(tmp_path / "splint.fasta"),
+                                                "-o", str(out), "-l", "1000", "-d", "500"] + extra))
+        cons = {n.rsplit("_", 4)[0]: s for n, s, _ in fastx_read(str(out / "Splint1" / "R2C2_Consensus.fasta"))}
+        subs = [s[0] for s in fastx_read(str(out / "Splint1" / "R2C2_Subreads.fastq"))]
+        log = (out / "c3poa.log").read_text()
+        assert totals["errors"] == 0 and totals.get("held_back_long_reads") == 1 and totals.get("zero", 0) >= 3
+        assert f"Zero-repeat reads without consensus" in log and log.rstrip().endswith(str(totals["zero"]))
+        zrec = [n for n in subs if n.startswith("z")]
+        if extra:
+            assert not zrec and totals.get("zero_records", 0) == 0
+        else:
+            assert totals["zero_records"] == totals["zero"] and len(zrec) == 2 * totals["zero"]
+            assert {n[-2:] for n in zrec} == {"_0", "_1"}
+        # the long read: same consensus as the oracle's, produced by the batch of its own
+        sp = [synth.SPLINT1, synth.revcomp(synth.SPLINT1)]
+        ref = oracle.consensus_batch(lg["seqs"], sp, np.array([1 if lg["strand"][0] == "-" else 0], dtype=np.int32),
+                                     max_peaks=128, cons_cap=4096)
+        assert ref["results"]["status"][0] == 0 and ref["results"]["n_sub"][0] >= 30
+        assert cons["long0"] == ref["cons"][0, :ref["results"]["cons_len"][0]].tobytes().decode()
