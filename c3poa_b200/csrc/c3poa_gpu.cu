@@ -43,6 +43,7 @@ struct c3_handle {
     // Host waits go through an event created with cudaEventBlockingSync: the waiting thread sleeps instead of spinning, so
     // a handle does not burn a core per batch in flight (the driver's reader / writer threads want them).
     cudaEvent_t ev_wait = nullptr;
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_chunk[4] = {nullptr};     // copy stream of the fused call
     cudaError_t sync()
     {
         if (!ev_wait) return cudaStreamSynchronize(stream);
@@ -158,6 +159,8 @@ extern "C" void c3_destroy(c3_handle *h)
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->kt_ev) cudaEventDestroy(e);
     if (h->ev_wait) cudaEventDestroy(h->ev_wait);
+    for (int k = 0; k < 4; ++k) if (h->ev_chunk[k]) cudaEventDestroy(h->ev_chunk[k]);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -224,27 +227,30 @@ static int launch_encode(c3_handle *h, const void *in, void *out, int64_t n)
     return 0;
 }
 
+// reads [r0, r1) of the staged batch: the offsets are absolute, so a range is a pointer shift; `slot`: its work counter
 template <int R>
-static cudaError_t launch_conk_R(c3_handle *h, int grid, int penalty, int32_t *brow, int64_t brow_stride)
+static cudaError_t launch_conk_R(c3_handle *h, int grid, int penalty, int32_t *brow, int64_t brow_stride, int r0, int r1, int slot)
 {
     c3_conk_kernel<R><<<grid, C3_CONK_THREADS, 0, h->stream>>>(
-        h->d_codes.as<uint8_t>(), h->d_off.as<int64_t>(), h->n_reads, h->d_sp_codes.as<uint8_t>(),
-        h->d_sp_off.as<int32_t>(), h->d_sp_idx.as<int32_t>(), penalty, h->d_prof.as<int32_t>(), brow, brow_stride,
-        h->d_counter.as<unsigned>());
+        h->d_codes.as<uint8_t>(), h->d_off.as<int64_t>() + r0, r1 - r0, h->d_sp_codes.as<uint8_t>(),
+        h->d_sp_off.as<int32_t>(), h->d_sp_idx.as<int32_t>() + r0, penalty, h->d_prof.as<int32_t>(), brow, brow_stride,
+        h->d_counter.as<unsigned>() + slot);
     return cudaGetLastError();
 }
 
-static int launch_conk(c3_handle *h, int penalty)
+static int launch_conk(c3_handle *h, int penalty, int r0 = 0, int r1 = -1, int slot = 0)
 {
+    if (r1 < 0) r1 = h->n_reads;
+    if (r1 <= r0) return 0;
     CK(h->d_prof.ensure((size_t)h->total_bases * 4 + 16));
     CK(h->d_counter.ensure(64));
-    CK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
+    if (slot == 0) CK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
     int R = (h->max_ls + 31) / 32;
     if (R < 1) R = 1;
     if (R > C3_CONK_MAXR) R = C3_CONK_MAXR;
     const int warps_per_block = C3_CONK_THREADS / 32;
     int grid = h->sm_count * 4;
-    grid = std::max(1, std::min(grid, (h->n_reads + warps_per_block - 1) / warps_per_block));
+    grid = std::max(1, std::min(grid, (r1 - r0 + warps_per_block - 1) / warps_per_block));
     int32_t *brow = nullptr; int64_t bstride = 0;
     if (h->max_ls > 32 * R) {
         bstride = ((int64_t)h->max_lr + 31) & ~31ll;
@@ -253,7 +259,7 @@ static int launch_conk(c3_handle *h, int penalty)
     }
     cudaError_t e;
     switch (R) {
-#define C3_CASE(r) case r: e = launch_conk_R<r>(h, grid, penalty, brow, bstride); break;
+#define C3_CASE(r) case r: e = launch_conk_R<r>(h, grid, penalty, brow, bstride, r0, r1, slot); break;
         C3_CASE(1) C3_CASE(2) C3_CASE(3) C3_CASE(4) C3_CASE(5) C3_CASE(6) C3_CASE(7) C3_CASE(8)
         C3_CASE(9) C3_CASE(10) C3_CASE(11) C3_CASE(12) C3_CASE(13) C3_CASE(14) C3_CASE(15) C3_CASE(16)
 #undef C3_CASE
@@ -650,7 +656,8 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     // steady state (batch after batch of the same shape): the growth share chosen last time, inside the workspace the
     // handle already owns -- no driver query.  Otherwise ask once and choose again.
     size_for(grow_env ? grow_env : grow_try[h->grp_grow_idx]);
-    const bool may_ask = h->d_ws_grp.cap == 0 || h->grp_ask_wait <= 0;      // a batch that needs several waves: not every call
+    // (a batch that needs several waves does not ask on every call, unless what the handle owns holds no decent wave)
+    const bool may_ask = h->d_ws_grp.cap == 0 || h->grp_ask_wait <= 0 || budget / read_bytes < std::min(ng, 12000);
     if (h->grp_ask_wait > 0) --h->grp_ask_wait;
     if (!grow_env && budget / read_bytes < ng && may_ask) {
         h->grp_ask_wait = 64;
@@ -802,7 +809,8 @@ static int launch_poa(c3_handle *h, c3_poa_args &A, int max_q, int max_nseq, int
 // staging of reads + splints (shared by B1 and B4)
 // ---------------------------------------------------------------------------
 static int stage_reads(c3_handle *h, int32_t n_reads, const char *reads, const int64_t *read_off,
-                       int32_t n_splints, const char *splints, const int32_t *splint_off, const int32_t *splint_idx)
+                       int32_t n_splints, const char *splints, const int32_t *splint_off, const int32_t *splint_idx,
+                       bool defer_reads = false)
 {
     if (!h) return -1;
     if (n_reads <= 0 || !reads || !read_off || n_splints <= 0 || !splints || !splint_off || !splint_idx)
@@ -833,12 +841,13 @@ static int stage_reads(c3_handle *h, int32_t n_reads, const char *reads, const i
     CK(h->d_sp_codes.ensure((size_t)total_sp + 64));
     CK(h->d_sp_off.ensure((size_t)(n_splints + 1) * 4));
     CK(h->d_sp_idx.ensure((size_t)n_reads * 4));
-    CK(cudaMemcpyAsync(h->d_ascii.p, reads, (size_t)total, cudaMemcpyHostToDevice, h->stream));
+    // defer_reads (fused call): the read bytes follow in chunks on the copy stream, under the conk kernel of the chunk before
+    if (!defer_reads) CK(cudaMemcpyAsync(h->d_ascii.p, reads, (size_t)total, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_off.p, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_sp_ascii.p, splints, (size_t)total_sp, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_sp_off.p, splint_off, (size_t)(n_splints + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_sp_idx.p, splint_idx, (size_t)n_reads * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(h->sync());
+    if (!defer_reads) CK(h->sync());
     h->staged = true; h->ran = false;
     return 0;
 }
@@ -1101,8 +1110,11 @@ extern "C" int c3_stage(c3_handle *h, int32_t n_reads, const char *reads, const 
     return stage_reads(h, n_reads, reads, read_off, n_splints, splints, splint_off, splint_idx);
 }
 
-extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t window, int32_t iters,
-                      int32_t min_dist, const c3_poa_params *params, int32_t max_peaks, int32_t cons_cap)
+// pipe_reads / pipe_off != null (fused call): the reads' bytes are still on the host; they are copied in up to 4 chunks on
+// a second stream, and chunk k's encode + conk run while chunk k + 1 is on its way (PCIe under the conk kernel).
+static int run_impl(c3_handle *h, int32_t penalty, const double *coef, int32_t window, int32_t iters,
+                    int32_t min_dist, const c3_poa_params *params, int32_t max_peaks, int32_t cons_cap,
+                    const char *pipe_reads, const int64_t *pipe_off)
 {
     if (!h) return -1;
     if (!h->staged) return fail(h, -8, "c3_run without c3_stage");
@@ -1122,9 +1134,41 @@ extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t
     CK(cudaMemsetAsync(h->d_cons.p, 0, (size_t)n * cons_cap, h->stream));
     int rc;
     CK(cudaEventRecord(h->ev[0], h->stream));
-    if ((rc = encode_staged(h))) return rc;
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    if ((rc = launch_conk(h, penalty))) return rc;
+    if (!pipe_reads) {
+        if ((rc = encode_staged(h))) return rc;
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        if ((rc = launch_conk(h, penalty))) return rc;
+    } else {
+        if (!h->stream2) {
+            CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+            for (int k = 0; k < 4; ++k) CK(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
+        }
+        if ((rc = launch_encode(h, h->d_sp_ascii.p, h->d_sp_codes.p, h->total_sp))) return rc;
+        CK(cudaEventRecord(h->ev[1], h->stream));                 // (encode_ms then only covers the splints)
+        const int nchunk = h->total_bases >= (64ll << 20) && n >= 64 ? 4 : 1;
+        int rb[5]; int64_t bb[5];
+        for (int k = 0; k <= nchunk; ++k) {
+            // chunk borders at reads holding equal shares of the bytes; byte ranges start 16-aligned (the encode kernel
+            // works on 16-byte words) and overlap by at most one word, which is copied and encoded twice
+            int r = k == nchunk ? n : (int)(std::lower_bound(pipe_off, pipe_off + n, h->total_bases * k / nchunk) - pipe_off);
+            rb[k] = std::min(r, n);
+            bb[k] = pipe_off[rb[k]];
+        }
+        // the copy stream may only overwrite d_ascii once everything queued on the launch stream so far has passed
+        CK(cudaEventRecord(h->ev_chunk[0], h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, h->ev_chunk[0], 0));
+        for (int k = 0; k < nchunk; ++k) {
+            const int64_t b0 = bb[k] & ~15ll, b1 = std::min<int64_t>(h->total_bases, (bb[k + 1] + 15) & ~15ll);
+            if (b1 > b0) CK(cudaMemcpyAsync(h->d_ascii.as<uint8_t>() + b0, pipe_reads + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, h->stream2));
+            CK(cudaEventRecord(h->ev_chunk[k], h->stream2));
+        }
+        for (int k = 0; k < nchunk; ++k) {
+            const int64_t b0 = bb[k] & ~15ll, b1 = std::min<int64_t>(h->total_bases, (bb[k + 1] + 15) & ~15ll);
+            CK(cudaStreamWaitEvent(h->stream, h->ev_chunk[k], 0));
+            if ((rc = launch_encode(h, h->d_ascii.as<uint8_t>() + b0, h->d_codes.as<uint8_t>() + b0, b1 - b0))) return rc;
+            if ((rc = launch_conk(h, penalty, rb[k], rb[k + 1], k))) return rc;
+        }
+    }
     CK(cudaEventRecord(h->ev[2], h->stream));
     if ((rc = launch_peaks(h, h->d_prof.as<int32_t>(), h->d_off.as<int64_t>(), n, h->max_lr, coef, window, iters,
                            min_dist, 3.0, 6.0, false, false, max_peaks, h->total_bases))) return rc;
@@ -1189,6 +1233,12 @@ extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t
     return 0;
 }
 
+extern "C" int c3_run(c3_handle *h, int32_t penalty, const double *coef, int32_t window, int32_t iters,
+                      int32_t min_dist, const c3_poa_params *params, int32_t max_peaks, int32_t cons_cap)
+{
+    return run_impl(h, penalty, coef, window, iters, min_dist, params, max_peaks, cons_cap, nullptr, nullptr);
+}
+
 extern "C" int c3_fetch(c3_handle *h, int32_t *out_peaks, int32_t *out_sub_bounds, int32_t *out_dang_bounds,
                         char *out_cons, c3_read_result *out_results)
 {
@@ -1214,9 +1264,11 @@ extern "C" int c3_consensus_batch(c3_handle *h, int32_t n_reads, const char *rea
                                   int32_t *out_peaks, int32_t *out_sub_bounds, int32_t *out_dang_bounds,
                                   char *out_cons, c3_read_result *out_results)
 {
-    int rc = c3_stage(h, n_reads, reads, read_off, n_splints, splints, splint_off, splint_idx);
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    int rc = stage_reads(h, n_reads, reads, read_off, n_splints, splints, splint_off, splint_idx, /*defer_reads=*/true);
     if (rc) return rc;
-    if ((rc = c3_run(h, penalty, coef, window, iters, min_dist, params, max_peaks, cons_cap))) return rc;
+    if ((rc = run_impl(h, penalty, coef, window, iters, min_dist, params, max_peaks, cons_cap, reads, read_off))) return rc;
     if ((rc = c3_fetch(h, out_peaks, out_sub_bounds, out_dang_bounds, out_cons, out_results))) return rc;
     return 0;
 }
