@@ -90,7 +90,7 @@ struct c3_handle {
     double dbg_sync_ms = 0; std::chrono::steady_clock::time_point dbg_t1;     // C3POA_GRP_TIMING only
     int grp_bps[2] = {0, 0}, warp_bps = 0, grp_grow_idx = 0, grp_ask_wait = 0;
     int sw_int8_lanes = 0, sw_end_clamp = 0;   // c3_set_abpoa_switches: only the warp kernel implements them
-    DevBuf d_order_lane, d_done, d_order_grp, d_ws_grp, d_order_scratch;
+    DevBuf d_order_lane, d_done, d_order_grp, d_ws_grp, d_order_scratch, d_pairs;
     int n_work_grp = 0, grp_max_nseq = 0, grp_max_q = 0; int64_t grp_max_total = 0;
     std::vector<int32_t> grp_nseq;   // sequences per item of the group kernels' list (host copy: launches per wave)
     int n_work_lane = 0, lane_items = 0, lane_n_items = 0;
@@ -154,7 +154,7 @@ extern "C" void c3_destroy(c3_handle *h)
                       &h->d_prof, &h->d_brow, &h->d_counter, &h->d_coef, &h->d_pk_scratch, &h->d_smoothed, &h->d_median,
                       &h->d_peaks, &h->d_npk, &h->d_sub, &h->d_dang, &h->d_res, &h->d_stats, &h->d_cons, &h->d_ws,
                       &h->d_item_base, &h->d_bounds, &h->d_nseq, &h->d_status, &h->d_clen, &h->d_nodes, &h->d_cells, &h->d_order,
-                      &h->d_order_lane, &h->d_done, &h->d_order_grp, &h->d_ws_grp, &h->d_order_scratch};
+                      &h->d_order_lane, &h->d_done, &h->d_order_grp, &h->d_ws_grp, &h->d_order_scratch, &h->d_pairs};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->kt_ev) cudaEventDestroy(e);
@@ -238,6 +238,50 @@ static cudaError_t launch_conk_R(c3_handle *h, int grid, int penalty, int32_t *b
     return cudaGetLastError();
 }
 
+// packed conk (two reads per warp, conk.cuh): pair list of the range on the device, then the kernel; no readback
+template <int R>
+static cudaError_t launch_conk2_R(c3_handle *h, int grid, int penalty, const int32_t *pairs, const int *n_pairs, int slot)
+{
+    c3_conk2_kernel<R><<<grid, C3_CONK_THREADS, 0, h->stream>>>(
+        h->d_codes.as<uint8_t>(), h->d_off.as<int64_t>(), pairs, n_pairs, h->d_sp_codes.as<uint8_t>(),
+        h->d_sp_off.as<int32_t>(), h->d_sp_idx.as<int32_t>(), penalty, h->d_prof.as<int32_t>(), h->d_counter.as<unsigned>() + slot);
+    return cudaGetLastError();
+}
+
+static int launch_conk2(c3_handle *h, int penalty, int r0, int r1, int slot, int R)
+{
+    const int nkeys = h->n_splints * 32;
+    const int nr = r1 - r0;
+    // per slot: hist, start, fill (nkeys each), n_pairs; the pair list of the range sits at r0 + slot * nkeys
+    const size_t meta = (size_t)3 * C3_CONK2_MAXKEYS + 4;
+    CK(h->d_pairs.ensure(((size_t)h->n_reads + (size_t)4 * C3_CONK2_MAXKEYS + 4 * meta + 64) * 4));
+    int32_t *base = h->d_pairs.as<int32_t>();
+    unsigned *hist = reinterpret_cast<unsigned *>(base) + (size_t)slot * meta, *start = hist + C3_CONK2_MAXKEYS, *fill = start + C3_CONK2_MAXKEYS;
+    int *n_pairs = reinterpret_cast<int *>(fill + C3_CONK2_MAXKEYS);
+    int32_t *pairs = base + 4 * meta + (size_t)r0 + (size_t)slot * C3_CONK2_MAXKEYS;
+    pairs = reinterpret_cast<int32_t *>((reinterpret_cast<uintptr_t>(pairs) + 7) & ~(uintptr_t)7);
+    CK(cudaMemsetAsync(hist, 0, meta * 4, h->stream));
+    CK(cudaMemsetAsync(pairs, 0xff, ((size_t)nr + nkeys + 2) * 4, h->stream));
+    c3_conk2_count_kernel<<<(nr + 255) / 256, 256, 0, h->stream>>>(r0, r1, h->d_off.as<int64_t>(), h->d_sp_idx.as<int32_t>(), hist);
+    c3_conk2_scan_kernel<<<1, 1024, 0, h->stream>>>(nkeys, hist, start, n_pairs);
+    c3_conk2_scatter_kernel<<<(nr + 255) / 256, 256, 0, h->stream>>>(r0, r1, h->d_off.as<int64_t>(), h->d_sp_idx.as<int32_t>(), start, fill, pairs);
+    CK(cudaGetLastError());
+    h->tim.kernel_launches += 3;
+    const int warps_per_block = C3_CONK_THREADS / 32;
+    const int grid = std::max(1, std::min(h->sm_count * 4, ((nr + 1) / 2 + nkeys + warps_per_block - 1) / warps_per_block));
+    cudaError_t e;
+    switch (R) {
+#define C3_CASE(r) case r: e = launch_conk2_R<r>(h, grid, penalty, pairs, n_pairs, slot); break;
+        C3_CASE(1) C3_CASE(2) C3_CASE(3) C3_CASE(4) C3_CASE(5) C3_CASE(6) C3_CASE(7) C3_CASE(8)
+        C3_CASE(9) C3_CASE(10) C3_CASE(11) C3_CASE(12) C3_CASE(13) C3_CASE(14) C3_CASE(15)
+#undef C3_CASE
+        default: e = cudaErrorInvalidValue;
+    }
+    CK(e);
+    h->tim.kernel_launches++;
+    return 0;
+}
+
 static int launch_conk(c3_handle *h, int penalty, int r0 = 0, int r1 = -1, int slot = 0)
 {
     if (r1 < 0) r1 = h->n_reads;
@@ -248,6 +292,12 @@ static int launch_conk(c3_handle *h, int penalty, int r0 = 0, int r1 = -1, int s
     int R = (h->max_ls + 31) / 32;
     if (R < 1) R = 1;
     if (R > C3_CONK_MAXR) R = C3_CONK_MAXR;
+    // two reads per warp when everything fits 16-bit halves: one pass over the splint (<= 480 rows), a sane penalty,
+    // a pairing key space that the scan kernel covers, and enough reads to fill the grid with pairs (C3POA_CONK_PACKED_MIN:
+    // tests lower the bound to run small cases through the packed kernel; C3POA_CONK_INT32 forces the one-read kernel)
+    if (R <= 15 && h->max_ls <= 32 * R && penalty >= 0 && penalty <= 8000 && h->n_splints * 32 <= C3_CONK2_MAXKEYS &&
+        r1 - r0 >= (getenv("C3POA_CONK_PACKED_MIN") ? atoi(getenv("C3POA_CONK_PACKED_MIN")) : 4096) && !getenv("C3POA_CONK_INT32"))
+        return launch_conk2(h, penalty, r0, r1, slot, R);
     const int warps_per_block = C3_CONK_THREADS / 32;
     int grid = h->sm_count * 4;
     grid = std::max(1, std::min(grid, (r1 - r0 + warps_per_block - 1) / warps_per_block));

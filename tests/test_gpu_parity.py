@@ -700,3 +700,35 @@ def test_driver_zero_repeat_records_and_long_read_batches(gpu, oracle, tmp_path)
                                      max_peaks=128, cons_cap=4096)
         assert ref["results"]["status"][0] == 0 and ref["results"]["n_sub"][0] >= 30
         assert cons["long0"] == ref["cons"][0, :ref["results"]["cons_len"][0]].tobytes().decode()
+
+
+@pytest.mark.gpu
+def test_conk_packed_kernel_small_cases(gpu, oracle):
+    """c3_conk2_kernel (two reads per warp in 16-bit halves; what batches of >= 4096 reads get): forced onto small and
+    awkward inputs -- reads without partner, pairs of very different length, N bases, two splints of different length,
+    splint lengths around the lane multiples, penalties 1-50 -- and compared with the oracle read by read."""
+    if gpu.poa_mode != "auto":
+        pytest.skip("runs once")
+    rng = np.random.default_rng(5)
+    os.environ["C3POA_CONK_PACKED_MIN"] = "1"
+    try:
+        for ls in (31, 32, 33, 200, 284, 288, 289, 479, 480):
+            sps = [synth.random_seq(rng, ls).tobytes().decode(), synth.random_seq(rng, max(20, ls - 37)).tobytes().decode()]
+            seqs, idx = [], []
+            for k, L in enumerate((900, 4100, 60, 2049, 2047, 5000, 1500, 33, 7000)):
+                sp = k % 2
+                core = synth.random_seq(rng, max(10, L // 3)).tobytes().decode()
+                s = (core + sps[sp] + core + sps[sp] + core)[:L]
+                if k == 1:
+                    s = s[:50] + "N" + s[51:200] + "n" + s[201:]
+                seqs.append(s); idx.append(sp)
+            b = ReadBatch.from_strings(seqs, sps, np.array(idx, dtype=np.int32))
+            for pen in ((20,) if ls not in (284, 33) else (1, 7, 20, 50)):
+                prof = gpu.conk_batch(b, penalty=pen)
+                for i, s in enumerate(seqs):
+                    assert np.array_equal(oracle.conk(sps[idx[i]], s, pen), prof[b.off[i]:b.off[i + 1]]), (ls, pen, i)
+        # the same inputs through the one-read kernel give the same bytes
+        os.environ["C3POA_CONK_INT32"] = "1"
+        assert np.array_equal(gpu.conk_batch(b, penalty=20), prof)
+    finally:
+        os.environ.pop("C3POA_CONK_PACKED_MIN", None); os.environ.pop("C3POA_CONK_INT32", None)
