@@ -12,8 +12,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef C3_PK_THREADS
 #define C3_PK_THREADS 256
-#define C3_PK_TILE 1024
+#endif
+#define C3_PK_TILE (4 * C3_PK_THREADS)   // four consecutive outputs per thread
 #define C3_PK_MAXWIN 127
 #define C3_PK_MAXC 1024      // candidate local maxima above the height threshold, per read
 
