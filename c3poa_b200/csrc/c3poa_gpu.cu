@@ -18,6 +18,8 @@
 
 #define C3_VERSION "c3poa_b200 0.1.0 (sm_100a)"
 
+#define C3_PIPE_CHUNKS 8               // chunks of the fused call's read upload (copy stream under the conk kernel)
+
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
     cudaError_t ensure(size_t bytes)
@@ -43,7 +45,7 @@ struct c3_handle {
     // Host waits go through an event created with cudaEventBlockingSync: the waiting thread sleeps instead of spinning, so
     // a handle does not burn a core per batch in flight (the driver's reader / writer threads want them).
     cudaEvent_t ev_wait = nullptr;
-    cudaStream_t stream2 = nullptr; cudaEvent_t ev_chunk[4] = {nullptr};     // copy stream of the fused call
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_chunk[C3_PIPE_CHUNKS] = {nullptr};     // copy stream of the fused call
     cudaError_t sync()
     {
         if (!ev_wait) return cudaStreamSynchronize(stream);
@@ -159,7 +161,7 @@ extern "C" void c3_destroy(c3_handle *h)
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->kt_ev) cudaEventDestroy(e);
     if (h->ev_wait) cudaEventDestroy(h->ev_wait);
-    for (int k = 0; k < 4; ++k) if (h->ev_chunk[k]) cudaEventDestroy(h->ev_chunk[k]);
+    for (int k = 0; k < C3_PIPE_CHUNKS; ++k) if (h->ev_chunk[k]) cudaEventDestroy(h->ev_chunk[k]);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -254,11 +256,11 @@ static int launch_conk2(c3_handle *h, int penalty, int r0, int r1, int slot, int
     const int nr = r1 - r0;
     // per slot: hist, start, fill (nkeys each), n_pairs; the pair list of the range sits at r0 + slot * nkeys
     const size_t meta = (size_t)3 * C3_CONK2_MAXKEYS + 4;
-    CK(h->d_pairs.ensure(((size_t)h->n_reads + (size_t)4 * C3_CONK2_MAXKEYS + 4 * meta + 64) * 4));
+    CK(h->d_pairs.ensure(((size_t)h->n_reads + (size_t)C3_PIPE_CHUNKS * C3_CONK2_MAXKEYS + C3_PIPE_CHUNKS * meta + 64) * 4));
     int32_t *base = h->d_pairs.as<int32_t>();
     unsigned *hist = reinterpret_cast<unsigned *>(base) + (size_t)slot * meta, *start = hist + C3_CONK2_MAXKEYS, *fill = start + C3_CONK2_MAXKEYS;
     int *n_pairs = reinterpret_cast<int *>(fill + C3_CONK2_MAXKEYS);
-    int32_t *pairs = base + 4 * meta + (size_t)r0 + (size_t)slot * C3_CONK2_MAXKEYS;
+    int32_t *pairs = base + C3_PIPE_CHUNKS * meta + (size_t)r0 + (size_t)slot * C3_CONK2_MAXKEYS;
     pairs = reinterpret_cast<int32_t *>((reinterpret_cast<uintptr_t>(pairs) + 7) & ~(uintptr_t)7);
     CK(cudaMemsetAsync(hist, 0, meta * 4, h->stream));
     CK(cudaMemsetAsync(pairs, 0xff, ((size_t)nr + nkeys + 2) * 4, h->stream));
@@ -1160,7 +1162,7 @@ extern "C" int c3_stage(c3_handle *h, int32_t n_reads, const char *reads, const 
     return stage_reads(h, n_reads, reads, read_off, n_splints, splints, splint_off, splint_idx);
 }
 
-// pipe_reads / pipe_off != null (fused call): the reads' bytes are still on the host; they are copied in up to 4 chunks on
+// pipe_reads / pipe_off != null (fused call): the reads' bytes are still on the host; they are copied in up to 8 chunks on
 // a second stream, and chunk k's encode + conk run while chunk k + 1 is on its way (PCIe under the conk kernel).
 static int run_impl(c3_handle *h, int32_t penalty, const double *coef, int32_t window, int32_t iters,
                     int32_t min_dist, const c3_poa_params *params, int32_t max_peaks, int32_t cons_cap,
@@ -1191,12 +1193,12 @@ static int run_impl(c3_handle *h, int32_t penalty, const double *coef, int32_t w
     } else {
         if (!h->stream2) {
             CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-            for (int k = 0; k < 4; ++k) CK(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
+            for (int k = 0; k < C3_PIPE_CHUNKS; ++k) CK(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
         }
         if ((rc = launch_encode(h, h->d_sp_ascii.p, h->d_sp_codes.p, h->total_sp))) return rc;
         CK(cudaEventRecord(h->ev[1], h->stream));                 // (encode_ms then only covers the splints)
-        const int nchunk = h->total_bases >= (64ll << 20) && n >= 64 ? 4 : 1;
-        int rb[5]; int64_t bb[5];
+        const int nchunk = h->total_bases >= (64ll << 20) && n >= 64 * C3_PIPE_CHUNKS ? C3_PIPE_CHUNKS : 1;
+        int rb[C3_PIPE_CHUNKS + 1]; int64_t bb[C3_PIPE_CHUNKS + 1];
         for (int k = 0; k <= nchunk; ++k) {
             // chunk borders at reads holding equal shares of the bytes; byte ranges start 16-aligned (the encode kernel
             // works on 16-byte words) and overlap by at most one word, which is copied and encoded twice

@@ -226,6 +226,11 @@ def main(args):
         print("Total thrown away reads:", short_reads + no_splint,
               "({:.2f}%)".format((short_reads + no_splint) / max(all_reads, 1) * 100), file=log)
         print("Reads after preprocessing:", all_reads - (short_reads + no_splint), file=log)
+        if getattr(args, "polish", False):
+            print("Polishing: one racon process per batch on the >= 3-repeat consensi (2-repeat pairwise consensi and the",
+                  "dangling ends are not polished); polished:", totals.get("polished", 0), file=log)
+        else:
+            print("Polishing: off (pre-polish abPOA consensi; the reference always runs racon -- use --polish)", file=log)
         # not in the reference's log: what this driver does not produce must not disappear silently
         print("Zero-repeat reads without consensus (zero_repeats needs mappy; dangling subreads written:",
               str(totals.get("zero_records", 0)) + "):", totals.get("zero", 0), file=log)
