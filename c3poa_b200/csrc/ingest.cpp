@@ -80,9 +80,16 @@ static bool next_record(c3_fastq *q)
         if (ln[0] == '@') {
             set_name(q, ln);
             if (!read_line(q, q->seq)) return false;
-            std::string plus;
-            if (!read_line(q, plus)) return false;
+            // multi-line records (sequence and quality wrapped over several lines): sequence lines run up to the '+'
+            // line, quality lines until they cover the sequence (a quality line may itself start with '@' or '+')
+            std::string nx;
+            for (;;) {
+                if (!read_line(q, nx)) return false;
+                if (!nx.empty() && nx[0] == '+') break;
+                q->seq += nx;
+            }
             if (!read_line(q, q->qual)) q->qual.clear();
+            while (q->qual.size() < q->seq.size() && read_line(q, nx)) q->qual += nx;
             return true;
         }
         if (ln[0] == '>') {

@@ -127,6 +127,12 @@ def test_cxx_ingest_matches_python_reader(tmp_path):
                     assert b["qual_sum"][i] == sum(ord(c) - 33 for c in got[-1][2])
             exp = [r for r in ref if len(r[1]) >= min_len]
             assert got == exp and fb.n_short.value == len(ref) - len(exp)
+    # multi-line FASTQ (wrapped sequence and quality; quality lines that start with '@' and '+')
+    ml = tmp_path / "ml.fastq"
+    ml.write_text("@m1 c\nACGTAC\nGTTT\n+\n@IIIII\n+III\n@m2\nAC\n+m2\nII\n")
+    b = next(FastqBatches(str(ml), pinned=False))
+    assert b["names"] == ["m1", "m2"] and b["blob"].tobytes() == b"ACGTACGTTTAC" and b["off"].tolist() == [0, 10, 12]
+    assert b["qual"].tobytes() == b"@IIIII+IIIII"
     fa = tmp_path / "s.fasta"
     fa.write_text(">A desc\nACGT\nAC\n>B\nTTTT\n")
     b = next(FastqBatches(str(fa), pinned=False))
