@@ -767,6 +767,7 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
         else for (int k = 0; k < nw; ++k) wave_nseq = std::max(wave_nseq, h->grp_nseq[(size_t)(w0 + k)]);
         CK(cudaMemsetAsync(counters, 0, (size_t)n_counters * 4, h->stream));
         L.A.order = h->d_order_grp.as<int32_t>() + w0; L.A.n_work = nw;
+        L.eager = nw < 48000;
         const int w_dp = (nw + 3) / 4;                              // warps that can be busy
         const int grid_dp = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * bps_dp, (w_dp + wpb - 1) / wpb));
         const int grid_gr = (nw + C3S_THREADS - 1) / C3S_THREADS;  // one thread per read

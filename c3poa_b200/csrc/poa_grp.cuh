@@ -81,7 +81,7 @@ struct c3g_args {
     int rv_shift;                     // log2 RV: vectors per shared-memory ring slot (RV <= VS)
     int32_t *done;                    // [n_items] 1 = finished here
     struct c3g_state *state;          // per read of the wave
-    int first;                        // graph kernel: 1 = first launch of a wave (first sequence -> graph)
+    int eager;                        // graph kernel: 1 = small wave (bound by round trips): the backtrack asks early for what its gap tests may need
 };
 
 // per-group workspace

@@ -61,6 +61,7 @@ extern "C" int c3g_emul_batch(int n_items, const uint8_t *codes, const int64_t *
     memset(state.data(), 0xA5, state.size() * sizeof(c3g_state));
     L.ws = ws; L.ws_stride = ws_bytes; L.arena = arena; L.arena_stride4 = arena4;
     L.vs_shift = vs_shift; L.rv_shift = rv_shift; L.done = done; L.state = state.data();
+    L.eager = graph_gl & 1;            // (the former graph_gl argument: odd = the small-wave variant of the backtrack)
     int rc = 0, launch = 0;
     // the host's launch sequence: init kernel, then (DP kernel, graph kernel) per further sequence.  Init and graph
     // kernel are scalar code, one worker per read: called directly.  The DP kernel's warps run on the fiber emulator

@@ -137,6 +137,7 @@ def _check(r, groups, oracle, para=None, must_finish=True):
 def test_grp_body_matches_oracle(emul, oracle):
     groups = _groups()
     _check(run_emul(emul, groups), groups, oracle)
+    _check(run_emul(emul, groups, graph_gl=1), groups, oracle)        # small-wave variant of the backtrack (eager loads)
 
 
 def test_grp_bench_shape(emul, oracle):
