@@ -759,7 +759,6 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     unsigned *counters = reinterpret_cast<unsigned *>(base + wave * read_bytes + 128);
     L.done = h->d_done.as<int32_t>();
     const bool timing = getenv("C3POA_GRP_TIMING") != nullptr;
-    if (const char *e = getenv("C3POA_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));   // tuning only
     for (int64_t w0 = 0; w0 < ng; w0 += wave) {
         const int nw = (int)std::min<int64_t>(wave, ng - w0);
         int wave_nseq = 1;
@@ -1251,14 +1250,6 @@ static int run_impl(c3_handle *h, int32_t penalty, const double *coef, int32_t w
         A.codes = h->d_codes.as<uint8_t>(); A.item_base = h->d_off.as<int64_t>(); A.bounds = h->d_sub.as<int32_t>();
         A.n_seqs = &res->n_sub; A.n_seqs_stride = sizeof(c3_read_result) / 4; A.n_items = n; A.max_seqs = max_peaks; A.min_seqs = 2;
         A.msa2 = 1; A.ok_status = 2;    // 2-repeat reads: [row0 | row1] of the pairwise MSA in the consensus slot
-        if (getenv("C3POA_HOST_ORDER")) {                          // tuning only: round 1's host-side order
-            std::vector<c3_read_result> hr((size_t)n);
-            CK(cudaMemcpyAsync(hr.data(), h->d_res.p, (size_t)n * sizeof(c3_read_result), cudaMemcpyDeviceToHost, h->stream));
-            CK(h->sync());
-            std::vector<int32_t> ns((size_t)n); std::vector<int64_t> tot((size_t)n);
-            for (int i = 0; i < n; ++i) { ns[i] = hr[i].status >= 0 ? hr[i].n_sub : 0; tot[i] = ns[i] >= 2 ? hr[i].poa_cells : 0; }
-            if ((rc = upload_poa_order(h, A, ns, tot, 2, params))) return rc;
-        } else
         if ((rc = build_poa_order_device(h, A, n, h->d_res.as<c3_read_result_dev>(), 2, params))) return rc;
         h->tim.poa_items = stats[3];
         A.cons = h->d_cons.as<char>(); A.cons_cap = cons_cap; A.status = &res->status; A.cons_len = &res->cons_len;

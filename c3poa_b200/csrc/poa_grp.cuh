@@ -412,10 +412,20 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
             const int lim = min(qlen, end_sn * 16 + 15) - j0;        // last column of this vector that exists (>= 15: all)
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                unsigned klo = C3L_PRMT(hh[t], (uint32_t)((15 - 2 * t) << 12), 0x1054u) ^ 0x80000000u;   // lo half -> high half, priority below
-                unsigned khi = C3L_PRMT(hh[t], (uint32_t)((14 - 2 * t) << 12), 0x3254u) ^ 0x80000000u;
-                if (lim < 15) { if (2 * t > lim) klo = 0u; if (2 * t + 1 > lim) khi = 0u; }
+                const unsigned klo = C3L_PRMT(hh[t], (uint32_t)((15 - 2 * t) << 12), 0x1054u) ^ 0x80000000u;   // lo half -> high half, priority below
+                const unsigned khi = C3L_PRMT(hh[t], (uint32_t)((14 - 2 * t) << 12), 0x3254u) ^ 0x80000000u;
                 lk = max(lk, max(klo, khi));
+            }
+            if (lim < 15) {                                          // the row's last vector when it reaches past qlen: again, masked
+                lk = 0u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    unsigned klo = C3L_PRMT(hh[t], (uint32_t)((15 - 2 * t) << 12), 0x1054u) ^ 0x80000000u;
+                    unsigned khi = C3L_PRMT(hh[t], (uint32_t)((14 - 2 * t) << 12), 0x3254u) ^ 0x80000000u;
+                    if (2 * t > lim) klo = 0u;
+                    if (2 * t + 1 > lim) khi = 0u;
+                    lk = max(lk, max(klo, khi));
+                }
             }
             const unsigned vp = (sn == end_sn) ? 0xfffu : (unsigned)(0xffe - (sn - beg_sn));
             bestkey = max(bestkey, lk | vp);
