@@ -325,7 +325,7 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
     const int d21 = oe1 - oe2;
     int pc1 = C3L_FLOOR, pc2 = C3L_FLOOR;                          // F1, F2' entering the pass (chain domain, see below)
     uint32_t mcarry = C3L_FLOOR2;                                  // merged predecessor H of the vector before the pass
-    unsigned bestkey = 0u;
+    int bestkey = -0x7fffffff - 1;      // row arg-max key, compared as a signed word (see below)
     int h_first = 0x7fff;
     // everything read from the ring must be in registers before any lane overwrites the slot of row pos - C3G_R:
     // a row of several passes stores its first vectors before it has read the last ones, so it does not use that slot
@@ -405,29 +405,30 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
             n2[t] = C3L_VADDMAX2(x2[t], ne2, C3L_VADDMAX2(hh[t], noe2, C3L_FLOOR2));
         }
         if (sn == beg_sn) h_first = (int)(int16_t)(hh[0] & 0xffffu);
-        // simd_abpoa_ada_max_i as one packed max: value (biased to unsigned) in the high half, tie-break priority in
-        // the low half (lowest SIMD lane, then the last vector, then the earliest vector)
+        // simd_abpoa_ada_max_i as one packed max: the value in the high half, tie-break priority in the low half (lowest
+        // SIMD lane, then the last vector, then the earliest vector); compared as SIGNED 32-bit words: the high half is
+        // the signed value, and between equal values the low halves compare as the unsigned numbers they are
         if (act) {
-            unsigned lk = 0u;
+            int lk = -0x7fffffff - 1;
             const int lim = min(qlen, end_sn * 16 + 15) - j0;        // last column of this vector that exists (>= 15: all)
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                const unsigned klo = C3L_PRMT(hh[t], (uint32_t)((15 - 2 * t) << 12), 0x1054u) ^ 0x80000000u;   // lo half -> high half, priority below
-                const unsigned khi = C3L_PRMT(hh[t], (uint32_t)((14 - 2 * t) << 12), 0x3254u) ^ 0x80000000u;
+                const int klo = (int)C3L_PRMT(hh[t], (uint32_t)((15 - 2 * t) << 12), 0x1054u);   // lo half -> high half, priority below
+                const int khi = (int)C3L_PRMT(hh[t], (uint32_t)((14 - 2 * t) << 12), 0x3254u);
                 lk = max(lk, max(klo, khi));
             }
             if (lim < 15) {                                          // the row's last vector when it reaches past qlen: again, masked
-                lk = 0u;
+                lk = -0x7fffffff - 1;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    unsigned klo = C3L_PRMT(hh[t], (uint32_t)((15 - 2 * t) << 12), 0x1054u) ^ 0x80000000u;
-                    unsigned khi = C3L_PRMT(hh[t], (uint32_t)((14 - 2 * t) << 12), 0x3254u) ^ 0x80000000u;
-                    if (2 * t > lim) klo = 0u;
-                    if (2 * t + 1 > lim) khi = 0u;
+                    int klo = (int)C3L_PRMT(hh[t], (uint32_t)((15 - 2 * t) << 12), 0x1054u);
+                    int khi = (int)C3L_PRMT(hh[t], (uint32_t)((14 - 2 * t) << 12), 0x3254u);
+                    if (2 * t > lim) klo = -0x7fffffff - 1;
+                    if (2 * t + 1 > lim) khi = -0x7fffffff - 1;
                     lk = max(lk, max(klo, khi));
                 }
             }
-            const unsigned vp = (sn == end_sn) ? 0xfffu : (unsigned)(0xffe - (sn - beg_sn));
+            const int vp = (sn == end_sn) ? 0xfff : (0xffe - (sn - beg_sn));
             bestkey = max(bestkey, lk | vp);
         }
         C3G_SYNC(C3_FULL);
@@ -461,15 +462,15 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
     {
         const int end = min(qlen, end_sn * 16 + 15);
         const int D = max(min(oe1, oe2), max(e1, e2));
-        if (bad || h_first < C3L_FLOOR + C3L_LOW_GUARD + oe2 + D * (end - (beg_sn << 4) + 1)) bestkey = 0xffffffffu;
+        if (bad || h_first < C3L_FLOOR + C3L_LOW_GUARD + oe2 + D * (end - (beg_sn << 4) + 1)) bestkey = 0x7fffffff;
     }
 #pragma unroll
-    for (int dd = 1; dd < C3G_GL; dd <<= 1) bestkey = max(bestkey, (unsigned)C3G_SHFL(C3_FULL, bestkey, gbase + (li ^ dd)));
-    if (bestkey == 0xffffffffu && live) { C3G_DECLINE(); G.err = C3G_E_RETRY; }
+    for (int dd = 1; dd < C3G_GL; dd <<= 1) bestkey = max(bestkey, (int)C3G_SHFL(C3_FULL, bestkey, gbase + (li ^ dd)));
+    if (bestkey == 0x7fffffff && live) { C3G_DECLINE(); G.err = C3G_E_RETRY; }
     int best_i = -1;
-    if ((int)(bestkey >> 16) - 32768 > C3L_FLOOR) {
-        const int sl = 15 - (int)((bestkey >> 12) & 15u);
-        const int vp = (int)(bestkey & 0xfffu);
+    if ((bestkey >> 16) > C3L_FLOOR) {
+        const int sl = 15 - ((bestkey >> 12) & 15);
+        const int vp = bestkey & 0xfff;
         const int snb = (vp == 0xfff) ? end_sn : beg_sn + (0xffe - vp);
         best_i = (snb << 4) + sl;
     }
