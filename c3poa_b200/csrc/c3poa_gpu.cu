@@ -391,9 +391,9 @@ __host__ __device__ inline int c3_order_class(const int nseq, const long long to
 __host__ __device__ inline int c3_order_flags(const int nseq, const long long total, const c3_order_rule &R, int *grp_q)
 {
     int f = 0;
-    if (R.msa2 && nseq == 2) return 0;
+    const bool rows = R.msa2 && nseq == 2;                        // MSA rows wanted: the group path and the warp kernel emit them
     const long long L = total / nseq;
-    if (R.lane_ok && L <= 5000 && nseq <= 40) f |= 1;             // long / deep reads: per-thread arenas would not fit
+    if (R.lane_ok && !rows && L <= 5000 && nseq <= 40) f |= 1;    // long / deep reads: per-thread arenas would not fit
     if (R.grp_ok) {
         // int16 score mode of an alignment: max(qlen * 5, max(qlen, nodes) * e1 + o1) <= lim, with the usual graph
         // growth (the kernel re-checks per alignment and declines what turns out larger)

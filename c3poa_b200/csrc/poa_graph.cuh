@@ -75,7 +75,7 @@ C3_HD inline void c3s_item_begin(c3g_grp &G, const c3_poa_args &A, const c3_poa_
     G.item = item; G.sq = 1; G.err = 0; G.nseq = 0; G.node_n = 0; G.pool_n = 0; G.cells_total = 0; G.ob = 0;
     G.qlen = 0; G.n = 0; G.w = 0;
     const int nseq = A.n_seqs[(int64_t)item * A.n_seqs_stride];
-    if (nseq < A.min_seqs || nseq > A.max_seqs || nseq < 1 || (A.msa2 && nseq == 2)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
+    if (nseq < A.min_seqs || nseq > A.max_seqs || nseq < 1) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
     G.ibase = A.codes + A.item_base[item];
     G.bnd = A.bounds + (int64_t)item * A.max_seqs * 2;
     G.nseq = nseq;
@@ -410,6 +410,10 @@ C3_HD inline int c3s_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const
     c3_graph g; g.nodes = W.nodes; g.pool = W.pool; g.node_n = G.node_n; g.pool_n = G.pool_n;
     g.node_cap = L.A.node_cap; g.pool_cap = L.A.pool_cap; g.err = 0;
     int last_id = C3_SRC, last_new = 0;
+    // items whose two MSA rows are wanted (c3s_emit_msa) record which sequence passes through which node (rmask, as
+    // poa.cuh): they take the generic code for every op
+    const bool track = L.A.msa2 && G.nseq == 2;
+    const uint16_t rbit = (uint16_t)(1u << (G.sq < 16 ? G.sq : 15));
     int last_gap = 0, last_p = 0;                // gap of the last new node / old position its group walk starts at
     c3s_q4 qc; c3s_q4_init(qc, q);
     int t = nc - 1;
@@ -419,7 +423,7 @@ C3_HD inline int c3s_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const
         // the hot halves of their node records are requested together -- two memory round trips for the block instead
         // of two per op -- and consumed while they are of that kind; the first op that is anything else is left to the
         // generic code below, which reads everything afresh.
-        {
+        if (!track) {
             unsigned long long ok_[C3S_MK]; c3_nrec rk[C3S_MK];
 #pragma unroll
             for (int k = 0; k < C3S_MK; ++k) ok_[k] = t - k >= 0 ? cg[t - k] : C3_CG_DEL;
@@ -462,9 +466,11 @@ C3_HD inline int c3s_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const
                 if (al != -1) {
                     c3_g_add_edge(g, last_id, al, 1 - last_new);
                     last_id = al; last_new = 0;
+                    if (track) g.nodes[al].rmask |= rbit;
                 } else {
                     const int id = c3_g_add_node(g, bq);
                     if (g.err) break;
+                    if (track) g.nodes[id].rmask = rbit;
                     last_p = W.posof[nid]; last_gap = last_p;          // placed right before nid
                     W.gaps[id - n_old] = (uint16_t)last_gap;
                     c3_g_add_edge(g, last_id, id, 0);
@@ -480,10 +486,12 @@ C3_HD inline int c3s_merge(c3g_grp &G, const c3g_args &L, const c3g_ws &W, const
             } else {
                 c3_g_add_edge(g, last_id, nid, 1 - last_new);
                 last_id = nid; last_new = 0;
+                if (track) g.nodes[nid].rmask |= rbit;
             }
         } else {                                                     // insertion: right after the aligned block of last_id
             const int id = c3_g_add_node(g, (uint8_t)c3s_q4_get(qc, qp));
             if (g.err) break;
+            if (track) g.nodes[id].rmask = rbit;
             const c3_pnode nl = g.nodes[last_id];
             int gap;
             if (last_id >= n_old) gap = nl.aln_n ? c3s_tail_gap(ord, n_old, nl, last_p) : last_gap;
@@ -572,15 +580,65 @@ C3_HD inline int c3s_consensus(const c3g_grp &G, const c3_poa_args &A, const c3g
     return cons_len;
 }
 
-// last sequence merged: heaviest bundling, consensus and the per-read outputs
+// The two MSA rows of a 2-sequence item (abpoa_generate_rc_msa: ranks by the LIFO traversal in which a node is pushed once
+// its in-edges and those of its aligned nodes are used up; same code as poa.cuh's c3_emit_msa, one thread).  Rows go to
+// co as [row0 | row1]; returns the number of columns or a negative code.  rank / in-degree / stack live in the
+// descriptor array (no alignment follows).
+C3_HD inline int c3s_emit_msa(const c3g_grp &G, const c3_poa_args &A, const c3g_ws &W, char *co)
+{
+    const int node_n = G.node_n;
+    int32_t *rank = reinterpret_cast<int32_t *>(W.desc), *indeg = rank + A.node_cap, *stk = indeg + A.node_cap;
+    for (int v = 0; v < node_n; ++v) { rank[v] = 0; indeg[v] = W.nodes[v].in_n; }
+    int top = 0, msa_rank = 0, ok = 0;
+    stk[top++] = C3_SRC; rank[C3_SRC] = -1;
+    while (top > 0) {
+        const int cur = stk[--top];
+        const c3_pnode nd = W.nodes[cur];
+        if (rank[cur] < 0) {
+            rank[cur] = msa_rank;
+            for (int k = 0; k < nd.aln_n; ++k) rank[c3_aln_get(nd, k)] = msa_rank;
+            ++msa_rank;
+        }
+        if (cur == C3_SINK) { ok = 1; break; }
+        uint16_t e = nd.out_more;
+        for (int k = 0; k < nd.out_n; ++k) {
+            int o;
+            if (k == 0) o = nd.out0; else { const c3_pedge pe = W.pool[e]; o = pe.id; e = pe.next; }
+            if (--indeg[o] == 0) {
+                const c3_pnode on = W.nodes[o];
+                bool ready = true;
+                for (int a = 0; a < on.aln_n; ++a) if (indeg[c3_aln_get(on, a)] != 0) { ready = false; break; }
+                if (!ready) continue;
+                if (top + 5 > A.node_cap) { C3G_DECLINE(); return C3G_E_RETRY; }
+                stk[top++] = o; rank[o] = -1;
+                for (int a = 0; a < on.aln_n; ++a) { const int al = c3_aln_get(on, a); stk[top++] = al; rank[al] = -1; }
+            }
+        }
+    }
+    const int msa_len = ok ? rank[C3_SINK] - 1 : -1;
+    if (msa_len < 0 || 2 * msa_len > A.cons_cap) { C3G_DECLINE(); return C3G_E_RETRY; }
+    for (int c = 0; c < 2 * msa_len; ++c) co[c] = '-';
+    for (int v = 2; v < node_n; ++v) {
+        const c3_pnode nd = W.nodes[v];
+        int rk = rank[v];
+        for (int k = 0; k < nd.aln_n; ++k) rk = max(rk, rank[c3_aln_get(nd, k)]);
+        const char ch = "ACGTN"[nd.base];
+        if (nd.rmask & 1) co[rk - 1] = ch;
+        if (nd.rmask & 2) co[msa_len + rk - 1] = ch;
+    }
+    return msa_len;
+}
+
+// last sequence merged: heaviest bundling, consensus (or the two MSA rows) and the per-read outputs
 C3_HD inline void c3s_finish(c3g_grp &G, const c3g_args &L, const c3g_ws &W)
 {
     const c3_poa_args &A = L.A;
     char *co = A.cons + (int64_t)G.item * A.cons_cap;
-    const int r = c3s_consensus(G, A, W, co);
+    const bool do_msa = A.msa2 && G.nseq == 2;
+    const int r = do_msa ? c3s_emit_msa(G, A, W, co) : c3s_consensus(G, A, W, co);
     if (r >= 0) {
         const int64_t o = (int64_t)G.item * A.out_stride;
-        A.status[o] = 0;
+        A.status[o] = do_msa ? A.ok_status : 0;
         A.cons_len[o] = r;
         A.nodes_out[o] = G.node_n;
         *(long long *)((int32_t *)A.cells_out + (int64_t)G.item * A.cells_stride) = G.cells_total;

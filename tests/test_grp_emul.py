@@ -43,7 +43,7 @@ def emul():
     return build_emul()
 
 
-def run_emul(lib, groups, para=None, msa2=0, min_seqs=1, node_cap=None, vs_shift=None, rv_shift=3, n_warps=1, graph_gl=32):
+def run_emul(lib, groups, para=None, msa2=0, min_seqs=1, node_cap=None, vs_shift=None, rv_shift=3, n_warps=1, graph_gl=32, want_rows=False):
     n = len(groups)
     max_seqs = max(len(g) for g in groups)
     blob = []
@@ -78,7 +78,7 @@ def run_emul(lib, groups, para=None, msa2=0, min_seqs=1, node_cap=None, vs_shift
         while (1 << vs_shift) < need:
             vs_shift += 1
     rv_shift = min(rv_shift, vs_shift)
-    cons_cap = max_q * 2 + 64
+    cons_cap = max_q * (4 if want_rows else 2) + 64
     cons = np.zeros((n, cons_cap), dtype=np.uint8)
     status = np.full(n, -1, dtype=np.int32)
     clen = np.zeros(n, dtype=np.int32)
@@ -96,8 +96,11 @@ def run_emul(lib, groups, para=None, msa2=0, min_seqs=1, node_cap=None, vs_shift
                             cons.ctypes.data, cons_cap, status.ctypes.data, clen.ctypes.data, nodes.ctypes.data,
                             cells.ctypes.data, done.ctypes.data)
     assert rc == 0, "warp emulator reported a deadlock"
-    return dict(done=done, status=status, cells=cells, nodes=nodes,
-                cons=[cons[i, :clen[i]].tobytes().decode() for i in range(n)])
+    out = dict(done=done, status=status, cells=cells, nodes=nodes,
+               cons=[cons[i, :clen[i]].tobytes().decode() for i in range(n)])
+    if want_rows:      # 2-sequence groups with msa2: [row0 | row1], clen columns each
+        out["rows"] = [[cons[i, :clen[i]].tobytes().decode(), cons[i, clen[i]:2 * clen[i]].tobytes().decode()] for i in range(n)]
+    return out
 
 
 def _groups(seed=3):
@@ -167,13 +170,38 @@ def test_grp_wide_and_deep(emul, oracle):
         _check(run_emul(emul, groups, rv_shift=rv), groups, oracle)
 
 
+def test_grp_pairwise_msa_rows(emul, oracle):
+    """2-sequence groups with msa2: the group path returns the two MSA rows [row0 | row1] (abPOA's rc_msa order), equal to
+    the oracle's; groups of more sequences in the same batch still return their consensus."""
+    rng = np.random.default_rng(17)
+    groups = []
+    for L in (50, 300, 700, 1300, 2500):
+        a = synth.random_seq(rng, L)
+        groups.append([synth.mutate(rng, a).tobytes().decode(), synth.mutate(rng, a).tobytes().decode()])
+    groups.append([groups[0][0], groups[0][0]])
+    a = synth.random_seq(rng, 400)
+    groups.append([synth.mutate(rng, a, 0.08, 0.06, 0.06).tobytes().decode(), synth.mutate(rng, a, 0.08, 0.06, 0.06).tobytes().decode()])
+    groups.append([synth.mutate(rng, a).tobytes().decode() for _ in range(4)])
+    n = len(groups)
+    max_q = max(len(s) for g in groups for s in g)
+    lib = emul
+    # run_emul returns cons[:cons_len]; the rows need 2 * cons_len bytes: call the harness directly through a wider slice
+    r = run_emul(lib, groups, msa2=1, want_rows=True)
+    assert all(r["done"]) and not any(r["status"])
+    for i, g in enumerate(groups[:-1]):
+        o = oracle.poa_msa(g, out_cons=False, out_msa=True)
+        assert r["rows"][i] == o["msa"], i
+        assert r["rows"][i][0].replace("-", "") == g[0] and r["rows"][i][1].replace("-", "") == g[1]
+    assert r["cons"][-1] == oracle.poa_msa(groups[-1])["cons"]
+
+
 def test_grp_declines_what_it_does_not_cover(emul):
     rng = np.random.default_rng(5)
     a = synth.random_seq(rng, 300)
     g = [synth.mutate(rng, a).tobytes().decode() for _ in range(4)]
     pair = g[:2]
     r = run_emul(emul, [g, pair], msa2=1)
-    assert list(r["done"]) == [1, 0]
+    assert list(r["done"]) == [1, 1]                       # (2-sequence groups: see test_grp_pairwise_msa_rows)
     assert not run_emul(emul, [g], para=dict(simd_bits=128))["done"][0]
     assert not run_emul(emul, [g], para=dict(wb=-1))["done"][0]
     assert not run_emul(emul, [g], node_cap=320)["done"][0]
