@@ -90,7 +90,7 @@ struct c3_handle {
     // eligible, 3 group kernel whenever eligible (= auto); the warp kernel always takes what the others leave
     int poa_mode = 0;
     double dbg_sync_ms = 0; std::chrono::steady_clock::time_point dbg_t1;     // C3POA_GRP_TIMING only
-    int grp_bps[2] = {0, 0}, warp_bps = 0, grp_grow_idx = 0, grp_ask_wait = 0;
+    int grp_bps[3] = {0, 0, 0}, warp_bps = 0, grp_grow_idx = 0, grp_ask_wait = 0;
     int sw_int8_lanes = 0, sw_end_clamp = 0;   // c3_set_abpoa_switches: only the warp kernel implements them
     DevBuf d_order_lane, d_done, d_order_grp, d_ws_grp, d_order_scratch, d_pairs;
     int n_work_grp = 0, grp_max_nseq = 0, grp_max_q = 0; int64_t grp_max_total = 0;
@@ -691,7 +691,11 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     const int need = (2 * w + 1 + 48) / 16 + 2;
     int vs_shift = 3;
     while ((1 << vs_shift) < need && vs_shift < 8) ++vs_shift;
-    const int rv_shift = vs_shift == 3 ? 3 : 4;
+    // lanes per read: short sequences (band half-width <= 20: bands of 3-4 vectors) run 8 reads per warp with 4 lanes each
+    // and a 4-vector ring; everything else 4 reads per warp with 8 lanes each
+    int gl = (vs_shift == 3 && w <= 20) ? 4 : 8;
+    if (const char *e = getenv("C3POA_GRP_GL")) gl = (atoi(e) == 4 && vs_shift == 3) ? 4 : 8;          // tests / tuning
+    const int rv_shift = gl == 4 ? 2 : (vs_shift == 3 ? 3 : 4);
     const int qp_stride = (max_q + 48) & ~15;
     int64_t node_cap = 0, ws_bytes = 0, arena4 = 0, read_bytes = 0;
     int cigar_cap = 0;
@@ -722,11 +726,11 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
     } else if (grow_env && budget / read_bytes < ng && may_ask) { h->grp_ask_wait = 64; if (int rc = ask()) return rc; }
     const int pool_cap = (int)node_cap;
     const int wpb = C3G_THREADS / 32;
-    const size_t sm_dp = (size_t)wpb * 4 * c3g_smem_group_bytes(rv_shift);
-    void (*kdp)(c3g_args) = vs_shift == 3 ? c3_poa_grp_dp_kernel<3, false> : c3_poa_grp_dp_kernel<4, true>;
+    const size_t sm_dp = (size_t)wpb * (32 / gl) * c3g_smem_group_bytes(rv_shift);
+    void (*kdp)(c3g_args) = gl == 4 ? c3_poa_grp_dp_kernel<2, true, 4> : vs_shift == 3 ? c3_poa_grp_dp_kernel<3, false> : c3_poa_grp_dp_kernel<4, true>;
     // function attributes and occupancy once per handle and instantiation: driver calls on the path between the batch's
     // only mid-pipeline synchronisation and the first POA launch were seen to stall for milliseconds now and then
-    const int kv = vs_shift == 3 ? 0 : 1;
+    const int kv = gl == 4 ? 2 : vs_shift == 3 ? 0 : 1;
     if (!h->grp_bps[kv]) {
         CK(cudaFuncSetAttribute(kdp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dp));
         int b = 1;
@@ -767,7 +771,7 @@ static int launch_poa_grp(c3_handle *h, c3_poa_args &A, int max_q, const c3_poa_
         CK(cudaMemsetAsync(counters, 0, (size_t)n_counters * 4, h->stream));
         L.A.order = h->d_order_grp.as<int32_t>() + w0; L.A.n_work = nw;
         L.eager = nw < 48000;
-        const int w_dp = (nw + 3) / 4;                              // warps that can be busy
+        const int w_dp = (nw + 32 / gl - 1) / (32 / gl);            // warps that can be busy
         const int grid_dp = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * bps_dp, (w_dp + wpb - 1) / wpb));
         const int grid_gr = (nw + C3S_THREADS - 1) / C3S_THREADS;  // one thread per read
         int launch = 0;

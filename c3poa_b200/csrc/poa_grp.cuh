@@ -33,7 +33,7 @@
 #include "poa_lane.cuh"
 
 #define C3G_R 4                       // ring slots (rows) per group
-#define C3G_GL 8                      // lanes per group
+#define C3G_GL 8                      // lanes per group (the usual instantiation; GL = 4 for short sequences, see c3g_dp_body)
 #define C3G_E_RETRY (-298)
 #if defined(C3G_EMUL) && !defined(__CUDA_ARCH__)
 extern "C" int c3emu_shfl(unsigned mask, int v, int src, int tag);
@@ -215,11 +215,12 @@ C3G_FN void c3g_fetch_pred(uint32_t (&h)[8], uint32_t (&x1)[8], uint32_t (&x2)[8
 // score profile of the read's current sequence: qp[b][j] = score of node base b against column j (= q[j-1]); column 0
 // and the padding score 0; row 4 (an N node) scores 0 against everything.  The 8 lanes of the group write 32 columns
 // per step.
+template <int GL>
 C3G_FN void c3g_build_qp(const c3g_grp &G, const c3_poa_args &A, const c3_poa_para_dev &P, const c3g_ws &W, const int li)
 {
     const int qs = A.qp_stride, qlen = G.qlen;
     const uint8_t *q = G.q;
-    for (int j0 = 4 * li; j0 < qs; j0 += 4 * C3G_GL) {
+    for (int j0 = 4 * li; j0 < qs; j0 += 4 * GL) {
         uint32_t wv[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -237,7 +238,7 @@ C3G_FN void c3g_build_qp(const c3g_grp &G, const c3_poa_args &A, const c3_poa_pa
 }
 
 // source row: cells, ring slot 0, arena, record
-template <int RVS>
+template <int RVS, int GL>
 C3G_FN void c3g_source_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, uint4 *ring, uint2 *srr,
                            uint4 *arena, uint2 &rec_out, const int li, const unsigned gmask)
 {
@@ -251,7 +252,7 @@ C3G_FN void c3g_source_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev 
     if (nvec > (1 << L.vs_shift)) { C3G_DECLINE(); G.err = C3G_E_RETRY; return; }
     const int vsm = (1 << L.vs_shift) - 1;
     bool low = false;
-    for (int sn = li; sn <= end_sn; sn += C3G_GL) {
+    for (int sn = li; sn <= end_sn; sn += GL) {
         uint32_t h[8], x1[8], x2[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -290,7 +291,7 @@ C3G_FN void c3g_source_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev 
 // load -- nothing they compute is stored or enters the row's arg-max.  Columns past qlen inside the last vector are
 // computed like any other (nothing at or left of qlen depends on them) and only kept out of the arg-max.
 // MULTI = false: the arena rows hold 8 vectors, so a row is one pass of the 8 lanes.
-template <int RVS, bool MULTI>
+template <int RVS, bool MULTI, int GL>
 C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, const c3g_ws &W, uint4 *ring, uint2 *srr,
                    uint4 *arena, const int pos, const uint4 d, uint2 &rprev, const bool live, const int li, const int gbase)
 {
@@ -318,7 +319,7 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
     int end_sn = max(min(qlen, max(mpr, rr) + G.w) >> 4, beg_sn);
     if (!live) { beg_sn = 0; end_sn = 0; }
     bool bad = false;
-    if (end_sn - beg_sn + 1 > (MULTI ? (1 << L.vs_shift) : C3G_GL)) { bad = true; end_sn = beg_sn; }   // wider than an arena row
+    if (end_sn - beg_sn + 1 > (MULTI ? (1 << L.vs_shift) : GL)) { bad = true; end_sn = beg_sn; }   // wider than an arena row
     const int nvec = end_sn - beg_sn + 1;
     const bool to_ring = MULTI ? nvec <= (1 << RVS) : true;
     const uint32_t ne1 = C3L_PACK2(-e1, -e1), ne2 = C3L_PACK2(-e2, -e2), noe1 = C3L_PACK2(-oe1, -oe1), noe2 = C3L_PACK2(-oe2, -oe2);
@@ -329,10 +330,10 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
     int h_first = 0x7fff;
     // everything read from the ring must be in registers before any lane overwrites the slot of row pos - C3G_R:
     // a row of several passes stores its first vectors before it has read the last ones, so it does not use that slot
-    const int ring_delta = (!MULTI || nvec <= C3G_GL) ? C3G_R : C3G_R - 1;
+    const int ring_delta = (!MULTI || nvec <= GL) ? C3G_R : C3G_R - 1;
     int sn0 = beg_sn;
     do {
-        const int l = (li - sn0) & 7, sn = sn0 + l;
+        const int l = (li - sn0) & (GL - 1), sn = sn0 + l;
         const bool act = sn <= end_sn;
         const int j0 = sn << 4;
         // scores of the 16 columns against the node base (row 4 of the profile: zeros, an N node)
@@ -348,9 +349,9 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
             for (int u = 0; u < 8; ++u) { h[u] = C3L_VMAX2(h[u], th[u]); x1[u] = C3L_VMAX2(x1[u], t1[u]); x2[u] = C3L_VMAX2(x2[u], t2[u]); }
         }
         // M: merged predecessor H one column to the left (the first cell of the band never takes M)
-        uint32_t top = (uint32_t)C3G_SHFL(C3_FULL, h[7], gbase + ((li - 1) & 7));
+        uint32_t top = (uint32_t)C3G_SHFL(C3_FULL, h[7], gbase + ((li - 1) & (GL - 1)));
         if (l == 0) top = mcarry;
-        if (MULTI) mcarry = (uint32_t)C3G_SHFL(C3_FULL, h[7], gbase + ((sn0 + 7) & 7));      // (every lane of the warp: no group-dependent condition around a collective)
+        if (MULTI) mcarry = (uint32_t)C3G_SHFL(C3_FULL, h[7], gbase + ((sn0 + GL - 1) & (GL - 1)));      // (every lane of the warp: no group-dependent condition around a collective)
         uint32_t hme[8];
         {
             const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -380,18 +381,18 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
         const uint32_t dec = C3L_PACK2(16 * e1, 16 * e2);
         uint32_t tt = C3G_VADD2(C3L_PACK2(g1, g2), dec * (uint32_t)l);
 #pragma unroll
-        for (int dd = 1; dd < C3G_GL; dd <<= 1) {
-            const uint32_t v = (uint32_t)C3G_SHFL(C3_FULL, tt, gbase + ((li - dd) & 7));
+        for (int dd = 1; dd < GL; dd <<= 1) {
+            const uint32_t v = (uint32_t)C3G_SHFL(C3_FULL, tt, gbase + ((li - dd) & (GL - 1)));
             if (l >= dd) tt = C3L_VMAX2(tt, v);
         }
-        const uint32_t ex = (uint32_t)C3G_SHFL(C3_FULL, tt, gbase + ((li - 1) & 7));
+        const uint32_t ex = (uint32_t)C3G_SHFL(C3_FULL, tt, gbase + ((li - 1) & (GL - 1)));
         int c1 = (int)(int16_t)(ex & 0xffffu) - 16 * e1 * (l - 1), c2 = ((int)ex >> 16) - 16 * e2 * (l - 1);
         if (MULTI) {
             c1 = l == 0 ? pc1 : max(c1, pc1 - 16 * e1 * l);
             c2 = l == 0 ? pc2 : max(c2, pc2 - 16 * e2 * l);
-            const uint32_t tot = (uint32_t)C3G_SHFL(C3_FULL, tt, gbase + ((sn0 + 7) & 7));
-            pc1 = max((int)(int16_t)(tot & 0xffffu) - 16 * e1 * 7, pc1 - 16 * e1 * 8);
-            pc2 = max(((int)tot >> 16) - 16 * e2 * 7, pc2 - 16 * e2 * 8);
+            const uint32_t tot = (uint32_t)C3G_SHFL(C3_FULL, tt, gbase + ((sn0 + GL - 1) & (GL - 1)));
+            pc1 = max((int)(int16_t)(tot & 0xffffu) - 16 * e1 * (GL - 1), pc1 - 16 * e1 * GL);
+            pc2 = max(((int)tot >> 16) - 16 * e2 * (GL - 1), pc2 - 16 * e2 * GL);
         } else if (l == 0) { c1 = C3L_FLOOR; c2 = C3L_FLOOR; }
         c1 = max(c1, C3L_FLOOR); c2 = max(c2 + d21, C3L_FLOOR);    // F1, F2 entering the vector
         const uint32_t c1p = C3L_PACK2(c1, c1), c2p = C3L_PACK2(c2, c2);
@@ -455,7 +456,7 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
             dst[2] = make_uint4(C3L_PRMT(eb[0], eb[1], 0x6420u), C3L_PRMT(eb[2], eb[3], 0x6420u),
                                 C3L_PRMT(eb[4], eb[5], 0x6420u), C3L_PRMT(eb[6], eb[7], 0x6420u));
         }
-        sn0 += C3G_GL;
+        sn0 += GL;
     } while (MULTI && C3G_ANYG(C3_FULL, sn0 <= end_sn));
     // exactness of the int16 form (see poa_lane.cuh): the first band cell comfortably above the floor means that
     // every cell of the row is reachable and was never clamped.  The verdict rides on the arg-max reduction.
@@ -465,7 +466,7 @@ C3G_FN int c3g_row(c3g_grp &G, const c3g_args &L, const c3_poa_para_dev &P, cons
         if (bad || h_first < C3L_FLOOR + C3L_LOW_GUARD + oe2 + D * (end - (beg_sn << 4) + 1)) bestkey = 0x7fffffff;
     }
 #pragma unroll
-    for (int dd = 1; dd < C3G_GL; dd <<= 1) bestkey = max(bestkey, (int)C3G_SHFL(C3_FULL, bestkey, gbase + (li ^ dd)));
+    for (int dd = 1; dd < GL; dd <<= 1) bestkey = max(bestkey, (int)C3G_SHFL(C3_FULL, bestkey, gbase + (li ^ dd)));
     if (bestkey == 0x7fffffff && live) { C3G_DECLINE(); G.err = C3G_E_RETRY; }
     int best_i = -1;
     if ((bestkey >> 16) > C3L_FLOOR) {
@@ -524,13 +525,16 @@ C3_HD inline void c3g_state_store(const c3g_grp &G, c3g_state *S)
     S->ob = G.ob; S->qlen = G.qlen; S->n = G.n; S->w = G.w; S->cells_total = G.cells_total;
 }
 
-template <int RVS, bool MULTI>
+// GL lanes per read, 32 / GL reads per warp.  GL = 8 is the usual shape (a ~70-column band spans 4-6 vectors); GL = 4 with
+// a 4-vector ring (RVS = 2) serves short sequences, whose ~40-column bands span 3-4 vectors: eight reads per warp instead
+// of four at the same instruction count per row step (a row of 5-8 vectors takes a second pass).
+template <int RVS, bool MULTI, int GL = C3G_GL>
 C3G_FN void c3g_dp_body(const c3g_args &L, uint8_t *smem_warp, const int lane)
 {
     const c3_poa_args &A = L.A;
     const c3_poa_para_dev P = A.P;
-    const int li = lane & 7, gbase = lane & 24, grp = lane >> 3;
-    const unsigned gmask = 0xffu << gbase;
+    const int li = lane & (GL - 1), gbase = lane & (32 - GL), grp = lane / GL;
+    const unsigned gmask = ((1u << GL) - 1u) << gbase;
     uint8_t *sg = smem_warp + (size_t)grp * c3g_smem_group_bytes(RVS);
     uint4 *ring = reinterpret_cast<uint4 *>(sg);
     uint2 *srr = reinterpret_cast<uint2 *>(sg + (C3G_R * 6 * 16 << RVS));
@@ -558,8 +562,8 @@ C3G_FN void c3g_dp_body(const c3g_args &L, uint8_t *smem_warp, const int lane)
                 if (!G.err && G.sq < G.nseq) {
                     W = c3g_ws_carve(L.ws + (int64_t)it * L.ws_stride, A.node_cap, A.pool_cap, A.cigar_cap);
                     arena = L.arena + (int64_t)it * L.arena_stride4;
-                    c3g_build_qp(G, A, P, W, li);
-                    c3g_source_row<RVS>(G, L, P, W, ring, srr, arena, rprev, li, gmask);
+                    c3g_build_qp<GL>(G, A, P, W, li);
+                    c3g_source_row<RVS, GL>(G, L, P, W, ring, srr, arena, rprev, li, gmask);
                     C3G_SYNC(gmask);
                     if (G.err) { if (li == 0) S->err = G.err; }
                     else { have = true; pos = 1; dn = W.desc[1]; }
@@ -573,7 +577,7 @@ C3G_FN void c3g_dp_body(const c3g_args &L, uint8_t *smem_warp, const int lane)
         {
             const uint4 d = dn;
             if (have) dn = W.desc[pos + 1];
-            const int wd = c3g_row<RVS, MULTI>(G, L, P, W, ring, srr, arena, pos, d, rprev, have, li, gbase);
+            const int wd = c3g_row<RVS, MULTI, GL>(G, L, P, W, ring, srr, arena, pos, d, rprev, have, li, gbase);
             if (have) {
                 G.cells_total += wd;
                 ++pos;
@@ -593,12 +597,12 @@ C3G_FN void c3g_dp_body(const c3g_args &L, uint8_t *smem_warp, const int lane)
 #ifndef C3G_MINB
 #define C3G_MINB 4
 #endif
-template <int RVS, bool MULTI>
+template <int RVS, bool MULTI, int GL = C3G_GL>
 __global__ void __launch_bounds__(C3G_THREADS, C3G_MINB) c3_poa_grp_dp_kernel(c3g_args L)
 {
     extern __shared__ uint4 c3g_smem[];
     const int wib = threadIdx.x >> 5;
-    uint8_t *sw = reinterpret_cast<uint8_t *>(c3g_smem) + (size_t)wib * 4 * c3g_smem_group_bytes(RVS);
-    c3g_dp_body<RVS, MULTI>(L, sw, threadIdx.x & 31);
+    uint8_t *sw = reinterpret_cast<uint8_t *>(c3g_smem) + (size_t)wib * (32 / GL) * c3g_smem_group_bytes(RVS);
+    c3g_dp_body<RVS, MULTI, GL>(L, sw, threadIdx.x & 31);
 }
 #endif

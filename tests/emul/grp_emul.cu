@@ -20,7 +20,8 @@ struct WarpArg { const c3g_args *L; uint8_t *smem; };
 void warp_lane(void *p, int lane)
 {
     const WarpArg *a = (const WarpArg *)p;
-    if (a->L->vs_shift == 3) c3g_dp_body<3, false>(*a->L, a->smem, lane);
+    if (a->L->rv_shift == 2) c3g_dp_body<2, true, 4>(*a->L, a->smem, lane);        // 4 lanes per read, 8 reads per warp
+    else if (a->L->vs_shift == 3) c3g_dp_body<3, false>(*a->L, a->smem, lane);
     else if (a->L->rv_shift == 3) c3g_dp_body<3, true>(*a->L, a->smem, lane);
     else c3g_dp_body<4, true>(*a->L, a->smem, lane);
 }
@@ -51,7 +52,7 @@ extern "C" int c3g_emul_batch(int n_items, const uint8_t *codes, const int64_t *
     const int64_t arena4 = ((int64_t)node_cap << vs_shift) * 3;
     uint8_t *ws = (uint8_t *)aligned_alloc(256, (size_t)ws_bytes * n_items);
     uint4 *arena = (uint4 *)aligned_alloc(256, (size_t)arena4 * 16 * n_items);
-    size_t smw = (size_t)4 * c3g_smem_group_bytes(rv_shift);
+    size_t smw = (size_t)(rv_shift == 2 ? 8 : 4) * c3g_smem_group_bytes(rv_shift);
     uint8_t *smem = (uint8_t *)aligned_alloc(256, (smw * n_warps + 255) & ~(size_t)255);
     std::vector<c3g_state> state((size_t)n_items);
     if (!ws || !arena || !smem) return -1;

@@ -77,7 +77,7 @@ def run_emul(lib, groups, para=None, msa2=0, min_seqs=1, node_cap=None, vs_shift
         vs_shift = 3
         while (1 << vs_shift) < need:
             vs_shift += 1
-    rv_shift = min(rv_shift, vs_shift)
+    rv_shift = min(rv_shift, vs_shift)         # rv_shift 2 (with vs_shift 3) selects the 4-lanes-per-read instantiation
     cons_cap = max_q * (4 if want_rows else 2) + 64
     cons = np.zeros((n, cons_cap), dtype=np.uint8)
     status = np.full(n, -1, dtype=np.int32)
@@ -193,6 +193,21 @@ def test_grp_pairwise_msa_rows(emul, oracle):
         assert r["rows"][i] == o["msa"], i
         assert r["rows"][i][0].replace("-", "") == g[0] and r["rows"][i][1].replace("-", "") == g[1]
     assert r["cons"][-1] == oracle.poa_msa(groups[-1])["cons"]
+
+
+def test_grp_four_lane_variant(emul, oracle):
+    """GL = 4 (8 reads per warp, 4-vector ring; what short sequences get): the standard groups -- including bands wider than
+    one pass of 4 lanes -- and 16 short-insert groups that fill two warps, bit-exact vs the oracle."""
+    groups = _groups()
+    _check(run_emul(emul, groups, vs_shift=3, rv_shift=2), groups, oracle, must_finish=False)
+    rng = np.random.default_rng(91)
+    short = []
+    for _ in range(16):
+        a = synth.random_seq(rng, int(rng.integers(500, 900)))
+        short.append([synth.mutate(rng, a).tobytes().decode() for _ in range(int(rng.integers(3, 9)))])
+    r = run_emul(emul, short, vs_shift=3, rv_shift=2, n_warps=2)
+    assert all(r["done"])
+    _check(r, short, oracle)
 
 
 def test_grp_declines_what_it_does_not_cover(emul):
