@@ -580,6 +580,63 @@ C3_HD inline int c3s_consensus(const c3g_grp &G, const c3_poa_args &A, const c3g
     return cons_len;
 }
 
+C3_HD inline int c3s_consensus_small(const c3g_grp &G, const c3_poa_args &A, const c3g_ws &W, char *co)
+{
+    // The variant for small waves (bound by the chain of round trips; at 100 000 reads its two extra streams cost 4 %).
+    // Reverse sweep in blocks of 8 positions like c3s_prepare (order entries as one 16-byte piece, node records requested
+    // together).  The heaviest successor and the base of every node go to two dense arrays that are free by now (posof,
+    // gaps: 2 bytes per node), so the node records stay clean and the walk along the consensus path reads 16 nodes per
+    // sector instead of chasing 32-byte records through DRAM one round trip at a time.
+    int32_t *score = reinterpret_cast<int32_t *>(W.desc);
+    const uint16_t *ord = W.order[G.ob];
+    uint16_t *nxt = W.posof, *nbase = W.gaps;
+    const int n = G.node_n;
+    for (int pc = (n - 1) & ~7; pc >= 0; pc -= 8) {
+        const uint4 oc = *reinterpret_cast<const uint4 *>(ord + pc);
+        c3_nrec rk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (pc + k < n) rk[k] = c3_ld_node(&W.nodes[c3s_u16_of(oc, k)]);
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            if (pc + k >= n) continue;
+            const int v = c3s_u16_of(oc, k);
+            const c3_nrec nd = rk[k];
+            const int out_n = C3_N_OUTN(nd);
+            int max_id = -1;
+            if (v == C3_SINK) score[v] = 0;
+            else if (v == C3_SRC) {
+                int path_score = -1, path_w = -1;
+                uint16_t e = out_n > 1 ? W.nodes[v].out_more : (uint16_t)C3_NONE;
+                for (int t = 0; t < out_n; ++t) {
+                    int o, wv;
+                    if (t == 0) { o = C3_N_OUT0(nd); wv = C3_N_W0(nd); } else { const c3_pedge pe = W.pool[e]; o = pe.id; wv = pe.w; e = pe.next; }
+                    if (wv > path_w || (wv == path_w && score[o] > path_score)) { max_id = o; path_score = score[o]; path_w = wv; }
+                }
+            } else {
+                int max_w = -0x7fffffff - 1;
+                uint16_t e = out_n > 1 ? W.nodes[v].out_more : (uint16_t)C3_NONE;
+                for (int t = 0; t < out_n; ++t) {
+                    int o, wv;
+                    if (t == 0) { o = C3_N_OUT0(nd); wv = C3_N_W0(nd); } else { const c3_pedge pe = W.pool[e]; o = pe.id; wv = pe.w; e = pe.next; }
+                    if (max_w < wv) { max_w = wv; max_id = o; }
+                    else if (max_w == wv && score[max_id] <= score[o]) max_id = o;
+                }
+                score[v] = max_w + score[max_id];
+            }
+            nxt[v] = (uint16_t)max_id;                              // (-1 -> C3_NONE)
+            nbase[v] = (uint16_t)C3_N_BASE(nd);
+        }
+    }
+    int cons_len = 0;
+    int id = nxt[C3_SRC];
+    while (id != C3_SINK) {
+        if (id == C3_NONE || cons_len >= A.cons_cap) { C3G_DECLINE(); return C3G_E_RETRY; }
+        co[cons_len++] = "ACGTN"[nbase[id]];
+        id = nxt[id];
+    }
+    return cons_len;
+}
+
 // The two MSA rows of a 2-sequence item (abpoa_generate_rc_msa: ranks by the LIFO traversal in which a node is pushed once
 // its in-edges and those of its aligned nodes are used up; same code as poa.cuh's c3_emit_msa, one thread).  Rows go to
 // co as [row0 | row1]; returns the number of columns or a negative code.  rank / in-degree / stack live in the
@@ -635,7 +692,7 @@ C3_HD inline void c3s_finish(c3g_grp &G, const c3g_args &L, const c3g_ws &W)
     const c3_poa_args &A = L.A;
     char *co = A.cons + (int64_t)G.item * A.cons_cap;
     const bool do_msa = A.msa2 && G.nseq == 2;
-    const int r = do_msa ? c3s_emit_msa(G, A, W, co) : c3s_consensus(G, A, W, co);
+    const int r = do_msa ? c3s_emit_msa(G, A, W, co) : L.eager ? c3s_consensus_small(G, A, W, co) : c3s_consensus(G, A, W, co);
     if (r >= 0) {
         const int64_t o = (int64_t)G.item * A.out_stride;
         A.status[o] = do_msa ? A.ok_status : 0;
