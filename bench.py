@@ -127,6 +127,11 @@ def make_workload(cfg, n_reads, seed):
     return synth.make_mixed_batch(n_reads, c["inserts"], c["repeats"], sp, seed=seed, flank=c.get("flank", (100, 400)))
 
 
+def rank_share(total, world, rank):
+    """Strong scaling: reads of rank `rank` when `total` reads are split over `world` ranks (shares differ by at most one)."""
+    return total // world + (1 if rank < total % world else 0)
+
+
 def oracle_kind():
     """"real" when the reference's own natives (pyabpoa 1.0.5 + conk, built by `make -C oracle ref`) are importable AND the
     restated oracle agrees with them on a probe; else "restated" (parity with upstream unpinned)."""
@@ -196,7 +201,7 @@ def main():
     cfg = CONFIGS[a.config]
     reads_arg = a.reads or cfg["reads"]
     if a.scaling == "strong":
-        n_rank = reads_arg // world + (1 if rank < reads_arg % world else 0)
+        n_rank = rank_share(reads_arg, world, rank)
         wl_size = f"{reads_arg} synthetic R2C2 reads in total, split over {world} GPU(s)"
     else:
         n_rank = reads_arg

@@ -51,3 +51,12 @@ def test_two_ranks_gloo(tmp_path):
     idx = np.array([1 if s == "-" else 0 for s in d["strand"]], dtype=np.int32)
     full = O.consensus_batch(d["seqs"], sp, idx)
     assert r["n_ok"] == float((full["results"]["status"] == 0).sum())
+
+
+def test_strong_scaling_shares_cover_the_batch():
+    """bench.py --scaling strong: the per-rank shares add up to the batch and differ by at most one read."""
+    import bench
+    for total in (0, 1, 7, 100000, 100003):
+        for world in (1, 2, 3, 8):
+            shares = [bench.rank_share(total, world, r) for r in range(world)]
+            assert sum(shares) == total and max(shares) - min(shares) <= 1
