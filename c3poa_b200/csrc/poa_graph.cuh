@@ -205,6 +205,7 @@ C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa
     const uint8_t *q = G.q; const int qlen = G.qlen, n = G.n;
     const int cap = L.A.cigar_cap;
     unsigned long long *cg = W.cigar;
+    const bool eager = L.eager != 0, cs = !eager;       // small wave: eager gap-test loads; large wave: streaming cell loads
     int nc = 0, j, pos, hij;
     {
         const uint4 ds = W.desc[n - 1];
@@ -214,7 +215,7 @@ C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa
             const int pk = c3g_pred_pos(W, ds, k);
             const uint2 rp = W.rowrec[pk];
             const int en = min(qlen, C3G_R_END(rp) * 16 + 15);
-            const int val = c3g_cell_h(arena, vs, pk, en);
+            const int val = c3g_cell_h(arena, vs, pk, en, cs);
             if (val > best) { best = val; bj = en; bk = pk; }
         }
         if (bk < 0 || qlen - bj + 8 > cap) { C3G_DECLINE(); return C3G_E_RETRY; }
@@ -223,7 +224,6 @@ C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa
         nc = qlen - bj; j = bj; pos = bk; hij = best;
     }
     int cur_op = C3_OP_ALL;
-    const bool eager = L.eager != 0;
     c3s_q4 qc; c3s_q4_init(qc, q);
     uint4 d = W.desc[pos];
     uint2 rt = W.rowrec[pos];
@@ -240,7 +240,7 @@ C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa
             for (int k = 0; k < C3S_BK; ++k) {
                 const int pp = max(pos - 1 - k, 0), jj = max(j - 1 - k, 0);
                 dk[k] = W.desc[pp]; rk[k] = W.rowrec[pp];
-                hk[k] = c3g_cell_h(arena, vs, pp, jj); qk[k] = c3s_q4_get(qc, jj);
+                hk[k] = c3g_cell_h(arena, vs, pp, jj, cs); qk[k] = c3s_q4_get(qc, jj);
             }
             bool ok = true;
 #pragma unroll
@@ -270,7 +270,7 @@ C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa
         const int p0 = C3G_D_P0(d);
         const uint2 r0 = W.rowrec[p0];
         const uint4 d0 = W.desc[p0];
-        const int ph0 = c3g_cell_h(arena, vs, p0, j - 1);           // (inside the read's arena whatever the band is)
+        const int ph0 = c3g_cell_h(arena, vs, p0, j - 1, cs);           // (inside the read's arena whatever the band is)
         // ... and what the gap tests of this cell would ask for next (its own E byte, the first predecessor's cell above
         // it), and the row's H vectors the F test rebuilds F from: all addresses are known now, so a deletion or an
         // insertion costs one more round trip instead of two or three
@@ -278,8 +278,8 @@ C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa
         // the extra sectors cost 3 %, at 12 500 the saved round trips gain 6 %)
         int ceb0 = 0, ph0j = 0, peb0j = 0;
         if (eager) {
-            ceb0 = c3g_cell_eb(arena, vs, pos, j);
-            ph0j = c3g_cell_h(arena, vs, p0, j); peb0j = c3g_cell_eb(arena, vs, p0, j);
+            ceb0 = c3g_cell_eb(arena, vs, pos, j, cs);
+            ph0j = c3g_cell_h(arena, vs, p0, j, cs); peb0j = c3g_cell_eb(arena, vs, p0, j, cs);
             if (cur_op & C3_OP_F)
                 for (int c0 = b; c0 < j; c0 += 16) C3L_PREFETCH(arena + (((int64_t)pos << vs) + ((c0 >> 4) & ((1 << vs) - 1))) * 3);
         }
@@ -289,7 +289,7 @@ C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa
                 const uint2 pr = k == 0 ? r0 : W.rowrec[pk];
                 const int pbeg = C3G_R_BEG(pr) * 16, pend = min(qlen, C3G_R_END(pr) * 16 + 15);
                 if (j - 1 < max(pbeg, b) || j - 1 > pend) continue;
-                const int ph = k == 0 ? ph0 : c3g_cell_h(arena, vs, pk, j - 1);
+                const int ph = k == 0 ? ph0 : c3g_cell_h(arena, vs, pk, j - 1, cs);
                 if (ph + s == hij) {
                     opw = C3_CG_MATCH | ((unsigned long long)i << 8) | ((unsigned long long)(j - 1) << 32);
                     pos = pk; --j; hit = 1; cur_op = C3_OP_ALL; hij = ph;
@@ -299,17 +299,17 @@ C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa
             }
         }
         if (!hit && (cur_op & C3_OP_E)) {
-            const int ceb = eager ? ceb0 : c3g_cell_eb(arena, vs, pos, j);
+            const int ceb = eager ? ceb0 : c3g_cell_eb(arena, vs, pos, j, cs);
             const int ce1 = hij - (ceb & 7), ce2 = hij - (ceb >> 3);
             for (int k = 0; k < npre; ++k) {
                 const int pk = k == 0 ? p0 : c3g_pred_pos(W, d, k);
                 const uint2 pr = k == 0 ? r0 : W.rowrec[pk];
                 const int pbeg = C3G_R_BEG(pr) * 16, pend = min(qlen, C3G_R_END(pr) * 16 + 15);
                 if (j < pbeg || j > pend) continue;
-                const int ph = (k == 0 && eager) ? ph0j : c3g_cell_h(arena, vs, pk, j);
+                const int ph = (k == 0 && eager) ? ph0j : c3g_cell_h(arena, vs, pk, j, cs);
                 int pe1, pe2;
                 if (pk == 0) { pe1 = j == 0 ? -oe1 : C3_NEG_INF; pe2 = j == 0 ? -oe2 : C3_NEG_INF; }
-                else { const int peb = (k == 0 && eager) ? peb0j : c3g_cell_eb(arena, vs, pk, j); pe1 = ph - (peb & 7); pe2 = ph - (peb >> 3); }
+                else { const int peb = (k == 0 && eager) ? peb0j : c3g_cell_eb(arena, vs, pk, j, cs); pe1 = ph - (peb & 7); pe2 = ph - (peb >> 3); }
                 if (cur_op & C3_OP_E1) {
                     if (cur_op & C3_OP_M) {
                         if (hij == pe1) { cur_op = (ph - oe1 == pe1) ? (C3_OP_M | C3_OP_F) : C3_OP_E1; hit = 1; }
@@ -341,10 +341,10 @@ C3_HD inline int c3s_backtrack(const c3g_grp &G, const c3g_args &L, const c3_poa
                 for (int c0 = b; c0 < j; c0 += 16) {
                     const uint4 *hp = arena + (((int64_t)pos << vs) + ((c0 >> 4) & ((1 << vs) - 1))) * 3;
                     int t16[16];
-                    { int t8[8]; c3l_unpack8(hp[0], t8);
+                    { int t8[8]; c3l_unpack8(cs ? C3G_LDCS(hp) : hp[0], t8);
 #pragma unroll
                       for (int k = 0; k < 8; ++k) t16[k] = t8[k];
-                      c3l_unpack8(hp[1], t8);
+                      c3l_unpack8(cs ? C3G_LDCS(hp + 1) : hp[1], t8);
 #pragma unroll
                       for (int k = 0; k < 8; ++k) t16[8 + k] = t8[k]; }
 #pragma unroll
