@@ -1201,7 +1201,8 @@ static int run_impl(c3_handle *h, int32_t penalty, const double *coef, int32_t w
         }
         if ((rc = launch_encode(h, h->d_sp_ascii.p, h->d_sp_codes.p, h->total_sp))) return rc;
         CK(cudaEventRecord(h->ev[1], h->stream));                 // (encode_ms then only covers the splints)
-        const int nchunk = h->total_bases >= (64ll << 20) && n >= 64 * C3_PIPE_CHUNKS ? C3_PIPE_CHUNKS : 1;
+        // (chunks of at least 4 096 reads: what the packed conk kernel wants to fill the grid with pairs)
+        const int nchunk = h->total_bases >= (64ll << 20) ? std::max(1, std::min(C3_PIPE_CHUNKS, n / 4096)) : 1;
         int rb[C3_PIPE_CHUNKS + 1]; int64_t bb[C3_PIPE_CHUNKS + 1];
         for (int k = 0; k <= nchunk; ++k) {
             // chunk borders at reads holding equal shares of the bytes; byte ranges start 16-aligned (the encode kernel
