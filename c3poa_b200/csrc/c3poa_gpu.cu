@@ -1317,7 +1317,13 @@ extern "C" int c3_consensus_batch(c3_handle *h, int32_t n_reads, const char *rea
     CK(cudaSetDevice(h->device));
     int rc = stage_reads(h, n_reads, reads, read_off, n_splints, splints, splint_off, splint_idx, /*defer_reads=*/true);
     if (rc) return rc;
-    if ((rc = run_impl(h, penalty, coef, window, iters, min_dist, params, max_peaks, cons_cap, reads, read_off))) return rc;
+    if ((rc = run_impl(h, penalty, coef, window, iters, min_dist, params, max_peaks, cons_cap, reads, read_off))) {
+        // the deferred staging queued copies from the caller's buffers without waiting: nothing may still read them
+        // once this call has returned
+        (void)cudaStreamSynchronize(h->stream);
+        if (h->stream2) (void)cudaStreamSynchronize(h->stream2);
+        return rc;
+    }
     if ((rc = c3_fetch(h, out_peaks, out_sub_bounds, out_dang_bounds, out_cons, out_results))) return rc;
     return 0;
 }
