@@ -18,7 +18,7 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", params=["auto", "grp", "lane"])
 def gpu(request):
     """The CUDA handle.  No skip: on a GPU box a missing library/device must FAIL the test.
-    Every GPU test runs three times: "auto" (the group kernel for the bulk of short subreads in batches of >= 24 000
+    Every GPU test runs three times: "auto" (the group kernel for the bulk of short subreads in batches of >= 12 000
     reads, else the warp-per-read kernel), "grp" (the group kernel -- 8 lanes per read for the DP, one thread per read
     for the graph phases -- for everything it covers, the warp kernel takes what it declines) and "lane" (the
     thread-per-read lane kernel of round 1, same fallback)."""
